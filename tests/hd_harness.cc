@@ -1,0 +1,117 @@
+// hd_harness.cc -- TEST INFRASTRUCTURE.  Compiles the __host__ __device__ building blocks of the
+// CUDA path (nextdenovo_b200/csrc/nd_core.cuh) for the host and checks them, stage by stage,
+// against the oracle restatement on a .2bit file.  Lets the exact-semantics logic be validated on a
+// box without a GPU; the product never runs this code on the CPU.
+//
+// usage: hd_harness reads.2bit preset(k,w,hpc as "ava-ont"|"ava-pb"|"k17w10") [max_reads] [chunk]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../nextdenovo_b200/csrc/nd_core.cuh"
+#include "../oracle/nd_oracle.h"
+
+static std::vector<uint32_t> pack2bit(const char *s, int len)
+{
+    std::vector<uint32_t> w((len + 15) / 16 + 1, 0);
+    for (int i = 0; i < len; ++i) {
+        int c = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : 3;
+        w[i >> 4] |= (uint32_t)c << (30 - 2 * (i & 15));
+    }
+    return w;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: hd_harness reads.2bit preset [max_reads] [chunk]\n"); return 2; }
+    ndo_reads *R = ndo_read_2bit(argv[1]);
+    if (!R) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+    ndo_opt o; ndo_opt_preset(&o, NULL);
+    if (!strcmp(argv[2], "k17w10")) { ndo_opt_preset(&o, "ava-ont"); o.k = 17; o.w = 10; }
+    else ndo_opt_preset(&o, argv[2]);
+    int max_reads = argc > 3 ? atoi(argv[3]) : R->n;
+    int chunk = argc > 4 ? atoi(argv[4]) : 256;
+    if (max_reads > R->n) max_reads = R->n;
+    long bad_sketch = 0, bad_sort = 0, bad_hits = 0, n_hits_tot = 0, n_mz_tot = 0, n_a_tot = 0;
+
+    ndo_index *idx = ndo_index_build(R->n, (const char *const *)R->seq, R->len, (const char *const *)R->name, o.w, o.k, o.hpc);
+    int mid_occ = ndo_index_mid_occ(idx, o.mid_occ_frac);
+    fprintf(stderr, "[hd] n=%d mid_occ=%d keys=%zu\n", R->n, mid_occ, ndo_index_n_keys(idx));
+    nd_chain_par par = { o.max_gap, o.max_gap, o.bw, o.max_chain_skip, o.max_chain_iter, o.min_cnt, o.min_chain_score };
+
+    for (int r = 0; r < max_reads; ++r) {
+        int len = R->len[r];
+        // --- sketch, chunked ---
+        std::vector<ndo_u128> ref(len + 1);
+        size_t n_ref = ndo_sketch(R->seq[r], len, o.w, o.k, 0, o.hpc, ref.data(), 0);
+        std::vector<uint32_t> words = pack2bit(R->seq[r], len);
+        nd_seqview sv = { words.data(), nullptr, len };
+        std::vector<nd_u128> got;
+        int cl = chunk + (r % 7) * 13;                  // vary the chunking between reads
+        for (int cs = 0; cs < len; cs += cl) {
+            int ce = cs + cl < len ? cs + cl : len;
+            std::vector<nd_u128> tmp(cl + o.w + 8);
+            int n = nd_sketch_chunk<16>(sv, o.w, o.k, o.hpc, 0, cs, ce, tmp.data(), (int)tmp.size());
+            if (n > (int)tmp.size()) { fprintf(stderr, "overflow read %d\n", r); return 1; }
+            got.insert(got.end(), tmp.begin(), tmp.begin() + n);
+        }
+        bool ok = got.size() == n_ref;
+        for (size_t i = 0; ok && i < n_ref; ++i) ok = got[i].x == ref[i].x && got[i].y == ref[i].y;
+        if (!ok) { if (bad_sketch < 5) fprintf(stderr, "sketch mismatch read %d: %zu vs %zu\n", r, got.size(), n_ref); ++bad_sketch; }
+        n_mz_tot += n_ref;
+
+        // --- seeds (oracle, unsorted) + exact sort ---
+        int64_t n_a;
+        ndo_u128 *a0 = ndo_collect_seeds(idx, &o, mid_occ, R->name[r], len, ref.data(), n_ref, &n_a, 0);
+        std::vector<nd_u128> mine(n_a);
+        memcpy(mine.data(), a0, n_a * 16);
+        ndo_rs_sort_128x(a0, a0 + n_a);
+        {
+            std::vector<nd_rs_job> jobs(2 * (n_a / 65 + 1) + 2);
+            uint32_t head[256], tail[256];
+            nd_rs_sort_128x_seq(mine.data(), (uint32_t)n_a, jobs.data(), head, tail);
+        }
+        if (n_a && memcmp(mine.data(), a0, n_a * 16) != 0) { if (bad_sort < 5) fprintf(stderr, "sort mismatch read %d (n_a=%ld)\n", r, (long)n_a); ++bad_sort; }
+        n_a_tot += n_a;
+
+        // --- chain per segment ---
+        std::vector<nd_hit> hits;
+        {
+            uint64_t sum_span = 0;
+            for (int64_t i = 0; i < n_a; ++i) sum_span += mine[i].y >> 32 & 0xff;
+            float avg = n_a ? (float)sum_span / n_a : 0.f;
+            std::vector<int32_t> f(n_a), p(n_a), v(n_a), t(n_a), e(n_a);
+            uint32_t qh = ndo_query_hash(R->name[r], len, o.seed);
+            int64_t s0 = 0;
+            for (int64_t i = 1; i <= n_a; ++i) {
+                if (i == n_a || mine[i].x > mine[i - 1].x + (nd_u64)par.max_dist_x) {
+                    int n = (int)(i - s0);
+                    if (n >= par.min_cnt) {
+                        nd_chain_fill_seq(mine.data() + s0, n, par, avg, f.data() + s0, p.data() + s0, v.data() + s0, t.data() + s0);
+                        nd_chain_backtrack_seq(mine.data() + s0, n, par, f.data() + s0, p.data() + s0, v.data() + s0, t.data() + s0,
+                                               e.data() + s0, qh, len, r, (int)s0, [&](const nd_hit &h) { hits.push_back(h); });
+                    }
+                    s0 = i;
+                }
+            }
+            std::sort(hits.begin(), hits.end(), [](const nd_hit &a, const nd_hit &b) { return a.zkey > b.zkey; });
+        }
+        int n_regs;
+        ndo_reg *regs = ndo_map_read(idx, &o, mid_occ, R->name[r], R->seq[r], len, &n_regs);
+        bool hok = (int)hits.size() == n_regs;
+        for (int i = 0; hok && i < n_regs; ++i) {
+            const nd_hit &h = hits[i]; const ndo_reg &g = regs[i];
+            hok = h.rid == g.rid && h.rev == g.rev && h.qs == g.qs && h.qe == g.qe && h.rs == g.rs && h.re == g.re &&
+                  h.mlen == g.mlen && h.blen == g.blen && h.score == g.score && h.cnt == g.cnt && (uint32_t)h.zkey == g.hash;
+        }
+        if (!hok) { if (bad_hits < 5) fprintf(stderr, "hits mismatch read %d: %zu vs %d\n", r, hits.size(), n_regs); ++bad_hits; }
+        n_hits_tot += n_regs;
+        free(regs); free(a0);
+    }
+    printf("reads=%d minimizers=%ld anchors=%ld hits=%ld bad_sketch=%ld bad_sort=%ld bad_hits=%ld\n",
+           max_reads, n_mz_tot, n_a_tot, n_hits_tot, bad_sketch, bad_sort, bad_hits);
+    ndo_index_free(idx);
+    ndo_reads_free(R);
+    return (bad_sketch || bad_sort || bad_hits) ? 1 : 0;
+}

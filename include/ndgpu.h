@@ -1,0 +1,153 @@
+/*
+ * ndgpu.h -- C ABI of the B200-native read-overlap engine (libndgpu.so).
+ *
+ * The reference (Nextomics/NextDenovo, minimap2-nd) has no plugin/FFI interface for this path: its
+ * contract is the process boundary (argv in, .ovl bytes out).  This header is the seam *inside*
+ * that process where "host C calls CUDA": each entry point below replaces one stage of the
+ * reference's in-process pipeline and is exactly what a maintainer would bind from
+ * minimap2/main.c / minimap2/map.c (see INTEGRATION.md for the stub).  All "ref:" citations are
+ * relative to the reference tree.
+ *
+ * Conventions: plain C, caller-owned host buffers unless stated, int return codes (0 = success,
+ * negative = failure; ndg_last_error() gives the message), no exceptions cross the boundary, one
+ * context per GPU and per host thread.  There is no CPU fallback: every compute entry point fails
+ * with NDG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NDGPU_H
+#define NDGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDG_OK            0
+#define NDG_ERR_ARG      (-1)
+#define NDG_ERR_CUDA     (-2)
+#define NDG_ERR_NOMEM    (-3)
+#define NDG_ERR_OVERFLOW (-4)
+#define NDG_ERR_STATE    (-5)
+
+typedef struct ndg_ctx ndg_ctx_t;
+
+/* Effective options of the hot path.
+ * ref: mm_idxopt_t / mm_mapopt_t, minimap2/minimap.h:102-170; defaults minimap2/options.c:4-64;
+ *      presets minimap2/options.c:89-97. */
+typedef struct {
+    int32_t k, w, hpc;                    /* -k -w -H */
+    int32_t flag_no_diag, flag_no_dual;   /* MM_F_NO_DIAG, MM_F_NO_DUAL (minimap.h:8-9) */
+    int32_t min_cnt, min_chain_score;     /* -n -m */
+    int32_t bw, max_gap;                  /* -r -g */
+    int32_t max_chain_skip, max_chain_iter;
+    int32_t seed;                         /* --seed (options.c:16) */
+    float   mid_occ_frac;                 /* -f (<1) */
+    int32_t mid_occ;                      /* -f (>=1); <=0: derive from the first index part */
+    int32_t min_mid_occ;                  /* --min-occ-floor */
+} ndg_opt_t;
+
+/* A batch of reads, 2-bit packed exactly as the words of a .2bit record
+ * (ref: lib/bseq.c:114-139: 16 bases per little-endian u32, first base in the top two bits).
+ * name_key: any u64 whose unsigned order equals strcmp() order of the read names and whose
+ * equality equals string equality, consistently between the targets of the current index part and
+ * the queries (ref: minimap2/map.c:126-148 uses strcmp on names).  name_hash: __ac_X31_hash_string
+ * of the name (ref: minimap2/khash.h:383-388, used at minimap2/map.c:525). */
+typedef struct {
+    int32_t n_reads;
+    const uint32_t *words;      /* all reads, concatenated */
+    const uint64_t *word_off;   /* n_reads+1 offsets into words[] (even when nmask != NULL) */
+    const uint32_t *len;        /* bases per read */
+    const uint32_t *nmask;      /* optional: 1 bit per base, bit (i&31) of nmask[word_off/2 + (i>>5)] = ambiguous */
+    const uint64_t *name_key;
+    const uint32_t *name_hash;
+} ndg_reads_t;
+
+/* One chain-derived hit: the fields of mm_reg1_t (ref: minimap2/minimap.h:84-99) that leave the
+ * hot path (.ovl writer minimap2/map.c:1299-1310, PAF writer minimap2/format.c:304-318). */
+typedef struct {
+    uint64_t zkey;              /* (score<<32|cnt) ^ hash: order key of mm_gen_regs (hit.c:62-71) */
+    int32_t  qidx;              /* query index within the batch */
+    int32_t  rid;               /* target index within the index part */
+    int32_t  qs, qe, rs, re;
+    int32_t  mlen, blen;
+    int32_t  score, cnt;
+    int32_t  rev;
+    int32_t  as;
+} ndg_hit_t;
+
+typedef struct {
+    int64_t n_hits;
+    const ndg_hit_t *hits;      /* pinned host memory owned by the context; sorted by qidx, then in the
+                                   reference's per-query output order; valid until the next map call */
+    uint64_t n_minimizers, n_anchors, n_segments;   /* work counters of this call */
+} ndg_map_result_t;
+
+typedef struct {
+    uint64_t n_seq, n_minimizers, n_distinct, n_singletons, sum_len;
+    int32_t mid_occ;
+} ndg_index_stat_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int  ndg_init(int device, ndg_ctx_t **ctx);
+void ndg_destroy(ndg_ctx_t *ctx);
+const char *ndg_last_error(const ndg_ctx_t *ctx);
+const char *ndg_version(void);
+int  ndg_set_opt(ndg_ctx_t *ctx, const ndg_opt_t *opt);
+/* tuning: bases per device sub-batch, anchors per sub-batch (0 = default) */
+int  ndg_set_limits(ndg_ctx_t *ctx, uint64_t sub_batch_bases, uint64_t max_anchors);
+/* variant 0 = one thread per read/segment (baseline kernels), 1 = warp-cooperative kernels */
+int  ndg_set_variant(ndg_ctx_t *ctx, int sort_variant, int chain_variant);
+
+/* ---- index: replaces mm_idx_gen()/mm_idx_post() (ref: minimap2/index.c:353-372,191-248) and
+ *      mm_idx_cal_max_occ() (index.c:164-185) for one index part ------------------------------ */
+int ndg_index_begin(ndg_ctx_t *ctx);
+/* register target metadata (len, name_key) and sketch the targets on this GPU; rid continues */
+int ndg_index_add(ndg_ctx_t *ctx, const ndg_reads_t *targets);
+/* register metadata only (targets sketched on another GPU, see ndg_index_import) */
+int ndg_index_add_meta(ndg_ctx_t *ctx, const ndg_reads_t *targets);
+/* multi-GPU: raw (x,y) minimizers sketched so far, device pointer; and the converse */
+int ndg_index_export(ndg_ctx_t *ctx, const void **dev_minimizers, uint64_t *n);
+int ndg_index_import(ndg_ctx_t *ctx, const void *dev_minimizers, uint64_t n);
+int ndg_index_clear_minimizers(ndg_ctx_t *ctx);
+int ndg_index_finalize(ndg_ctx_t *ctx, ndg_index_stat_t *stat);
+/* point query, for tests: replaces mm_idx_get (ref: minimap2/index.c:81-98). positions copied to host */
+int ndg_index_get(ndg_ctx_t *ctx, uint64_t minier, uint64_t *pos, int cap, int *n);
+
+/* ---- mapping: replaces kt_for(worker_for) -> mm_map_frag() for a batch of queries
+ *      (ref: minimap2/map.c:1241-1244, 879-906, 507-623), chain-only regime ------------------ */
+int ndg_map_batch(ndg_ctx_t *ctx, const ndg_reads_t *queries, ndg_map_result_t *out);
+/* the same in three steps, for measurement with inputs resident in HBM */
+int ndg_map_upload(ndg_ctx_t *ctx, const ndg_reads_t *queries);      /* H2D only (single sub-batch) */
+int ndg_map_resident(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* kernels only; hits stay on device */
+int ndg_map_download(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* D2H of the hits */
+
+/* ---- sketch only, for tests: replaces mm_sketch (ref: minimap2/sketch.c:358-361) ----------- */
+/* returns minimizers of all reads, concatenated; off has n_reads+1 entries */
+int ndg_sketch(ndg_ctx_t *ctx, const ndg_reads_t *reads, uint32_t rid0, uint64_t *xy, uint64_t cap, uint64_t *off);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+/* copy a stage buffer of the last ndg_map_resident()/ndg_map_batch() sub-batch to the host.
+ * what: "mz" (u128), "mz_off" (u64), "anchors" (u128, sorted), "a_off" (u64), "f","p","v" (i32) */
+int64_t ndg_debug_fetch(ndg_ctx_t *ctx, const char *what, void *dst, uint64_t cap_bytes);
+/* accumulated device time per kernel family since the last reset: names/ms/launches/bytes arrays */
+int ndg_prof_get(ndg_ctx_t *ctx, int max, const char **names, double *ms, uint64_t *launches);
+int ndg_prof_reset(ndg_ctx_t *ctx);
+uint64_t ndg_kernel_launches(const ndg_ctx_t *ctx);
+
+/* ---- .ovl codec (host side, table-free; byte-identical to lib/ovl.c:10-29,109-150) --------- */
+int ndg_ovl_encode8(uint8_t *dst, uint32_t state[2], int rev, uint32_t qname, uint32_t qs, uint32_t qe,
+                    uint32_t tname, uint32_t ts, uint32_t te, uint32_t match);
+
+/* Step-1 emitter: applies the reference's output filter (ref: minimap2/map.c:1297-1304: drop hits whose
+ * target is the query itself, keep qe-qs >= minlen, optional --dvt test :804-821) to a sorted hit list
+ * and appends 8-field records.  q_id/q_key/q_len are indexed by hit.qidx, t_id/t_key/t_len by hit.rid
+ * (ids = strtoul(name)).  Returns bytes written or <0; *n_rec and *sum_qspan are incremented. */
+int64_t ndg_ovl_emit_step1(const ndg_hit_t *hits, int64_t n_hits,
+                           const uint32_t *q_id, const uint64_t *q_key, const uint32_t *q_len,
+                           const uint32_t *t_id, const uint64_t *t_key, const uint32_t *t_len,
+                           int32_t minlen, int32_t dvt, int32_t maxhan1, int32_t maxhan2,
+                           uint32_t state[2], uint8_t *dst, uint64_t cap, uint64_t *n_rec, uint64_t *sum_qspan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

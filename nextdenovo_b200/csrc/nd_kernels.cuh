@@ -1,0 +1,357 @@
+// nd_kernels.cuh -- sm_100a kernels of the overlap hot path (baseline generation: one thread per
+// chunk / minimizer / read / segment; the warp-cooperative generation lives in nd_warp.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "nd_core.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+
+// last index r in [0,n) with off[r] <= v   (off is non-decreasing, off[0] <= v)
+__device__ __forceinline__ int nd_find_owner(const nd_u64 *off, int n, nd_u64 v)
+{
+    int lo = 0, hi = n;            // invariant: off[lo] <= v, (hi == n or off[hi] > v)
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index hash table: open addressing, linear probing.  key = minimizer hash (< 2^56),
+// val = offset<<24 | min(count, 2^24-1).  ref: replaces khash buckets of minimap2/index.c:191-243
+// ------------------------------------------------------------------------------------------------
+struct nd_ht_slot { nd_u64 key, val; };
+#define ND_HT_EMPTY ND_U64_MAX
+
+__device__ __forceinline__ nd_u64 nd_ht_hash(nd_u64 key) { return key * 0x9E3779B97F4A7C15ULL; }
+
+__device__ __forceinline__ bool nd_ht_lookup(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u64 *off, uint32_t *n)
+{
+    const nd_u64 maskc = (1ULL << log2cap) - 1;
+    nd_u64 s = nd_ht_hash(key) >> (64 - log2cap);
+    for (;;) {
+        // 16-byte vector load of the slot
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(tab + s));
+        if (e.x == key) { *off = e.y >> 24; *n = (uint32_t)(e.y & 0xffffff); return true; }
+        if (e.x == ND_HT_EMPTY) return false;
+        s = (s + 1) & maskc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sketch
+// ------------------------------------------------------------------------------------------------
+
+struct nd_reads_dev {
+    const uint32_t *words;
+    const nd_u64 *word_off;
+    const uint32_t *len;
+    const uint32_t *nmask;
+    const nd_u64 *name_key;
+    const uint32_t *name_hash;
+    int n_reads;
+};
+
+// one thread per chunk of C bases; chunk_off[r] = index of read r's first chunk
+template <int RW>
+__global__ void __launch_bounds__(128)
+k_sketch_chunks(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int C, int w, int k, int hpc,
+                uint32_t rid0, int use_rid, nd_u128 *staging, int S, uint32_t *cnt, int *overflow)
+{
+    nd_u64 g = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    int r = nd_find_owner(chunk_off, R.n_reads, g);
+    int len = (int)R.len[r];
+    int cs = (int)(g - chunk_off[r]) * C;
+    int ce = cs + C < len ? cs + C : len;
+    nd_seqview sv;
+    sv.words = R.words + R.word_off[r];
+    sv.nmask = R.nmask ? R.nmask + (R.word_off[r] >> 1) : nullptr;
+    sv.len = len;
+    int n = nd_sketch_chunk<RW>(sv, w, k, hpc, use_rid ? rid0 + (uint32_t)r : 0u, cs, ce, staging + g * (nd_u64)S, S);
+    if (n > S) { atomicExch(overflow, 1); n = S; }
+    cnt[g] = (uint32_t)n;
+}
+
+// one warp per chunk: staging -> packed minimizer array
+__global__ void k_sketch_compact(const nd_u128 *staging, int S, const uint32_t *cnt, const nd_u64 *pos,
+                                 nd_u64 n_chunks, nd_u128 *mz)
+{
+    nd_u64 g = ((nd_u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= n_chunks) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(staging + g * (nd_u64)S);
+    uint4 *dst = reinterpret_cast<uint4 *>(mz + pos[g]);
+    int n = (int)cnt[g];
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// off_out[r] = pos[chunk_off[r]] (pos has n_chunks+1 entries)
+__global__ void k_gather_off(const nd_u64 *pos, const nd_u64 *chunk_off, int n_plus1, nd_u64 *off_out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_plus1) off_out[r] = pos[chunk_off[r]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// index build helpers
+// ------------------------------------------------------------------------------------------------
+
+__global__ void k_split_xy(const nd_u128 *mz, nd_u64 n, nd_u64 *key, nd_u64 *val)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nd_u128 m = mz[i];
+    key[i] = m.x >> 8; val[i] = m.y;
+}
+
+__global__ void k_count_heads(const nd_u64 *key, nd_u64 n, nd_u64 *n_distinct)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool head = i < n && (i == 0 || key[i] != key[i - 1]);
+    unsigned m = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_distinct, (nd_u64)__popc(m));
+}
+
+// per run head: run length by binary search, insert into the table, histogram of run lengths
+__global__ void k_index_table(const nd_u64 *key, nd_u64 n, nd_ht_slot *tab, int log2cap, uint32_t *hist, int hist_bins)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nd_u64 kx = key[i];
+    if (i > 0 && key[i - 1] == kx) return;
+    nd_u64 lo = i, hi = n;                           // first index > i with key != kx
+    {   // gallop then bisect (runs are short)
+        nd_u64 step = 1;
+        while (lo + step < n && key[lo + step] == kx) { lo += step; step <<= 1; }
+        hi = lo + step < n ? lo + step : n;
+        while (hi - lo > 1) { nd_u64 mid = (lo + hi) >> 1; if (key[mid] == kx) lo = mid; else hi = mid; }
+    }
+    nd_u64 cnt = hi - i;
+    const nd_u64 maskc = (1ULL << log2cap) - 1;
+    nd_u64 s = nd_ht_hash(kx) >> (64 - log2cap);
+    for (;;) {
+        nd_u64 prev = atomicCAS(&tab[s].key, ND_HT_EMPTY, kx);
+        if (prev == ND_HT_EMPTY) { tab[s].val = i << 24 | (cnt < 0xffffffULL ? cnt : 0xffffffULL); break; }
+        s = (s + 1) & maskc;
+    }
+    atomicAdd(&hist[cnt < (nd_u64)hist_bins - 1 ? cnt : (nd_u64)hist_bins - 1], 1u);
+}
+
+__global__ void k_index_get(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u64 *out)
+{
+    nd_u64 off = 0; uint32_t n = 0;
+    nd_ht_lookup(tab, log2cap, key, &off, &n);
+    out[0] = off; out[1] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seeds: probe + count, then fill.  ref: minimap2/map.c:91-148,216-245
+// ------------------------------------------------------------------------------------------------
+
+struct nd_seed_par {
+    const nd_ht_slot *tab; int log2cap;
+    const nd_u64 *pos;                 // index position lists
+    const nd_u64 *t_key; const uint32_t *t_len;
+    int mid_occ, no_diag, no_dual;
+};
+
+__device__ __forceinline__ bool nd_skip_seed(const nd_seed_par &P, nd_u64 r, uint32_t q_pos, nd_u64 qkey, uint32_t qlen, int *is_self)
+{
+    *is_self = 0;
+    if (P.no_diag | P.no_dual) {
+        uint32_t rid = (uint32_t)(r >> 32);
+        nd_u64 tkey = __ldg(P.t_key + rid);
+        if (P.no_diag && tkey == qkey && __ldg(P.t_len + rid) == qlen) {
+            if ((uint32_t)r >> 1 == q_pos >> 1) return true;
+            if ((r & 1) == (q_pos & 1)) *is_self = 1;
+        }
+        if (P.no_dual && qkey > tkey) return true;
+    }
+    return false;
+}
+
+// one thread per query minimizer
+__global__ void __launch_bounds__(256)
+k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
+              nd_u64 *m_off, uint32_t *m_n, uint32_t *m_keep)
+{
+    nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mz) return;
+    nd_u128 z = mz[m];
+    nd_u64 off = 0; uint32_t n = 0, keep = 0;
+    if (nd_ht_lookup(P.tab, P.log2cap, z.x >> 8, &off, &n) && n < (uint32_t)P.mid_occ) {
+        int r = nd_find_owner(mz_off, Q.n_reads, m);
+        nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y;
+        for (uint32_t kk = 0; kk < n; ++kk) {
+            int self;
+            keep += !nd_skip_seed(P, __ldg(P.pos + off + kk), q_pos, qkey, qlen, &self);
+        }
+    } else n = 0;
+    m_off[m] = off; m_n[m] = n; m_keep[m] = keep;
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
+               const nd_u64 *m_off, const uint32_t *m_n, const uint32_t *m_keep, const nd_u64 *a_pos, nd_u128 *a)
+{
+    nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mz) return;
+    if (m_keep[m] == 0) return;
+    nd_u128 z = mz[m];
+    int r = nd_find_owner(mz_off, Q.n_reads, m);
+    nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y, q_span = (uint32_t)(z.x & 0xff);
+    bool tandem = false;                                   // ref: map.c:113-115
+    if (m > mz_off[r] && (mz[m - 1].x >> 8) == (z.x >> 8)) tandem = true;
+    if (m + 1 < mz_off[r + 1] && (mz[m + 1].x >> 8) == (z.x >> 8)) tandem = true;
+    nd_u64 off = m_off[m]; uint32_t n = m_n[m];
+    nd_u128 *dst = a + a_pos[m];
+    for (uint32_t kk = 0; kk < n; ++kk) {
+        nd_u64 rr = __ldg(P.pos + off + kk);
+        int self;
+        if (nd_skip_seed(P, rr, q_pos, qkey, qlen, &self)) continue;
+        nd_u128 o;
+        uint32_t rpos = (uint32_t)rr >> 1;
+        if ((rr & 1) == (q_pos & 1)) {
+            o.x = (rr & 0xffffffff00000000ULL) | rpos;
+            o.y = (nd_u64)q_span << 32 | (q_pos >> 1);
+        } else {
+            o.x = 1ULL << 63 | (rr & 0xffffffff00000000ULL) | rpos;
+            o.y = (nd_u64)q_span << 32 | (uint32_t)((int32_t)qlen - (int32_t)((q_pos >> 1) + 1 - q_span) - 1);
+        }
+        if (tandem) o.y |= ND_SEED_TANDEM;
+        if (self) o.y |= ND_SEED_SELF;
+        *dst++ = o;
+    }
+}
+
+// per read: anchor offsets and the float average query span (ref: chain.c:41-42)
+__global__ void k_read_stats(const nd_u128 *mz, const nd_u64 *mz_off, const uint32_t *m_keep, const nd_u64 *a_pos,
+                             int n_reads, nd_u64 *a_off, float *avg_qspan)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    nd_u64 b = mz_off[r];
+    a_off[r] = a_pos[b];
+    if (r == n_reads) return;
+    nd_u64 e = mz_off[r + 1], sum = 0, n = a_pos[e] - a_pos[b];
+    for (nd_u64 m = b; m < e; ++m) sum += (nd_u64)m_keep[m] * (mz[m].x & 0xff);
+    avg_qspan[r] = n ? __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n)) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// anchor sort, baseline: one thread per read runs the exact flag-sort emulation
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_sort_seq(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    nd_u64 b = a_off[r], n = a_off[r + 1] - b;
+    if (n < 2) return;
+    uint32_t head[256], tail[256];
+    nd_rs_sort_128x_seq(a + b, (uint32_t)n, jobs + 2 * (b / 65) + 4 * (nd_u64)r, head, tail);
+}
+
+// ------------------------------------------------------------------------------------------------
+// segments
+// ------------------------------------------------------------------------------------------------
+__global__ void k_seg_flags(const nd_u128 *a, nd_u64 n, nd_u64 max_dist_x, uint8_t *flag)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0 || a[i].x > a[i - 1].x + max_dist_x) ? 1 : 0;
+}
+__global__ void k_seg_read_starts(const nd_u64 *a_off, int n_reads, uint8_t *flag)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads && a_off[r] < a_off[r + 1]) flag[a_off[r]] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain
+// ------------------------------------------------------------------------------------------------
+struct nd_chain_bufs { int32_t *f, *p, *v, *t, *e; };
+
+// query hash used to randomise the order of a read's hits.  ref: minimap2/map.c:525-527, khash.h:400-409
+__device__ __forceinline__ uint32_t nd_wang32(uint32_t key)
+{
+    key += ~(key << 15); key ^= (key >> 10); key += (key << 3);
+    key ^= (key >> 6);   key += ~(key << 11); key ^= (key >> 16);
+    return key;
+}
+__device__ __forceinline__ uint32_t nd_query_hash(uint32_t name_hash, uint32_t qlen, int seed)
+{
+    uint32_t h = name_hash;
+    h ^= nd_wang32(qlen) + nd_wang32((uint32_t)seed);
+    return nd_wang32(h);
+}
+
+struct nd_seg_view {
+    const nd_u128 *a; nd_u64 n_a;
+    const uint32_t *seg_start; uint32_t n_seg;
+    const nd_u64 *a_off;
+};
+
+// segment s -> [b, e); returns false when the segment cannot yield a chain (too few anchors / too
+// little total span to reach min_cnt / min_chain_score)
+__device__ __forceinline__ bool nd_seg_bounds(const nd_seg_view &S, uint32_t s, const nd_chain_par &par, int max_span, nd_u64 *b, int *n)
+{
+    nd_u64 lo = S.seg_start[s], hi = s + 1 < S.n_seg ? S.seg_start[s + 1] : S.n_a;
+    *b = lo; *n = (int)(hi - lo);
+    return *n >= par.min_cnt && (nd_i64)(*n) * max_span >= par.min_sc;
+}
+
+// forward DP, baseline: one thread per segment
+__global__ void __launch_bounds__(64)
+k_chain_fill_seq(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chain_par par, int max_span, nd_chain_bufs B)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S.n_seg) return;
+    nd_u64 b; int n;
+    if (!nd_seg_bounds(S, s, par, max_span, &b, &n)) return;
+    int r = nd_find_owner(S.a_off, Q.n_reads, b);
+    nd_chain_fill_seq(S.a + b, n, par, avg_qspan[r], B.f + b, B.p + b, B.v + b, B.t + b);
+}
+
+// chain ends -> backtrack -> hits: one thread per segment (pointer chasing; latency is hidden by
+// the number of segments in flight)
+__global__ void __launch_bounds__(64)
+k_chain_backtrack(nd_seg_view S, nd_reads_dev Q, nd_chain_par par, int max_span, int seed_h,
+                  nd_chain_bufs B, nd_hit *hits, nd_u64 hit_cap, nd_u64 *n_hits)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S.n_seg) return;
+    nd_u64 b; int n;
+    if (!nd_seg_bounds(S, s, par, max_span, &b, &n)) return;
+    int r = nd_find_owner(S.a_off, Q.n_reads, b);
+    uint32_t h = nd_query_hash(Q.name_hash[r], Q.len[r], seed_h);
+    nd_chain_backtrack_seq(S.a + b, n, par, B.f + b, B.p + b, B.v + b, B.t + b, B.e + b, h, (int)Q.len[r], r,
+                           (int)(b - S.a_off[r]),
+                           [&](const nd_hit &hit) {
+                               nd_u64 slot = atomicAdd(n_hits, 1ULL);
+                               if (slot < hit_cap) hits[slot] = hit;
+                           });
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit ordering helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hit_keys(const nd_hit *hits, nd_u64 n, nd_u64 *zkey, uint32_t *idx)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { zkey[i] = hits[i].zkey; idx[i] = (uint32_t)i; }
+}
+__global__ void k_hit_qidx(const nd_hit *hits, const uint32_t *idx, nd_u64 n, uint32_t *qidx)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) qidx[i] = (uint32_t)hits[idx[i]].qidx;
+}
+__global__ void k_hit_gather(const nd_hit *hits, const uint32_t *idx, nd_u64 n, int qidx_base, nd_hit *out)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { nd_hit h = hits[idx[i]]; h.qidx += qidx_base; out[i] = h; }
+}

@@ -1,0 +1,773 @@
+// ndgpu.cu -- C-ABI implementation (include/ndgpu.h): device memory, streams, kernel sequencing.
+// Compute happens only in the sm_100a kernels of nd_kernels.cuh / nd_warp.cuh; there is no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include "../../include/ndgpu.h"
+#include "nd_kernels.cuh"
+#include "nd_warp.cuh"
+
+static_assert(sizeof(nd_hit) == sizeof(ndg_hit_t), "hit layout");
+static_assert(sizeof(nd_hit) == 56, "hit size");
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; } want = bytes; }
+        cap = want;
+        return 0;
+    }
+    int grow_keep(size_t bytes, size_t used, cudaStream_t st) {   // preserves the first `used` bytes
+        if (bytes <= cap) return 0;
+        void *np = nullptr; size_t want = std::max(bytes + bytes / 2, (size_t)1 << 20);
+        if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); want = bytes; if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); return -1; } }
+        if (p && used) cudaMemcpyAsync(np, p, used, cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {   // pinned
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct ProfEntry { std::string name; double ms = 0; uint64_t launches = 0; };
+struct ProfPending { int id; cudaEvent_t a, b; };
+
+struct ReadsDev {            // a batch of reads resident on the device
+    DevBuf words, word_off, len, nmask, name_key, name_hash, chunk_off;
+    int n_reads = 0; uint64_t n_words = 0, n_chunks = 0, n_bases = 0; bool has_nmask = false;
+    nd_reads_dev view() const {
+        nd_reads_dev v;
+        v.words = words.as<uint32_t>(); v.word_off = word_off.as<nd_u64>(); v.len = len.as<uint32_t>();
+        v.nmask = has_nmask ? nmask.as<uint32_t>() : nullptr;
+        v.name_key = name_key.as<nd_u64>(); v.name_hash = name_hash.as<uint32_t>(); v.n_reads = n_reads;
+        return v;
+    }
+    void release() { words.release(); word_off.release(); len.release(); nmask.release(); name_key.release(); name_hash.release(); chunk_off.release(); }
+};
+
+} // namespace
+
+struct ndg_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    ndg_opt_t opt;
+    std::string err;
+    uint64_t sub_batch_bases = 64ull << 20, max_anchors = 0;
+    int sort_variant = 1, chain_variant = 1;
+    int chunk_bases = 512;
+    int n_sm = 148;
+    void *hk_scope = nullptr;
+    uint64_t launches = 0;
+    // profiling
+    std::vector<ProfEntry> prof; std::vector<ProfPending> pending; std::vector<cudaEvent_t> ev_pool;
+    // index
+    DevBuf tmz; uint64_t n_tmz = 0;               // raw target minimizers (x,y)
+    DevBuf t_key, t_len; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen; uint32_t n_targets = 0; uint64_t t_sum_len = 0;
+    DevBuf idx_pos, idx_tab; int log2cap = 0; uint64_t n_pos = 0; bool index_ready = false;
+    int mid_occ = 0;
+    // mapping workspace
+    ReadsDev q;
+    DevBuf staging, cnt, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a_off, avgq, jobs, flags, seg_start,
+           f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
+    HostBuf h_scalars, h_hits, h_stage;
+    uint64_t n_mz = 0, n_a = 0, n_seg = 0, n_hits = 0;
+    int overflow_flag = 0;
+    // upload staging
+    HostBuf up;
+};
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int fail(ndg_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    c->err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(c, NDG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } while (0)
+#define RSV(buf, bytes) do { if ((buf).reserve(bytes)) return fail(c, NDG_ERR_NOMEM, "%s:%d out of device memory reserving %zu bytes for " #buf, __FILE__, __LINE__, (size_t)(bytes)); } while (0)
+
+int prof_id(ndg_ctx *c, const char *name)
+{
+    for (size_t i = 0; i < c->prof.size(); ++i) if (c->prof[i].name == name) return (int)i;
+    ProfEntry e; e.name = name; c->prof.push_back(e); return (int)c->prof.size() - 1;
+}
+cudaEvent_t ev_get(ndg_ctx *c)
+{
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+    ndg_ctx *c; ProfPending pp;
+    ProfScope(ndg_ctx *c_, const char *name) : c(c_) { pp.id = prof_id(c, name); pp.a = ev_get(c); pp.b = ev_get(c); cudaEventRecord(pp.a, c->st); }
+    ~ProfScope() { cudaEventRecord(pp.b, c->st); c->pending.push_back(pp); c->prof[pp.id].launches++; c->launches++; }
+};
+void prof_flush(ndg_ctx *c)
+{
+    for (auto &pp : c->pending) {
+        float ms = 0; cudaEventSynchronize(pp.b);
+        if (cudaEventElapsedTime(&ms, pp.a, pp.b) == cudaSuccess) c->prof[pp.id].ms += ms;
+        c->ev_pool.push_back(pp.a); c->ev_pool.push_back(pp.b);
+    }
+    c->pending.clear();
+}
+#define KLAUNCH(name, ...) do { ProfScope ps__(c, name); __VA_ARGS__; } while (0)
+
+void hk_begin(void *ctx, const char *name) { ndg_ctx *c = (ndg_ctx *)ctx; c->hk_scope = new ProfScope(c, name); }
+void hk_end(void *ctx) { ndg_ctx *c = (ndg_ctx *)ctx; delete (ProfScope *)c->hk_scope; c->hk_scope = nullptr; }
+
+inline unsigned nblk(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// exclusive prefix sum u32 -> u64 (n+1 outputs: out[n] = total)
+int scan_u32_to_u64(ndg_ctx *c, const uint32_t *in, nd_u64 *out, uint64_t n)
+{
+    size_t tmp = 0;
+    auto it = cub::TransformInputIterator<nd_u64, cub::CastOp<nd_u64>, const uint32_t *>(in, cub::CastOp<nd_u64>());
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, out, (long long)(n + 1), c->st));
+    RSV(c->cubtmp, tmp);
+    KLAUNCH("scan", CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, it, out, (long long)(n + 1), c->st)));
+    return 0;
+}
+
+// copy a host read batch (or a slice of it) to the device; computes chunk offsets
+int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
+{
+    int n = r1 - r0;
+    if (n <= 0) return fail(c, NDG_ERR_ARG, "empty read batch");
+    uint64_t w0 = R->word_off[r0], w1 = R->word_off[r1], nw = w1 - w0;
+    size_t hdr = (size_t)(n + 1) * 8 * 2 + (size_t)n * (4 + 8 + 4);
+    if (c->up.reserve(hdr)) return fail(c, NDG_ERR_NOMEM, "pinned staging");
+    uint64_t *h_woff = c->up.as<uint64_t>(), *h_coff = h_woff + (n + 1), *h_key = h_coff + (n + 1);
+    uint32_t *h_len = reinterpret_cast<uint32_t *>(h_key + n), *h_hash = h_len + n;
+    uint64_t chunks = 0, bases = 0;
+    for (int i = 0; i < n; ++i) {
+        h_woff[i] = R->word_off[r0 + i] - w0;
+        h_coff[i] = chunks;
+        uint32_t L = R->len[r0 + i];
+        chunks += (L + c->chunk_bases - 1) / c->chunk_bases;
+        bases += L;
+        h_len[i] = L;
+        h_key[i] = R->name_key ? R->name_key[r0 + i] : (uint64_t)(r0 + i);
+        h_hash[i] = R->name_hash ? R->name_hash[r0 + i] : 0;
+    }
+    h_woff[n] = nw; h_coff[n] = chunks;
+    D.n_reads = n; D.n_words = nw; D.n_chunks = chunks; D.n_bases = bases; D.has_nmask = R->nmask != nullptr;
+    RSV(D.words, (nw + 4) * 4); RSV(D.word_off, (size_t)(n + 1) * 8); RSV(D.chunk_off, (size_t)(n + 1) * 8);
+    RSV(D.len, (size_t)n * 4); RSV(D.name_key, (size_t)n * 8); RSV(D.name_hash, (size_t)n * 4);
+    CK(cudaMemcpyAsync(D.words.p, R->words + w0, nw * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.word_off.p, h_woff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.chunk_off.p, h_coff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.len.p, h_len, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.name_key.p, h_key, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.name_hash.p, h_hash, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    if (R->nmask) {
+        if ((w0 & 1) != 0) return fail(c, NDG_ERR_ARG, "nmask requires even word offsets");
+        RSV(D.nmask, (nw / 2 + 4) * 4);
+        CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, (nw / 2 + 1) * 4, cudaMemcpyHostToDevice, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));   // staging buffer is reused by the next call
+    return 0;
+}
+
+// sketch the device-resident reads D; result packed into `dst` (+dst_used entries kept), offsets into off_out
+// (n_reads+1 entries, relative to dst_used).  Returns number of minimizers via *n_out.
+int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevBuf &dst, uint64_t dst_used, bool keep,
+                 nd_u64 *off_out, uint64_t *n_out)
+{
+    const ndg_opt_t &o = c->opt;
+    if (o.k < 1 || o.k > 28 || o.w < 1 || o.w > 255) return fail(c, NDG_ERR_ARG, "k must be in [1,28] and w in [1,255] (long-k-mer sketch not implemented on the GPU path)");
+    int C = c->chunk_bases, S = C + o.w + 8;
+    uint64_t nc = D.n_chunks;
+    *n_out = 0;
+    RSV(c->scalars, 1024);
+    if (nc == 0) { if (off_out) CK(cudaMemsetAsync(off_out, 0, (size_t)(D.n_reads + 1) * 8, c->st)); return 0; }
+    RSV(c->staging, nc * (size_t)S * 16); RSV(c->cnt, (nc + 1) * 4); RSV(c->pos, (nc + 1) * 8);
+    int *d_over = c->scalars.as<int>();
+    CK(cudaMemsetAsync(d_over, 0, 4, c->st));
+    CK(cudaMemsetAsync(c->cnt.as<uint32_t>() + nc, 0, 4, c->st));
+    nd_reads_dev V = D.view();
+    if (o.w < 16)
+        KLAUNCH("sketch", (k_sketch_chunks<16><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
+                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over)));
+    else
+        KLAUNCH("sketch", (k_sketch_chunks<256><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
+                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over)));
+    CK(cudaGetLastError());
+    if (int rc = scan_u32_to_u64(c, c->cnt.as<uint32_t>(), c->pos.as<nd_u64>(), nc)) return rc;
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    CK(cudaMemcpyAsync(h, c->pos.as<nd_u64>() + nc, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(h + 1, d_over, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    uint64_t total = h[0];
+    if ((int)h[1]) return fail(c, NDG_ERR_OVERFLOW, "sketch staging overflow");
+    if (keep) { if (dst.grow_keep((dst_used + total + 1) * 16, dst_used * 16, c->st)) return fail(c, NDG_ERR_NOMEM, "minimizer buffer"); }
+    else RSV(dst, (dst_used + total + 1) * 16);
+    KLAUNCH("sketch_compact", (k_sketch_compact<<<nblk(nc * 32, 256), 256, 0, c->st>>>(c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->pos.as<nd_u64>(), nc,
+                               dst.as<nd_u128>() + dst_used)));
+    CK(cudaGetLastError());
+    if (off_out) {
+        KLAUNCH("misc", (k_gather_off<<<nblk(D.n_reads + 1, 256), 256, 0, c->st>>>(c->pos.as<nd_u64>(), D.chunk_off.as<nd_u64>(), D.n_reads + 1, off_out)));
+        CK(cudaGetLastError());
+    }
+    *n_out = total;
+    return 0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *ndg_version(void) { return "ndgpu 0.1 (sm_100a)"; }
+
+extern "C" int ndg_init(int device, ndg_ctx_t **out)
+{
+    if (!out) return NDG_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return NDG_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) return NDG_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NDG_ERR_CUDA;
+    if (prop.major != 10) { fprintf(stderr, "[ndgpu] device %d is sm_%d%d; this library carries sm_100a code only\n", device, prop.major, prop.minor); return NDG_ERR_CUDA; }
+    ndg_ctx *c = new ndg_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NDG_ERR_CUDA; }
+    memset(&c->opt, 0, sizeof c->opt);
+    c->opt.k = 15; c->opt.w = 10; c->opt.min_cnt = 3; c->opt.min_chain_score = 40; c->opt.bw = 500; c->opt.max_gap = 5000;
+    c->opt.max_chain_skip = 25; c->opt.max_chain_iter = 5000; c->opt.seed = 11; c->opt.mid_occ_frac = 2e-4f;
+    if (c->h_scalars.reserve(4096)) { delete c; return NDG_ERR_NOMEM; }
+    c->n_sm = prop.multiProcessorCount;
+    cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+    *out = c;
+    return NDG_OK;
+}
+
+extern "C" void ndg_destroy(ndg_ctx_t *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    prof_flush(c);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
+                       &c->m_keep, &c->a_pos, &c->a, &c->a_off, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
+                       &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
+    for (auto b : bufs) b->release();
+    c->q.release();
+    c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" const char *ndg_last_error(const ndg_ctx_t *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" uint64_t ndg_kernel_launches(const ndg_ctx_t *c) { return c ? c->launches : 0; }
+
+extern "C" int ndg_set_opt(ndg_ctx_t *c, const ndg_opt_t *o)
+{
+    if (!c || !o) return NDG_ERR_ARG;
+    c->opt = *o;
+    if (o->mid_occ > 0) c->mid_occ = o->mid_occ;
+    return NDG_OK;
+}
+extern "C" int ndg_set_limits(ndg_ctx_t *c, uint64_t sub_batch_bases, uint64_t max_anchors)
+{
+    if (!c) return NDG_ERR_ARG;
+    if (sub_batch_bases) c->sub_batch_bases = sub_batch_bases;
+    c->max_anchors = max_anchors;
+    return NDG_OK;
+}
+extern "C" int ndg_set_variant(ndg_ctx_t *c, int sort_variant, int chain_variant)
+{
+    if (!c) return NDG_ERR_ARG;
+    c->sort_variant = sort_variant; c->chain_variant = chain_variant;
+    return NDG_OK;
+}
+
+extern "C" int ndg_prof_get(ndg_ctx_t *c, int max, const char **names, double *ms, uint64_t *launches)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    prof_flush(c);
+    int n = std::min<int>(max, (int)c->prof.size());
+    for (int i = 0; i < n; ++i) { names[i] = c->prof[i].name.c_str(); ms[i] = c->prof[i].ms; launches[i] = c->prof[i].launches; }
+    return n;
+}
+extern "C" int ndg_prof_reset(ndg_ctx_t *c)
+{
+    if (!c) return NDG_ERR_ARG;
+    prof_flush(c);
+    for (auto &e : c->prof) { e.ms = 0; e.launches = 0; }
+    return NDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------------------
+extern "C" int ndg_index_begin(ndg_ctx_t *c)
+{
+    if (!c) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear();
+    c->index_ready = false; c->n_pos = 0;
+    return NDG_OK;
+}
+
+static int index_meta(ndg_ctx *c, const ndg_reads_t *T)
+{
+    for (int i = 0; i < T->n_reads; ++i) {
+        c->h_tkey.push_back(T->name_key ? T->name_key[i] : (uint64_t)(c->n_targets + i));
+        c->h_tlen.push_back(T->len[i]);
+        c->t_sum_len += T->len[i];
+    }
+    c->n_targets += T->n_reads;
+    return 0;
+}
+
+extern "C" int ndg_index_add_meta(ndg_ctx_t *c, const ndg_reads_t *T)
+{
+    if (!c || !T) return NDG_ERR_ARG;
+    return index_meta(c, T);
+}
+
+extern "C" int ndg_index_add(ndg_ctx_t *c, const ndg_reads_t *T)
+{
+    if (!c || !T || T->n_reads <= 0) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    uint32_t rid0 = c->n_targets;
+    int r0 = 0;
+    while (r0 < T->n_reads) {           // device sub-batches bounded by bases
+        int r1 = r0; uint64_t bases = 0;
+        while (r1 < T->n_reads && (r1 == r0 || bases + T->len[r1] <= c->sub_batch_bases)) bases += T->len[r1++];
+        if (int rc = upload_reads(c, c->q, T, r0, r1)) return rc;
+        uint64_t n = 0;
+        if (int rc = sketch_reads(c, c->q, rid0 + r0, 1, c->tmz, c->n_tmz, true, nullptr, &n)) return rc;
+        c->n_tmz += n;
+        r0 = r1;
+    }
+    return index_meta(c, T);
+}
+
+extern "C" int ndg_index_export(ndg_ctx_t *c, const void **dev, uint64_t *n)
+{
+    if (!c || !dev || !n) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    *dev = c->tmz.p; *n = c->n_tmz;
+    return NDG_OK;
+}
+extern "C" int ndg_index_clear_minimizers(ndg_ctx_t *c) { if (!c) return NDG_ERR_ARG; c->n_tmz = 0; return NDG_OK; }
+
+extern "C" int ndg_index_import(ndg_ctx_t *c, const void *dev, uint64_t n)
+{
+    if (!c || (!dev && n)) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->tmz.grow_keep((c->n_tmz + n + 1) * 16, c->n_tmz * 16, c->st)) return fail(c, NDG_ERR_NOMEM, "minimizer buffer");
+    CK(cudaMemcpyAsync(c->tmz.as<nd_u128>() + c->n_tmz, dev, n * 16, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->n_tmz += n;
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
+{
+    if (!c) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const uint64_t n = c->n_tmz;
+    const int HB = 65536;
+    if (n == 0) return fail(c, NDG_ERR_STATE, "index has no minimizers");
+    DevBuf key_in, val_in, key_out;
+    if (key_in.reserve(n * 8) || val_in.reserve(n * 8) || key_out.reserve(n * 8)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "index sort buffers"); }
+    RSV(c->idx_pos, n * 8);
+    KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, key_in.as<nd_u64>(), val_in.as<nd_u64>())));
+    size_t tmp = 0;
+    int end_bit = 2 * c->opt.k; if (end_bit > 64) end_bit = 64;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in.as<nd_u64>(), key_out.as<nd_u64>(), val_in.as<nd_u64>(), c->idx_pos.as<nd_u64>(), (long long)n, 0, end_bit, c->st);
+    if (c->cubtmp.reserve(tmp)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "cub temp"); }
+    {
+        ProfScope ps(c, "index_sort");
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, key_in.as<nd_u64>(), key_out.as<nd_u64>(), val_in.as<nd_u64>(), c->idx_pos.as<nd_u64>(), (long long)n, 0, end_bit, c->st);
+        if (e != cudaSuccess) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_CUDA, "radix sort: %s", cudaGetErrorString(e)); }
+    }
+    RSV(c->scalars, 1024);
+    nd_u64 *d_nd = c->scalars.as<nd_u64>() + 8;
+    cudaMemsetAsync(d_nd, 0, 8, c->st);
+    KLAUNCH("index_heads", (k_count_heads<<<nblk(n, 256), 256, 0, c->st>>>(key_out.as<nd_u64>(), n, d_nd)));
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    cudaMemcpyAsync(h, d_nd, 8, cudaMemcpyDeviceToHost, c->st);
+    cudaError_t e0 = cudaStreamSynchronize(c->st);
+    key_in.release(); val_in.release();
+    if (e0 != cudaSuccess) { key_out.release(); return fail(c, NDG_ERR_CUDA, "index: %s", cudaGetErrorString(e0)); }
+    uint64_t n_distinct = h[0];
+    int lg = 4; while ((1ULL << lg) < 2 * n_distinct) ++lg;
+    c->log2cap = lg;
+    DevBuf hist;
+    if (c->idx_tab.reserve((size_t)16 << lg) || hist.reserve(HB * 4)) { key_out.release(); hist.release(); return fail(c, NDG_ERR_NOMEM, "index table"); }
+    cudaMemsetAsync(c->idx_tab.p, 0xff, (size_t)16 << lg, c->st);
+    cudaMemsetAsync(hist.p, 0, HB * 4, c->st);
+    KLAUNCH("index_table", (k_index_table<<<nblk(n, 256), 256, 0, c->st>>>(key_out.as<nd_u64>(), n, c->idx_tab.as<nd_ht_slot>(), lg, hist.as<uint32_t>(), HB)));
+    std::vector<uint32_t> hh(HB);
+    cudaMemcpyAsync(hh.data(), hist.p, HB * 4, cudaMemcpyDeviceToHost, c->st);
+    e0 = cudaStreamSynchronize(c->st);
+    key_out.release(); hist.release();
+    if (e0 != cudaSuccess) return fail(c, NDG_ERR_CUDA, "index table: %s", cudaGetErrorString(e0));
+    // targets' metadata
+    RSV(c->t_key, (size_t)c->n_targets * 8 + 8); RSV(c->t_len, (size_t)c->n_targets * 4 + 4);
+    CK(cudaMemcpyAsync(c->t_key.p, c->h_tkey.data(), (size_t)c->n_targets * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->t_len.p, c->h_tlen.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    // mid_occ: ref minimap2/index.c:164-185 + options.c:66-76 (computed on the first part only)
+    if (c->mid_occ <= 0) {
+        if (c->opt.mid_occ_frac <= 0.f) c->mid_occ = INT32_MAX;
+        else {
+            uint32_t kth = (uint32_t)((1. - c->opt.mid_occ_frac) * n_distinct);
+            uint64_t acc = 0; int vbin = -1;
+            for (int b = 0; b < HB; ++b) { acc += hh[b]; if (acc > kth) { vbin = b; break; } }
+            if (vbin < 0 || vbin == HB - 1) return fail(c, NDG_ERR_OVERFLOW, "mid_occ order statistic beyond histogram range");
+            c->mid_occ = vbin + 1;
+        }
+        if (c->mid_occ < c->opt.min_mid_occ) c->mid_occ = c->opt.min_mid_occ;
+    }
+    c->n_pos = n; c->index_ready = true;
+    c->tmz.release(); c->n_tmz = 0;
+    if (stat) {
+        stat->n_seq = c->n_targets; stat->n_minimizers = n; stat->n_distinct = n_distinct; stat->n_singletons = hh[1];
+        stat->sum_len = c->t_sum_len; stat->mid_occ = c->mid_occ;
+    }
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_get(ndg_ctx_t *c, uint64_t minier, uint64_t *pos, int cap, int *n)
+{
+    if (!c || !n) return NDG_ERR_ARG;
+    if (!c->index_ready) return fail(c, NDG_ERR_STATE, "index not finalized");
+    cudaSetDevice(c->device);
+    RSV(c->scalars, 1024);
+    nd_u64 *d = c->scalars.as<nd_u64>() + 16;
+    k_index_get<<<1, 1, 0, c->st>>>(c->idx_tab.as<nd_ht_slot>(), c->log2cap, minier, d);
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    *n = (int)h[1];
+    int m = std::min<int>(cap, *n);
+    if (m > 0 && pos) { CK(cudaMemcpyAsync(pos, c->idx_pos.as<nd_u64>() + h[0], (size_t)m * 8, cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st)); }
+    return NDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sketch only (tests)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ndg_sketch(ndg_ctx_t *c, const ndg_reads_t *R, uint32_t rid0, uint64_t *xy, uint64_t cap, uint64_t *off)
+{
+    if (!c || !R || !off) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = upload_reads(c, c->q, R, 0, R->n_reads)) return rc;
+    RSV(c->mz_off, (size_t)(R->n_reads + 1) * 8);
+    uint64_t n = 0;
+    if (int rc = sketch_reads(c, c->q, rid0, 1, c->mz, 0, false, c->mz_off.as<nd_u64>(), &n)) return rc;
+    CK(cudaMemcpyAsync(off, c->mz_off.p, (size_t)(R->n_reads + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+    if (n > cap) { cudaStreamSynchronize(c->st); return fail(c, NDG_ERR_OVERFLOW, "sketch output needs %llu entries", (unsigned long long)n); }
+    if (n && xy) CK(cudaMemcpyAsync(xy, c->mz.p, n * 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return NDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mapping
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// all kernels of one device-resident sub-batch; hits left (sorted) in c->hits_sorted, count in c->n_hits
+int map_resident(ndg_ctx *c, int qidx_base)
+{
+    const ndg_opt_t &o = c->opt;
+    if (!c->index_ready) return fail(c, NDG_ERR_STATE, "index not finalized");
+    ReadsDev &Q = c->q;
+    const int nr = Q.n_reads;
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    c->n_mz = c->n_a = c->n_seg = c->n_hits = 0;
+    RSV(c->scalars, 1024);
+
+    // 1. sketch
+    RSV(c->mz_off, (size_t)(nr + 1) * 8);
+    if (int rc = sketch_reads(c, Q, 0, 0, c->mz, 0, false, c->mz_off.as<nd_u64>(), &c->n_mz)) return rc;
+    const uint64_t M = c->n_mz;
+    if (M == 0) return 0;
+
+    // 2. probe + count
+    nd_seed_par P; P.tab = c->idx_tab.as<nd_ht_slot>(); P.log2cap = c->log2cap; P.pos = c->idx_pos.as<nd_u64>();
+    P.t_key = c->t_key.as<nd_u64>(); P.t_len = c->t_len.as<uint32_t>(); P.mid_occ = c->mid_occ; P.no_diag = o.flag_no_diag; P.no_dual = o.flag_no_dual;
+    nd_reads_dev V = Q.view();
+    RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8);
+    CK(cudaMemsetAsync(c->m_keep.as<uint32_t>() + M, 0, 4, c->st));
+    KLAUNCH("probe_count", (k_probe_count<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
+                            c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>())));
+    CK(cudaGetLastError());
+    if (int rc = scan_u32_to_u64(c, c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), M)) return rc;
+    CK(cudaMemcpyAsync(h, c->a_pos.as<nd_u64>() + M, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NA = h[0];
+    c->n_a = NA;
+    if (NA == 0) return 0;
+    if (NA >= (1ULL << 32) - 64) return fail(c, NDG_ERR_OVERFLOW, "sub-batch yields %llu anchors; lower sub_batch_bases", (unsigned long long)NA);
+
+    // 3. fill + per-read stats
+    RSV(c->a, (NA + 1) * 16); RSV(c->a_off, (size_t)(nr + 1) * 8); RSV(c->avgq, (size_t)nr * 4 + 4);
+    KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
+                             c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), c->a.as<nd_u128>())));
+    KLAUNCH("read_stats", (k_read_stats<<<nblk(nr + 1, 128), 128, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_keep.as<uint32_t>(),
+                           c->a_pos.as<nd_u64>(), nr, c->a_off.as<nd_u64>(), c->avgq.as<float>())));
+    CK(cudaGetLastError());
+
+    // 4. exact sort (ref: minimap2/map.c:246 radix_sort_128x; tie order must match)
+    if (c->sort_variant == 0) {
+        RSV(c->jobs, (2 * (NA / 65) + 4 * (size_t)nr + 8) * sizeof(nd_rs_job));
+        KLAUNCH("sort_seq", (k_sort_seq<<<nblk(nr, 64), 64, 0, c->st>>>(c->a.as<nd_u128>(), c->a_off.as<nd_u64>(), nr, c->jobs.as<nd_rs_job>())));
+    } else {
+        RSV(c->jobs, 2 * (NA / 65 + (size_t)nr + 2) * sizeof(nd_rs_job));
+        ndw_launch_hooks hk = { hk_begin, hk_end, c };
+        ndw_sort_launch(c->st, c->a.as<nd_u128>(), c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 32, c->n_sm, hk);
+    }
+    CK(cudaGetLastError());
+
+    // 5. segments
+    RSV(c->flags, NA + 16); RSV(c->seg_start, (NA / 2 + 16) * 4);
+    KLAUNCH("seg_flags", (k_seg_flags<<<nblk(NA, 256), 256, 0, c->st>>>(c->a.as<nd_u128>(), NA, (nd_u64)o.max_gap, c->flags.as<uint8_t>())));
+    KLAUNCH("seg_flags", (k_seg_read_starts<<<nblk(nr, 256), 256, 0, c->st>>>(c->a_off.as<nd_u64>(), nr, c->flags.as<uint8_t>())));
+    {
+        // segments shorter than min_cnt can never produce a chain: they are dropped inside the chain kernel;
+        // the list itself can have up to NA entries, so select into a buffer of NA u32.
+        RSV(c->seg_start, (NA + 16) * 4);
+        size_t tmp = 0;
+        cub::CountingInputIterator<uint32_t> it(0);
+        uint32_t *d_nsel = c->scalars.as<uint32_t>() + 4;
+        CK(cub::DeviceSelect::Flagged(nullptr, tmp, it, c->flags.as<uint8_t>(), c->seg_start.as<uint32_t>(), d_nsel, (long long)NA, c->st));
+        RSV(c->cubtmp, tmp);
+        KLAUNCH("seg_select", CK(cub::DeviceSelect::Flagged(c->cubtmp.p, tmp, it, c->flags.as<uint8_t>(), c->seg_start.as<uint32_t>(), d_nsel, (long long)NA, c->st)));
+        CK(cudaMemcpyAsync(h, d_nsel, 4, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->n_seg = (uint32_t)h[0];
+    }
+
+    // 6. chain
+    const uint64_t hit_cap = NA / (o.min_cnt > 0 ? o.min_cnt : 1) + 16;
+    RSV(c->f, NA * 4); RSV(c->p, NA * 4); RSV(c->v, NA * 4); RSV(c->t, NA * 4); RSV(c->e, NA * 4);
+    RSV(c->hits, hit_cap * sizeof(nd_hit));
+    nd_u64 *d_nh = c->scalars.as<nd_u64>() + 4;
+    CK(cudaMemsetAsync(d_nh, 0, 8, c->st));
+    nd_chain_par par = { o.max_gap, o.max_gap, o.bw, o.max_chain_skip, o.max_chain_iter, o.min_cnt, o.min_chain_score };
+    nd_chain_bufs B = { c->f.as<int32_t>(), c->p.as<int32_t>(), c->v.as<int32_t>(), c->t.as<int32_t>(), c->e.as<int32_t>() };
+    const int max_span = o.hpc ? 255 : o.k;
+    nd_seg_view SV = { c->a.as<nd_u128>(), NA, c->seg_start.as<uint32_t>(), (uint32_t)c->n_seg, c->a_off.as<nd_u64>() };
+    if (c->chain_variant == 0) {
+        KLAUNCH("chain_fill_seq", (k_chain_fill_seq<<<nblk(c->n_seg, 64), 64, 0, c->st>>>(SV, V, c->avgq.as<float>(), par, max_span, B)));
+    } else {
+        KLAUNCH("chain_fill_warp", ndw_chain_fill_launch(c->st, SV, V, c->avgq.as<float>(), par, max_span, B, c->scalars.as<uint32_t>() + 48, c->n_sm));
+    }
+    CK(cudaGetLastError());
+    KLAUNCH("chain_backtrack", (k_chain_backtrack<<<nblk(c->n_seg, 64), 64, 0, c->st>>>(SV, V, par, max_span, o.seed, B, c->hits.as<nd_hit>(), hit_cap, d_nh)));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, d_nh, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NH = h[0];
+    if (NH > hit_cap) return fail(c, NDG_ERR_OVERFLOW, "hit buffer overflow (%llu > %llu)", (unsigned long long)NH, (unsigned long long)hit_cap);
+    c->n_hits = NH;
+    if (NH == 0) return 0;
+
+    // 7. order hits: by query, then by zkey descending (ref: minimap2/hit.c:69-71)
+    RSV(c->zkey, NH * 8); RSV(c->zkey2, NH * 8); RSV(c->hidx, NH * 4); RSV(c->hidx2, NH * 4); RSV(c->hq, NH * 4); RSV(c->hq2, NH * 4);
+    RSV(c->hits_sorted, NH * sizeof(nd_hit));
+    KLAUNCH("hit_order", (k_hit_keys<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), NH, c->zkey.as<nd_u64>(), c->hidx.as<uint32_t>())));
+    {
+        size_t t1 = 0, t2 = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx.as<uint32_t>(), c->hidx2.as<uint32_t>(), (long long)NH, 0, 64, c->st));
+        int qbits = 1; while ((1 << qbits) < nr + 1 && qbits < 31) ++qbits;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, t2, c->hq.as<uint32_t>(), c->hq2.as<uint32_t>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, qbits, c->st));
+        RSV(c->cubtmp, std::max(t1, t2));
+        KLAUNCH("hit_order", CK(cub::DeviceRadixSort::SortPairsDescending(c->cubtmp.p, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx.as<uint32_t>(), c->hidx2.as<uint32_t>(), (long long)NH, 0, 64, c->st)));
+        KLAUNCH("hit_order", (k_hit_qidx<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), c->hidx2.as<uint32_t>(), NH, c->hq.as<uint32_t>())));
+        KLAUNCH("hit_order", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, t2, c->hq.as<uint32_t>(), c->hq2.as<uint32_t>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, qbits, c->st)));
+    }
+    KLAUNCH("hit_order", (k_hit_gather<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), c->hidx.as<uint32_t>(), NH, qidx_base, c->hits_sorted.as<nd_hit>())));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ndg_map_upload(ndg_ctx_t *c, const ndg_reads_t *Q)
+{
+    if (!c || !Q || Q->n_reads <= 0) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    return upload_reads(c, c->q, Q, 0, Q->n_reads);
+}
+
+extern "C" int ndg_map_resident(ndg_ctx_t *c, ndg_map_result_t *out)
+{
+    if (!c) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    int rc = map_resident(c, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    if (out) { out->n_hits = (int64_t)c->n_hits; out->hits = nullptr; out->n_minimizers = c->n_mz; out->n_anchors = c->n_a; out->n_segments = c->n_seg; }
+    return NDG_OK;
+}
+
+extern "C" int ndg_map_download(ndg_ctx_t *c, ndg_map_result_t *out)
+{
+    if (!c || !out) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->h_hits.reserve((c->n_hits + 1) * sizeof(nd_hit))) return fail(c, NDG_ERR_NOMEM, "pinned hit buffer");
+    if (c->n_hits) CK(cudaMemcpyAsync(c->h_hits.p, c->hits_sorted.p, c->n_hits * sizeof(nd_hit), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    out->n_hits = (int64_t)c->n_hits; out->hits = c->h_hits.as<ndg_hit_t>();
+    out->n_minimizers = c->n_mz; out->n_anchors = c->n_a; out->n_segments = c->n_seg;
+    return NDG_OK;
+}
+
+extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_t *out)
+{
+    if (!c || !Q || !out || Q->n_reads <= 0) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    uint64_t tot_hits = 0, tot_mz = 0, tot_a = 0, tot_seg = 0;
+    int r0 = 0;
+    uint64_t budget = c->sub_batch_bases;
+    while (r0 < Q->n_reads) {
+        int r1 = r0; uint64_t bases = 0;
+        while (r1 < Q->n_reads && (r1 == r0 || bases + Q->len[r1] <= budget)) bases += Q->len[r1++];
+        if (int rc = upload_reads(c, c->q, Q, r0, r1)) return rc;
+        int rc = map_resident(c, r0);
+        if (rc == NDG_ERR_OVERFLOW && r1 - r0 > 1 && c->err.find("anchors") != std::string::npos) { budget = std::max<uint64_t>(bases / 2, 1); continue; }
+        if (rc) return rc;
+        if (c->h_hits.cap < (tot_hits + c->n_hits + 1) * sizeof(nd_hit)) {       // grow, preserving content
+            HostBuf nb; if (nb.reserve((tot_hits + c->n_hits + 1) * sizeof(nd_hit) * 2)) return fail(c, NDG_ERR_NOMEM, "pinned hit buffer");
+            if (tot_hits) memcpy(nb.p, c->h_hits.p, tot_hits * sizeof(nd_hit));
+            c->h_hits.release(); c->h_hits = nb;
+        }
+        if (c->n_hits) CK(cudaMemcpyAsync(c->h_hits.as<nd_hit>() + tot_hits, c->hits_sorted.p, c->n_hits * sizeof(nd_hit), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        tot_hits += c->n_hits; tot_mz += c->n_mz; tot_a += c->n_a; tot_seg += c->n_seg;
+        r0 = r1;
+    }
+    out->n_hits = (int64_t)tot_hits; out->hits = c->h_hits.as<ndg_hit_t>();
+    out->n_minimizers = tot_mz; out->n_anchors = tot_a; out->n_segments = tot_seg;
+    return NDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t ndg_debug_fetch(ndg_ctx_t *c, const char *what, void *dst, uint64_t cap)
+{
+    if (!c || !what) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const void *src = nullptr; uint64_t bytes = 0;
+    std::string w = what;
+    if (w == "mz") { src = c->mz.p; bytes = c->n_mz * 16; }
+    else if (w == "mz_off") { src = c->mz_off.p; bytes = (uint64_t)(c->q.n_reads + 1) * 8; }
+    else if (w == "anchors") { src = c->a.p; bytes = c->n_a * 16; }
+    else if (w == "a_off") { src = c->a_off.p; bytes = (uint64_t)(c->q.n_reads + 1) * 8; }
+    else if (w == "f") { src = c->f.p; bytes = c->n_a * 4; }
+    else if (w == "p") { src = c->p.p; bytes = c->n_a * 4; }
+    else if (w == "v") { src = c->v.p; bytes = c->n_a * 4; }
+    else if (w == "seg_start") { src = c->seg_start.p; bytes = c->n_seg * 4; }
+    else return fail(c, NDG_ERR_ARG, "unknown stage buffer '%s'", what);
+    if (!dst) return (int64_t)bytes;
+    if (bytes > cap) return fail(c, NDG_ERR_OVERFLOW, "buffer too small");
+    if (bytes) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->st); if (cudaStreamSynchronize(c->st) != cudaSuccess) return fail(c, NDG_ERR_CUDA, "fetch"); }
+    return (int64_t)bytes;
+}
+
+// ------------------------------------------------------------------------------------------------
+// .ovl encoder, host side, table-free.  ref: lib/ovl.c:10-29 (varint table) and :109-150 (encode_ovl)
+// ------------------------------------------------------------------------------------------------
+static inline int ndg_put_varint(uint8_t *dst, uint32_t v)
+{
+    if (v < 0x80) { dst[0] = (uint8_t)v; return 1; }
+    int ng = v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
+    for (int g = 0; g < ng; ++g) dst[g] = (uint8_t)((v >> (7 * (ng - 1 - g)) & 0x7f) | (g + 1 < ng ? 0x80 : 0));
+    return ng;
+}
+
+extern "C" int ndg_ovl_encode8(uint8_t *dst, uint32_t state[2], int rev, uint32_t qname, uint32_t qs, uint32_t qe,
+                               uint32_t tname, uint32_t ts, uint32_t te, uint32_t match)
+{
+    uint32_t fld[8]; uint32_t ql = qe - qs, tl = te - ts; uint32_t flags = (uint32_t)rev & 0xff;
+    if (qname >= state[0]) fld[0] = qname - state[0]; else { flags |= 2; fld[0] = state[0] - qname; }
+    if (tname >= state[1]) fld[4] = tname - state[1]; else { flags |= 4; fld[4] = state[1] - tname; }
+    if (ql >= tl) fld[6] = ql - tl; else { flags |= 8; fld[6] = tl - ql; }
+    state[0] = qname; state[1] = tname;
+    fld[1] = flags; fld[2] = qs; fld[3] = ql; fld[5] = ts; fld[7] = match;
+    int n = 0;
+    for (int i = 0; i < 8; ++i) n += ndg_put_varint(dst + n, fld[i]);
+    return n;
+}
+
+// ref: minimap2/map.c:804-821 (check_realign_nextdenovo), used by --dvt at map.c:1302
+static inline int ndg_check_dovetail(int rev, uint32_t qs, uint32_t qe, uint32_t qlen, uint32_t ts, uint32_t te, uint32_t tlen,
+                                     int32_t maxhan1, int32_t maxhan2)
+{
+    if (rev) {
+        if (qs <= (uint32_t)maxhan1 && ts <= (uint32_t)maxhan1) return 1;
+        else if (qlen - qe <= (uint32_t)maxhan1 && tlen - te <= (uint32_t)maxhan1) return 2;
+    } else {
+        if (qlen - qe <= (uint32_t)maxhan1 && ts <= (uint32_t)maxhan1) return 4;
+        else if (qs <= (uint32_t)maxhan1 && tlen - te <= (uint32_t)maxhan1) return 7;
+    }
+    if (maxhan2 > 0) {
+        if (qs <= (uint32_t)maxhan2 && qe + maxhan2 >= qlen) return 8;
+        if (ts <= (uint32_t)maxhan2 && te + maxhan2 >= tlen) return 9;
+    }
+    return 0;
+}
+
+extern "C" int64_t ndg_ovl_emit_step1(const ndg_hit_t *hits, int64_t n_hits,
+                                      const uint32_t *q_id, const uint64_t *q_key, const uint32_t *q_len,
+                                      const uint32_t *t_id, const uint64_t *t_key, const uint32_t *t_len,
+                                      int32_t minlen, int32_t dvt, int32_t maxhan1, int32_t maxhan2,
+                                      uint32_t state[2], uint8_t *dst, uint64_t cap, uint64_t *n_rec, uint64_t *sum_qspan)
+{
+    uint64_t n = 0, rec = 0, sq = 0;
+    for (int64_t i = 0; i < n_hits; ++i) {
+        const ndg_hit_t &h = hits[i];
+        if (q_key[h.qidx] == t_key[h.rid]) continue;
+        if (h.qe - h.qs < minlen) continue;
+        if (dvt && !ndg_check_dovetail(h.rev, h.qs, h.qe, q_len[h.qidx], h.rs, h.re, t_len[h.rid], maxhan1, maxhan2)) continue;
+        if (n + 40 > cap) return NDG_ERR_OVERFLOW;
+        n += ndg_ovl_encode8(dst + n, state, h.rev, q_id[h.qidx], (uint32_t)h.qs, (uint32_t)h.qe, t_id[h.rid], (uint32_t)h.rs, (uint32_t)h.re, (uint32_t)h.mlen);
+        ++rec; sq += (uint64_t)(h.qe - h.qs);
+    }
+    if (n_rec) *n_rec += rec;
+    if (sum_qspan) *sum_qspan += sq;
+    return (int64_t)n;
+}

@@ -1,0 +1,328 @@
+"""ctypes binding of libndgpu.so (include/ndgpu.h) and the step-1 driver that mirrors
+minimap2-nd's main loop (ref: minimap2/main.c:477-509, minimap2/index.c:280-372 index parts,
+minimap2/map.c:1188-1354 query batches + ordered .ovl output).
+
+No CPU fallback: a missing library or a missing sm_100 device raises NdgError.
+"""
+import ctypes as C
+import os
+import numpy as np
+from .formats import Reads
+from .options import IdxOpt, MapOpt, MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_I_HPC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libndgpu.so")
+
+
+class NdgError(RuntimeError):
+    pass
+
+
+class _Opt(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("hpc", C.c_int32),
+                ("flag_no_diag", C.c_int32), ("flag_no_dual", C.c_int32),
+                ("min_cnt", C.c_int32), ("min_chain_score", C.c_int32),
+                ("bw", C.c_int32), ("max_gap", C.c_int32),
+                ("max_chain_skip", C.c_int32), ("max_chain_iter", C.c_int32),
+                ("seed", C.c_int32), ("mid_occ_frac", C.c_float),
+                ("mid_occ", C.c_int32), ("min_mid_occ", C.c_int32)]
+
+
+class _Reads(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
+                ("nmask", C.c_void_p), ("name_key", C.c_void_p), ("name_hash", C.c_void_p)]
+
+
+class _MapResult(C.Structure):
+    _fields_ = [("n_hits", C.c_int64), ("hits", C.c_void_p),
+                ("n_minimizers", C.c_uint64), ("n_anchors", C.c_uint64), ("n_segments", C.c_uint64)]
+
+
+class _IndexStat(C.Structure):
+    _fields_ = [("n_seq", C.c_uint64), ("n_minimizers", C.c_uint64), ("n_distinct", C.c_uint64),
+                ("n_singletons", C.c_uint64), ("sum_len", C.c_uint64), ("mid_occ", C.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("zkey", "<u8"), ("qidx", "<i4"), ("rid", "<i4"), ("qs", "<i4"), ("qe", "<i4"),
+                      ("rs", "<i4"), ("re", "<i4"), ("mlen", "<i4"), ("blen", "<i4"), ("score", "<i4"),
+                      ("cnt", "<i4"), ("rev", "<i4"), ("as_", "<i4")])
+assert HIT_DTYPE.itemsize == 56
+
+EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
+           "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta", "ndg_index_export",
+           "ndg_index_import", "ndg_index_clear_minimizers", "ndg_index_finalize", "ndg_index_get",
+           "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
+           "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
+           "ndg_ovl_emit_step1"]
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise NdgError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % p)
+    L = C.CDLL(p)
+    for s in EXPORTS:
+        if not hasattr(L, s):
+            raise NdgError("libndgpu.so lacks symbol %s" % s)
+    L.ndg_last_error.restype = C.c_char_p
+    L.ndg_version.restype = C.c_char_p
+    L.ndg_debug_fetch.restype = C.c_int64
+    L.ndg_kernel_launches.restype = C.c_uint64
+    L.ndg_ovl_emit_step1.restype = C.c_int64
+    L.ndg_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.ndg_destroy.argtypes = [C.c_void_p]
+    L.ndg_last_error.argtypes = [C.c_void_p]
+    L.ndg_set_opt.argtypes = [C.c_void_p, C.POINTER(_Opt)]
+    L.ndg_set_limits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.ndg_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ndg_index_begin.argtypes = [C.c_void_p]
+    L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.ndg_index_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ndg_index_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.ndg_index_clear_minimizers.argtypes = [C.c_void_p]
+    L.ndg_index_finalize.argtypes = [C.c_void_p, C.POINTER(_IndexStat)]
+    L.ndg_index_get.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.ndg_map_batch.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
+    L.ndg_map_upload.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.ndg_map_resident.argtypes = [C.c_void_p, C.POINTER(_MapResult)]
+    L.ndg_map_download.argtypes = [C.c_void_p, C.POINTER(_MapResult)]
+    L.ndg_sketch.argtypes = [C.c_void_p, C.POINTER(_Reads), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ndg_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
+    L.ndg_prof_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.ndg_prof_reset.argtypes = [C.c_void_p]
+    L.ndg_kernel_launches.argtypes = [C.c_void_p]
+    L.ndg_ovl_encode8.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] + [C.c_uint32] * 7
+    L.ndg_ovl_emit_step1.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int32] * 4 + \
+                                    [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _reads_struct(r: Reads):
+    # keep references alive on the struct object
+    s = _Reads()
+    s._keep = (np.ascontiguousarray(r.words, dtype=np.uint32), np.ascontiguousarray(r.word_off, dtype=np.uint64),
+               np.ascontiguousarray(r.length, dtype=np.uint32), np.ascontiguousarray(r.name_key, dtype=np.uint64),
+               np.ascontiguousarray(r.name_hash, dtype=np.uint32))
+    s.n_reads = r.n
+    s.words, s.word_off, s.len = _ptr(s._keep[0]), _ptr(s._keep[1]), _ptr(s._keep[2])
+    s.nmask = None
+    s.name_key, s.name_hash = _ptr(s._keep[3]), _ptr(s._keep[4])
+    return s
+
+
+class Engine:
+    """One GPU context.  Mirrors the life cycle of one `minimap2-nd --step 1` process."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.ndg_init(device, C.byref(h))
+        if rc != 0:
+            raise NdgError("ndg_init(device=%d) failed with %d: no usable sm_100 GPU (no CPU fallback exists)" % (device, rc))
+        self.h = h
+        self.io, self.mo = IdxOpt(), MapOpt()
+        self.targets = None
+        self.stat = None
+
+    def close(self):
+        if self.h:
+            self.L.ndg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NdgError("libndgpu error %d: %s" % (rc, self.L.ndg_last_error(self.h).decode()))
+
+    def set_options(self, io: IdxOpt, mo: MapOpt):
+        if mo.flag & MM_F_CIGAR:
+            raise NdgError("-c (base-level extension) is not available through this entry point")
+        self.io, self.mo = io, mo
+        o = _Opt(k=io.k, w=io.w, hpc=1 if io.flag & MM_I_HPC else 0,
+                 flag_no_diag=1 if mo.flag & MM_F_NO_DIAG else 0, flag_no_dual=1 if mo.flag & MM_F_NO_DUAL else 0,
+                 min_cnt=mo.min_cnt, min_chain_score=mo.min_chain_score, bw=mo.bw, max_gap=mo.max_gap,
+                 max_chain_skip=mo.max_chain_skip, max_chain_iter=mo.max_chain_iter, seed=mo.seed,
+                 mid_occ_frac=mo.mid_occ_frac, mid_occ=mo.mid_occ, min_mid_occ=mo.min_mid_occ)
+        self._ck(self.L.ndg_set_opt(self.h, C.byref(o)))
+
+    def set_limits(self, sub_batch_bases=0, max_anchors=0):
+        self._ck(self.L.ndg_set_limits(self.h, sub_batch_bases, max_anchors))
+
+    def set_variant(self, sort_variant=1, chain_variant=1):
+        self._ck(self.L.ndg_set_variant(self.h, sort_variant, chain_variant))
+
+    # ---- index -------------------------------------------------------------------------------
+    def build_index(self, targets: Reads):
+        self._ck(self.L.ndg_index_begin(self.h))
+        s = _reads_struct(targets)
+        self._ck(self.L.ndg_index_add(self.h, C.byref(s)))
+        return self.finalize_index(targets)
+
+    def finalize_index(self, targets: Reads):
+        st = _IndexStat()
+        self._ck(self.L.ndg_index_finalize(self.h, C.byref(st)))
+        self.targets = targets
+        self.stat = dict(n_seq=st.n_seq, n_minimizers=st.n_minimizers, n_distinct=st.n_distinct,
+                         n_singletons=st.n_singletons, sum_len=st.sum_len, mid_occ=st.mid_occ)
+        return self.stat
+
+    def index_get(self, minier, cap=4096):
+        pos = np.zeros(cap, dtype=np.uint64)
+        n = C.c_int()
+        self._ck(self.L.ndg_index_get(self.h, int(minier), _ptr(pos), cap, C.byref(n)))
+        return pos[:min(n.value, cap)].copy(), n.value
+
+    # ---- sketch (tests) ----------------------------------------------------------------------
+    def sketch(self, reads: Reads, rid0=0):
+        cap = int(reads.n_bases) + reads.n + 16
+        xy = np.zeros((cap, 2), dtype=np.uint64)
+        off = np.zeros(reads.n + 1, dtype=np.uint64)
+        s = _reads_struct(reads)
+        self._ck(self.L.ndg_sketch(self.h, C.byref(s), rid0, _ptr(xy), cap, _ptr(off)))
+        return xy[:int(off[-1])].copy(), off
+
+    # ---- mapping -----------------------------------------------------------------------------
+    def _result(self, res):
+        n = res.n_hits
+        if n and res.hits:
+            buf = (C.c_char * (n * HIT_DTYPE.itemsize)).from_address(res.hits)
+            hits = np.frombuffer(buf, dtype=HIT_DTYPE, count=n).copy()
+        else:
+            hits = np.zeros(0, dtype=HIT_DTYPE)
+        return hits, dict(n_minimizers=res.n_minimizers, n_anchors=res.n_anchors, n_segments=res.n_segments)
+
+    def map_batch(self, queries: Reads):
+        """End-to-end call with host buffers: H2D, kernels, D2H (ndg_map_batch)."""
+        s = _reads_struct(queries)
+        res = _MapResult()
+        self._ck(self.L.ndg_map_batch(self.h, C.byref(s), C.byref(res)))
+        return self._result(res)
+
+    def map_upload(self, queries: Reads):
+        s = _reads_struct(queries)
+        self._ck(self.L.ndg_map_upload(self.h, C.byref(s)))
+
+    def map_resident(self):
+        res = _MapResult()
+        self._ck(self.L.ndg_map_resident(self.h, C.byref(res)))
+        return dict(n_hits=res.n_hits, n_minimizers=res.n_minimizers, n_anchors=res.n_anchors, n_segments=res.n_segments)
+
+    def map_download(self):
+        res = _MapResult()
+        self._ck(self.L.ndg_map_download(self.h, C.byref(res)))
+        return self._result(res)
+
+    def debug_fetch(self, what, dtype):
+        nb = self.L.ndg_debug_fetch(self.h, what.encode(), None, 0)
+        if nb < 0:
+            self._ck(int(nb))
+        out = np.zeros(nb // np.dtype(dtype).itemsize, dtype=dtype)
+        if nb:
+            rc = self.L.ndg_debug_fetch(self.h, what.encode(), _ptr(out), nb)
+            if rc < 0:
+                self._ck(int(rc))
+        return out
+
+    def prof(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_double * 64)()
+        ln = (C.c_uint64 * 64)()
+        n = self.L.ndg_prof_get(self.h, 64, names, ms, ln)
+        return {names[i].decode(): (ms[i], ln[i]) for i in range(n)}
+
+    def prof_reset(self):
+        self.L.ndg_prof_reset(self.h)
+
+    def kernel_launches(self):
+        return int(self.L.ndg_kernel_launches(self.h))
+
+    # ---- step 1 ------------------------------------------------------------------------------
+    def emit_step1(self, hits, queries: Reads, state, out: bytearray):
+        """Apply the step-1 filter and append 8-field records (ndg_ovl_emit_step1)."""
+        t = self.targets
+        cap = hits.shape[0] * 40 + 64
+        dst = np.zeros(cap, dtype=np.uint8)
+        n_rec, sq = C.c_uint64(0), C.c_uint64(0)
+        hits = np.ascontiguousarray(hits)
+        nb = self.L.ndg_ovl_emit_step1(_ptr(hits), hits.shape[0], _ptr(queries.ids), _ptr(queries.name_key), _ptr(queries.length),
+                                       _ptr(t.ids), _ptr(t.name_key), _ptr(t.length), self.mo.minlen, self.mo.dvt,
+                                       self.mo.maxhan1, self.mo.maxhan2, _ptr(state), _ptr(dst), cap, C.byref(n_rec), C.byref(sq))
+        if nb < 0:
+            self._ck(int(nb))
+        out += dst[:nb].tobytes()
+        return n_rec.value, sq.value
+
+
+def index_parts(targets: Reads, io: IdxOpt):
+    """Split the target file into index parts exactly as mm_idx_gen does
+    (ref: minimap2/index.c:284-288,353-358: read mini-batches of >= mini_batch_size bases until the
+    running total exceeds batch_size)."""
+    mini = min(io.mini_batch_size, io.batch_size)
+    parts, r, n = [], 0, targets.n
+    lens = targets.length
+    while r < n:
+        start, total = r, 0
+        while r < n and not total > io.batch_size:
+            size = 0
+            while r < n:
+                size += int(lens[r]); r += 1
+                if size >= mini:
+                    break
+            total += size
+        parts.append((start, r))
+    return parts
+
+
+def query_batches(queries: Reads, mini_batch_size):
+    """ref: minimap2/bseq.c:86-123 (mm_bseq_read3: stop once >= chunk_size bases were read)."""
+    out, r, n = [], 0, queries.n
+    while r < n:
+        start, size = r, 0
+        while r < n:
+            size += int(queries.length[r]); r += 1
+            if size >= mini_batch_size:
+                break
+        out.append((start, r))
+    return out
+
+
+def run_step1(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: MapOpt, same_file=False):
+    """`minimap2-nd --step 1 ... TARGET QUERY -o OUT` (ref: minimap2/main.c:452-509).  Returns
+    (ovl_bytes, stats)."""
+    engine.set_options(io, mo)
+    out = bytearray()
+    state = np.zeros(2, dtype=np.uint32)
+    n_rec = sq = 0
+    work = dict(n_minimizers=0, n_anchors=0, n_segments=0, n_hits=0)
+    for (t0, t1) in index_parts(targets, io):
+        tp = targets.slice(t0, t1)
+        engine.build_index(tp)
+        for (q0, q1) in query_batches(queries, mo.mini_batch_size):
+            qb = queries.slice(q0, q1)
+            hits, w = engine.map_batch(qb)
+            for k in ("n_minimizers", "n_anchors", "n_segments"):
+                work[k] += w[k]
+            work["n_hits"] += hits.shape[0]
+            r, s = engine.emit_step1(hits, qb, state, out)
+            n_rec += r; sq += s
+    return bytes(out), dict(records=n_rec, sum_qspan=sq, mid_occ=engine.stat["mid_occ"], **work)

@@ -1,0 +1,201 @@
+"""On-disk formats either side of the hot path: the `.2bit` read container and the `.ovl` record
+stream.  Host logic only (numpy); byte-exact with the reference.
+
+ref: lib/bseq.c:93-97 (header {0,254}), :114-139 (seq2bit), :257-302 (kbit_read);
+     lib/ovl.c:10-29 (varint), :109-150 (encode_ovl), :150-203 (decode_ovl).
+"""
+from dataclasses import dataclass
+import numpy as np
+
+
+@dataclass
+class Reads:
+    """A batch of reads in the layout the C ABI takes (include/ndgpu.h: ndg_reads_t)."""
+    words: np.ndarray        # uint32, concatenated 2-bit words
+    word_off: np.ndarray     # uint64, n+1
+    length: np.ndarray       # uint32
+    ids: np.ndarray          # uint32 numeric names (strtoul of the name)
+    name_key: np.ndarray     # uint64 strcmp-order-preserving key
+    name_hash: np.ndarray    # uint32 X31 hash of the decimal name
+
+    @property
+    def n(self):
+        return int(self.length.shape[0])
+
+    @property
+    def n_bases(self):
+        return int(self.length.sum(dtype=np.uint64))
+
+    def slice(self, r0, r1):
+        w0, w1 = int(self.word_off[r0]), int(self.word_off[r1])
+        return Reads(self.words[w0:w1], (self.word_off[r0:r1 + 1] - np.uint64(w0)).astype(np.uint64),
+                     self.length[r0:r1], self.ids[r0:r1], self.name_key[r0:r1], self.name_hash[r0:r1])
+
+
+def _ndigits(ids):
+    ids = ids.astype(np.uint64)
+    nd = np.ones(ids.shape, dtype=np.int64)
+    p = np.uint64(10)
+    for _ in range(9):
+        nd += (ids >= p)
+        p = p * np.uint64(10)
+    return nd
+
+
+def name_keys(ids):
+    """strcmp-order-preserving u64 key of the decimal string of each id: digit d at string position i
+    becomes nibble (d+1) at bits [60-4i, 64-4i); shorter strings are zero padded, so a proper prefix
+    sorts first exactly as strcmp does (ref: minimap2/map.c:132 strcmp(qname, s->name))."""
+    ids = np.asarray(ids, dtype=np.uint64)
+    nd = _ndigits(ids)
+    key = np.zeros(ids.shape, dtype=np.uint64)
+    for i in range(10):
+        valid = nd > i
+        e = np.where(valid, nd - 1 - i, 0).astype(np.uint64)
+        dig = (ids // (np.uint64(10) ** e)) % np.uint64(10)
+        key |= np.where(valid, (dig + np.uint64(1)) << np.uint64(60 - 4 * i), np.uint64(0))
+    return key
+
+
+def x31_hash(ids):
+    """__ac_X31_hash_string of the decimal string (ref: minimap2/khash.h:383-388)."""
+    ids = np.asarray(ids, dtype=np.uint64)
+    nd = _ndigits(ids)
+    h = np.zeros(ids.shape, dtype=np.uint64)
+    for i in range(10):
+        valid = nd > i
+        e = np.where(valid, nd - 1 - i, 0).astype(np.uint64)
+        ch = (ids // (np.uint64(10) ** e)) % np.uint64(10) + np.uint64(48)
+        nh = ch if i == 0 else ((h * np.uint64(31) + ch) & np.uint64(0xffffffff))
+        h = np.where(valid, nh, h)
+    return h.astype(np.uint32)
+
+
+def make_reads(words_list, lengths, ids):
+    lengths = np.asarray(lengths, dtype=np.uint32)
+    ids = np.asarray(ids, dtype=np.uint32)
+    nw = (lengths.astype(np.uint64) + np.uint64(15)) // np.uint64(16)
+    off = np.zeros(len(lengths) + 1, dtype=np.uint64)
+    np.cumsum(nw, out=off[1:])
+    words = np.concatenate(words_list).astype(np.uint32) if len(words_list) else np.zeros(0, np.uint32)
+    assert words.shape[0] == int(off[-1])
+    return Reads(np.ascontiguousarray(words), off, lengths, ids, name_keys(ids), x31_hash(ids))
+
+
+def read_2bit(path, max_reads=None):
+    """Parse a .2bit container into the C-ABI layout (words copied verbatim, record headers stripped)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw.shape[0] < 2 or raw[0] not in (0, 254):
+        raise ValueError("%s: not a .2bit file" % path)
+    pos, n = 2, raw.shape[0]
+    words, lens, ids = [], [], []
+    while pos + 8 <= n:
+        name, ln = np.frombuffer(raw, dtype="<u4", count=2, offset=pos)
+        nw = (int(ln) + 15) // 16
+        pos += 8
+        if pos + 4 * nw > n:
+            break
+        words.append(np.frombuffer(raw, dtype="<u4", count=nw, offset=pos))
+        lens.append(int(ln)); ids.append(int(name))
+        pos += 4 * nw
+        if max_reads is not None and len(lens) >= max_reads:
+            break
+    return make_reads(words, lens, ids)
+
+
+def write_2bit(path, reads: Reads, idx_path=None):
+    """ref: lib/bseq.c:114-139 (seq2bit) + util/seq_dump.c:36-41 (.idx sidecar line)."""
+    with open(path, "wb") as fo:
+        fo.write(bytes([0, 254]))
+        off = 2
+        lines = []
+        for i in range(reads.n):
+            w0, w1 = int(reads.word_off[i]), int(reads.word_off[i + 1])
+            fo.write(np.array([reads.ids[i], reads.length[i]], dtype="<u4").tobytes())
+            fo.write(reads.words[w0:w1].astype("<u4").tobytes())
+            lines.append("%u\t%u\t%u\n" % (reads.ids[i], off + 8, reads.length[i]))
+            off += 8 + 4 * (w1 - w0)
+    if idx_path:
+        with open(idx_path, "w") as fi:
+            fi.writelines(lines)
+
+
+def pack_bases(codes):
+    """codes: uint8 array of 0..3 -> uint32 words (first base in the top bits)."""
+    n = codes.shape[0]
+    nw = (n + 15) // 16
+    pad = np.zeros(nw * 16, dtype=np.uint32)
+    pad[:n] = codes
+    pad = pad.reshape(nw, 16)
+    sh = (30 - 2 * np.arange(16, dtype=np.uint32)).astype(np.uint32)
+    return np.bitwise_or.reduce(pad << sh, axis=1).astype(np.uint32)
+
+
+def unpack_bases(words, length):
+    sh = (30 - 2 * np.arange(16, dtype=np.uint32)).astype(np.uint32)
+    c = ((words[:, None] >> sh[None, :]) & np.uint32(3)).astype(np.uint8).reshape(-1)
+    return c[:length]
+
+
+def decode_ovl8(buf):
+    """Decode an 8-field .ovl stream to an (n, 8) uint32 array: qname rev qs qe tname ts te match
+    (ref: lib/ovl.c:150-203 decode_ovl; util/ovl_cvt.c:38-40 column order)."""
+    b = np.frombuffer(buf, dtype=np.uint8)
+    ends = np.nonzero(b < 128)[0]
+    starts = np.concatenate(([0], ends[:-1] + 1))
+    nv = ends.shape[0]
+    if nv % 8:
+        raise ValueError("truncated .ovl stream")
+    vals = np.zeros(nv, dtype=np.uint64)
+    ln = ends - starts + 1
+    for k in range(int(ln.max()) if nv else 0):
+        sel = ln > k
+        vals[sel] = (vals[sel] << np.uint64(7)) | (b[starts[sel] + k] & 127).astype(np.uint64)
+    v = vals.reshape(-1, 8).astype(np.int64)
+    flags = v[:, 1]
+    out = np.zeros((v.shape[0], 8), dtype=np.int64)
+    dq = np.where(flags & 2, -v[:, 0], v[:, 0])
+    dt = np.where(flags & 4, -v[:, 4], v[:, 4])
+    out[:, 0] = np.cumsum(dq)
+    out[:, 4] = np.cumsum(dt)
+    out[:, 1] = flags & 1
+    out[:, 2] = v[:, 2]
+    out[:, 3] = v[:, 2] + v[:, 3]
+    out[:, 5] = v[:, 5]
+    out[:, 6] = np.where(flags & 8, v[:, 5] + v[:, 3] + v[:, 6], v[:, 5] + v[:, 3] - v[:, 6])
+    out[:, 7] = v[:, 7]
+    return out.astype(np.uint32)
+
+
+def encode_ovl8_py(records):
+    """Pure-Python reference encoder for small cases (tests).  records: iterable of 8-tuples in
+    ovl_cvt column order.  ref: lib/ovl.c:109-150."""
+    out = bytearray()
+    pq = pt = 0
+
+    def put(v):
+        if v <= 127:
+            out.append(v)
+            return
+        groups = []
+        while v:
+            groups.append(v & 127)
+            v >>= 7
+        groups.reverse()
+        for g in groups[:-1]:
+            out.append(g | 128)
+        out.append(groups[-1])
+
+    for (qn, rev, qs, qe, tn, ts, te, match) in records:
+        flags = rev
+        f0 = qn - pq if qn >= pq else pq - qn
+        if qn < pq: flags |= 2
+        f4 = tn - pt if tn >= pt else pt - tn
+        if tn < pt: flags |= 4
+        pq, pt = qn, tn
+        ql, tl = qe - qs, te - ts
+        f6 = ql - tl if ql >= tl else tl - ql
+        if ql < tl: flags |= 8
+        for v in (f0, flags, qs, ql, f4, ts, f6, match):
+            put(int(v))
+    return bytes(out)

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures from the UNMODIFIED reference (needs /root/reference and a built
+oracle/_ref: `make -C oracle`).  Run from the repo root.  Committed outputs:
+
+  reads_test.seed.2bit      seq_dump -f 1000 -s 1001 -b 10g -n 1 of test_data/reads_test.fa.gz (997 reads)
+  G1_ava-ont.ovl            minimap2-nd --step 1 -x ava-ont              T T   (md5 9fce14e8...)
+  G2_ava-ont_k17w10.ovl     minimap2-nd --step 1 -x ava-ont -k 17 -w 10  T T   (md5 270d357d...)
+  G3_ava-pb.ovl             minimap2-nd --step 1 -x ava-pb               T T   (md5 7fb430f9...)
+  sub120.2bit               first 120 reads of reads_test.seed.2bit
+  S1_sub120_ava-ont.ovl, S3_sub120_ava-pb.ovl, S5_sub120_dual.ovl (sub120 x full with --dual=yes -I 20M: 2 index parts)
+"""
+import os, subprocess, sys, tempfile, hashlib
+sys.path.insert(0, os.getcwd())
+import nextdenovo_b200 as nd
+
+REF = "oracle/_ref"
+G = "tests/golden"
+
+
+def run(args, out):
+    subprocess.check_call([REF + "/minimap2-nd", "--step", "1", "-t", "8"] + args + ["-o", out],
+                          stderr=subprocess.DEVNULL)
+    print(out, hashlib.md5(open(out, "rb").read()).hexdigest())
+
+
+def main():
+    with tempfile.TemporaryDirectory() as td:
+        open(td + "/input.fofn", "w").write("/root/reference/test_data/reads_test.fa.gz\n")
+        subprocess.check_call([REF + "/seq_dump", "-f", "1000", "-s", "1001", "-b", "10g", "-n", "1", "-d", td + "/db",
+                               td + "/input.fofn"], stderr=subprocess.DEVNULL)
+        os.replace(td + "/db/input.seed.001.2bit", G + "/reads_test.seed.2bit")
+    T = G + "/reads_test.seed.2bit"
+    run(["-x", "ava-ont", T, T], G + "/G1_ava-ont.ovl")
+    run(["-x", "ava-ont", "-k", "17", "-w", "10", T, T], G + "/G2_ava-ont_k17w10.ovl")
+    run(["-x", "ava-pb", T, T], G + "/G3_ava-pb.ovl")
+    r = nd.read_2bit(T, max_reads=120)
+    nd.write_2bit(G + "/sub120.2bit", r)
+    S = G + "/sub120.2bit"
+    run(["-x", "ava-ont", S, S], G + "/S1_sub120_ava-ont.ovl")
+    run(["-x", "ava-pb", S, S], G + "/S3_sub120_ava-pb.ovl")
+    run(["--dual=yes", "-I", "20M", "-x", "ava-ont", T, S], G + "/S5_sub120_dual.ovl")
+
+
+if __name__ == "__main__":
+    main()

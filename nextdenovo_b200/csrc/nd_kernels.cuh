@@ -228,18 +228,19 @@ k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *m
     }
 }
 
-// per read: anchor offsets and the float average query span (ref: chain.c:41-42)
+// per read (one warp each): anchor offsets and the float average query span (ref: chain.c:41-42)
 __global__ void k_read_stats(const nd_u128 *mz, const nd_u64 *mz_off, const uint32_t *m_keep, const nd_u64 *a_pos,
                              int n_reads, nd_u64 *a_off, float *avg_qspan)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r > n_reads) return;
     nd_u64 b = mz_off[r];
-    a_off[r] = a_pos[b];
+    if (lane == 0) a_off[r] = a_pos[b];
     if (r == n_reads) return;
     nd_u64 e = mz_off[r + 1], sum = 0, n = a_pos[e] - a_pos[b];
-    for (nd_u64 m = b; m < e; ++m) sum += (nd_u64)m_keep[m] * (mz[m].x & 0xff);
-    avg_qspan[r] = n ? __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n)) : 0.f;
+    for (nd_u64 m = b + lane; m < e; m += 32) sum += (nd_u64)m_keep[m] * (mz[m].x & 0xff);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) avg_qspan[r] = n ? __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n)) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------

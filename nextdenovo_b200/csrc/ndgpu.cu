@@ -297,7 +297,7 @@ extern "C" int ndg_set_opt(ndg_ctx_t *c, const ndg_opt_t *o)
 {
     if (!c || !o) return NDG_ERR_ARG;
     c->opt = *o;
-    if (o->mid_occ > 0) c->mid_occ = o->mid_occ;
+    c->mid_occ = o->mid_occ > 0 ? o->mid_occ : 0;   // <=0: derived from the first index part built after this call
     return NDG_OK;
 }
 extern "C" int ndg_set_limits(ndg_ctx_t *c, uint64_t sub_batch_bases, uint64_t max_anchors)
@@ -545,7 +545,7 @@ int map_resident(ndg_ctx *c, int qidx_base)
     RSV(c->a, (NA + 1) * 16); RSV(c->a_off, (size_t)(nr + 1) * 8); RSV(c->avgq, (size_t)nr * 4 + 4);
     KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
                              c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), c->a.as<nd_u128>())));
-    KLAUNCH("read_stats", (k_read_stats<<<nblk(nr + 1, 128), 128, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_keep.as<uint32_t>(),
+    KLAUNCH("read_stats", (k_read_stats<<<nblk((uint64_t)(nr + 1) * 32, 128), 128, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_keep.as<uint32_t>(),
                            c->a_pos.as<nd_u64>(), nr, c->a_off.as<nd_u64>(), c->avgq.as<float>())));
     CK(cudaGetLastError());
 

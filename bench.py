@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- overlaps/s (+ aligned Gbp/s) of the read-overlap hot path on synthetic 20 kb ONT reads.
+
+Workload = BASELINE.json configs[1]: 100k synthetic 20 kb ONT reads (15 % error: 5 % sub, 4 % ins,
+6 % del), `-x ava-ont -k 17 -w 10`, self-overlap, .ovl step-1 records.  The index over all reads is
+built once (reported separately); a *step* maps one query batch of `--batch-reads` reads against it.
+
+  value : whole-job overlaps/s with the step's query batch already resident in HBM (kernels only,
+          CUDA events on the launching stream, max over ranks)
+  e2e   : the same through ndg_map_batch() with HOST buffers: H2D of the packed reads, all kernels,
+          D2H of the hits and the host-side .ovl encoding inside the timed region
+  roofline : dominant kernel of the step (largest accumulated device time), algorithmic bytes per
+          DESIGN.md / SURVEY.md 8(d) divided by its event-timed duration, against MEASURED_PEAKS.json
+  cpu_baseline : the unmodified reference (oracle/_ref/minimap2-nd, SSE path) on the box's host
+          cores, on a bounded sample of the same workload (same read model and depth, smaller genome)
+
+`--impl reference` times that reference binary as the measured arm.
+N > 1: one process per GPU (torchrun), NCCL all-gather of the target sketches at start-up, then
+independent per-GPU query batches (no data-path collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240923
+READ_LEN = 20000
+ERR = dict(sub=0.05, ins=0.04, dele=0.06)
+DEPTH = 40
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100000, help="reads in the index (configs[1]: 100k)")
+    ap.add_argument("--batch-reads", type=int, default=3000, help="query reads per step")
+    ap.add_argument("--cpu-sample-reads", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="1,1")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_reads(n, genome_bp, first=0):
+    from nextdenovo_b200 import synth
+    g = synth.genome(genome_bp, SEED)
+    return synth.reads(g, n, READ_LEN, seed=SEED, first=first, **ERR)
+
+
+def run_reference(reads, threads):
+    """Run the unmodified reference binary on `reads` (self-overlap, config-1 options).  Returns
+    (records, sum_qspan, mapping_seconds, total_seconds)."""
+    import nextdenovo_b200 as nd
+    exe = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/minimap2-nd missing (build() makes it when /root/reference is present)")
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.2bit")
+        nd.write_2bit(p, reads)
+        out = os.path.join(td, "s.ovl")
+        t0 = time.time()
+        r = subprocess.run([exe, "--step", "1", "-t", str(threads), "-I", "100G", "-x", "ava-ont", "-k", "17", "-w", "10", p, p, "-o", out],
+                           stderr=subprocess.PIPE, text=True, check=True)
+        total = time.time() - t0
+        t_idx = t_map = None
+        for line in r.stderr.splitlines():
+            m = re.match(r"\[M::mm_idx_stat::([0-9.]+)\*", line)
+            if m:
+                t_idx = float(m.group(1))
+            m = re.match(r"\[M::worker_pipeline::([0-9.]+)\*", line)
+            if m:
+                t_map = float(m.group(1))
+        d = nd.decode_ovl8(open(out, "rb").read())
+        recs = d.shape[0]
+        sq = int((d[:, 3].astype(np.int64) - d[:, 2].astype(np.int64)).sum())
+    return recs, sq, (t_map - t_idx) if (t_idx is not None and t_map is not None) else total, total
+
+
+def cpu_sample(n):
+    genome_bp = max(int(n * READ_LEN / DEPTH), 200000)
+    return make_reads(n, genome_bp), "%d reads x %d bp at %dx depth (genome %d bp), self-overlap, mapping phase only" % (n, READ_LEN, DEPTH, genome_bp)
+
+
+def main_reference(a, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    reads, desc = cpu_sample(a.cpu_sample_reads)
+    rec = sq = 0
+    tsum = 0.0
+    for i in range(a.warmup + a.steps):
+        r, s, tm, _ = run_reference(reads, threads)
+        if i >= a.warmup:
+            rec += r; sq += s; tsum += tm
+    v = rec / tsum
+    line = {"metric": "overlaps/sec", "value": v, "unit": "overlaps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * tsum / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "impl": "reference",
+            "aligned_gbp_per_s": sq / tsum / 1e9,
+            "config": {"workload": "configs[1] sample: " + desc, "options": "--step 1 -x ava-ont -k 17 -w 10"},
+            "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": desc},
+            "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_ours(a, rank, world, local_rank):
+    import torch
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200 import engine
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    hbm_peak, peak_kind = peaks()
+
+    # ---- workload ---------------------------------------------------------------------------
+    genome_bp = int(a.reads * READ_LEN / DEPTH)
+    t0 = time.time()
+    reads = make_reads(a.reads, genome_bp)
+    t_gen = time.time() - t0
+    io, mo = nd.IdxOpt(), nd.MapOpt()
+    nd.set_opt("ava-ont", io, mo)
+    io.k, io.w = 17, 10
+    mo.step = 1
+    eng = engine.Engine(dev)
+    eng.set_options(io, mo)
+    sv, cv = [int(x) for x in a.variant.split(",")]
+    eng.set_variant(sv, cv)
+
+    # ---- index: each rank sketches 1/world of the targets, NCCL all-gather, identical table everywhere
+    torch.cuda.synchronize(dev)
+    t0 = time.time()
+    if world == 1:
+        stat = eng.build_index(reads)
+    else:
+        stat = engine.build_index_sharded(eng, reads, rank, world, dist, torch)
+    torch.cuda.synchronize(dev)
+    t_index = time.time() - t0
+
+    # ---- query batches: rank r takes batches r, r+world, ... (no data-path collective)
+    nb = a.warmup + a.steps
+    B = a.batch_reads
+    batches = []
+    for i in range(nb):
+        q0 = ((i * world + rank) * B) % max(reads.n - B, 1)
+        batches.append(reads.slice(q0, q0 + B))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- resident-input timing (value)
+    for i in range(a.warmup):
+        eng.map_upload(batches[i]); eng.map_resident()
+    eng.prof_reset()
+    launches0 = eng.kernel_launches()
+    barrier()
+    clk = ClockSampler(dev); clk.start()
+    t_res = 0.0
+    rec = sq = n_mz = n_a = n_hits = 0
+    state = np.zeros(2, dtype=np.uint32)
+    for i in range(a.warmup, nb):
+        eng.map_upload(batches[i])                      # untimed: inputs resident before the timed region
+        torch.cuda.synchronize(dev)
+        e0 = time.perf_counter()
+        r = eng.map_resident()                          # all kernels of the step; internally event-timed per kernel
+        torch.cuda.synchronize(dev)
+        t_res += time.perf_counter() - e0
+        n_mz += r["n_minimizers"]; n_a += r["n_anchors"]; n_hits += r["n_hits"]
+        hits, _ = eng.map_download()
+        out = bytearray()
+        rr, ss = eng.emit_step1(hits, batches[i], state, out)
+        rec += rr; sq += ss
+    barrier()
+    clocks = clk.stop()
+    launches = eng.kernel_launches() - launches0
+    prof = eng.prof()
+    dev_ms = sum(v[0] for v in prof.values())           # sum of CUDA-event kernel durations over the K steps
+
+    # ---- end-to-end timing (host buffers)
+    barrier()
+    t_e2e = 0.0
+    rec_e = 0
+    h2d = d2h = 0
+    for i in range(a.warmup, nb):
+        b = batches[i]
+        t1 = time.perf_counter()
+        hits, _ = eng.map_batch(b)
+        out = bytearray()
+        rr, _ = eng.emit_step1(hits, b, state, out)
+        t_e2e += time.perf_counter() - t1
+        rec_e += rr
+        h2d += b.words.nbytes + b.word_off.nbytes + b.length.nbytes + b.name_key.nbytes + b.name_hash.nbytes
+        d2h += hits.nbytes
+    barrier()
+
+    # ---- reduce over ranks: total units / max time
+    t_res_dev = dev_ms / 1e3
+    if dist is not None:
+        tt = torch.tensor([t_res_dev, t_e2e, t_res], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cc = torch.tensor([rec, sq, rec_e, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        t_res_dev, t_e2e, t_res = [float(x) for x in tt.tolist()]
+        rec, sq, rec_e, launches = [int(x) for x in cc.tolist()]
+
+    if rank == 0:
+        # dominant kernel + roofline (algorithmic bytes: DESIGN.md "Kernels and rooflines")
+        top = max(prof.items(), key=lambda kv: kv[1][0])
+        bytes_per = {"chain_fill_warp": 32 * n_a, "chain_fill_seq": 32 * n_a, "sort_level": 32 * n_a, "sort_seq": 32 * n_a,
+                     "sort_perm": 32 * n_a, "chain_backtrack": 16 * n_a + 56 * n_hits, "sketch": READ_LEN / 4 * B * a.steps + 16 * n_mz,
+                     "probe_count": 32 * n_mz + 8 * n_a, "fill_anchors": 16 * n_mz + 8 * n_a + 16 * n_a}
+        alg = float(bytes_per.get(top[0], 32 * n_a))
+        achieved = alg / (top[1][0] / 1e3) / 1e9 if top[1][0] > 0 else 0.0
+        cpu = None
+        if not a.no_cpu_baseline:
+            try:
+                sample, desc = cpu_sample(a.cpu_sample_reads)
+                threads = os.cpu_count() or 1
+                r_, s_, tm, tot = run_reference(sample, threads)
+                cpu = {"value": r_ / tm, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": desc,
+                       "aligned_gbp_per_s": s_ / tm / 1e9, "mapping_s": tm, "process_s": tot}
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": "overlaps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % ex}
+        line = {
+            "metric": "overlaps/sec", "value": rec / t_res_dev, "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t_res_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "aligned_gbp_per_s": sq / t_res_dev / 1e9,
+            "config": {"workload": "configs[1]: %d synthetic %d bp ONT reads (sub/ins/del %.0f/%.0f/%.0f %%, %dx depth), -x ava-ont -k 17 -w 10, self-overlap step 1"
+                                   % (a.reads, READ_LEN, 100 * ERR["sub"], 100 * ERR["ins"], 100 * ERR["dele"], DEPTH),
+                       "batch_reads_per_step": B, "parallelism": "query-sharded x%d, index replicated (all-gather of sketches)" % world,
+                       "l2": "per-step working set (index %.1f GB + anchors) exceeds L2; each step maps a different batch" % (stat["n_minimizers"] * 8 / 1e9),
+                       "kernel_variant": a.variant},
+            "e2e": {"value": rec_e / t_e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps},
+            "cpu_baseline": cpu,
+            "work": {"records": rec, "sum_qspan": sq, "minimizers": n_mz, "anchors": n_a, "hits": n_hits, "host_wall_resident_s": t_res},
+            "kernels_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "index": {"build_s": t_index, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"]},
+            "gen_s": t_gen,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        main_reference(a, rank, world)
+    else:
+        main_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,8 @@ int ndg_index_add_meta(ndg_ctx_t *ctx, const ndg_reads_t *targets);
 int ndg_index_export(ndg_ctx_t *ctx, const void **dev_minimizers, uint64_t *n);
 int ndg_index_import(ndg_ctx_t *ctx, const void *dev_minimizers, uint64_t n);
 int ndg_index_clear_minimizers(ndg_ctx_t *ctx);
+/* device-to-device copy on the context's stream, synchronous (glue for torch.distributed buffers) */
+int ndg_copy_d2d(ndg_ctx_t *ctx, void *dst_dev, const void *src_dev, uint64_t bytes);
 int ndg_index_finalize(ndg_ctx_t *ctx, ndg_index_stat_t *stat);
 /* point query, for tests: replaces mm_idx_get (ref: minimap2/index.c:81-98). positions copied to host */
 int ndg_index_get(ndg_ctx_t *ctx, uint64_t minier, uint64_t *pos, int cap, int *n);

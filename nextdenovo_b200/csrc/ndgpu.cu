@@ -386,6 +386,14 @@ extern "C" int ndg_index_export(ndg_ctx_t *c, const void **dev, uint64_t *n)
     *dev = c->tmz.p; *n = c->n_tmz;
     return NDG_OK;
 }
+extern "C" int ndg_copy_d2d(ndg_ctx_t *c, void *dst, const void *src, uint64_t bytes)
+{
+    if (!c || (bytes && (!dst || !src))) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return NDG_OK;
+}
 extern "C" int ndg_index_clear_minimizers(ndg_ctx_t *c) { if (!c) return NDG_ERR_ARG; c->n_tmz = 0; return NDG_OK; }
 
 extern "C" int ndg_index_import(ndg_ctx_t *c, const void *dev, uint64_t n)

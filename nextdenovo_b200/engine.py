@@ -53,7 +53,7 @@ assert HIT_DTYPE.itemsize == 56
 
 EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
            "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta", "ndg_index_export",
-           "ndg_index_import", "ndg_index_clear_minimizers", "ndg_index_finalize", "ndg_index_get",
+           "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
            "ndg_ovl_emit_step1"]
@@ -90,6 +90,7 @@ def load_library():
     L.ndg_index_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.ndg_index_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.ndg_index_clear_minimizers.argtypes = [C.c_void_p]
+    L.ndg_copy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.ndg_index_finalize.argtypes = [C.c_void_p, C.POINTER(_IndexStat)]
     L.ndg_index_get.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.ndg_map_batch.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
@@ -271,6 +272,48 @@ class Engine:
             self._ck(int(nb))
         out += dst[:nb].tobytes()
         return n_rec.value, sq.value
+
+
+def shard_bounds(n, world):
+    """contiguous, near-equal read ranges per rank"""
+    return [(n * r) // world for r in range(world + 1)]
+
+
+def build_index_sharded(eng: Engine, targets: Reads, rank, world, dist, torch):
+    """Multi-GPU index build: rank r sketches targets[b[r]:b[r+1]] on its GPU, one
+    all-gather of the (x, y) minimizers over NCCL, then every rank sorts/tabulates the identical
+    full set locally.  Read ids (rid) are global, so the result equals the single-GPU index."""
+    L, h = eng.L, eng.h
+    b = shard_bounds(targets.n, world)
+    eng._ck(L.ndg_index_begin(h))
+    if b[rank] > 0:
+        s0 = _reads_struct(targets.slice(0, b[rank]))
+        eng._ck(L.ndg_index_add_meta(h, C.byref(s0)))
+    mine = _reads_struct(targets.slice(b[rank], b[rank + 1]))
+    eng._ck(L.ndg_index_add(h, C.byref(mine)))
+    if b[rank + 1] < targets.n:
+        s1 = _reads_struct(targets.slice(b[rank + 1], targets.n))
+        eng._ck(L.ndg_index_add_meta(h, C.byref(s1)))
+    ptr, n = C.c_void_p(), C.c_uint64()
+    eng._ck(L.ndg_index_export(h, C.byref(ptr), C.byref(n)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cnt = torch.tensor([n.value], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    mx = max(cnts)
+    send = torch.zeros(mx * 2, dtype=torch.int64, device=dev)
+    if n.value:
+        eng._ck(L.ndg_copy_d2d(h, send.data_ptr(), ptr, n.value * 16))
+    recv = torch.empty(world * mx * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    torch.cuda.synchronize()
+    eng._ck(L.ndg_index_clear_minimizers(h))
+    for r in range(world):
+        if cnts[r]:
+            eng._ck(L.ndg_index_import(h, recv.data_ptr() + r * mx * 16, cnts[r]))
+    del recv, send
+    return eng.finalize_index(targets)
 
 
 def index_parts(targets: Reads, io: IdxOpt):

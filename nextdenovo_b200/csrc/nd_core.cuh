@@ -212,7 +212,7 @@ ND_HD void nd_ins_sort_128x(nd_u128 *beg, nd_u128 *end)
         }
 }
 
-struct nd_rs_job { uint32_t beg, n; int shift; };
+struct nd_rs_job { uint32_t beg, n; int shift; int buf; };   // buf: which of the two anchor buffers holds the bucket (warp sort)
 
 // One pass of the flag sort over a[beg, beg+n) on byte `shift`; appends child ranges that need
 // another pass to `next` (at most n/65 entries), insertion-sorts the small ones in place.

@@ -167,13 +167,35 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
 
 // ------------------------------------------------------------------------------------------------
 // exact flag-sort emulation, breadth first.  ref: minimap2/ksort.h:98-151.
-// A job is one call of rs_sort(): a bucket [beg, beg+n) and a byte position.  A pass over a bucket
-// whose elements all share the digit is a no-op and only re-queues the bucket; otherwise the
-// cycle-leader permutation is replayed by lane 0 (its order of moves is what makes the reference's
-// tie order what it is), while histogramming, re-queueing and the <=64 insertion sorts of the child
-// buckets run across the lanes.
+//
+// A job is one call of rs_sort(): a bucket [beg, beg+n) and a byte position.  The reference's
+// cycle-leader permutation is sequential by nature (which region is popped next depends on the digit
+// just popped), and its order of moves decides the final order of equal keys, so it has to be
+// replayed -- but only its *control*: one warp
+//   1. extracts the digit of every element into a byte array and histograms it (all lanes);
+//   2. derives src_of[dst] (which original slot ends in slot dst):
+//        - one non-empty bucket: identity (the pass is a no-op);
+//        - two non-empty buckets: closed form from two rank scans (all lanes), see below;
+//        - otherwise lane 0 replays the pops/pushes on the 1-byte digits only (L1-resident stream
+//          per bucket, bucket heads in shared memory), writing src_of with fire-and-forget stores;
+//   3. gathers the 16-byte anchors into the other buffer (all lanes, no dependent chain);
+//   4. re-queues child buckets > 64 for the next byte, insertion-sorts the rest in place (one lane
+//      per child bucket) and lands finished ranges in buffer A.
+//
+// Two-bucket closed form.  Buckets d0 < d1 with regions R0 = [0, n0), R1 = [n0, n).  m_i = i-th
+// element of R0 with digit d1, z_i = i-th element of R1 with digit d0 (K of each).  Replaying the
+// reference: each m_i is dropped at R1's head and pushes the natives in front of it forward until a
+// z pops out, which fills m_i's hole.  Hence R0 keeps its natives and hole i receives z_i; in R1,
+// slot n0 receives m_0, a slot following z_r (r < K-1) receives m_{r+1}, every other slot up to the
+// last z receives its left neighbour, slots after the last z are untouched.
 // ------------------------------------------------------------------------------------------------
 #define NDW_SORT_WARPS 4
+
+struct ndw_sort_bufs {
+    nd_u128 *A, *B;            // A holds the input and the final result
+    uint8_t *dig;              // digit per element
+    uint32_t *src_of, *tmp;    // permutation, rank lists
+};
 
 __global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs, uint32_t *n_jobs)
 {
@@ -182,66 +204,150 @@ __global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_jo
     nd_u64 b = a_off[r], n = a_off[r + 1] - b;
     if (n > ND_RS_SMALL) {
         uint32_t q = atomicAdd(n_jobs, 1u);
-        jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56;
+        jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0;
     } else if (n > 1) nd_ins_sort_128x(a + b, a + b + n);
 }
 
 __global__ void __launch_bounds__(NDW_SORT_WARPS * 32)
-k_rs_level(nd_u128 *a, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_rs_job *jobs_out, uint32_t *n_out)
+k_rs_level(ndw_sort_bufs W, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_rs_job *jobs_out, uint32_t *n_out, uint32_t *work)
 {
     __shared__ uint32_t s_head[NDW_SORT_WARPS][256], s_tail[NDW_SORT_WARPS][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t *head = s_head[wib], *tail = s_tail[wib];
     const uint32_t nj = *n_in;
-    const uint32_t wid = blockIdx.x * NDW_SORT_WARPS + wib, nw = gridDim.x * NDW_SORT_WARPS;
-    for (uint32_t q = wid; q < nj; q += nw) {
+    const unsigned lt = (1u << lane) - 1;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(work, 1u);
+        q = __shfl_sync(NDW_FULL, q, 0);
+        if (q >= nj) break;
         const nd_rs_job job = jobs_in[q];
-        nd_u128 *base = a + job.beg;
+        const nd_u128 *in = (job.buf ? W.B : W.A) + job.beg;
+        nd_u128 *out = (job.buf ? W.A : W.B) + job.beg;
+        const bool out_is_A = job.buf != 0;
+        uint8_t *dig = W.dig + job.beg;
+        uint32_t *src_of = W.src_of + job.beg, *tmp = W.tmp + job.beg;
         const int s = job.shift;
+        const uint32_t n = job.n;
+
+        // 1. digits + histogram
         for (int d = lane; d < 256; d += 32) head[d] = 0;
         __syncwarp();
-        for (uint32_t i = lane; i < job.n; i += 32) atomicAdd(&head[base[i].x >> s & 255], 1u);
+        for (uint32_t i = lane; i < n; i += 32) {
+            uint32_t d = (uint32_t)(in[i].x >> s & 255);
+            dig[i] = (uint8_t)d; src_of[i] = i;
+            atomicAdd(&head[d], 1u);
+        }
         __syncwarp();
-        // exclusive prefix over 256 counters: 8 per lane + warp scan
-        uint32_t c[8], sum = 0, nonempty = 0;
+        uint32_t c[8], sum = 0, nonempty = 0, dmin = 256, dmax = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { c[k] = head[lane * 8 + k]; sum += c[k]; nonempty += c[k] != 0; }
+        for (int k = 0; k < 8; ++k) {
+            c[k] = head[lane * 8 + k]; sum += c[k];
+            if (c[k]) { ++nonempty; uint32_t d = lane * 8 + k; dmin = d < dmin ? d : dmin; dmax = d > dmax ? d : dmax; }
+        }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(NDW_FULL, incl, o); if (lane >= o) incl += y; }
         uint32_t run = incl - sum;
         nonempty = __reduce_add_sync(NDW_FULL, nonempty);
+        dmin = __reduce_min_sync(NDW_FULL, dmin); dmax = __reduce_max_sync(NDW_FULL, dmax);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) { head[lane * 8 + k] = run; run += c[k]; tail[lane * 8 + k] = run; }
         __syncwarp();
-        if (nonempty > 1 && lane == 0) {
-            for (uint32_t d = 0; d < 256;) {
+
+        if (nonempty == 1) {                       // no-op pass
+            if (s) {
+                if (lane == 0) { uint32_t o = atomicAdd(n_out, 1u); jobs_out[o] = job; jobs_out[o].shift = s > 8 ? s - 8 : 0; }
+            } else if (job.buf) {
+                for (uint32_t i = lane; i < n; i += 32) W.A[job.beg + i] = in[i];
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // 2. src_of
+        if (nonempty == 2) {
+            const uint32_t d0 = dmin, d1 = dmax, n0 = tail[d0];
+            uint32_t K = 0;
+            for (uint32_t b0 = 0; b0 < n0; b0 += 32) {                // m list
+                uint32_t i = b0 + lane; bool fl = i < n0 && dig[i] == d1;
+                unsigned m = __ballot_sync(NDW_FULL, fl);
+                if (fl) tmp[K + __popc(m & lt)] = i;
+                K += __popc(m);
+            }
+            uint32_t K1 = 0;
+            for (uint32_t b0 = n0; b0 < n; b0 += 32) {                // z list
+                uint32_t i = b0 + lane; bool fl = i < n && dig[i] == d0;
+                unsigned m = __ballot_sync(NDW_FULL, fl);
+                if (fl) tmp[n0 + K1 + __popc(m & lt)] = i;
+                K1 += __popc(m);
+            }
+            __syncwarp();
+            if (K) {
+                const uint32_t *mpos = tmp, *zpos = tmp + n0;
+                const uint32_t zl = zpos[K - 1];
+                uint32_t rk = 0;
+                for (uint32_t b0 = 0; b0 < n0; b0 += 32) {            // holes of R0 <- z_i
+                    uint32_t i = b0 + lane; bool fl = i < n0 && dig[i] == d1;
+                    unsigned m = __ballot_sync(NDW_FULL, fl);
+                    if (fl) src_of[i] = zpos[rk + __popc(m & lt)];
+                    rk += __popc(m);
+                }
+                rk = 0;
+                for (uint32_t b0 = n0; b0 <= zl; b0 += 32) {           // R1 up to the last z
+                    uint32_t j = b0 + lane; bool inr = j < zl;         // slot j+1 <= zl gets a new occupant
+                    bool fl = j <= zl && dig[j] == d0;
+                    unsigned m = __ballot_sync(NDW_FULL, fl);
+                    if (inr) src_of[j + 1] = fl ? mpos[rk + __popc(m & lt) + 1] : j;
+                    rk += __popc(m);
+                }
+                if (lane == 0) src_of[n0] = mpos[0];
+            }
+        } else if (lane == 0) {
+            for (uint32_t d = 0; d < 256; ++d) {
                 uint32_t hd = head[d];
-                if (hd == tail[d]) { ++d; continue; }
-                uint32_t t = (uint32_t)(base[hd].x >> s & 255);
-                if (t == d) { head[d] = hd + 1; continue; }
-                nd_u128 carry = base[hd];
-                do {
-                    uint32_t ht = head[t];
-                    nd_u128 evicted = base[ht];
-                    base[ht] = carry; head[t] = ht + 1;
-                    carry = evicted;
-                    t = (uint32_t)(carry.x >> s & 255);
-                } while (t != d);
-                base[hd] = carry; head[d] = hd + 1;
+                const uint32_t td = tail[d];
+                while (hd < td) {
+                    uint32_t t = dig[hd];
+                    if (t == d) { ++hd; continue; }
+                    uint32_t carry = hd;
+                    do {
+                        const uint32_t ht = head[t];
+                        const uint32_t x = dig[ht];
+                        src_of[ht] = carry; carry = ht; head[t] = ht + 1;
+                        t = x;
+                    } while (t != d);
+                    src_of[hd] = carry; ++hd;
+                }
+                head[d] = hd;
             }
         }
         __syncwarp();
+        __threadfence_block();
+
+        // 3. gather into the other buffer
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint4 vv = *reinterpret_cast<const uint4 *>(in + src_of[i]);
+            *reinterpret_cast<uint4 *>(out + i) = vv;
+        }
+        __syncwarp();
+
+        // 4. children
         if (s) {
             const int ns = s > 8 ? s - 8 : 0;
             for (int d = lane; d < 256; d += 32) {
-                uint32_t bb = d ? tail[d - 1] : 0, ee = tail[d];
+                const uint32_t bb = d ? tail[d - 1] : 0, ee = tail[d];
                 if (ee - bb > ND_RS_SMALL) {
                     uint32_t o = atomicAdd(n_out, 1u);
-                    jobs_out[o].beg = job.beg + bb; jobs_out[o].n = ee - bb; jobs_out[o].shift = ns;
-                } else if (ee - bb > 1) nd_ins_sort_128x(base + bb, base + ee);
+                    jobs_out[o].beg = job.beg + bb; jobs_out[o].n = ee - bb; jobs_out[o].shift = ns; jobs_out[o].buf = job.buf ^ 1;
+                } else if (ee > bb) {
+                    if (ee - bb > 1) nd_ins_sort_128x(out + bb, out + ee);
+                    if (!out_is_A) for (uint32_t i = bb; i < ee; ++i) W.A[job.beg + i] = out[i];
+                }
             }
+        } else if (!out_is_A) {
+            for (uint32_t i = lane; i < n; i += 32) W.A[job.beg + i] = out[i];
         }
         __syncwarp();
     }
@@ -250,19 +356,19 @@ k_rs_level(nd_u128 *a, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_rs_job
 // host-side sequencing ------------------------------------------------------------------------
 struct ndw_launch_hooks { void (*begin)(void *ctx, const char *name); void (*end)(void *ctx); void *ctx; };
 
-// jobs: device buffer for 2 * (NA/65 + n_reads + 1) jobs; counters: 10 u32 on the device
-static inline void ndw_sort_launch(cudaStream_t st, nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_u64 n_a,
+// jobs: device buffer for 2 * (NA/65 + n_reads + 1) jobs; counters: 24 u32 on the device
+static inline void ndw_sort_launch(cudaStream_t st, ndw_sort_bufs W, const nd_u64 *a_off, int n_reads, nd_u64 n_a,
                                    nd_rs_job *jobs, uint32_t *counters, int n_sm, ndw_launch_hooks hk)
 {
     const nd_u64 half = n_a / (ND_RS_SMALL + 1) + (nd_u64)n_reads + 1;
     nd_rs_job *buf[2] = { jobs, jobs + half };
-    cudaMemsetAsync(counters, 0, 10 * sizeof(uint32_t), st);
+    cudaMemsetAsync(counters, 0, 24 * sizeof(uint32_t), st);
     hk.begin(hk.ctx, "sort_init");
-    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(a, a_off, n_reads, buf[0], counters);
+    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(W.A, a_off, n_reads, buf[0], counters);
     hk.end(hk.ctx);
     for (int lvl = 0; lvl < 8; ++lvl) {
         hk.begin(hk.ctx, "sort_level");
-        k_rs_level<<<n_sm * 8, NDW_SORT_WARPS * 32, 0, st>>>(a, buf[lvl & 1], counters + lvl, buf[(lvl + 1) & 1], counters + lvl + 1);
+        k_rs_level<<<n_sm * 8, NDW_SORT_WARPS * 32, 0, st>>>(W, buf[lvl & 1], counters + lvl, buf[(lvl + 1) & 1], counters + lvl + 1, counters + 12 + lvl);
         hk.end(hk.ctx);
     }
 }

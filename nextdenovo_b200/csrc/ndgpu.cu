@@ -96,7 +96,7 @@ struct ndg_ctx {
     int mid_occ = 0;
     // mapping workspace
     ReadsDev q;
-    DevBuf staging, cnt, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a_off, avgq, jobs, flags, seg_start,
+    DevBuf staging, cnt, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
     uint64_t n_mz = 0, n_a = 0, n_seg = 0, n_hits = 0;
@@ -281,7 +281,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
-                       &c->m_keep, &c->a_pos, &c->a, &c->a_off, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
+                       &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
     for (auto b : bufs) b->release();
     c->q.release();
@@ -563,8 +563,12 @@ int map_resident(ndg_ctx *c, int qidx_base)
         KLAUNCH("sort_seq", (k_sort_seq<<<nblk(nr, 64), 64, 0, c->st>>>(c->a.as<nd_u128>(), c->a_off.as<nd_u64>(), nr, c->jobs.as<nd_rs_job>())));
     } else {
         RSV(c->jobs, 2 * (NA / 65 + (size_t)nr + 2) * sizeof(nd_rs_job));
+        // scratch of the warp sort aliases buffers the chain stage allocates anyway
+        RSV(c->f, NA * 4); RSV(c->p, NA * 4); RSV(c->v, NA * 4); RSV(c->hits, (NA / (o.min_cnt > 0 ? o.min_cnt : 1) + 16) * sizeof(nd_hit));
+        RSV(c->a2, (NA + 1) * 16);
+        ndw_sort_bufs W = { c->a.as<nd_u128>(), c->a2.as<nd_u128>(), c->v.as<uint8_t>(), c->f.as<uint32_t>(), c->p.as<uint32_t>() };
         ndw_launch_hooks hk = { hk_begin, hk_end, c };
-        ndw_sort_launch(c->st, c->a.as<nd_u128>(), c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 32, c->n_sm, hk);
+        ndw_sort_launch(c->st, W, c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 64, c->n_sm, hk);
     }
     CK(cudaGetLastError());
 

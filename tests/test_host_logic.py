@@ -1,0 +1,93 @@
+"""Host-side logic: formats, option parsing, batching.  CPU only."""
+import os
+import numpy as np
+import pytest
+import nextdenovo_b200 as nd
+from nextdenovo_b200 import options
+from nextdenovo_b200.formats import pack_bases, unpack_bases, make_reads
+
+
+def test_2bit_roundtrip(tmp_path, reads_sub, golden_dir):
+    p = str(tmp_path / "x.2bit")
+    nd.write_2bit(p, reads_sub, str(tmp_path / "x.idx"))
+    assert open(p, "rb").read() == open(os.path.join(golden_dir, "sub120.2bit"), "rb").read()
+    r2 = nd.read_2bit(p)
+    assert (r2.words == reads_sub.words).all() and (r2.length == reads_sub.length).all() and (r2.ids == reads_sub.ids).all()
+    first = open(str(tmp_path / "x.idx")).readline().split("\t")
+    assert first[0] == "0" and first[1] == "10" and int(first[2]) == int(reads_sub.length[0])   # util/seq_dump.c:36-41
+
+
+def test_pack_unpack():
+    rng = np.random.default_rng(1)
+    for n in (1, 15, 16, 17, 1000):
+        c = rng.integers(0, 4, n).astype(np.uint8)
+        assert (unpack_bases(pack_bases(c), n) == c).all()
+    assert pack_bases(np.array([3, 0, 1, 2], dtype=np.uint8))[0] == (3 << 30 | 0 << 28 | 1 << 26 | 2 << 24)
+
+
+def test_ovl_codec_against_golden(golden_dir):
+    buf = open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+    rec = nd.decode_ovl8(buf)
+    assert rec.shape == (7272, 8)
+    assert nd.encode_ovl8_py([tuple(int(x) for x in r) for r in rec]) == buf
+    assert (rec[:, 3] > rec[:, 2]).all() and (rec[:, 6] > rec[:, 5]).all() and set(np.unique(rec[:, 1])) <= {0, 1}
+
+
+def test_varint_edges():
+    recs = [(0, 0, 0, 127, 0, 0, 127, 0), (128, 1, 128, 16383 + 128, 5, 16384, 16384 + 2097152, 268435456),
+            (4294967295, 0, 99999999, 100000001, 4294967295, 7, 4294967290, 100000000), (3, 1, 1, 2, 1, 2, 100, 4294967295)]
+    got = nd.decode_ovl8(nd.encode_ovl8_py(recs))
+    assert [tuple(int(x) for x in r) for r in got] == recs
+
+
+def test_name_keys_follow_strcmp():
+    ids = np.array([0, 1, 9, 10, 11, 99, 100, 101, 1000, 123456789, 4294967295, 2, 20, 200], dtype=np.uint32)
+    keys = nd.name_keys(ids)
+    names = [str(int(i)) for i in ids]
+    for i in range(len(ids)):
+        for j in range(len(ids)):
+            assert (names[i] < names[j]) == (int(keys[i]) < int(keys[j]))
+            assert (names[i] == names[j]) == (int(keys[i]) == int(keys[j]))
+
+
+def test_x31_hash():
+    ids = np.array([0, 7, 10, 99, 12345, 4294967295], dtype=np.uint32)
+    def x31(s):
+        h = ord(s[0])
+        for ch in s[1:]:
+            h = (h * 31 + ord(ch)) & 0xffffffff
+        return h
+    assert [int(h) for h in nd.x31_hash(ids)] == [x31(str(int(i))) for i in ids]
+
+
+def test_parse_num():
+    assert nd.parse_num("3G") == 3000000000 and nd.parse_num("500m") == 500000000 and nd.parse_num("2.5k") == 2500 and nd.parse_num("17") == 17
+
+
+def test_parse_args_pipeline_commands():
+    """command lines emitted by nextDenovo:445-464 (raw_align)"""
+    io, mo, out, pos = options.parse_args("--step 1 --dual=yes -t 8 -x ava-ont seed.2bit part.2bit -o x.ovl".split())
+    assert (io.k, io.w, io.flag & options.MM_I_HPC) == (15, 5, 0)
+    assert mo.step == 1 and mo.minlen == 500 and mo.outraw == 0 and out == "x.ovl" and pos == ["seed.2bit", "part.2bit"]
+    assert not (mo.flag & options.MM_F_NO_DUAL) and (mo.flag & options.MM_F_NO_DIAG)
+    assert (mo.bw, mo.max_gap, mo.min_chain_score) == (2000, 10000, 100)
+    io, mo, out, pos = options.parse_args("-k 17 --step 1 -I 3G -t 8 -x ava-pb a b -o y".split())     # -x applies first
+    assert (io.k, io.w) == (17, 5) and io.flag & options.MM_I_HPC and io.batch_size == 3000000000
+    assert mo.flag & options.MM_F_NO_DUAL and mo.bw == 500
+    with pytest.raises(ValueError):
+        options.parse_args("--step 1 -x nonsense a b".split())
+    with pytest.raises(ValueError):
+        options.parse_args("--step 7 a b".split())
+
+
+def test_index_parts_and_query_batches():
+    from nextdenovo_b200.engine import index_parts, query_batches, shard_bounds
+    lens = [30] * 10
+    r = make_reads([np.zeros(2, np.uint32)] * 10, lens, list(range(10)))
+    io = nd.IdxOpt()
+    io.batch_size, io.mini_batch_size = 100, 50                  # mini-batches of >=50 bases (2 reads), part ends once >100
+    assert index_parts(r, io) == [(0, 4), (4, 8), (8, 10)]
+    io.batch_size = 10 ** 9
+    assert index_parts(r, io) == [(0, 10)]
+    assert query_batches(r, 100) == [(0, 4), (4, 8), (8, 10)]
+    assert shard_bounds(10, 4) == [0, 2, 5, 7, 10]

@@ -139,6 +139,18 @@ uint64_t ndg_kernel_launches(const ndg_ctx_t *ctx);
 int ndg_ovl_encode8(uint8_t *dst, uint32_t state[2], int rev, uint32_t qname, uint32_t qs, uint32_t qe,
                     uint32_t tname, uint32_t ts, uint32_t te, uint32_t match);
 
+/* ---- base-level extension: replaces ksw_extd2_sse (ref: minimap2/ksw2_extd2_sse.c:1-394; called from
+ *      mm_align_pair, minimap2/align.c:313-339) for a batch of independent alignments ---------------
+ * seqs: concatenated residue codes 0..m-1 (as mm_align1 prepares them); call i aligns
+ * query seqs[q_off .. q_off+qlen) to target seqs[t_off .. t_off+tlen).  Results are bit-identical to
+ * the reference function (score, end points, z-drop, CIGAR in BAM encoding).  cigar_off: n+1 offsets
+ * into cigar[] with cigar_off[i+1]-cigar_off[i] >= qlen+tlen+2. */
+typedef struct { int32_t qlen, tlen; uint64_t q_off, t_off; int32_t w, zdrop, end_bonus, flag; } ndg_ksw_call_t;
+typedef struct { int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end, reserved; } ndg_ksw_result_t;
+int ndg_ksw_extd2_batch(ndg_ctx_t *ctx, const ndg_ksw_call_t *calls, int32_t n_calls, const uint8_t *seqs, uint64_t seq_bytes,
+                        int32_t m, const int8_t *mat, int32_t q, int32_t e, int32_t q2, int32_t e2,
+                        ndg_ksw_result_t *res, uint32_t *cigar, const uint64_t *cigar_off);
+
 /* Step-1 emitter: applies the reference's output filter (ref: minimap2/map.c:1297-1304: drop hits whose
  * target is the query itself, keep qe-qs >= minlen, optional --dvt test :804-821) to a sorted hit list
  * and appends 8-field records.  q_id/q_key/q_len are indexed by hit.qidx, t_id/t_key/t_len by hit.rid

@@ -1,0 +1,195 @@
+// minimap2_nd_main.cc -- `minimap2-nd`-compatible executable for the read-overlap step
+// (`--step 1 ... TARGET QUERY -o OUT`), host side in C++ over the C ABI of libndgpu.so.
+//
+// Mirrors the parts of the reference's main() the NextDenovo pipeline drives for raw_align
+// (ref: nextDenovo:445-464): two-pass option handling (minimap2/main.c:177-363), index parts
+// (minimap2/index.c:284-288,353-358), query batches (minimap2/bseq.c:86-123), ordered .ovl output
+// (minimap2/map.c:1245-1352).  Input must be .2bit (what seq_dump writes, lib/bseq.c:93-139); other
+// modes of the reference binary (-c, --step 2/3, PAF/SAM) are rejected, never approximated.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <chrono>
+#include "ndgpu.h"
+
+struct Reads {
+    std::vector<uint32_t> words, len, id, hash;
+    std::vector<uint64_t> word_off, key;
+    int n() const { return (int)len.size(); }
+};
+
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static int64_t parse_num(const char *s)            // ref: minimap2/main.c:102-111
+{
+    char *p; double x = strtod(s, &p);
+    if (*p == 'G' || *p == 'g') x *= 1e9; else if (*p == 'M' || *p == 'm') x *= 1e6; else if (*p == 'K' || *p == 'k') x *= 1e3;
+    return (int64_t)(x + .499);
+}
+
+static void name_fields(uint32_t id, uint64_t *key, uint32_t *hash)
+{
+    char buf[16]; int n = snprintf(buf, sizeof buf, "%u", id);
+    uint64_t k = 0; uint32_t h = (uint32_t)buf[0];
+    for (int i = 0; i < n; ++i) k |= (uint64_t)(buf[i] - '0' + 1) << (60 - 4 * i);      // strcmp-order-preserving
+    for (int i = 1; i < n; ++i) h = (h << 5) - h + (uint32_t)buf[i];                     // khash.h:383-388
+    *key = k; *hash = h;
+}
+
+static bool read_2bit(const char *fn, Reads &R)
+{
+    FILE *fp = strcmp(fn, "-") ? fopen(fn, "rb") : stdin;
+    if (!fp) return false;
+    uint8_t hdr[2];
+    if (fread(hdr, 1, 2, fp) != 2 || !(hdr[0] == 0 || hdr[0] == 254)) {
+        fprintf(stderr, "[ERROR] '%s' is not a .2bit file; this build accepts the .2bit files written by seq_dump only\n", fn);
+        if (fp != stdin) fclose(fp);
+        return false;
+    }
+    R.word_off.push_back(0);
+    for (;;) {
+        uint32_t h2[2];
+        if (fread(h2, 4, 2, fp) != 2) break;
+        size_t nw = ((size_t)h2[1] + 15) / 16, o = R.words.size();
+        R.words.resize(o + nw);
+        if (nw && fread(&R.words[o], 4, nw, fp) != nw) { R.words.resize(o); break; }
+        uint64_t k; uint32_t h; name_fields(h2[0], &k, &h);
+        R.id.push_back(h2[0]); R.len.push_back(h2[1]); R.key.push_back(k); R.hash.push_back(h);
+        R.word_off.push_back(R.words.size());
+    }
+    if (fp != stdin) fclose(fp);
+    return true;
+}
+
+static ndg_reads_t view(const Reads &R, int r0, int r1)
+{
+    ndg_reads_t v; memset(&v, 0, sizeof v);
+    v.n_reads = r1 - r0; v.words = R.words.data(); v.word_off = R.word_off.data() + r0; v.len = R.len.data() + r0;
+    v.name_key = R.key.data() + r0; v.name_hash = R.hash.data() + r0;
+    return v;   // word_off entries are absolute into words[]; the library rebases them
+}
+
+int main(int argc, char **argv)
+{
+    ndg_opt_t o; memset(&o, 0, sizeof o);
+    o.k = 15; o.w = 10; o.min_cnt = 3; o.min_chain_score = 40; o.bw = 500; o.max_gap = 5000; o.max_chain_skip = 25; o.max_chain_iter = 5000;
+    o.seed = 11; o.mid_occ_frac = 2e-4f;
+    int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0;
+    uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
+    const char *out = nullptr; std::vector<const char *> pos;
+    bool cigar = false;
+    const double t0 = now();
+    auto takes = [](const std::string &a) {
+        static const char *t[] = { "-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen", "--maxhan1", "--maxhan2",
+                                   "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v", "--device", "-N", "-p", "-M", "-z", "-A", "-B", "-O", "-E", "-s" };
+        for (auto x : t) if (a == x) return true;
+        return false;
+    };
+    std::vector<std::pair<std::string, std::string>> tok;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        size_t eq;
+        if (a.rfind("--", 0) == 0 && (eq = a.find('=')) != std::string::npos) tok.push_back({ a.substr(0, eq), a.substr(eq + 1) });
+        else if (takes(a)) { if (i + 1 >= argc) { fprintf(stderr, "[ERROR] missing option argument\n"); return 1; } tok.push_back({ a, argv[++i] }); }
+        else if (a.size() > 1 && a[0] == '-') tok.push_back({ a, "" });
+        else pos.push_back(argv[i]);
+    }
+    for (auto &kv : tok) {                                      // pass 1: presets (main.c:177-205)
+        if (kv.first == "-x") {
+            if (kv.second == "ava-ont") { o.hpc = 0; o.k = 15; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; o.bw = 2000; }
+            else if (kv.second == "ava-pb") { o.hpc = 1; o.k = 19; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; }
+            else { fprintf(stderr, "[ERROR] unknown preset '%s'\n", kv.second.c_str()); return 1; }
+        } else if (kv.first == "--step") {
+            step = atoi(kv.second.c_str());
+            if (step == 1) minlen = 500; else if (step == 2 || step == 3) minlen = 2000;
+            else { fprintf(stderr, "[ERROR] unknown preset step '%s'\n", kv.second.c_str()); return 1; }
+        }
+    }
+    for (auto &kv : tok) {                                      // pass 2 (main.c:209-363)
+        const std::string &k = kv.first; const char *v = kv.second.c_str();
+        if (k == "-w") o.w = atoi(v); else if (k == "-k") o.k = atoi(v); else if (k == "-H") o.hpc = 1;
+        else if (k == "-r") o.bw = (int)parse_num(v); else if (k == "-g") o.max_gap = (int)parse_num(v);
+        else if (k == "-n") o.min_cnt = atoi(v); else if (k == "-m") o.min_chain_score = atoi(v);
+        else if (k == "-I") batch_size = (uint64_t)parse_num(v); else if (k == "-K") q_batch = parse_num(v);
+        else if (k == "-D") o.flag_no_diag = 1; else if (k == "-X") o.flag_no_diag = o.flag_no_dual = 1;
+        else if (k == "-c" || k == "-a" || k == "--cs" || k == "-S") cigar = true;
+        else if (k == "--minlen") minlen = (int)parse_num(v); else if (k == "--maxhan1") maxhan1 = (int)parse_num(v);
+        else if (k == "--maxhan2") maxhan2 = (int)parse_num(v); else if (k == "--dvt") dvt = 1;
+        else if (k == "--seed") o.seed = atoi(v); else if (k == "--max-chain-skip") o.max_chain_skip = atoi(v);
+        else if (k == "--max-chain-iter") o.max_chain_iter = atoi(v); else if (k == "--min-occ-floor") o.min_mid_occ = atoi(v);
+        else if (k == "-v") verbose = atoi(v); else if (k == "--device") device = atoi(v);
+        else if (k == "--dual") { if (kv.second == "yes" || kv.second == "y") o.flag_no_dual = 0; else if (kv.second == "no" || kv.second == "n") o.flag_no_dual = 1; }
+        else if (k == "-f") { double x = strtod(v, nullptr); if (x < 1.0) { o.mid_occ_frac = (float)x; o.mid_occ = 0; } else o.mid_occ = (int)(x + .499); }
+        else if (k == "-o") { if (kv.second != "-") out = v; }
+        else if (k == "-V" || k == "--version") { puts("2.17-r941-ndgpu"); return 0; }
+    }
+    if (pos.size() < 2) {
+        fprintf(stderr, "Usage: minimap2-nd --step 1 [options] <target.2bit> <query.2bit> -o out.ovl\n");
+        return 1;
+    }
+    if (step != 1 || cigar || !out) {
+        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 ... -o FILE` without base-level alignment only\n");
+        return 1;
+    }
+    FILE *fo = fopen(out, "wb");                                // main.c:259-262 (freopen)
+    if (!fo) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", out); return 1; }
+
+    Reads T;
+    if (!read_2bit(pos[0], T)) { fprintf(stderr, "[ERROR] failed to open file '%s'\n", pos[0]); return 1; }
+    ndg_ctx_t *g = nullptr;
+    if (ndg_init(device, &g) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device); return 1; }
+    ndg_set_opt(g, &o);
+
+    uint32_t state[2] = { 0, 0 };
+    uint64_t n_rec = 0, sum_qspan = 0;
+    std::vector<uint8_t> obuf;
+    const uint64_t mini = mini_batch < batch_size ? mini_batch : batch_size;
+    int t_at = 0, n_parts = 0;
+    while (t_at < T.n()) {                                     // one index part per iteration (main.c:477)
+        int t0i = t_at; uint64_t total = 0;
+        while (t_at < T.n() && !(total > batch_size)) {         // index.c:286: stop once sum_len > batch_size
+            uint64_t size = 0;
+            while (t_at < T.n()) { size += T.len[t_at++]; if (size >= mini) break; }
+            total += size;
+        }
+        ndg_reads_t tv = view(T, t0i, t_at);
+        ndg_index_stat_t st;
+        if (ndg_index_begin(g) || ndg_index_add(g, &tv) || ndg_index_finalize(g, &st)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+        ++n_parts;
+        if (verbose >= 3) {
+            fprintf(stderr, "[M::main::%.3f] loaded/built the index for %llu target sequence(s)\n", now() - t0, (unsigned long long)st.n_seq);
+            fprintf(stderr, "[M::mm_mapopt_update::%.3f] mid_occ = %d\n", now() - t0, st.mid_occ);
+            fprintf(stderr, "[M::mm_idx_stat::%.3f] distinct minimizers: %llu (%.2f%% are singletons); average occurrences: %.3lf; average spacing: %.3lf\n", now() - t0,
+                    (unsigned long long)st.n_distinct, 100.0 * st.n_singletons / st.n_distinct, (double)st.n_minimizers / st.n_distinct, (double)st.sum_len / st.n_minimizers);
+        }
+        for (size_t qf = 1; qf < pos.size(); ++qf) {
+            Reads Qown; const Reads *Q = &T;
+            if (strcmp(pos[qf], pos[0]) != 0) { if (!read_2bit(pos[qf], Qown)) { fprintf(stderr, "ERROR: failed to open file '%s'\n", pos[qf]); return 1; } Q = &Qown; }
+            int q_at = 0;
+            while (q_at < Q->n()) {                             // bseq.c:86-123: a batch ends once >= chunk_size bases were read
+                int q0 = q_at; int64_t size = 0;
+                while (q_at < Q->n()) { size += Q->len[q_at++]; if (size >= q_batch) break; }
+                ndg_reads_t qv = view(*Q, q0, q_at);
+                ndg_map_result_t R;
+                if (ndg_map_batch(g, &qv, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+                obuf.resize((size_t)R.n_hits * 40 + 64);
+                int64_t nb = ndg_ovl_emit_step1(R.hits, R.n_hits, Q->id.data() + q0, Q->key.data() + q0, Q->len.data() + q0,
+                                                T.id.data() + t0i, T.key.data() + t0i, T.len.data() + t0i, minlen, dvt, maxhan1, maxhan2,
+                                                state, obuf.data(), obuf.size(), &n_rec, &sum_qspan);
+                if (nb < 0 || fwrite(obuf.data(), 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+                if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, q_at - q0);
+            }
+        }
+    }
+    if (fclose(fo) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+    if (verbose >= 3) {
+        fprintf(stderr, "[M::main] Version: 2.17-r941-ndgpu (%s)\n[M::main] CMD:", ndg_version());
+        for (int i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
+        fprintf(stderr, "\n[M::main] Real time: %.3f sec; records: %llu; index parts: %d\n", now() - t0, (unsigned long long)n_rec, n_parts);
+    }
+    ndg_destroy(g);
+    return 0;
+}

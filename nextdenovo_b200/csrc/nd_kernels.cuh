@@ -116,29 +116,36 @@ __global__ void k_count_heads(const nd_u64 *key, nd_u64 n, nd_u64 *n_distinct)
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_distinct, (nd_u64)__popc(m));
 }
 
-// per run head: run length by binary search, insert into the table, histogram of run lengths
-__global__ void k_index_table(const nd_u64 *key, nd_u64 n, nd_ht_slot *tab, int log2cap, uint32_t *hist, int hist_bins)
+// per run head: run length by galloping search, insert into the table, histogram of run lengths
+// (small run lengths are histogrammed per block in shared memory: almost every run has length 1)
+__global__ void __launch_bounds__(256)
+k_index_table(const nd_u64 *key, nd_u64 n, nd_ht_slot *tab, int log2cap, uint32_t *hist, int hist_bins)
 {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    nd_u64 kx = key[i];
-    if (i > 0 && key[i - 1] == kx) return;
-    nd_u64 lo = i, hi = n;                           // first index > i with key != kx
-    {   // gallop then bisect (runs are short)
+    bool head = false; nd_u64 kx = 0;
+    if (i < n) { kx = key[i]; head = i == 0 || key[i - 1] != kx; }
+    if (head) {
+        nd_u64 lo = i, hi;
         nd_u64 step = 1;
         while (lo + step < n && key[lo + step] == kx) { lo += step; step <<= 1; }
         hi = lo + step < n ? lo + step : n;
         while (hi - lo > 1) { nd_u64 mid = (lo + hi) >> 1; if (key[mid] == kx) lo = mid; else hi = mid; }
+        nd_u64 cnt = hi - i;
+        const nd_u64 maskc = (1ULL << log2cap) - 1;
+        nd_u64 s = nd_ht_hash(kx) >> (64 - log2cap);
+        for (;;) {
+            nd_u64 prev = atomicCAS(&tab[s].key, ND_HT_EMPTY, kx);
+            if (prev == ND_HT_EMPTY) { tab[s].val = i << 24 | (cnt < 0xffffffULL ? cnt : 0xffffffULL); break; }
+            s = (s + 1) & maskc;
+        }
+        if (cnt < 256) atomicAdd(&sh[cnt], 1u);
+        else atomicAdd(&hist[cnt < (nd_u64)hist_bins - 1 ? cnt : (nd_u64)hist_bins - 1], 1u);
     }
-    nd_u64 cnt = hi - i;
-    const nd_u64 maskc = (1ULL << log2cap) - 1;
-    nd_u64 s = nd_ht_hash(kx) >> (64 - log2cap);
-    for (;;) {
-        nd_u64 prev = atomicCAS(&tab[s].key, ND_HT_EMPTY, kx);
-        if (prev == ND_HT_EMPTY) { tab[s].val = i << 24 | (cnt < 0xffffffULL ? cnt : 0xffffffULL); break; }
-        s = (s + 1) & maskc;
-    }
-    atomicAdd(&hist[cnt < (nd_u64)hist_bins - 1 ? cnt : (nd_u64)hist_bins - 1], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void k_index_get(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u64 *out)

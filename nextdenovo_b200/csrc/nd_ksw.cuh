@@ -1,0 +1,281 @@
+// nd_ksw.cuh -- batched dual-affine banded extension DP (ksw_extd2), one warp per alignment.
+// ref: minimap2/ksw2_extd2_sse.c:1-394, ksw2.h:119-176.
+//
+// The reference is a 16-lane int8 SSE kernel over anti-diagonals whose results depend on three
+// implementation details, all reproduced here so that score, end points, z-drop
+// decisions and CIGAR are bit-identical:
+//   (1) a diagonal's band [st0,en0] is widened to 16-cell boundaries [st,en]; the extra cells are
+//       computed from stale scores/state and feed the next diagonal (:139-152);
+//   (2) the score vector is rewritten only on 16-wide unaligned blocks starting at st0, reading the
+//       target / reversed query past their ends inside one zero-initialised block whose layout
+//       (u v x y x2 y2 s sf qr) we keep, so the overruns land where the reference's do (:99-103,158-176);
+//   (3) the exact maximum of H breaks ties in the order of the 4-lane SIMD search (:320-348).
+// Mapping: lanes = consecutive target positions t of the current anti-diagonal (32 per step), state
+// bytes in a per-warp global scratch that stays L1-resident across diagonals, neighbours (t-1) by
+// shuffle with a carry between 32-cell steps, one backtrack byte per cell streamed to HBM, CIGAR
+// walked by lane 0.  No tensor cores: this is integer DP.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+#define NDK_NEG_INF (-0x40000000)
+#define NDK_SCORE_ONLY  0x01
+#define NDK_RIGHT       0x02
+#define NDK_GENERIC_SC  0x04
+#define NDK_APPROX_MAX  0x08
+#define NDK_APPROX_DROP 0x10
+#define NDK_EXTZ_ONLY   0x40
+#define NDK_REV_CIGAR   0x80
+#define NDK_FULL 0xffffffffu
+
+struct ndk_call { int32_t qlen, tlen; unsigned long long q_off, t_off; int32_t w, zdrop, end_bonus, flag; unsigned long long p_off, cigar_off; };
+struct ndk_res { int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end, pad; };
+struct ndk_par { int m; int8_t mat[25]; int q, e, q2, e2; };
+
+__device__ __forceinline__ int ndk_w8(int v) { return (int)(int8_t)(uint8_t)v; }
+
+// ref: ksw2.h:160-176, is_rot = 1
+__device__ __forceinline__ bool ndk_zdrop(ndk_res &ez, int H, int r, int t, int zdrop, int e)
+{
+    if (H > ez.max) { ez.max = H; ez.max_t = t; ez.max_q = r - t; }
+    else if (t >= ez.max_t && r - t >= ez.max_q) {
+        int tl = t - ez.max_t, ql = (r - t) - ez.max_q, l = tl > ql ? tl - ql : ql - tl;
+        if (zdrop >= 0 && ez.max - H > zdrop + l * e) { ez.zdropped = 1; return true; }
+    }
+    return false;
+}
+
+// ref: ksw2.h:119-152, is_rot = 1, min_intron_len = 0 (lane 0)
+__device__ int ndk_backtrack(bool is_rev, const uint8_t *p, const int *off, const int *off_end, int n_col, int i0, int j0, uint32_t *cigar)
+{
+    int n = 0, i = i0, j = j0, state = 0;
+    while (i >= 0 && j >= 0) {
+        int force = -1, r = i + j;
+        int o = off[r];
+        if (i < o) force = 2;
+        if (i > off_end[r]) force = 1;
+        uint32_t tmp = force < 0 ? p[(size_t)r * n_col + i - o] : 0;
+        if (state == 0) state = tmp & 7;
+        else if (!(tmp >> (state + 2) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (force >= 0) state = force;
+        int op = state == 0 ? 0 : (state == 1 || state == 3) ? 2 : 1;
+        if (n == 0 || op != (int)(cigar[n - 1] & 0xf)) cigar[n++] = 1u << 4 | (uint32_t)op; else cigar[n - 1] += 1u << 4;
+        if (op == 0) { --i; --j; } else if (op == 2) --i; else --j;
+    }
+    if (i >= 0) { if (n == 0 || 2 != (int)(cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(i + 1) << 4 | 2u; else cigar[n - 1] += (uint32_t)(i + 1) << 4; }
+    if (j >= 0) { if (n == 0 || 1 != (int)(cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(j + 1) << 4 | 1u; else cigar[n - 1] += (uint32_t)(j + 1) << 4; }
+    if (!is_rev) for (int k = 0; k < n >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n - 1 - k]; cigar[n - 1 - k] = t; }
+    return n;
+}
+
+#define NDK_WARPS 2
+
+// scratch per warp slot: state_stride bytes of int8 state + H (int32 x Tmax) + off/off_end (int x 2 x rmax)
+__global__ void __launch_bounds__(NDK_WARPS * 32)
+k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
+            uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * NDK_WARPS + (threadIdx.x >> 5);
+    uint8_t *base = scratch + (size_t)slot * slot_bytes;
+    int32_t *H = reinterpret_cast<int32_t *>(base + state_bytes);
+    int *off = reinterpret_cast<int *>(base + state_bytes + h_bytes);
+
+    for (;;) {
+        int ci = 0;
+        if (lane == 0) ci = (int)atomicAdd(work, 1u);
+        ci = __shfl_sync(NDK_FULL, ci, 0);
+        if (ci >= n_calls) break;
+        const ndk_call c = calls[ci];
+        const int qlen = c.qlen, tlen = c.tlen, flag = c.flag, zdrop = c.zdrop;
+        const uint8_t *query = seqs + c.q_off, *target = seqs + c.t_off;
+        const bool with_cigar = !(flag & NDK_SCORE_ONLY), approx_max = (flag & NDK_APPROX_MAX) != 0, right = with_cigar && (flag & NDK_RIGHT);
+        ndk_res ez;
+        ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1; ez.max = 0; ez.score = ez.mqe = ez.mte = NDK_NEG_INF;
+        ez.n_cigar = 0; ez.zdropped = 0; ez.reach_end = 0; ez.pad = 0;
+        int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
+        const int qe0 = q + e;                              // the reference's scalar qe predates the swap (:58)
+        const int m = P.m;
+        bool run = !(m <= 1 || qlen <= 0 || tlen <= 0);
+        if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+        const int qe = q + e, qe2 = q2 + e2;
+        const int sc_mch = P.mat[0], sc_mis = P.mat[1], sc_N = P.mat[m * m - 1] == 0 ? -e2 : P.mat[m * m - 1];
+        int w = c.w;
+        if (w < 0) w = tlen > qlen ? tlen : qlen;
+        const int T = (tlen + 15) / 16 * 16;
+        int n_col_ = qlen < tlen ? qlen : tlen;
+        n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+        const int n_col = n_col_ * 16;
+        {
+            int min_sc = P.mat[1];
+            for (int t = 1; t < m * m; ++t) min_sc = min_sc < P.mat[t] ? min_sc : P.mat[t];
+            if (-min_sc > 2 * (q + e)) run = false;
+        }
+        int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+        if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+        const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+
+        int8_t *u = reinterpret_cast<int8_t *>(base), *v = u + T, *x = v + T, *y = x + T, *x2 = y + T, *y2 = x2 + T, *s = y2 + T;
+        uint8_t *sf = reinterpret_cast<uint8_t *>(s + T), *qr = sf + T;
+        int *off_end = off + qlen + tlen - 1;
+        uint8_t *p = pmat + c.p_off;
+        uint32_t *cigar = cigars + c.cigar_off;
+
+        if (run) {
+            const int qpad = ((qlen + 15) / 16 + 1) * 16 + 32;
+            const int8_t i1 = (int8_t)(-q - e), i2 = (int8_t)(-q2 - e2);
+            for (int t = lane; t < T; t += 32) {
+                u[t] = i1; v[t] = i1; x[t] = i1; y[t] = i1; x2[t] = i2; y2[t] = i2; s[t] = 0;
+                sf[t] = t < tlen ? target[t] : 0;
+                if (!approx_max) H[t] = NDK_NEG_INF;
+            }
+            for (int t = lane; t < qpad; t += 32) qr[t] = t < qlen ? query[qlen - 1 - t] : 0;
+            __syncwarp();
+
+            int last_st = -1, last_en = -1, H0 = 0, last_H0_t = 0;
+            for (int r = 0; r < qlen + tlen - 1; ++r) {
+                int st = 0, en = tlen - 1;
+                if (st < r - qlen + 1) st = r - qlen + 1;
+                if (en > r) en = r;
+                if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+                if (en > (r + w) >> 1) en = (r + w) >> 1;
+                if (st > en) { ez.zdropped = 1; break; }
+                const int st0 = st, en0 = en;
+                st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+                int x1, x21, v1;
+                const int vb = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+                if (st > 0) {
+                    if (st - 1 >= last_st && st - 1 <= last_en) { x1 = x[st - 1]; x21 = x2[st - 1]; v1 = v[st - 1]; }
+                    else { x1 = -q - e; x21 = -q2 - e2; v1 = -q - e; }
+                } else { x1 = -q - e; x21 = -q2 - e2; v1 = ndk_w8(vb); }
+                if (en >= r && lane == 0) { y[r] = (int8_t)(-q - e); y2[r] = (int8_t)(-q2 - e2); u[r] = (int8_t)vb; }
+                // scores: 16-wide unaligned blocks from st0; loads before stores (the last block may spill into sf[])
+                {
+                    const uint8_t *qrr = qr + (qlen - 1 - r);
+                    const int len16 = (en0 - st0 + 16) / 16 * 16;
+                    for (int k0 = 0; k0 < len16; k0 += 32) {
+                        const int k = k0 + lane;
+                        int sc = 0;
+                        if (k < len16) {
+                            const int sq = sf[st0 + k], sr = qrr[st0 + k];
+                            if (flag & NDK_GENERIC_SC) sc = (k <= en0 - st0) ? P.mat[sq * m + sr] : 0;
+                            else { sc = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) sc = sc_N; }
+                        }
+                        __syncwarp();
+                        if (k < len16 && (!(flag & NDK_GENERIC_SC) || k <= en0 - st0)) s[st0 + k] = (int8_t)sc;
+                    }
+                }
+                __syncwarp();
+                if (with_cigar && lane == 0) { off[r] = st; off_end[r] = en; }
+                // core: 32 cells per step, neighbours by shuffle, carry across steps
+                {
+                    int cx = x1, cx2 = x21, cv = v1;            // previous-diagonal values at (chunk start - 1)
+                    uint8_t *pr = p + (size_t)r * n_col - st;
+                    for (int t0 = st; t0 <= en; t0 += 32) {
+                        const int t = t0 + lane;
+                        const bool act = t <= en;
+                        int xo = 0, vo = 0, x2o = 0, z = 0, ut = 0, yo = 0, y2o = 0;
+                        if (act) { xo = x[t]; vo = v[t]; x2o = x2[t]; z = s[t]; ut = u[t]; yo = y[t]; y2o = y2[t]; }
+                        int xt1 = __shfl_up_sync(NDK_FULL, xo, 1), vt1 = __shfl_up_sync(NDK_FULL, vo, 1), x2t1 = __shfl_up_sync(NDK_FULL, x2o, 1);
+                        if (lane == 0) { xt1 = cx; vt1 = cv; x2t1 = cx2; }
+                        cx = __shfl_sync(NDK_FULL, xo, 31); cv = __shfl_sync(NDK_FULL, vo, 31); cx2 = __shfl_sync(NDK_FULL, x2o, 31);
+                        int a = ndk_w8(xt1 + vt1), b = ndk_w8(yo + ut), a2 = ndk_w8(x2t1 + vt1), b2 = ndk_w8(y2o + ut), d;
+                        if (!right) {
+                            d = a > z ? 1 : 0;  z = z > a ? z : a;
+                            d = b > z ? 2 : d;  z = z > b ? z : b;
+                            d = a2 > z ? 3 : d; z = z > a2 ? z : a2;
+                            d = b2 > z ? 4 : d; z = z > b2 ? z : b2;
+                        } else {
+                            d = z > a ? 0 : 1;  z = z > a ? z : a;
+                            d = z > b ? d : 2;  z = z > b ? z : b;
+                            d = z > a2 ? d : 3; z = z > a2 ? z : a2;
+                            d = z > b2 ? d : 4; z = z > b2 ? z : b2;
+                        }
+                        z = z < sc_mch ? z : sc_mch;
+                        const int un = ndk_w8(z - vt1), vn = ndk_w8(z - ut);
+                        int tmp = ndk_w8(z - q);  a = ndk_w8(a - tmp);  b = ndk_w8(b - tmp);
+                        tmp = ndk_w8(z - q2);     a2 = ndk_w8(a2 - tmp); b2 = ndk_w8(b2 - tmp);
+                        int xn, yn, x2n, y2n;
+                        if (!right) {
+                            xn  = ndk_w8((a  > 0 ? a  : 0) - qe);  d |= a  > 0 ? 0x08 : 0;
+                            yn  = ndk_w8((b  > 0 ? b  : 0) - qe);  d |= b  > 0 ? 0x10 : 0;
+                            x2n = ndk_w8((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
+                            y2n = ndk_w8((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
+                        } else {
+                            xn  = ndk_w8((0 > a  ? 0 : a)  - qe);  d |= 0 > a  ? 0 : 0x08;
+                            yn  = ndk_w8((0 > b  ? 0 : b)  - qe);  d |= 0 > b  ? 0 : 0x10;
+                            x2n = ndk_w8((0 > a2 ? 0 : a2) - qe2); d |= 0 > a2 ? 0 : 0x20;
+                            y2n = ndk_w8((0 > b2 ? 0 : b2) - qe2); d |= 0 > b2 ? 0 : 0x40;
+                        }
+                        if (act) {
+                            u[t] = (int8_t)un; v[t] = (int8_t)vn; x[t] = (int8_t)xn; y[t] = (int8_t)yn; x2[t] = (int8_t)x2n; y2[t] = (int8_t)y2n;
+                            if (with_cigar) pr[t] = (uint8_t)d;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (!approx_max) {
+                    int max_H, max_t;
+                    if (r > 0) {
+                        const int en1 = st0 + (en0 - st0) / 4 * 4;
+                        const int Hlast = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+                        __syncwarp();
+                        long long best = ((long long)Hlast << 32) | 0xffffffffLL;          // rank 0 = en0
+                        for (int t0 = st0; t0 <= en0; t0 += 32) {
+                            const int t = t0 + lane;
+                            if (t < en0) {
+                                const int h = H[t] + v[t];
+                                H[t] = h;
+                                const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2)
+                                                              : 1u + (4u << 20) + (unsigned)(t - en1);
+                                const long long key = ((long long)h << 32) | (long long)(0xffffffffu - rank);
+                                best = key > best ? key : best;
+                            } else if (t == en0) H[t] = Hlast;
+                        }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) { long long y2k = __shfl_xor_sync(NDK_FULL, best, o); best = y2k > best ? y2k : best; }
+                        max_H = (int)(best >> 32);
+                        const unsigned rank = 0xffffffffu - (unsigned)(best & 0xffffffffLL);
+                        if (rank == 0) max_t = en0;
+                        else if (rank - 1 < (4u << 20)) max_t = st0 + (int)((rank - 1) & 0xfffff) * 4 + (int)((rank - 1) >> 20);
+                        else max_t = en1 + (int)(rank - 1 - (4u << 20));
+                    } else {
+                        if (lane == 0) H[0] = v[0] - qe0;
+                        max_H = v[0] - qe0; max_t = 0;
+                    }
+                    __syncwarp();
+                    if (en0 == tlen - 1) { int h = H[en0]; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
+                    if (r - st0 == qlen - 1) { int h = H[st0]; if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; } }
+                    if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+                } else {
+                    if (r > 0) {
+                        if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+                            int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+                            if (d0 > d1) H0 += d0; else { H0 += d1; ++last_H0_t; }
+                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += v[last_H0_t];
+                        else { ++last_H0_t; H0 += u[last_H0_t]; }
+                    } else { H0 = v[0] - qe0; last_H0_t = 0; }
+                    if ((flag & NDK_APPROX_DROP) && ndk_zdrop(ez, H0, r, last_H0_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+                }
+                last_st = st; last_en = en;
+            }
+            __syncwarp();
+            if (with_cigar && lane == 0) {
+                const bool rev = (flag & NDK_REV_CIGAR) != 0;
+                if (!ez.zdropped && !(flag & NDK_EXTZ_ONLY))
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, tlen - 1, qlen - 1, cigar);
+                else if (!ez.zdropped && (flag & NDK_EXTZ_ONLY) && ez.mqe + c.end_bonus > ez.max) {
+                    ez.reach_end = 1;
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.mqe_t, qlen - 1, cigar);
+                } else if (ez.max_t >= 0 && ez.max_q >= 0)
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.max_t, ez.max_q, cigar);
+            }
+        }
+        if (lane == 0) res[ci] = ez;
+        __syncwarp();
+    }
+}

@@ -12,6 +12,7 @@
 #include "../../include/ndgpu.h"
 #include "nd_kernels.cuh"
 #include "nd_warp.cuh"
+#include "nd_ksw.cuh"
 
 static_assert(sizeof(nd_hit) == sizeof(ndg_hit_t), "hit layout");
 static_assert(sizeof(nd_hit) == 56, "hit size");
@@ -97,6 +98,7 @@ struct ndg_ctx {
     // mapping workspace
     ReadsDev q;
     DevBuf staging, cnt, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
+           ksw_calls, ksw_seqs, ksw_res, ksw_p, ksw_cig, ksw_scratch,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
     uint64_t n_mz = 0, n_a = 0, n_seg = 0, n_hits = 0;
@@ -281,7 +283,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
-                       &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
+                       &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
     for (auto b : bufs) b->release();
     c->q.release();
@@ -782,4 +784,54 @@ extern "C" int64_t ndg_ovl_emit_step1(const ndg_hit_t *hits, int64_t n_hits,
     if (n_rec) *n_rec += rec;
     if (sum_qspan) *sum_qspan += sq;
     return (int64_t)n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ksw_extd2 batch.  ref: minimap2/ksw2_extd2_sse.c (one call per alignment), here one warp each
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(ndg_ksw_result_t) == sizeof(ndk_res), "ksw result layout");
+
+extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, int32_t n, const uint8_t *seqs, uint64_t seq_bytes,
+                                   int32_t m, const int8_t *mat, int32_t q, int32_t e, int32_t q2, int32_t e2,
+                                   ndg_ksw_result_t *res, uint32_t *cigar, const uint64_t *cigar_off)
+{
+    if (!c || !calls || n <= 0 || !seqs || !mat || !res || !cigar_off || m < 2 || m > 5) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    std::vector<ndk_call> hc((size_t)n);
+    uint64_t p_total = 0; int Tmax = 16, rmax = 1, qmax = 1;
+    int qq = q, ee = e, qq2 = q2, ee2 = e2;
+    (void)qq; (void)ee; (void)qq2; (void)ee2;
+    for (int i = 0; i < n; ++i) {
+        const ndg_ksw_call_t &k = calls[i];
+        if (k.qlen < 0 || k.tlen < 0 || k.q_off + (uint64_t)k.qlen > seq_bytes || k.t_off + (uint64_t)k.tlen > seq_bytes) return fail(c, NDG_ERR_ARG, "ksw call %d out of range", i);
+        ndk_call &d = hc[i];
+        d.qlen = k.qlen; d.tlen = k.tlen; d.q_off = k.q_off; d.t_off = k.t_off; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag;
+        d.cigar_off = cigar_off[i]; d.p_off = p_total;
+        if (k.qlen > 0 && k.tlen > 0) {
+            int w = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
+            int ncol = std::min(k.qlen, k.tlen); ncol = (std::min(ncol, w + 1) + 15) / 16 + 1;
+            if (!(k.flag & NDK_SCORE_ONLY)) p_total += ((uint64_t)(k.qlen + k.tlen - 1) * ncol + 1) * 16;
+            Tmax = std::max(Tmax, (k.tlen + 15) / 16 * 16); rmax = std::max(rmax, k.qlen + k.tlen); qmax = std::max(qmax, k.qlen);
+        }
+    }
+    const size_t state_bytes = ((size_t)8 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 64 + 255) / 256 * 256;
+    const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
+    const size_t slot_bytes = state_bytes + h_bytes + off_bytes;
+    const int blocks = std::min<int>(c->n_sm * 16, (n + NDK_WARPS - 1) / NDK_WARPS);
+    const size_t slots = (size_t)blocks * NDK_WARPS;
+    const uint64_t cig_total = cigar_off[n];
+    RSV(c->ksw_calls, (size_t)n * sizeof(ndk_call)); RSV(c->ksw_seqs, seq_bytes + 64); RSV(c->ksw_res, (size_t)n * sizeof(ndk_res));
+    RSV(c->ksw_p, p_total + 64); RSV(c->ksw_cig, (cig_total + 4) * 4); RSV(c->ksw_scratch, slots * slot_bytes); RSV(c->scalars, 1024);
+    CK(cudaMemcpyAsync(c->ksw_calls.p, hc.data(), (size_t)n * sizeof(ndk_call), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->ksw_seqs.p, seqs, seq_bytes, cudaMemcpyHostToDevice, c->st));
+    uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
+    CK(cudaMemsetAsync(d_work, 0, 4, c->st));
+    ndk_par P; P.m = m; memset(P.mat, 0, sizeof P.mat); memcpy(P.mat, mat, (size_t)m * m); P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
+    KLAUNCH("ksw_extd2", (k_ksw_extd2<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
+                          c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(res, c->ksw_res.p, (size_t)n * sizeof(ndk_res), cudaMemcpyDeviceToHost, c->st));
+    if (cigar && cig_total) CK(cudaMemcpyAsync(cigar, c->ksw_cig.p, cig_total * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return NDG_OK;
 }

@@ -51,12 +51,18 @@ HIT_DTYPE = np.dtype([("zkey", "<u8"), ("qidx", "<i4"), ("rid", "<i4"), ("qs", "
                       ("cnt", "<i4"), ("rev", "<i4"), ("as_", "<i4")])
 assert HIT_DTYPE.itemsize == 56
 
+KSW_CALL_DTYPE = np.dtype([("qlen", "<i4"), ("tlen", "<i4"), ("q_off", "<u8"), ("t_off", "<u8"), ("w", "<i4"), ("zdrop", "<i4"),
+                           ("end_bonus", "<i4"), ("flag", "<i4")])
+KSW_RES_DTYPE = np.dtype([(n_, "<i4") for n_ in ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar",
+                                                 "reach_end", "reserved")])
+assert KSW_CALL_DTYPE.itemsize == 40 and KSW_RES_DTYPE.itemsize == 48
+
 EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
            "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta", "ndg_index_export",
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch"]
 
 _lib = None
 
@@ -105,6 +111,7 @@ def load_library():
     L.ndg_ovl_encode8.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] + [C.c_uint32] * 7
     L.ndg_ovl_emit_step1.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int32] * 4 + \
                                     [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.ndg_ksw_extd2_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3
     _lib = L
     return L
 
@@ -243,6 +250,21 @@ class Engine:
             if rc < 0:
                 self._ck(int(rc))
         return out
+
+    # ---- base-level extension (ksw_extd2) ----------------------------------------------------
+    def ksw_extd2_batch(self, calls, seqs, mat, q, e, q2, e2, m=5):
+        """calls: structured array KSW_CALL_DTYPE; seqs: uint8 codes.  Returns (results KSW_RES_DTYPE, cigars list)."""
+        n = calls.shape[0]
+        calls = np.ascontiguousarray(calls)
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        mat = np.ascontiguousarray(mat, dtype=np.int8)
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(calls["qlen"].astype(np.uint64) + calls["tlen"].astype(np.uint64) + np.uint64(2), out=coff[1:])
+        res = np.zeros(n, dtype=KSW_RES_DTYPE)
+        cig = np.zeros(int(coff[-1]) + 4, dtype=np.uint32)
+        self._ck(self.L.ndg_ksw_extd2_batch(self.h, _ptr(calls), n, _ptr(seqs), seqs.shape[0], m, _ptr(mat), q, e, q2, e2,
+                                            _ptr(res), _ptr(cig), _ptr(coff)))
+        return res, [cig[int(coff[i]):int(coff[i]) + int(res["n_cigar"][i])] for i in range(n)]
 
     def prof(self):
         names = (C.c_char_p * 64)()

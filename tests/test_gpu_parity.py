@@ -132,3 +132,52 @@ def test_index_stats(eng, reads_full):
 def test_library_loaded_is_in_tree(engine_mod):
     p = engine_mod.lib_path()
     assert os.path.exists(p) and "nextdenovo_b200" in p
+
+
+def test_cli_dropin_matches_reference_bytes(built, golden_dir, tmp_path):
+    """bin/minimap2-nd (C++ host over the C ABI) with the pipeline's own command line
+    (ref: nextDenovo:445-446) writes the reference's bytes; bad usage exits 1."""
+    import subprocess
+    root = os.path.dirname(golden_dir.rstrip("/")).rsplit("/tests", 1)[0]
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "sub120.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([exe, "--step", "1", "-t", "8", "-x", "ava-ont", src, src, "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+    assert "mid_occ" in r.stderr
+    full = os.path.join(golden_dir, "reads_test.seed.2bit")
+    r = subprocess.run([exe, "--step", "1", "--dual=yes", "-I", "20M", "-t", "8", "-x", "ava-ont", full, src, "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S5_sub120_dual.ovl"), "rb").read()
+    assert subprocess.run([exe, "--step", "1", "-x", "nope", src, src, "-o", out], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--step", "1", "-c", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+
+
+def test_ksw_extd2_batch_bit_exact(eng):
+    """ndg_ksw_extd2_batch == ksw_extd2_sse (via the oracle restatement, and the compiled reference when present):
+    score, max, end points, z-drop flag, reach_end and CIGAR, for every call of a mixed batch."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from ksw_cases import simple_mat, oracle_lib, oracle_call, ref_lib, ref_call, random_cases
+    from nextdenovo_b200.engine import KSW_CALL_DTYPE
+    mat = simple_mat()
+    cases = random_cases(1500, seed=23)
+    calls = np.zeros(len(cases), dtype=KSW_CALL_DTYPE)
+    chunks, off = [], 0
+    for i, (qs, ts, w, zd, eb, flag) in enumerate(cases):
+        calls[i] = (len(qs), len(ts), off, off + len(qs), w, zd, eb, flag)
+        chunks += [qs, ts]; off += len(qs) + len(ts)
+    seqs = np.concatenate(chunks)
+    res, cigs = eng.ksw_extd2_batch(calls, seqs, mat, 4, 2, 24, 1)
+    L, R = oracle_lib(), ref_lib()
+    names = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end")
+    bad = []
+    for i, (qs, ts, w, zd, eb, flag) in enumerate(cases):
+        want = oracle_call(L, qs, ts, mat, 4, 2, 24, 1, w, zd, eb, flag)
+        if R is not None and i % 5 == 0:
+            assert ref_call(R, qs, ts, mat, 4, 2, 24, 1, w, zd, eb, flag) == want
+        got = (tuple(int(res[n][i]) for n in names), [int(x) for x in cigs[i]])
+        if got != want:
+            bad.append((i, len(qs), len(ts), w, hex(flag), got[0], want[0]))
+    assert not bad, "%d/%d calls differ; first: %s" % (len(bad), len(cases), bad[:3])

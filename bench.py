@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="1,1")
+    ap.add_argument("--no-ksw", action="store_true", help="skip the regime-B (ksw_extd2) kernel measurement")
     return ap.parse_args()
 
 
@@ -137,6 +138,76 @@ def run_reference(reads, threads):
 def cpu_sample(n):
     genome_bp = max(int(n * READ_LEN / DEPTH), 200000)
     return make_reads(n, genome_bp), "%d reads x %d bp at %dx depth (genome %d bp), self-overlap, mapping phase only" % (n, READ_LEN, DEPTH, genome_bp)
+
+
+def ksw_cells(qlen, tlen, w):
+    """in-band DP cells of one ksw_extd2 call (ref band rule: minimap2/ksw2_extd2_sse.c:128-133)"""
+    r = np.arange(qlen + tlen - 1)
+    st = np.maximum(np.maximum(0, r - qlen + 1), (r - w + 1) >> 1)
+    en = np.minimum(np.minimum(tlen - 1, r), (r + w) >> 1)
+    return int(np.maximum(en - st + 1, 0).sum())
+
+
+def ksw_bench(eng, n_calls=20000, L=413, seed=SEED):
+    """Regime B kernel alone: a batch of gap-filling style ksw_extd2 calls (mean 413 x 413, the mean call of
+    `--step 1 -c` on reads_test), flag = KSW_EZ_APPROX_MAX, w = 3001, zdrop = 400, with CIGAR."""
+    from nextdenovo_b200.engine import KSW_CALL_DTYPE
+    rng = np.random.default_rng(seed)
+    mat = np.zeros(25, dtype=np.int8)
+    for i in range(4):
+        for j in range(4):
+            mat[i * 5 + j] = 2 if i == j else -4
+        mat[i * 5 + 4] = -1
+    mat[20:25] = -1
+    calls = np.zeros(n_calls, dtype=KSW_CALL_DTYPE)
+    chunks, off, cells, alg_bytes = [], 0, 0, 0
+    cache = {}
+    for i in range(n_calls):
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        u = rng.random(L)
+        qv = np.where((u >= 0.06) & (u < 0.11), (t + 1 + rng.integers(0, 3, L)) % 4, t).astype(np.uint8)[u >= 0.06]
+        ins = np.nonzero(rng.random(qv.shape[0]) < 0.04)[0]
+        qv = np.insert(qv, ins, rng.integers(0, 4, ins.shape[0]).astype(np.uint8))
+        calls[i] = (len(qv), L, off, off + len(qv), 3001, 400, -1, 0x08)
+        chunks += [qv, t]; off += len(qv) + L
+        key = (len(qv), L)
+        if key not in cache:
+            cache[key] = ksw_cells(len(qv), L, 3001)
+        cells += cache[key]
+    seqs = np.concatenate(chunks)
+    eng.ksw_extd2_batch(calls[:2000], seqs, mat, 4, 2, 24, 1)           # warm-up (allocations)
+    eng.ksw_extd2_batch(calls, seqs, mat, 4, 2, 24, 1)
+    eng.prof_reset()
+    t0 = time.perf_counter()
+    res, cigs = eng.ksw_extd2_batch(calls, seqs, mat, 4, 2, 24, 1)
+    wall = time.perf_counter() - t0
+    ms = eng.prof()["ksw_extd2"][0]
+    n_cig = int(res["n_cigar"].sum())
+    alg_bytes = int(2 * (calls["qlen"].sum() + calls["tlen"].sum()) + cells + 4 * n_cig)   # SURVEY 8(d) B_B
+    out = {"calls": n_calls, "cells": cells, "kernel_ms": ms, "gcups": cells / ms / 1e6, "e2e_gcups": cells / wall / 1e9,
+           "alg_bytes": alg_bytes, "achieved_GBps": alg_bytes / ms / 1e6}
+    # reference on one host core, bounded sample
+    try:
+        import ctypes as C
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from ksw_cases import ref_lib, ref_call
+        R = ref_lib()
+        if R is not None:
+            ns = 300
+            t1 = time.perf_counter()
+            csum = 0
+            for i in range(ns):
+                qo, to = int(calls["q_off"][i]), int(calls["t_off"][i])
+                qs, ts = seqs[qo:qo + int(calls["qlen"][i])].copy(), seqs[to:to + L].copy()
+                ref_call(R, qs, ts, mat, 4, 2, 24, 1, 3001, 400, -1, 0x08)
+                csum += cache[(len(qs), L)]
+            dt = time.perf_counter() - t1
+            out["cpu_reference_1core_gcups"] = csum / dt / 1e9
+            out["cpu_sample"] = "%d calls of the same batch through ksw_extd2_sse (SSE4.1), 1 thread" % ns
+    except Exception as ex:  # noqa: BLE001
+        out["cpu_reference_1core_gcups"] = None
+        out["cpu_sample"] = "failed: %r" % ex
+    return out
 
 
 def main_reference(a, rank, world):
@@ -284,6 +355,13 @@ def main_ours(a, rank, world, local_rank):
                        "aligned_gbp_per_s": s_ / tm / 1e9, "mapping_s": tm, "process_s": tot}
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": "overlaps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % ex}
+        ksw = None
+        if not a.no_ksw and world == 1:
+            try:
+                ksw = ksw_bench(eng)
+                ksw["roofline_frac_hbm"] = ksw["achieved_GBps"] / hbm_peak
+            except Exception as ex:  # noqa: BLE001
+                ksw = {"error": repr(ex)}
         line = {
             "metric": "overlaps/sec", "value": rec / t_res_dev, "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * t_res_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,6 +382,7 @@ def main_ours(a, rank, world, local_rank):
             "kernels_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "index": {"build_s": t_index, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"]},
             "gen_s": t_gen,
+            "ksw2_extd2": ksw,
         }
         print(json.dumps(line))
     eng.close()

@@ -198,6 +198,82 @@ ND_HD_NOINLINE int nd_sketch_chunk(const nd_seqview s, int w, int k, int hpc, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// closed form of the sketch for the common case (no ambiguous bases, no HPC, no strand-symmetric
+// k-mer anywhere in the read, at least one full window).  Then every position is a slot, l = p+1, a
+// k-mer is valid iff p >= k-1, and replaying minimap2/sketch.c:89-142 shows that position t is pushed
+// iff some full window [s, s+w-1] inside [k-1, len-1] contains t with x[t] equal to the window
+// minimum (ties are all pushed; the right-most one is the running "min"), each exactly once and in
+// position order.  Equivalently: with a/b the runs of neighbours (left/right, inside the valid range,
+// at most w-1) whose x is >= x[t], t is pushed iff a + b >= w-1.
+// One start-up irregularity of the reference is kept (nd_first_window_fix): at the step that completes
+// the first window (position P = k+w-2, l == w+k-1) the ties of the running minimum are pushed
+// unconditionally (sketch.c:114-119) while the running minimum t* itself can only be pushed later,
+// i.e. iff x[P] > x[t*] (a displacement at that step needs l >= w+k, sketch.c:121).
+// Reads that violate a precondition are routed to the state machine above.
+// ------------------------------------------------------------------------------------------------
+
+// 32 bases ending at p (base p in the two lowest bits, zeros before the read start), from the packed words
+ND_HD nd_u64 nd_bases32(const uint32_t *words, int p)
+{
+    const int j = p >> 4, s = 2 * (15 - (p & 15));
+    const nd_u64 w2 = words[j], w1 = j >= 1 ? words[j - 1] : 0, w0 = j >= 2 ? words[j - 2] : 0;
+    const nd_u64 hi = w0 << 32 | w1;
+    return (hi << (32 - s)) | (w2 >> s);
+}
+
+ND_HD nd_u64 nd_rev2(nd_u64 v)     // reverse the order of the 32 two-bit groups
+{
+#if defined(__CUDA_ARCH__)
+    v = __brevll(v);
+#else
+    v = ((v >> 1) & 0x5555555555555555ULL) | ((v & 0x5555555555555555ULL) << 1);
+    v = ((v >> 2) & 0x3333333333333333ULL) | ((v & 0x3333333333333333ULL) << 2);
+    v = ((v >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((v & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    v = ((v >> 8) & 0x00FF00FF00FF00FFULL) | ((v & 0x00FF00FF00FF00FFULL) << 8);
+    v = ((v >> 16) & 0x0000FFFF0000FFFFULL) | ((v & 0x0000FFFF0000FFFFULL) << 16);
+    v = (v >> 32) | (v << 32);
+#endif
+    return ((v & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((v & 0x5555555555555555ULL) << 1);
+}
+
+// x (hash<<8|k, or ND_U64_MAX when p < k-1) and strand of position p; *sym set when forward == reverse
+ND_HD nd_u64 nd_kmer_x(const uint32_t *words, int p, int k, int *z, bool *sym)
+{
+    const nd_u64 mask = (1ULL << 2 * k) - 1;
+    const nd_u64 fw = nd_bases32(words, p) & mask;
+    nd_u64 rv = (~nd_rev2(fw)) >> (64 - 2 * k);
+    if (p < k - 1) rv &= ~((1ULL << 2 * (k - 1 - p)) - 1);    // bases before the read start contribute 0 (sketch.c:79)
+    *sym = fw == rv;
+    *z = fw < rv ? 0 : 1;
+    if (p < k - 1) return ND_U64_MAX;
+    return nd_hash64_masked(*z ? rv : fw, mask) << 8 | (nd_u64)k;
+}
+
+// First-window irregularity: for t in [k-1, P-1], P = k+w-2.  xs[i] = x of position lo+i, lo <= k-1.
+// Returns -1 when the general rule applies to t, else 0/1 = pushed.
+ND_HD int nd_first_window_fix(const nd_u64 *xs, int lo, int t, int w, int k)
+{
+    const int P = k + w - 2;
+    if (t >= P) return -1;
+    nd_u64 m1 = ND_U64_MAX; int tstar = -1;
+    for (int j = k - 1; j < P; ++j) if (xs[j - lo] <= m1) { m1 = xs[j - lo]; tstar = j; }
+    if (xs[t - lo] != m1) return -1;
+    if (t != tstar) return 1;
+    return xs[P - lo] > m1 ? 1 : 0;
+}
+
+// xs[i] = x of position lo+i.  Is position t pushed?
+ND_HD bool nd_window_emit(const nd_u64 *xs, int lo, int t, int w, int k, int len)
+{
+    const nd_u64 xt = xs[t - lo];
+    int a = 0, b = 0;
+    while (a < w - 1 && t - 1 - a >= k - 1 && xs[t - 1 - a - lo] >= xt) ++a;
+    const int need = w - 1 - a;
+    while (b < need && t + 1 + b <= len - 1 && xs[t + 1 + b - lo] >= xt) ++b;
+    return a + b >= w - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // exact emulation of the reference's in-place MSD radix sort (tie order is observable)
 // ref: minimap2/ksort.h:98-151 (rs_insertsort / rs_sort / radix_sort), minimap2/misc.c:155-156
 // ------------------------------------------------------------------------------------------------

@@ -59,11 +59,12 @@ struct nd_reads_dev {
 template <int RW>
 __global__ void __launch_bounds__(128)
 k_sketch_chunks(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int C, int w, int k, int hpc,
-                uint32_t rid0, int use_rid, nd_u128 *staging, int S, uint32_t *cnt, int *overflow)
+                uint32_t rid0, int use_rid, nd_u128 *staging, int S, uint32_t *cnt, int *overflow, const uint32_t *slow)
 {
     nd_u64 g = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_chunks) return;
     int r = nd_find_owner(chunk_off, R.n_reads, g);
+    if (slow && !slow[r]) return;                       // this read was sketched by k_sketch_fast
     int len = (int)R.len[r];
     int cs = (int)(g - chunk_off[r]) * C;
     int ce = cs + C < len ? cs + C : len;
@@ -74,6 +75,72 @@ k_sketch_chunks(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int C,
     int n = nd_sketch_chunk<RW>(sv, w, k, hpc, use_rid ? rid0 + (uint32_t)r : 0u, cs, ce, staging + g * (nd_u64)S, S);
     if (n > S) { atomicExch(overflow, 1); n = S; }
     cnt[g] = (uint32_t)n;
+}
+
+// Fast path: one block per 512-base chunk, closed form of the window state machine (nd_core.cuh).
+// Hashes of the chunk plus a (w-1) halo are computed once into shared memory (one k-mer per thread
+// step, k-mers cut out of the packed words by funnel shifts), every position then decides locally
+// whether it is pushed, and the block compacts the survivors in position order.  Reads that break a
+// precondition (symmetric k-mer, too short for one window) are flagged in slow[] and redone by
+// k_sketch_chunks.
+#define NDS_C 512
+#define NDS_T 128
+#define NDS_MAXW 64
+__global__ void __launch_bounds__(NDS_T)
+k_sketch_fast(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int w, int k, uint32_t rid0, int use_rid,
+              nd_u128 *staging, int S, uint32_t *cnt, uint32_t *slow)
+{
+    __shared__ nd_u64 sx[NDS_C + 2 * NDS_MAXW];
+    __shared__ uint8_t sz[NDS_C + 2 * NDS_MAXW];
+    __shared__ uint32_t swords[(NDS_C + 2 * NDS_MAXW) / 16 + 8];
+    __shared__ int s_r;
+    __shared__ uint32_t s_wsum[NDS_T / 32];
+    const nd_u64 g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_r = nd_find_owner(chunk_off, R.n_reads, g);
+    __syncthreads();
+    const int r = s_r, len = (int)R.len[r];
+    const int cs = (int)(g - chunk_off[r]) * NDS_C, ce = cs + NDS_C < len ? cs + NDS_C : len;
+    if (len < k + w - 1) { if (tid == 0) { slow[r] = 1; cnt[g] = 0; } return; }
+    const int lo = cs - (w - 1) > 0 ? cs - (w - 1) : 0, hi = ce + (w - 1) < len ? ce + (w - 1) : len;
+    const uint32_t *words = R.words + R.word_off[r];
+    const int w0 = (lo >> 4) - 2 > 0 ? (lo >> 4) - 2 : 0, w1 = (hi - 1) >> 4;
+    for (int i = tid; i <= w1 - w0; i += NDS_T) swords[i] = words[w0 + i];
+    __syncthreads();
+    int any_sym = 0;
+    for (int idx = tid; idx < hi - lo; idx += NDS_T) {
+        int z; bool sym;
+        sx[idx] = nd_kmer_x(swords - w0, lo + idx, k, &z, &sym);
+        sz[idx] = (uint8_t)z;
+        any_sym |= sym;
+    }
+    if (__syncthreads_or(any_sym)) { if (tid == 0) { slow[r] = 1; cnt[g] = 0; } return; }
+    const nd_u64 ridbits = (nd_u64)(use_rid ? rid0 + (uint32_t)r : 0u) << 32;
+    nd_u128 *dst = staging + g * (nd_u64)S;
+    uint32_t base = 0;
+    for (int j = 0; j < NDS_C / NDS_T; ++j) {
+        const int t = cs + j * NDS_T + tid;
+        bool flag = false;
+        if (t < ce && t >= k - 1) {
+            const int fix = (cs == 0 && t < k + w - 2) ? nd_first_window_fix(sx, lo, t, w, k) : -1;
+            flag = fix >= 0 ? fix == 1 : nd_window_emit(sx, lo, t, w, k, len);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_wsum[wid] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < NDS_T / 32; ++q) { const uint32_t c = s_wsum[q]; before += q < wid ? c : 0; total += c; }
+        if (flag) {
+            nd_u128 o;
+            o.x = sx[t - lo];
+            o.y = ridbits | (nd_u64)(uint32_t)t << 1 | (nd_u64)sz[t - lo];
+            dst[base + before + __popc(m & ((1u << lane) - 1))] = o;
+        }
+        base += total;
+        __syncthreads();
+    }
+    if (tid == 0) cnt[g] = base;
 }
 
 // one warp per chunk: staging -> packed minimizer array

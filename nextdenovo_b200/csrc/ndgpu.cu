@@ -97,7 +97,7 @@ struct ndg_ctx {
     int mid_occ = 0;
     // mapping workspace
     ReadsDev q;
-    DevBuf staging, cnt, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
+    DevBuf staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
            ksw_calls, ksw_seqs, ksw_res, ksw_p, ksw_cig, ksw_scratch,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
@@ -218,12 +218,19 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     CK(cudaMemsetAsync(d_over, 0, 4, c->st));
     CK(cudaMemsetAsync(c->cnt.as<uint32_t>() + nc, 0, 4, c->st));
     nd_reads_dev V = D.view();
+    // fast path (closed form) where its preconditions can hold; flagged reads fall through to the state machine
+    const bool fast = !o.hpc && !D.has_nmask && o.w <= NDS_MAXW && C == NDS_C;
+    RSV(c->slow, (size_t)D.n_reads * 4 + 4);
+    CK(cudaMemsetAsync(c->slow.p, fast ? 0 : 1, (size_t)D.n_reads * 4, c->st));
+    if (fast)
+        KLAUNCH("sketch_fast", (k_sketch_fast<<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.w, o.k, rid0, use_rid,
+                                c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
     if (o.w < 16)
         KLAUNCH("sketch", (k_sketch_chunks<16><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
-                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over)));
+                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over, c->slow.as<uint32_t>())));
     else
         KLAUNCH("sketch", (k_sketch_chunks<256><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
-                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over)));
+                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over, c->slow.as<uint32_t>())));
     CK(cudaGetLastError());
     if (int rc = scan_u32_to_u64(c, c->cnt.as<uint32_t>(), c->pos.as<nd_u64>(), nc)) return rc;
     uint64_t *h = c->h_scalars.as<uint64_t>();
@@ -282,7 +289,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     cudaStreamSynchronize(c->st);
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
+    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
     for (auto b : bufs) b->release();

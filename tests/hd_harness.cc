@@ -29,6 +29,8 @@ int main(int argc, char **argv)
     if (!R) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
     ndo_opt o; ndo_opt_preset(&o, NULL);
     if (!strcmp(argv[2], "k17w10")) { ndo_opt_preset(&o, "ava-ont"); o.k = 17; o.w = 10; }
+    else if (!strcmp(argv[2], "k16w7")) { ndo_opt_preset(&o, "ava-ont"); o.k = 16; o.w = 7; }
+    else if (!strcmp(argv[2], "k11w1")) { ndo_opt_preset(&o, "ava-ont"); o.k = 11; o.w = 1; }
     else ndo_opt_preset(&o, argv[2]);
     int max_reads = argc > 3 ? atoi(argv[3]) : R->n;
     int chunk = argc > 4 ? atoi(argv[4]) : 256;
@@ -60,6 +62,18 @@ int main(int argc, char **argv)
         for (size_t i = 0; ok && i < n_ref; ++i) ok = got[i].x == ref[i].x && got[i].y == ref[i].y;
         if (!ok) { if (bad_sketch < 5) fprintf(stderr, "sketch mismatch read %d: %zu vs %zu\n", r, got.size(), n_ref); ++bad_sketch; }
         n_mz_tot += n_ref;
+        if (!o.hpc && len >= o.k + o.w - 1) {           // closed form (fast path of the GPU sketch)
+            std::vector<nd_u64> xs(len); std::vector<int> zs(len); bool any_sym = false;
+            for (int p = 0; p < len; ++p) { bool sy; xs[p] = nd_kmer_x(words.data(), p, o.k, &zs[p], &sy); any_sym |= sy; }
+            if (!any_sym) {
+                std::vector<nd_u128> cf;
+                for (int t = o.k - 1; t < len; ++t)
+                    if (nd_first_window_fix(xs.data(), 0, t, o.w, o.k) >= 0 ? nd_first_window_fix(xs.data(), 0, t, o.w, o.k) == 1 : nd_window_emit(xs.data(), 0, t, o.w, o.k, len)) { nd_u128 m; m.x = xs[t]; m.y = (nd_u64)(uint32_t)t << 1 | (nd_u64)zs[t]; cf.push_back(m); }
+                bool okc = cf.size() == n_ref;
+                for (size_t i = 0; okc && i < n_ref; ++i) okc = cf[i].x == ref[i].x && cf[i].y == ref[i].y;
+                if (!okc) { if (bad_sketch < 5) fprintf(stderr, "closed-form sketch mismatch read %d: %zu vs %zu\n", r, cf.size(), n_ref); ++bad_sketch; }
+            }
+        }
 
         // --- seeds (oracle, unsorted) + exact sort ---
         int64_t n_a;

@@ -181,3 +181,37 @@ def test_ksw_extd2_batch_bit_exact(eng):
         if got != want:
             bad.append((i, len(qs), len(ts), w, hex(flag), got[0], want[0]))
     assert not bad, "%d/%d calls differ; first: %s" % (len(bad), len(cases), bad[:3])
+
+
+@pytest.mark.parametrize("w,k,hpc", [(5, 15, 0), (10, 17, 0), (7, 16, 0), (1, 11, 0), (19, 19, 0), (5, 19, 1), (70, 21, 0)])
+def test_sketch_adversarial_reads(eng, w, k, hpc):
+    """fast closed-form path + state-machine path vs mm_sketch restatement on homopolymers, short-period
+    repeats (ties, palindromic k-mers for even k), reads around the one-window length, duplicated segments"""
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200.formats import pack_bases, make_reads
+    from oracle import oracle
+    rng = np.random.default_rng(10)
+    seqs = []
+    for i in range(600):
+        L = int(rng.integers(max(k - 3, 1), k + w + 60))
+        mode = i % 4
+        if mode == 0: s = rng.integers(0, 2, L)
+        elif mode == 1: s = np.tile(rng.integers(0, 4, int(rng.integers(1, 6))), L)[:L]
+        elif mode == 2: s = rng.integers(0, 4, L)
+        else:
+            s = rng.integers(0, 4, L); a = int(rng.integers(0, max(L - 5, 1))); s[a:a + int(rng.integers(3, 40))] = int(rng.integers(0, 4))
+        seqs.append(s.astype(np.uint8))
+    seqs += [np.zeros(3000, np.uint8), np.tile(np.array([0, 3], np.uint8), 1500), np.tile(np.array([0, 1, 2, 3], np.uint8), 700)]
+    base = rng.integers(0, 4, 700).astype(np.uint8)
+    seqs.append(np.concatenate([base, base, rng.integers(0, 4, 50).astype(np.uint8), base]))
+    seqs += [rng.integers(0, 4, int(rng.integers(400, 4000))).astype(np.uint8) for _ in range(30)]
+    reads = make_reads([pack_bases(s) for s in seqs], [len(s) for s in seqs], list(range(len(seqs))))
+    io, mo = _opts("ava-ont", k, w)
+    if hpc: io.flag |= 1
+    eng.set_options(io, mo)
+    xy, off = eng.sketch(reads, rid0=3)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for r, s in enumerate(seqs):
+        want = oracle.sketch(bytes(lut[s]), w, k, rid=3 + r, hpc=hpc)
+        got = xy[int(off[r]):int(off[r + 1])]
+        assert got.shape == want.shape and (got == want).all(), "read %d len %d" % (r, len(s))

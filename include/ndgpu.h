@@ -59,6 +59,7 @@ typedef struct {
     const uint32_t *nmask;      /* optional: 1 bit per base, bit (i&31) of nmask[word_off/2 + (i>>5)] = ambiguous */
     const uint64_t *name_key;
     const uint32_t *name_hash;
+    const uint32_t *name_id;    /* optional: strtoul(name) (ref: minimap2/map.c:1300-1301); needed by ndg_map_batch_ovl */
 } ndg_reads_t;
 
 /* One chain-derived hit: the fields of mm_reg1_t (ref: minimap2/minimap.h:84-99) that leave the
@@ -97,6 +98,10 @@ int  ndg_set_limits(ndg_ctx_t *ctx, uint64_t sub_batch_bases, uint64_t max_ancho
 /* variant 0 = one thread per read/segment (baseline kernels), 1 = warp-cooperative kernels */
 int  ndg_set_variant(ndg_ctx_t *ctx, int sort_variant, int chain_variant);
 
+/* page-locked host memory for batch inputs (optional; lets the H2D copy run at full PCIe speed) */
+void *ndg_host_alloc(uint64_t bytes);
+void  ndg_host_free(void *p);
+
 /* ---- index: replaces mm_idx_gen()/mm_idx_post() (ref: minimap2/index.c:353-372,191-248) and
  *      mm_idx_cal_max_occ() (index.c:164-185) for one index part ------------------------------ */
 int ndg_index_begin(ndg_ctx_t *ctx);
@@ -117,6 +122,14 @@ int ndg_index_get(ndg_ctx_t *ctx, uint64_t minier, uint64_t *pos, int cap, int *
 /* ---- mapping: replaces kt_for(worker_for) -> mm_map_frag() for a batch of queries
  *      (ref: minimap2/map.c:1241-1244, 879-906, 507-623), chain-only regime ------------------ */
 int ndg_map_batch(ndg_ctx_t *ctx, const ndg_reads_t *queries, ndg_map_result_t *out);
+/* Whole step 1 for a batch: mapping plus the reference's output stage (filter + delta/varint records,
+ * ref: minimap2/map.c:1297-1304, lib/ovl.c:109-150) done on the GPU; returns the .ovl bytes of the batch
+ * (pinned host memory owned by the context, valid until the next call).  state[2] = the encoder's
+ * running (prev_qname, prev_tname) (ref: minimap2/main.c:29), updated in place.  Needs name_id on both the
+ * targets (at ndg_index_add) and the queries. */
+typedef struct { int32_t minlen, dvt, maxhan1, maxhan2; } ndg_emit_opt_t;
+int ndg_map_batch_ovl(ndg_ctx_t *ctx, const ndg_reads_t *queries, const ndg_emit_opt_t *eo, uint32_t state[2],
+                      const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work);
 /* the same in three steps, for measurement with inputs resident in HBM */
 int ndg_map_upload(ndg_ctx_t *ctx, const ndg_reads_t *queries);      /* H2D only (single sub-batch) */
 int ndg_map_resident(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* kernels only; hits stay on device */

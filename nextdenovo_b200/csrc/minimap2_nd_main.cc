@@ -66,7 +66,7 @@ static bool read_2bit(const char *fn, Reads &R)
 
 static ndg_reads_t view(const Reads &R, int r0, int r1)
 {
-    ndg_reads_t v; memset(&v, 0, sizeof v);
+    ndg_reads_t v; memset(&v, 0, sizeof v); v.name_id = R.id.data() + r0;
     v.n_reads = r1 - r0; v.words = R.words.data(); v.word_off = R.word_off.data() + r0; v.len = R.len.data() + r0;
     v.name_key = R.key.data() + r0; v.name_hash = R.hash.data() + r0;
     return v;   // word_off entries are absolute into words[]; the library rebases them
@@ -174,12 +174,11 @@ int main(int argc, char **argv)
                 while (q_at < Q->n()) { size += Q->len[q_at++]; if (size >= q_batch) break; }
                 ndg_reads_t qv = view(*Q, q0, q_at);
                 ndg_map_result_t R;
-                if (ndg_map_batch(g, &qv, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
-                obuf.resize((size_t)R.n_hits * 40 + 64);
-                int64_t nb = ndg_ovl_emit_step1(R.hits, R.n_hits, Q->id.data() + q0, Q->key.data() + q0, Q->len.data() + q0,
-                                                T.id.data() + t0i, T.key.data() + t0i, T.len.data() + t0i, minlen, dvt, maxhan1, maxhan2,
-                                                state, obuf.data(), obuf.size(), &n_rec, &sum_qspan);
-                if (nb < 0 || fwrite(obuf.data(), 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+                ndg_emit_opt_t eo = { minlen, dvt, maxhan1, maxhan2 };
+                const uint8_t *bytes = nullptr; uint64_t nb = 0;
+                // mapping + output stage (filter, delta/varint records) on the GPU; only the .ovl bytes come back
+                if (ndg_map_batch_ovl(g, &qv, &eo, state, &bytes, &nb, &n_rec, &sum_qspan, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+                if (nb && fwrite(bytes, 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
                 if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, q_at - q0);
             }
         }

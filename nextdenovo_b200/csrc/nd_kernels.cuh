@@ -52,6 +52,7 @@ struct nd_reads_dev {
     const uint32_t *nmask;
     const nd_u64 *name_key;
     const uint32_t *name_hash;
+    const uint32_t *name_id;
     int n_reads;
 };
 
@@ -429,4 +430,95 @@ __global__ void k_hit_gather(const nd_hit *hits, const uint32_t *idx, nd_u64 n, 
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { nd_hit h = hits[idx[i]]; h.qidx += qidx_base; out[i] = h; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step-1 output stage on the device.  ref: minimap2/map.c:1297-1304 (filter), :804-821 (--dvt test),
+// lib/ovl.c:109-150 (delta + big-endian base-128 varints; flag bits 1/2/3 for decreasing names and
+// tlen > qlen)
+// ------------------------------------------------------------------------------------------------
+struct nd_emit_par {
+    const uint32_t *q_id, *q_len; const nd_u64 *q_key;     // indexed by hit.qidx - qidx_base
+    const uint32_t *t_id, *t_len; const nd_u64 *t_key;     // indexed by hit.rid
+    int qidx_base, minlen, dvt, maxhan1, maxhan2;
+};
+
+__device__ __forceinline__ int nd_check_dovetail(int rev, uint32_t qs, uint32_t qe, uint32_t qlen, uint32_t ts, uint32_t te, uint32_t tlen,
+                                                 int maxhan1, int maxhan2)
+{
+    if (rev) {
+        if (qs <= (uint32_t)maxhan1 && ts <= (uint32_t)maxhan1) return 1;
+        else if (qlen - qe <= (uint32_t)maxhan1 && tlen - te <= (uint32_t)maxhan1) return 2;
+    } else {
+        if (qlen - qe <= (uint32_t)maxhan1 && ts <= (uint32_t)maxhan1) return 4;
+        else if (qs <= (uint32_t)maxhan1 && tlen - te <= (uint32_t)maxhan1) return 7;
+    }
+    if (maxhan2 > 0) {
+        if (qs <= (uint32_t)maxhan2 && qe + maxhan2 >= qlen) return 8;
+        if (ts <= (uint32_t)maxhan2 && te + maxhan2 >= tlen) return 9;
+    }
+    return 0;
+}
+
+__global__ void k_emit_flags(const nd_hit *hits, nd_u64 n, nd_emit_par P, uint8_t *keep)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nd_hit h = hits[i];
+    const int q = h.qidx - P.qidx_base;
+    bool k = P.q_key[q] != P.t_key[h.rid] && h.qe - h.qs >= P.minlen;
+    if (k && P.dvt) k = nd_check_dovetail(h.rev, h.qs, h.qe, P.q_len[q], h.rs, h.re, P.t_len[h.rid], P.maxhan1, P.maxhan2) != 0;
+    keep[i] = k;
+}
+
+__device__ __forceinline__ int nd_varint_len(uint32_t v) { return v < 0x80 ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5; }
+__device__ __forceinline__ int nd_varint_put(uint8_t *dst, uint32_t v)
+{
+    const int ng = nd_varint_len(v);
+    for (int g = 0; g < ng; ++g) dst[g] = (uint8_t)((v >> (7 * (ng - 1 - g)) & 0x7f) | (g + 1 < ng ? 0x80 : 0));
+    return ng;
+}
+
+// fields of record j given its predecessor's names (the previous kept record, or the carried state)
+__device__ __forceinline__ void nd_emit_fields(const nd_hit *kept, const uint32_t *kidx, nd_u64 j, const nd_emit_par &P, const uint32_t *state, uint32_t f[8])
+{
+    const nd_hit h = kept[kidx[j]];
+    uint32_t pq, pt;
+    if (j == 0) { pq = state[0]; pt = state[1]; }
+    else { const nd_hit g = kept[kidx[j - 1]]; pq = P.q_id[g.qidx - P.qidx_base]; pt = P.t_id[g.rid]; }
+    const uint32_t qn = P.q_id[h.qidx - P.qidx_base], tn = P.t_id[h.rid];
+    const uint32_t ql = (uint32_t)(h.qe - h.qs), tl = (uint32_t)(h.re - h.rs);
+    uint32_t flags = (uint32_t)h.rev & 0xff;
+    if (qn >= pq) f[0] = qn - pq; else { flags |= 2; f[0] = pq - qn; }
+    if (tn >= pt) f[4] = tn - pt; else { flags |= 4; f[4] = pt - tn; }
+    if (ql >= tl) f[6] = ql - tl; else { flags |= 8; f[6] = tl - ql; }
+    f[1] = flags; f[2] = (uint32_t)h.qs; f[3] = ql; f[5] = (uint32_t)h.rs; f[7] = (uint32_t)h.mlen;
+}
+
+__global__ void k_emit_len(const nd_hit *hits, const uint32_t *kidx, nd_u64 n_kept, nd_emit_par P, const uint32_t *state, uint32_t *len, nd_u64 *sum_qspan)
+{
+    nd_u64 j = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    nd_u64 span = 0;
+    if (j < n_kept) {
+        uint32_t f[8]; nd_emit_fields(hits, kidx, j, P, state, f);
+        int nb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nb += nd_varint_len(f[i]);
+        len[j] = (uint32_t)nb;
+        span = f[3];
+    }
+    for (int o = 16; o; o >>= 1) span += __shfl_xor_sync(0xffffffffu, span, o);
+    if ((threadIdx.x & 31) == 0 && span) atomicAdd(sum_qspan, span);
+}
+
+__global__ void k_emit_write(const nd_hit *hits, const uint32_t *kidx, nd_u64 n_kept, nd_emit_par P, const uint32_t *state, const nd_u64 *off,
+                             uint8_t *out, uint32_t *new_state)
+{
+    nd_u64 j = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_kept) return;
+    uint32_t f[8]; nd_emit_fields(hits, kidx, j, P, state, f);
+    uint8_t *dst = out + off[j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst += nd_varint_put(dst, f[i]);
+    if (j == n_kept - 1) { const nd_hit h = hits[kidx[j]]; new_state[0] = P.q_id[h.qidx - P.qidx_base]; new_state[1] = P.t_id[h.rid]; }
 }

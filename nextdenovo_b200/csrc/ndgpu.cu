@@ -63,16 +63,16 @@ struct ProfEntry { std::string name; double ms = 0; uint64_t launches = 0; };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
 struct ReadsDev {            // a batch of reads resident on the device
-    DevBuf words, word_off, len, nmask, name_key, name_hash, chunk_off;
+    DevBuf words, word_off, len, nmask, name_key, name_hash, name_id, chunk_off;
     int n_reads = 0; uint64_t n_words = 0, n_chunks = 0, n_bases = 0; bool has_nmask = false;
     nd_reads_dev view() const {
         nd_reads_dev v;
         v.words = words.as<uint32_t>(); v.word_off = word_off.as<nd_u64>(); v.len = len.as<uint32_t>();
         v.nmask = has_nmask ? nmask.as<uint32_t>() : nullptr;
-        v.name_key = name_key.as<nd_u64>(); v.name_hash = name_hash.as<uint32_t>(); v.n_reads = n_reads;
+        v.name_key = name_key.as<nd_u64>(); v.name_hash = name_hash.as<uint32_t>(); v.name_id = name_id.as<uint32_t>(); v.n_reads = n_reads;
         return v;
     }
-    void release() { words.release(); word_off.release(); len.release(); nmask.release(); name_key.release(); name_hash.release(); chunk_off.release(); }
+    void release() { words.release(); word_off.release(); len.release(); nmask.release(); name_key.release(); name_hash.release(); name_id.release(); chunk_off.release(); }
 };
 
 } // namespace
@@ -92,7 +92,8 @@ struct ndg_ctx {
     std::vector<ProfEntry> prof; std::vector<ProfPending> pending; std::vector<cudaEvent_t> ev_pool;
     // index
     DevBuf tmz; uint64_t n_tmz = 0;               // raw target minimizers (x,y)
-    DevBuf t_key, t_len; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen; uint32_t n_targets = 0; uint64_t t_sum_len = 0;
+    DevBuf t_key, t_len, t_id; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen, h_tid; bool t_has_id = true;
+    DevBuf em_keep, em_kidx, em_len, em_off, em_out; HostBuf h_ovl; uint32_t n_targets = 0; uint64_t t_sum_len = 0;
     DevBuf idx_pos, idx_tab; int log2cap = 0; uint64_t n_pos = 0; bool index_ready = false;
     int mid_occ = 0;
     // mapping workspace
@@ -167,10 +168,10 @@ int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
     int n = r1 - r0;
     if (n <= 0) return fail(c, NDG_ERR_ARG, "empty read batch");
     uint64_t w0 = R->word_off[r0], w1 = R->word_off[r1], nw = w1 - w0;
-    size_t hdr = (size_t)(n + 1) * 8 * 2 + (size_t)n * (4 + 8 + 4);
+    size_t hdr = (size_t)(n + 1) * 8 * 2 + (size_t)n * (4 + 8 + 4 + 4);
     if (c->up.reserve(hdr)) return fail(c, NDG_ERR_NOMEM, "pinned staging");
     uint64_t *h_woff = c->up.as<uint64_t>(), *h_coff = h_woff + (n + 1), *h_key = h_coff + (n + 1);
-    uint32_t *h_len = reinterpret_cast<uint32_t *>(h_key + n), *h_hash = h_len + n;
+    uint32_t *h_len = reinterpret_cast<uint32_t *>(h_key + n), *h_hash = h_len + n, *h_id = h_hash + n;
     uint64_t chunks = 0, bases = 0;
     for (int i = 0; i < n; ++i) {
         h_woff[i] = R->word_off[r0 + i] - w0;
@@ -181,17 +182,19 @@ int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
         h_len[i] = L;
         h_key[i] = R->name_key ? R->name_key[r0 + i] : (uint64_t)(r0 + i);
         h_hash[i] = R->name_hash ? R->name_hash[r0 + i] : 0;
+        h_id[i] = R->name_id ? R->name_id[r0 + i] : (uint32_t)(r0 + i);
     }
     h_woff[n] = nw; h_coff[n] = chunks;
     D.n_reads = n; D.n_words = nw; D.n_chunks = chunks; D.n_bases = bases; D.has_nmask = R->nmask != nullptr;
     RSV(D.words, (nw + 4) * 4); RSV(D.word_off, (size_t)(n + 1) * 8); RSV(D.chunk_off, (size_t)(n + 1) * 8);
-    RSV(D.len, (size_t)n * 4); RSV(D.name_key, (size_t)n * 8); RSV(D.name_hash, (size_t)n * 4);
+    RSV(D.len, (size_t)n * 4); RSV(D.name_key, (size_t)n * 8); RSV(D.name_hash, (size_t)n * 4); RSV(D.name_id, (size_t)n * 4);
     CK(cudaMemcpyAsync(D.words.p, R->words + w0, nw * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.word_off.p, h_woff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.chunk_off.p, h_coff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.len.p, h_len, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.name_key.p, h_key, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.name_hash.p, h_hash, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.name_id.p, h_id, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     if (R->nmask) {
         if ((w0 & 1) != 0) return fail(c, NDG_ERR_ARG, "nmask requires even word offsets");
         RSV(D.nmask, (nw / 2 + 4) * 4);
@@ -289,15 +292,18 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     cudaStreamSynchronize(c->st);
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
+    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
     for (auto b : bufs) b->release();
     c->q.release();
-    c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
+    c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
     cudaStreamDestroy(c->st);
     delete c;
 }
+
+extern "C" void *ndg_host_alloc(uint64_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+extern "C" void ndg_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char *ndg_last_error(const ndg_ctx_t *c) { return c ? c->err.c_str() : "null context"; }
 extern "C" uint64_t ndg_kernel_launches(const ndg_ctx_t *c) { return c ? c->launches : 0; }
@@ -347,7 +353,7 @@ extern "C" int ndg_index_begin(ndg_ctx_t *c)
 {
     if (!c) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
-    c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear();
+    c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->t_has_id = true;
     c->index_ready = false; c->n_pos = 0;
     return NDG_OK;
 }
@@ -357,8 +363,10 @@ static int index_meta(ndg_ctx *c, const ndg_reads_t *T)
     for (int i = 0; i < T->n_reads; ++i) {
         c->h_tkey.push_back(T->name_key ? T->name_key[i] : (uint64_t)(c->n_targets + i));
         c->h_tlen.push_back(T->len[i]);
+        c->h_tid.push_back(T->name_id ? T->name_id[i] : 0);
         c->t_sum_len += T->len[i];
     }
+    if (!T->name_id) c->t_has_id = false;
     c->n_targets += T->n_reads;
     return 0;
 }
@@ -459,7 +467,8 @@ extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
     key_out.release(); hist.release();
     if (e0 != cudaSuccess) return fail(c, NDG_ERR_CUDA, "index table: %s", cudaGetErrorString(e0));
     // targets' metadata
-    RSV(c->t_key, (size_t)c->n_targets * 8 + 8); RSV(c->t_len, (size_t)c->n_targets * 4 + 4);
+    RSV(c->t_key, (size_t)c->n_targets * 8 + 8); RSV(c->t_len, (size_t)c->n_targets * 4 + 4); RSV(c->t_id, (size_t)c->n_targets * 4 + 4);
+    CK(cudaMemcpyAsync(c->t_id.p, c->h_tid.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->t_key.p, c->h_tkey.data(), (size_t)c->n_targets * 8, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->t_len.p, c->h_tlen.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -645,6 +654,91 @@ int map_resident(ndg_ctx *c, int qidx_base)
 }
 
 } // namespace
+
+namespace {
+// filter + encode the sorted hits of the resident sub-batch on the device; appends to c->h_ovl at h_used
+int emit_resident(ndg_ctx *c, int qidx_base, const ndg_emit_opt_t *eo, uint32_t *d_state, uint64_t *h_used, uint64_t *n_rec, uint64_t *sum_qspan)
+{
+    const uint64_t NH = c->n_hits;
+    if (NH == 0) return 0;
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    nd_emit_par P;
+    P.q_id = c->q.name_id.as<uint32_t>(); P.q_len = c->q.len.as<uint32_t>(); P.q_key = c->q.name_key.as<nd_u64>();
+    P.t_id = c->t_id.as<uint32_t>(); P.t_len = c->t_len.as<uint32_t>(); P.t_key = c->t_key.as<nd_u64>();
+    P.qidx_base = qidx_base; P.minlen = eo->minlen; P.dvt = eo->dvt; P.maxhan1 = eo->maxhan1; P.maxhan2 = eo->maxhan2;
+    RSV(c->em_keep, NH + 16); RSV(c->em_kidx, (NH + 16) * 4); RSV(c->em_len, (NH + 16) * 4); RSV(c->em_off, (NH + 16) * 8);
+    const nd_hit *hits = c->hits_sorted.as<nd_hit>();
+    KLAUNCH("emit", (k_emit_flags<<<nblk(NH, 256), 256, 0, c->st>>>(hits, NH, P, c->em_keep.as<uint8_t>())));
+    uint32_t *d_nk = c->scalars.as<uint32_t>() + 160;
+    nd_u64 *d_span = c->scalars.as<nd_u64>() + 96;      // byte 768; d_nk @640, new_state @656, d_state @672
+    {
+        size_t tmp = 0;
+        cub::CountingInputIterator<uint32_t> it(0);
+        CK(cub::DeviceSelect::Flagged(nullptr, tmp, it, c->em_keep.as<uint8_t>(), c->em_kidx.as<uint32_t>(), d_nk, (long long)NH, c->st));
+        RSV(c->cubtmp, tmp);
+        KLAUNCH("emit", CK(cub::DeviceSelect::Flagged(c->cubtmp.p, tmp, it, c->em_keep.as<uint8_t>(), c->em_kidx.as<uint32_t>(), d_nk, (long long)NH, c->st)));
+    }
+    CK(cudaMemcpyAsync(h, d_nk, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NK = (uint32_t)h[0];
+    if (NK == 0) return 0;
+    CK(cudaMemsetAsync(d_span, 0, 8, c->st));
+    CK(cudaMemsetAsync(c->em_len.as<uint32_t>() + NK, 0, 4, c->st));
+    KLAUNCH("emit", (k_emit_len<<<nblk(NK, 256), 256, 0, c->st>>>(hits, c->em_kidx.as<uint32_t>(), NK, P, d_state, c->em_len.as<uint32_t>(), d_span)));
+    if (int rc = scan_u32_to_u64(c, c->em_len.as<uint32_t>(), c->em_off.as<nd_u64>(), NK)) return rc;
+    RSV(c->em_out, NK * 40 + 64);
+    KLAUNCH("emit", (k_emit_write<<<nblk(NK, 256), 256, 0, c->st>>>(hits, c->em_kidx.as<uint32_t>(), NK, P, d_state, c->em_off.as<nd_u64>(), c->em_out.as<uint8_t>(),
+                     c->scalars.as<uint32_t>() + 164)));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, c->em_off.as<nd_u64>() + NK, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(h + 1, d_span, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(d_state, c->scalars.as<uint32_t>() + 164, 8, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t nb = h[0];
+    if (c->h_ovl.cap < *h_used + nb + 64) {
+        HostBuf nbuf; if (nbuf.reserve((*h_used + nb + 64) * 2)) return fail(c, NDG_ERR_NOMEM, "pinned ovl buffer");
+        if (*h_used) memcpy(nbuf.p, c->h_ovl.p, *h_used);
+        c->h_ovl.release(); c->h_ovl = nbuf;
+    }
+    CK(cudaMemcpyAsync(c->h_ovl.as<uint8_t>() + *h_used, c->em_out.p, nb, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    *h_used += nb; *n_rec += NK; *sum_qspan += h[1];
+    return 0;
+}
+} // namespace
+
+extern "C" int ndg_map_batch_ovl(ndg_ctx_t *c, const ndg_reads_t *Q, const ndg_emit_opt_t *eo, uint32_t state[2],
+                                 const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work)
+{
+    if (!c || !Q || !eo || !state || !ovl || !n_bytes || Q->n_reads <= 0) return NDG_ERR_ARG;
+    if (!Q->name_id || !c->t_has_id) return fail(c, NDG_ERR_ARG, "ndg_map_batch_ovl needs name_id for targets and queries");
+    cudaSetDevice(c->device);
+    RSV(c->scalars, 1024);
+    uint32_t *d_state = c->scalars.as<uint32_t>() + 168;
+    CK(cudaMemcpyAsync(d_state, state, 8, cudaMemcpyHostToDevice, c->st));
+    uint64_t used = 0, rec = 0, sq = 0, tot_hits = 0, tot_mz = 0, tot_a = 0, tot_seg = 0;
+    int r0 = 0;
+    uint64_t budget = c->sub_batch_bases;
+    while (r0 < Q->n_reads) {
+        int r1 = r0; uint64_t bases = 0;
+        while (r1 < Q->n_reads && (r1 == r0 || bases + Q->len[r1] <= budget)) bases += Q->len[r1++];
+        if (int rc = upload_reads(c, c->q, Q, r0, r1)) return rc;
+        int rc = map_resident(c, r0);
+        if (rc == NDG_ERR_OVERFLOW && r1 - r0 > 1 && c->err.find("anchors") != std::string::npos) { budget = std::max<uint64_t>(bases / 2, 1); continue; }
+        if (rc) return rc;
+        if (int rc2 = emit_resident(c, r0, eo, d_state, &used, &rec, &sq)) return rc2;
+        tot_hits += c->n_hits; tot_mz += c->n_mz; tot_a += c->n_a; tot_seg += c->n_seg;
+        r0 = r1;
+    }
+    CK(cudaMemcpyAsync(c->h_scalars.p, d_state, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    memcpy(state, c->h_scalars.p, 8);
+    *ovl = c->h_ovl.as<uint8_t>(); *n_bytes = used;
+    if (n_rec) *n_rec += rec;
+    if (sum_qspan) *sum_qspan += sq;
+    if (work) { work->n_hits = (int64_t)tot_hits; work->hits = nullptr; work->n_minimizers = tot_mz; work->n_anchors = tot_a; work->n_segments = tot_seg; }
+    return NDG_OK;
+}
 
 extern "C" int ndg_map_upload(ndg_ctx_t *c, const ndg_reads_t *Q)
 {

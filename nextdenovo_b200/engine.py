@@ -33,7 +33,7 @@ class _Opt(C.Structure):
 
 class _Reads(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
-                ("nmask", C.c_void_p), ("name_key", C.c_void_p), ("name_hash", C.c_void_p)]
+                ("nmask", C.c_void_p), ("name_key", C.c_void_p), ("name_hash", C.c_void_p), ("name_id", C.c_void_p)]
 
 
 class _MapResult(C.Structure):
@@ -62,7 +62,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl"]
 
 _lib = None
 
@@ -112,6 +112,11 @@ def load_library():
     L.ndg_ovl_emit_step1.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int32] * 4 + \
                                     [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.ndg_ksw_extd2_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3
+    L.ndg_map_batch_ovl.argtypes = [C.c_void_p, C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_MapResult)]
+    L.ndg_host_alloc.restype = C.c_void_p
+    L.ndg_host_alloc.argtypes = [C.c_uint64]
+    L.ndg_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -125,11 +130,11 @@ def _reads_struct(r: Reads):
     s = _Reads()
     s._keep = (np.ascontiguousarray(r.words, dtype=np.uint32), np.ascontiguousarray(r.word_off, dtype=np.uint64),
                np.ascontiguousarray(r.length, dtype=np.uint32), np.ascontiguousarray(r.name_key, dtype=np.uint64),
-               np.ascontiguousarray(r.name_hash, dtype=np.uint32))
+               np.ascontiguousarray(r.name_hash, dtype=np.uint32), np.ascontiguousarray(r.ids, dtype=np.uint32))
     s.n_reads = r.n
     s.words, s.word_off, s.len = _ptr(s._keep[0]), _ptr(s._keep[1]), _ptr(s._keep[2])
     s.nmask = None
-    s.name_key, s.name_hash = _ptr(s._keep[3]), _ptr(s._keep[4])
+    s.name_key, s.name_hash, s.name_id = _ptr(s._keep[3]), _ptr(s._keep[4]), _ptr(s._keep[5])
     return s
 
 
@@ -226,6 +231,17 @@ class Engine:
         self._ck(self.L.ndg_map_batch(self.h, C.byref(s), C.byref(res)))
         return self._result(res)
 
+    def map_batch_ovl(self, queries: Reads, state):
+        """Whole step 1 for a batch with the output stage on the GPU (ndg_map_batch_ovl): returns (.ovl bytes, stats)."""
+        s = _reads_struct(queries)
+        eo = np.array([self.mo.minlen, self.mo.dvt, self.mo.maxhan1, self.mo.maxhan2], dtype=np.int32)
+        ptr, nb, nrec, sq = C.c_void_p(), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        res = _MapResult()
+        self._ck(self.L.ndg_map_batch_ovl(self.h, C.byref(s), _ptr(eo), _ptr(state), C.byref(ptr), C.byref(nb), C.byref(nrec), C.byref(sq), C.byref(res)))
+        data = C.string_at(ptr.value, nb.value) if nb.value else b""
+        return data, dict(records=nrec.value, sum_qspan=sq.value, n_hits=res.n_hits, n_minimizers=res.n_minimizers,
+                          n_anchors=res.n_anchors, n_segments=res.n_segments)
+
     def map_upload(self, queries: Reads):
         s = _reads_struct(queries)
         self._ck(self.L.ndg_map_upload(self.h, C.byref(s)))
@@ -294,6 +310,30 @@ class Engine:
             self._ck(int(nb))
         out += dst[:nb].tobytes()
         return n_rec.value, sq.value
+
+
+class PinnedReads:
+    """A copy of a read batch whose arrays live in page-locked host memory (ndg_host_alloc)."""
+
+    def __init__(self, reads: Reads):
+        self.L = load_library()
+        self._ptrs = []
+        def pin(a):
+            a = np.ascontiguousarray(a)
+            p = self.L.ndg_host_alloc(max(a.nbytes, 16))
+            if not p:
+                raise NdgError("ndg_host_alloc failed")
+            self._ptrs.append(p)
+            out = np.frombuffer((C.c_char * a.nbytes).from_address(p), dtype=a.dtype, count=a.size)
+            out[...] = a.reshape(-1)
+            return out
+        self.reads = Reads(pin(reads.words), pin(reads.word_off), pin(reads.length), pin(reads.ids), pin(reads.name_key), pin(reads.name_hash))
+
+    def free(self):
+        self.reads = None
+        for p in self._ptrs:
+            self.L.ndg_host_free(p)
+        self._ptrs = []
 
 
 def shard_bounds(n, world):
@@ -371,7 +411,7 @@ def query_batches(queries: Reads, mini_batch_size):
     return out
 
 
-def run_step1(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: MapOpt, same_file=False):
+def run_step1(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: MapOpt, same_file=False, device_emit=True):
     """`minimap2-nd --step 1 ... TARGET QUERY -o OUT` (ref: minimap2/main.c:452-509).  Returns
     (ovl_bytes, stats)."""
     engine.set_options(io, mo)
@@ -384,10 +424,16 @@ def run_step1(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: Ma
         engine.build_index(tp)
         for (q0, q1) in query_batches(queries, mo.mini_batch_size):
             qb = queries.slice(q0, q1)
-            hits, w = engine.map_batch(qb)
+            if device_emit:
+                data, w = engine.map_batch_ovl(qb, state)
+                out += data
+                r, s = w["records"], w["sum_qspan"]
+                work["n_hits"] += w["n_hits"]
+            else:
+                hits, w = engine.map_batch(qb)
+                work["n_hits"] += hits.shape[0]
+                r, s = engine.emit_step1(hits, qb, state, out)
             for k in ("n_minimizers", "n_anchors", "n_segments"):
                 work[k] += w[k]
-            work["n_hits"] += hits.shape[0]
-            r, s = engine.emit_step1(hits, qb, state, out)
             n_rec += r; sq += s
     return bytes(out), dict(records=n_rec, sum_qspan=sq, mid_occ=engine.stat["mid_occ"], **work)

@@ -73,6 +73,41 @@ __device__ int ndk_backtrack(bool is_rev, const uint8_t *p, const int *off, cons
 #define NDK_WARPS 2
 
 // scratch per warp slot: state_stride bytes of int8 state + H (int32 x Tmax) + off/off_end (int x 2 x rmax)
+template <bool RIGHTV>
+__device__ __forceinline__ void ndk_cell(int xt1, int vt1, int x2t1, int ut, int yo, int y2o, int &z, int q, int q2, int qe, int qe2, int sc_mch,
+                                         int &un, int &vn, int &xn, int &yn, int &x2n, int &y2n, int &d)
+{
+    // int8 wrap-around of the reference (_mm_add_epi8/_mm_sub_epi8) cannot trigger while (q+e)+(q2+e2) <= 127 and |score| <= 127
+    // (minimap2/options.c:204): every intermediate below then stays inside [-128,127], so plain int arithmetic is identical.
+    int a = xt1 + vt1, b = yo + ut, a2 = x2t1 + vt1, b2 = y2o + ut;
+    if (!RIGHTV) {
+        d = a > z ? 1 : 0;  z = max(z, a);
+        d = b > z ? 2 : d;  z = max(z, b);
+        d = a2 > z ? 3 : d; z = max(z, a2);
+        d = b2 > z ? 4 : d; z = max(z, b2);
+    } else {
+        d = z > a ? 0 : 1;  z = max(z, a);
+        d = z > b ? d : 2;  z = max(z, b);
+        d = z > a2 ? d : 3; z = max(z, a2);
+        d = z > b2 ? d : 4; z = max(z, b2);
+    }
+    z = min(z, sc_mch);
+    un = z - vt1; vn = z - ut;
+    int tmp = z - q;  a -= tmp;  b -= tmp;
+    tmp = z - q2;     a2 -= tmp; b2 -= tmp;
+    if (!RIGHTV) {
+        xn  = max(a, 0) - qe;   d |= a  > 0 ? 0x08 : 0;
+        yn  = max(b, 0) - qe;   d |= b  > 0 ? 0x10 : 0;
+        x2n = max(a2, 0) - qe2; d |= a2 > 0 ? 0x20 : 0;
+        y2n = max(b2, 0) - qe2; d |= b2 > 0 ? 0x40 : 0;
+    } else {
+        xn  = max(a, 0) - qe;   d |= a  < 0 ? 0 : 0x08;
+        yn  = max(b, 0) - qe;   d |= b  < 0 ? 0 : 0x10;
+        x2n = max(a2, 0) - qe2; d |= a2 < 0 ? 0 : 0x20;
+        y2n = max(b2, 0) - qe2; d |= b2 < 0 ? 0 : 0x40;
+    }
+}
+
 __global__ void __launch_bounds__(NDK_WARPS * 32)
 k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
             uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work)
@@ -117,19 +152,32 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
         if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
         const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 
-        int8_t *u = reinterpret_cast<int8_t *>(base), *v = u + T, *x = v + T, *y = x + T, *x2 = y + T, *y2 = x2 + T, *s = y2 + T;
-        uint8_t *sf = reinterpret_cast<uint8_t *>(s + T), *qr = sf + T;
+        // per-cell state packed in 8 bytes: x v x2 u | y y2 s - ; then the target copy sf (indices >= T alias the
+        // reversed query, as in the reference's single block) and the reversed query qr
+        uint2 *cell = reinterpret_cast<uint2 *>(base);
+        int8_t *cb = reinterpret_cast<int8_t *>(base);
+        uint8_t *sf = base + (size_t)8 * T, *qr = sf + T;
+#define NDK_X(t)  cb[8 * (t) + 0]
+#define NDK_V(t)  cb[8 * (t) + 1]
+#define NDK_X2(t) cb[8 * (t) + 2]
+#define NDK_U(t)  cb[8 * (t) + 3]
+#define NDK_Y(t)  cb[8 * (t) + 4]
+#define NDK_Y2(t) cb[8 * (t) + 5]
+#define NDK_S(t)  cb[8 * (t) + 6]
         int *off_end = off + qlen + tlen - 1;
         uint8_t *p = pmat + c.p_off;
         uint32_t *cigar = cigars + c.cigar_off;
 
         if (run) {
             const int qpad = ((qlen + 15) / 16 + 1) * 16 + 32;
-            const int8_t i1 = (int8_t)(-q - e), i2 = (int8_t)(-q2 - e2);
-            for (int t = lane; t < T; t += 32) {
-                u[t] = i1; v[t] = i1; x[t] = i1; y[t] = i1; x2[t] = i2; y2[t] = i2; s[t] = 0;
-                sf[t] = t < tlen ? target[t] : 0;
-                if (!approx_max) H[t] = NDK_NEG_INF;
+            {
+                const unsigned b1 = (unsigned)(uint8_t)(-q - e), b2 = (unsigned)(uint8_t)(-q2 - e2);
+                const uint2 init = make_uint2(b1 | b1 << 8 | b2 << 16 | b1 << 24, b1 | b2 << 8);
+                for (int t = lane; t < T; t += 32) {
+                    cell[t] = init;
+                    sf[t] = t < tlen ? target[t] : 0;
+                    if (!approx_max) H[t] = NDK_NEG_INF;
+                }
             }
             for (int t = lane; t < qpad; t += 32) qr[t] = t < qlen ? query[qlen - 1 - t] : 0;
             __syncwarp();
@@ -144,75 +192,64 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
                 if (st > en) { ez.zdropped = 1; break; }
                 const int st0 = st, en0 = en;
                 st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
-                int x1, x21, v1;
+                unsigned carry;                                     // x | v<<8 | x2<<16 of cell st-1 on the previous diagonal
                 const int vb = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
-                if (st > 0) {
-                    if (st - 1 >= last_st && st - 1 <= last_en) { x1 = x[st - 1]; x21 = x2[st - 1]; v1 = v[st - 1]; }
-                    else { x1 = -q - e; x21 = -q2 - e2; v1 = -q - e; }
-                } else { x1 = -q - e; x21 = -q2 - e2; v1 = ndk_w8(vb); }
-                if (en >= r && lane == 0) { y[r] = (int8_t)(-q - e); y2[r] = (int8_t)(-q2 - e2); u[r] = (int8_t)vb; }
-                // scores: 16-wide unaligned blocks from st0; loads before stores (the last block may spill into sf[])
                 {
-                    const uint8_t *qrr = qr + (qlen - 1 - r);
-                    const int len16 = (en0 - st0 + 16) / 16 * 16;
-                    for (int k0 = 0; k0 < len16; k0 += 32) {
-                        const int k = k0 + lane;
-                        int sc = 0;
-                        if (k < len16) {
-                            const int sq = sf[st0 + k], sr = qrr[st0 + k];
-                            if (flag & NDK_GENERIC_SC) sc = (k <= en0 - st0) ? P.mat[sq * m + sr] : 0;
-                            else { sc = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) sc = sc_N; }
-                        }
-                        __syncwarp();
-                        if (k < len16 && (!(flag & NDK_GENERIC_SC) || k <= en0 - st0)) s[st0 + k] = (int8_t)sc;
-                    }
+                    const unsigned d1 = (unsigned)(uint8_t)(-q - e), d2 = (unsigned)(uint8_t)(-q2 - e2);
+                    if (st > 0) {
+                        if (st - 1 >= last_st && st - 1 <= last_en) carry = cell[st - 1].x & 0xffffffu;
+                        else carry = d1 | d1 << 8 | d2 << 16;
+                    } else carry = d1 | (unsigned)(uint8_t)vb << 8 | d2 << 16;
                 }
+                if (en >= r && lane == 0) { NDK_Y(r) = (int8_t)(-q - e); NDK_Y2(r) = (int8_t)(-q2 - e2); NDK_U(r) = (int8_t)vb; }
                 __syncwarp();
                 if (with_cigar && lane == 0) { off[r] = st; off_end[r] = en; }
-                // core: 32 cells per step, neighbours by shuffle, carry across steps
+                const uint8_t *qrr = qr + (qlen - 1 - r);
+                const int sc_end = st0 + (en0 - st0 + 16) / 16 * 16;   // scores are rewritten on [st0, sc_end) (:158-176)
+                const bool generic = (flag & NDK_GENERIC_SC) != 0;
+                // core: 32 cells per step; neighbour (t-1) words by shuffle with a carry across steps; score fused in
                 {
-                    int cx = x1, cx2 = x21, cv = v1;            // previous-diagonal values at (chunk start - 1)
                     uint8_t *pr = p + (size_t)r * n_col - st;
                     for (int t0 = st; t0 <= en; t0 += 32) {
                         const int t = t0 + lane;
                         const bool act = t <= en;
-                        int xo = 0, vo = 0, x2o = 0, z = 0, ut = 0, yo = 0, y2o = 0;
-                        if (act) { xo = x[t]; vo = v[t]; x2o = x2[t]; z = s[t]; ut = u[t]; yo = y[t]; y2o = y2[t]; }
-                        int xt1 = __shfl_up_sync(NDK_FULL, xo, 1), vt1 = __shfl_up_sync(NDK_FULL, vo, 1), x2t1 = __shfl_up_sync(NDK_FULL, x2o, 1);
-                        if (lane == 0) { xt1 = cx; vt1 = cv; x2t1 = cx2; }
-                        cx = __shfl_sync(NDK_FULL, xo, 31); cv = __shfl_sync(NDK_FULL, vo, 31); cx2 = __shfl_sync(NDK_FULL, x2o, 31);
-                        int a = ndk_w8(xt1 + vt1), b = ndk_w8(yo + ut), a2 = ndk_w8(x2t1 + vt1), b2 = ndk_w8(y2o + ut), d;
-                        if (!right) {
-                            d = a > z ? 1 : 0;  z = z > a ? z : a;
-                            d = b > z ? 2 : d;  z = z > b ? z : b;
-                            d = a2 > z ? 3 : d; z = z > a2 ? z : a2;
-                            d = b2 > z ? 4 : d; z = z > b2 ? z : b2;
-                        } else {
-                            d = z > a ? 0 : 1;  z = z > a ? z : a;
-                            d = z > b ? d : 2;  z = z > b ? z : b;
-                            d = z > a2 ? d : 3; z = z > a2 ? z : a2;
-                            d = z > b2 ? d : 4; z = z > b2 ? z : b2;
-                        }
-                        z = z < sc_mch ? z : sc_mch;
-                        const int un = ndk_w8(z - vt1), vn = ndk_w8(z - ut);
-                        int tmp = ndk_w8(z - q);  a = ndk_w8(a - tmp);  b = ndk_w8(b - tmp);
-                        tmp = ndk_w8(z - q2);     a2 = ndk_w8(a2 - tmp); b2 = ndk_w8(b2 - tmp);
-                        int xn, yn, x2n, y2n;
-                        if (!right) {
-                            xn  = ndk_w8((a  > 0 ? a  : 0) - qe);  d |= a  > 0 ? 0x08 : 0;
-                            yn  = ndk_w8((b  > 0 ? b  : 0) - qe);  d |= b  > 0 ? 0x10 : 0;
-                            x2n = ndk_w8((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
-                            y2n = ndk_w8((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
-                        } else {
-                            xn  = ndk_w8((0 > a  ? 0 : a)  - qe);  d |= 0 > a  ? 0 : 0x08;
-                            yn  = ndk_w8((0 > b  ? 0 : b)  - qe);  d |= 0 > b  ? 0 : 0x10;
-                            x2n = ndk_w8((0 > a2 ? 0 : a2) - qe2); d |= 0 > a2 ? 0 : 0x20;
-                            y2n = ndk_w8((0 > b2 ? 0 : b2) - qe2); d |= 0 > b2 ? 0 : 0x40;
-                        }
+                        uint2 cw = make_uint2(0, 0);
+                        int z = 0;
                         if (act) {
-                            u[t] = (int8_t)un; v[t] = (int8_t)vn; x[t] = (int8_t)xn; y[t] = (int8_t)yn; x2[t] = (int8_t)x2n; y2[t] = (int8_t)y2n;
+                            cw = cell[t];
+                            z = (int)(int8_t)(cw.y >> 16);                  // stale score unless rewritten this diagonal
+                            if (t >= st0 && (generic ? t <= en0 : t < sc_end)) {
+                                const int sq = sf[t], sr = qrr[t];
+                                if (generic) z = P.mat[sq * m + sr];
+                                else { z = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) z = sc_N; }
+                            }
+                        }
+                        const int sc_keep = z;
+                        unsigned nb = __shfl_up_sync(NDK_FULL, cw.x, 1);
+                        if (lane == 0) nb = carry;
+                        carry = __shfl_sync(NDK_FULL, cw.x, 31) & 0xffffffu;
+                        const int xt1 = (int)(int8_t)nb, vt1 = (int)(int8_t)(nb >> 8), x2t1 = (int)(int8_t)(nb >> 16);
+                        const int ut = (int)cw.x >> 24, yo = (int)(int8_t)cw.y, y2o = (int)(int8_t)(cw.y >> 8);
+                        int un, vn, xn, yn, x2n, y2n, d;
+                        if (right) ndk_cell<true>(xt1, vt1, x2t1, ut, yo, y2o, z, q, q2, qe, qe2, sc_mch, un, vn, xn, yn, x2n, y2n, d);
+                        else ndk_cell<false>(xt1, vt1, x2t1, ut, yo, y2o, z, q, q2, qe, qe2, sc_mch, un, vn, xn, yn, x2n, y2n, d);
+                        if (act) {
+                            cell[t] = make_uint2(((unsigned)xn & 255u) | ((unsigned)vn & 255u) << 8 | ((unsigned)x2n & 255u) << 16 | (unsigned)un << 24,
+                                                 ((unsigned)yn & 255u) | ((unsigned)y2n & 255u) << 8 | ((unsigned)sc_keep & 255u) << 16);
                             if (with_cigar) pr[t] = (uint8_t)d;
                         }
+                    }
+                    // score cells past the rounded band end: only s[] changes; beyond T the block spills into sf[] (:103,:175)
+                    if (!generic && sc_end - 1 > en) {
+                        const int t = en + 1 + lane;
+                        int z = 0;
+                        const bool on = t < sc_end;
+                        if (on) {
+                            const int sq = t < T ? sf[t] : qr[t - T], sr = qrr[t];
+                            z = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) z = sc_N;
+                        }
+                        __syncwarp();
+                        if (on) { if (t < T) NDK_S(t) = (int8_t)z; else sf[t - T] = (uint8_t)z; }
                     }
                 }
                 __syncwarp();
@@ -220,13 +257,13 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
                     int max_H, max_t;
                     if (r > 0) {
                         const int en1 = st0 + (en0 - st0) / 4 * 4;
-                        const int Hlast = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+                        const int Hlast = en0 > 0 ? H[en0 - 1] + NDK_U(en0) : H[en0] + NDK_V(en0);
                         __syncwarp();
                         long long best = ((long long)Hlast << 32) | 0xffffffffLL;          // rank 0 = en0
                         for (int t0 = st0; t0 <= en0; t0 += 32) {
                             const int t = t0 + lane;
                             if (t < en0) {
-                                const int h = H[t] + v[t];
+                                const int h = H[t] + NDK_V(t);
                                 H[t] = h;
                                 const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2)
                                                               : 1u + (4u << 20) + (unsigned)(t - en1);
@@ -242,8 +279,8 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
                         else if (rank - 1 < (4u << 20)) max_t = st0 + (int)((rank - 1) & 0xfffff) * 4 + (int)((rank - 1) >> 20);
                         else max_t = en1 + (int)(rank - 1 - (4u << 20));
                     } else {
-                        if (lane == 0) H[0] = v[0] - qe0;
-                        max_H = v[0] - qe0; max_t = 0;
+                        if (lane == 0) H[0] = NDK_V(0) - qe0;
+                        max_H = NDK_V(0) - qe0; max_t = 0;
                     }
                     __syncwarp();
                     if (en0 == tlen - 1) { int h = H[en0]; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
@@ -253,11 +290,11 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
                 } else {
                     if (r > 0) {
                         if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-                            int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+                            int d0 = NDK_V(last_H0_t), d1 = NDK_U(last_H0_t + 1);
                             if (d0 > d1) H0 += d0; else { H0 += d1; ++last_H0_t; }
-                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += v[last_H0_t];
-                        else { ++last_H0_t; H0 += u[last_H0_t]; }
-                    } else { H0 = v[0] - qe0; last_H0_t = 0; }
+                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += NDK_V(last_H0_t);
+                        else { ++last_H0_t; H0 += NDK_U(last_H0_t); }
+                    } else { H0 = NDK_V(0) - qe0; last_H0_t = 0; }
                     if ((flag & NDK_APPROX_DROP) && ndk_zdrop(ez, H0, r, last_H0_t, zdrop, (int)(int8_t)e2)) break;
                     if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
                 }

@@ -915,7 +915,7 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
             Tmax = std::max(Tmax, (k.tlen + 15) / 16 * 16); rmax = std::max(rmax, k.qlen + k.tlen); qmax = std::max(qmax, k.qlen);
         }
     }
-    const size_t state_bytes = ((size_t)8 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 64 + 255) / 256 * 256;
+    const size_t state_bytes = ((size_t)9 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;   // cells 8T, sf T, qr
     const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
     const size_t slot_bytes = state_bytes + h_bytes + off_bytes;
     const int blocks = std::min<int>(c->n_sm * 16, (n + NDK_WARPS - 1) / NDK_WARPS);

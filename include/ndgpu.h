@@ -97,6 +97,8 @@ int  ndg_set_opt(ndg_ctx_t *ctx, const ndg_opt_t *opt);
 int  ndg_set_limits(ndg_ctx_t *ctx, uint64_t sub_batch_bases, uint64_t max_anchors);
 /* variant 0 = one thread per read/segment (baseline kernels), 1 = warp-cooperative kernels */
 int  ndg_set_variant(ndg_ctx_t *ctx, int sort_variant, int chain_variant);
+/* ksw_extd2 kernel generation: 0 = one cell per lane, 1 = two cells per lane in s16x2 (DPX) registers */
+int  ndg_set_ksw_variant(ndg_ctx_t *ctx, int variant);
 
 /* page-locked host memory for batch inputs (optional; lets the H2D copy run at full PCIe speed) */
 void *ndg_host_alloc(uint64_t bytes);

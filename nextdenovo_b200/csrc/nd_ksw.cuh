@@ -316,3 +316,258 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
         __syncwarp();
     }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Packed generation: two adjacent target cells per lane in s16x2 registers, DPX integer SIMD
+// (VIADD.16x2, VIMNMX.S16x2 with predicate outputs, VIMNMX3.S16x2 on sm_100a).  64 cells per warp step.
+// Per-pair state in the scratch: 8 words {x v x2 u | y y2 s -}, low half = even cell.  Same observable
+// behaviour as above (16-cell rounding, stale scores, spill into sf[], SIMD tie order of the exact max).
+// ------------------------------------------------------------------------------------------------
+#define NDK_H16(t, f) h16[((t) >> 1) * 16 + (f) * 2 + ((t) & 1)]
+__device__ __forceinline__ unsigned ndk_pk(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+
+template <bool RIGHTV>
+__device__ __forceinline__ void ndk_pair(unsigned xt1, unsigned vt1, unsigned x2t1, unsigned ut, unsigned yo, unsigned y2o, unsigned z,
+                                         unsigned Q, unsigned Q2, unsigned NQE, unsigned NQE2, unsigned SCM,
+                                         unsigned &un, unsigned &vn, unsigned &xn, unsigned &yn, unsigned &x2n, unsigned &y2n, unsigned &d)
+{
+    unsigned a = __vadd2(xt1, vt1), b = __vadd2(yo, ut), a2 = __vadd2(x2t1, vt1), b2 = __vadd2(y2o, ut);
+    bool ph, pl; int dh, dl;
+    if (!RIGHTV) {                                   // d = cand > z ? k : d  (strict), ksw2_extd2_sse.c:220-228
+        z = __vibmax_s16x2(z, a, &ph, &pl);  dh = ph ? 0 : 1;  dl = pl ? 0 : 1;
+        z = __vibmax_s16x2(z, b, &ph, &pl);  dh = ph ? dh : 2; dl = pl ? dl : 2;
+        z = __vibmax_s16x2(z, a2, &ph, &pl); dh = ph ? dh : 3; dl = pl ? dl : 3;
+        z = __vibmax_s16x2(z, b2, &ph, &pl); dh = ph ? dh : 4; dl = pl ? dl : 4;
+    } else {                                         // d = z > cand ? d : k, :267-275
+        z = __vibmax_s16x2(a, z, &ph, &pl);  dh = ph ? 1 : 0;  dl = pl ? 1 : 0;
+        z = __vibmax_s16x2(b, z, &ph, &pl);  dh = ph ? 2 : dh; dl = pl ? 2 : dl;
+        z = __vibmax_s16x2(a2, z, &ph, &pl); dh = ph ? 3 : dh; dl = pl ? 3 : dl;
+        z = __vibmax_s16x2(b2, z, &ph, &pl); dh = ph ? 4 : dh; dl = pl ? 4 : dl;
+    }
+    z = __vimin3_s16x2(z, SCM, SCM);
+    un = __vsub2(z, vt1); vn = __vsub2(z, ut);
+    const unsigned nz = __vsub2(0u, z);
+    const unsigned t1 = __vadd2(nz, Q), t2 = __vadd2(nz, Q2);
+    a = __vadd2(a, t1); b = __vadd2(b, t1); a2 = __vadd2(a2, t2); b2 = __vadd2(b2, t2);
+    // continuation flags without predicate outputs (arithmetic on the packed halves): relu, then
+    //   left-aligned gaps:  flag = value > 0   <=> relu(value) >= 1 <=> bit 15 of relu + 0x7fff
+    //   right-aligned gaps: flag = value >= 0  <=> sign bit clear
+    const unsigned ra = __vimax_s16x2_relu(a, a), rb = __vimax_s16x2_relu(b, b), ra2 = __vimax_s16x2_relu(a2, a2), rb2 = __vimax_s16x2_relu(b2, b2);
+    xn = __vadd2(ra, NQE); yn = __vadd2(rb, NQE); x2n = __vadd2(ra2, NQE2); y2n = __vadd2(rb2, NQE2);
+    unsigned fa, fb, fa2, fb2;
+    if (!RIGHTV) {
+        fa = __vadd2(ra, 0x7fff7fffu) >> 15; fb = __vadd2(rb, 0x7fff7fffu) >> 15; fa2 = __vadd2(ra2, 0x7fff7fffu) >> 15; fb2 = __vadd2(rb2, 0x7fff7fffu) >> 15;
+    } else {
+        fa = ~a >> 15; fb = ~b >> 15; fa2 = ~a2 >> 15; fb2 = ~b2 >> 15;
+    }
+    const unsigned fl = ((fa & 0x00010001u) << 3) | ((fb & 0x00010001u) << 4) | ((fa2 & 0x00010001u) << 5) | ((fb2 & 0x00010001u) << 6);
+    dl |= (int)(fl & 0xffu); dh |= (int)(fl >> 16 & 0xffu);
+    d = (unsigned)dl | (unsigned)dh << 8;
+}
+
+__global__ void __launch_bounds__(NDK_WARPS * 32)
+k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
+               uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * NDK_WARPS + (threadIdx.x >> 5);
+    uint8_t *base = scratch + (size_t)slot * slot_bytes;
+    int32_t *H = reinterpret_cast<int32_t *>(base + state_bytes);
+    int *off = reinterpret_cast<int *>(base + state_bytes + h_bytes);
+
+    for (;;) {
+        int ci = 0;
+        if (lane == 0) ci = (int)atomicAdd(work, 1u);
+        ci = __shfl_sync(NDK_FULL, ci, 0);
+        if (ci >= n_calls) break;
+        const ndk_call c = calls[ci];
+        const int qlen = c.qlen, tlen = c.tlen, flag = c.flag, zdrop = c.zdrop;
+        const uint8_t *query = seqs + c.q_off, *target = seqs + c.t_off;
+        const bool with_cigar = !(flag & NDK_SCORE_ONLY), approx_max = (flag & NDK_APPROX_MAX) != 0, right = with_cigar && (flag & NDK_RIGHT);
+        ndk_res ez;
+        ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1; ez.max = 0; ez.score = ez.mqe = ez.mte = NDK_NEG_INF;
+        ez.n_cigar = 0; ez.zdropped = 0; ez.reach_end = 0; ez.pad = 0;
+        int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
+        const int qe0 = q + e;
+        const int m = P.m;
+        bool run = !(m <= 1 || qlen <= 0 || tlen <= 0);
+        if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+        const int qe = q + e, qe2 = q2 + e2;
+        const int sc_mch = P.mat[0], sc_mis = P.mat[1], sc_N = P.mat[m * m - 1] == 0 ? -e2 : P.mat[m * m - 1];
+        int w = c.w;
+        if (w < 0) w = tlen > qlen ? tlen : qlen;
+        const int T = (tlen + 15) / 16 * 16;
+        int n_col_ = qlen < tlen ? qlen : tlen;
+        n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+        const int n_col = n_col_ * 16;
+        {
+            int min_sc = P.mat[1];
+            for (int t = 1; t < m * m; ++t) min_sc = min_sc < P.mat[t] ? min_sc : P.mat[t];
+            if (-min_sc > 2 * (q + e)) run = false;
+        }
+        int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+        if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+        const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+
+        uint4 *pairw = reinterpret_cast<uint4 *>(base);                 // 2 x uint4 per pair of cells
+        int16_t *h16 = reinterpret_cast<int16_t *>(base);
+        uint8_t *sf = base + (size_t)16 * T, *qr = sf + T;
+        int *off_end = off + qlen + tlen - 1;
+        uint8_t *p = pmat + c.p_off;
+        uint32_t *cigar = cigars + c.cigar_off;
+        const unsigned Q = ndk_pk(q, q), Q2 = ndk_pk(q2, q2), NQE = ndk_pk(-qe, -qe), NQE2 = ndk_pk(-qe2, -qe2), SCM = ndk_pk(sc_mch, sc_mch);
+
+        if (run) {
+            const int qpad = ((qlen + 15) / 16 + 1) * 16 + 32;
+            {
+                const unsigned i1 = ndk_pk(-q - e, -q - e), i2 = ndk_pk(-q2 - e2, -q2 - e2);
+                for (int j = lane; j < T / 2; j += 32) {
+                    pairw[2 * j] = make_uint4(i1, i1, i2, i1);          // x v x2 u
+                    pairw[2 * j + 1] = make_uint4(i1, i2, 0u, 0u);      // y y2 s -
+                }
+                for (int t = lane; t < T; t += 32) {
+                    sf[t] = t < tlen ? target[t] : 0;
+                    if (!approx_max) H[t] = NDK_NEG_INF;
+                }
+            }
+            for (int t = lane; t < qpad; t += 32) qr[t] = t < qlen ? query[qlen - 1 - t] : 0;
+            __syncwarp();
+
+            int last_st = -1, last_en = -1, H0 = 0, last_H0_t = 0;
+            for (int r = 0; r < qlen + tlen - 1; ++r) {
+                int st = 0, en = tlen - 1;
+                if (st < r - qlen + 1) st = r - qlen + 1;
+                if (en > r) en = r;
+                if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+                if (en > (r + w) >> 1) en = (r + w) >> 1;
+                if (st > en) { ez.zdropped = 1; break; }
+                const int st0 = st, en0 = en;
+                st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+                const int vb = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+                unsigned cx, cv, cx2;                                   // previous-diagonal x, v, x2 of cell st-1, in the HIGH halves
+                if (st > 0) {
+                    if (st - 1 >= last_st && st - 1 <= last_en) { cx = (unsigned)NDK_H16(st - 1, 0) << 16; cv = (unsigned)NDK_H16(st - 1, 1) << 16; cx2 = (unsigned)NDK_H16(st - 1, 2) << 16; }
+                    else { cx = (unsigned)(-q - e) << 16; cv = cx; cx2 = (unsigned)(-q2 - e2) << 16; }
+                } else { cx = (unsigned)(-q - e) << 16; cv = (unsigned)vb << 16; cx2 = (unsigned)(-q2 - e2) << 16; }
+                if (en >= r && lane == 0) { NDK_H16(r, 4) = (int16_t)(-q - e); NDK_H16(r, 5) = (int16_t)(-q2 - e2); NDK_H16(r, 3) = (int16_t)vb; }
+                __syncwarp();
+                if (with_cigar && lane == 0) { off[r] = st; off_end[r] = en; }
+                const uint8_t *qrr = qr + (qlen - 1 - r);
+                const int sc_end = st0 + (en0 - st0 + 16) / 16 * 16;
+                const bool generic = (flag & NDK_GENERIC_SC) != 0;
+                const int sc_hi = generic ? en0 + 1 : sc_end;           // scores rewritten on [st0, sc_hi)
+                {
+                    uint8_t *pr = p + (size_t)r * n_col - st;
+                    for (int t0 = st; t0 <= en; t0 += 64) {
+                        const int t = t0 + 2 * lane;
+                        const bool act = t <= en;
+                        uint4 A = make_uint4(0, 0, 0, 0), Bw = make_uint4(0, 0, 0, 0);
+                        unsigned z = 0;
+                        if (act) {
+                            A = pairw[t]; Bw = pairw[t + 1];            // pair index t/2 -> words 2*(t/2), 2*(t/2)+1
+                            int zl = (int)(int16_t)(Bw.z & 0xffffu), zh = (int)Bw.z >> 16;
+                            if (t + 1 >= st0 && t < sc_hi) {
+                                const unsigned sq2 = *reinterpret_cast<const uint16_t *>(sf + t);
+                                const int sq0 = sq2 & 255, sq1 = sq2 >> 8, sr0 = qrr[t], sr1 = qrr[t + 1];
+                                if (t >= st0) {
+                                    if (generic) zl = P.mat[sq0 * m + sr0];
+                                    else { zl = sq0 == sr0 ? sc_mch : sc_mis; if (sq0 == m - 1 || sr0 == m - 1) zl = sc_N; }
+                                }
+                                if (t + 1 < sc_hi) {
+                                    if (generic) zh = P.mat[sq1 * m + sr1];
+                                    else { zh = sq1 == sr1 ? sc_mch : sc_mis; if (sq1 == m - 1 || sr1 == m - 1) zh = sc_N; }
+                                }
+                            }
+                            z = ndk_pk(zl, zh);
+                        }
+                        const unsigned zkeep = z;
+                        unsigned px = __shfl_up_sync(NDK_FULL, A.x, 1), pv = __shfl_up_sync(NDK_FULL, A.y, 1), px2 = __shfl_up_sync(NDK_FULL, A.z, 1);
+                        if (lane == 0) { px = cx; pv = cv; px2 = cx2; }
+                        cx = __shfl_sync(NDK_FULL, A.x, 31); cv = __shfl_sync(NDK_FULL, A.y, 31); cx2 = __shfl_sync(NDK_FULL, A.z, 31);
+                        const unsigned xt1 = __byte_perm(px, A.x, 0x5432), vt1 = __byte_perm(pv, A.y, 0x5432), x2t1 = __byte_perm(px2, A.z, 0x5432);
+                        unsigned un, vn, xn, yn, x2n, y2n, d;
+                        if (right) ndk_pair<true>(xt1, vt1, x2t1, A.w, Bw.x, Bw.y, z, Q, Q2, NQE, NQE2, SCM, un, vn, xn, yn, x2n, y2n, d);
+                        else ndk_pair<false>(xt1, vt1, x2t1, A.w, Bw.x, Bw.y, z, Q, Q2, NQE, NQE2, SCM, un, vn, xn, yn, x2n, y2n, d);
+                        if (act) {
+                            pairw[t] = make_uint4(xn, vn, x2n, un);
+                            pairw[t + 1] = make_uint4(yn, y2n, zkeep, 0u);
+                            if (with_cigar) *reinterpret_cast<uint16_t *>(pr + t) = (uint16_t)d;
+                        }
+                    }
+                    if (!generic && sc_end - 1 > en) {                  // score cells past the rounded band end (spill into sf[] beyond T)
+                        const int t = en + 1 + lane;
+                        int zz = 0;
+                        const bool on = t < sc_end;
+                        if (on) {
+                            const int sq = t < T ? sf[t] : qr[t - T], sr = qrr[t];
+                            zz = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) zz = sc_N;
+                        }
+                        __syncwarp();
+                        if (on) { if (t < T) NDK_H16(t, 6) = (int16_t)zz; else sf[t - T] = (uint8_t)zz; }
+                    }
+                }
+                __syncwarp();
+                if (!approx_max) {
+                    int max_H, max_t;
+                    if (r > 0) {
+                        const int en1 = st0 + (en0 - st0) / 4 * 4;
+                        const int Hlast = en0 > 0 ? H[en0 - 1] + NDK_H16(en0, 3) : H[en0] + NDK_H16(en0, 1);
+                        __syncwarp();
+                        long long best = ((long long)Hlast << 32) | 0xffffffffLL;
+                        for (int t0 = st0; t0 <= en0; t0 += 32) {
+                            const int t = t0 + lane;
+                            if (t < en0) {
+                                const int h = H[t] + NDK_H16(t, 1);
+                                H[t] = h;
+                                const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2)
+                                                              : 1u + (4u << 20) + (unsigned)(t - en1);
+                                const long long key = ((long long)h << 32) | (long long)(0xffffffffu - rank);
+                                best = key > best ? key : best;
+                            } else if (t == en0) H[t] = Hlast;
+                        }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) { long long y2k = __shfl_xor_sync(NDK_FULL, best, o); best = y2k > best ? y2k : best; }
+                        max_H = (int)(best >> 32);
+                        const unsigned rank = 0xffffffffu - (unsigned)(best & 0xffffffffLL);
+                        if (rank == 0) max_t = en0;
+                        else if (rank - 1 < (4u << 20)) max_t = st0 + (int)((rank - 1) & 0xfffff) * 4 + (int)((rank - 1) >> 20);
+                        else max_t = en1 + (int)(rank - 1 - (4u << 20));
+                    } else {
+                        if (lane == 0) H[0] = NDK_H16(0, 1) - qe0;
+                        max_H = NDK_H16(0, 1) - qe0; max_t = 0;
+                    }
+                    __syncwarp();
+                    if (en0 == tlen - 1) { int h = H[en0]; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
+                    if (r - st0 == qlen - 1) { int h = H[st0]; if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; } }
+                    if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+                } else {
+                    if (r > 0) {
+                        if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+                            int d0 = NDK_H16(last_H0_t, 1), d1 = NDK_H16(last_H0_t + 1, 3);
+                            if (d0 > d1) H0 += d0; else { H0 += d1; ++last_H0_t; }
+                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += NDK_H16(last_H0_t, 1);
+                        else { ++last_H0_t; H0 += NDK_H16(last_H0_t, 3); }
+                    } else { H0 = NDK_H16(0, 1) - qe0; last_H0_t = 0; }
+                    if ((flag & NDK_APPROX_DROP) && ndk_zdrop(ez, H0, r, last_H0_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+                }
+                last_st = st; last_en = en;
+            }
+            __syncwarp();
+            if (with_cigar && lane == 0) {
+                const bool rev = (flag & NDK_REV_CIGAR) != 0;
+                if (!ez.zdropped && !(flag & NDK_EXTZ_ONLY))
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, tlen - 1, qlen - 1, cigar);
+                else if (!ez.zdropped && (flag & NDK_EXTZ_ONLY) && ez.mqe + c.end_bonus > ez.max) {
+                    ez.reach_end = 1;
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.mqe_t, qlen - 1, cigar);
+                } else if (ez.max_t >= 0 && ez.max_q >= 0)
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.max_t, ez.max_q, cigar);
+            }
+        }
+        if (lane == 0) res[ci] = ez;
+        __syncwarp();
+    }
+}

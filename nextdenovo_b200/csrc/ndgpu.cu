@@ -83,7 +83,7 @@ struct ndg_ctx {
     ndg_opt_t opt;
     std::string err;
     uint64_t sub_batch_bases = 64ull << 20, max_anchors = 0;
-    int sort_variant = 1, chain_variant = 1;
+    int sort_variant = 1, chain_variant = 1, ksw_variant = 1;
     int chunk_bases = 512;
     int n_sm = 148;
     void *hk_scope = nullptr;
@@ -322,6 +322,7 @@ extern "C" int ndg_set_limits(ndg_ctx_t *c, uint64_t sub_batch_bases, uint64_t m
     c->max_anchors = max_anchors;
     return NDG_OK;
 }
+extern "C" int ndg_set_ksw_variant(ndg_ctx_t *c, int v) { if (!c) return NDG_ERR_ARG; c->ksw_variant = v; return NDG_OK; }
 extern "C" int ndg_set_variant(ndg_ctx_t *c, int sort_variant, int chain_variant)
 {
     if (!c) return NDG_ERR_ARG;
@@ -816,6 +817,7 @@ extern "C" int64_t ndg_debug_fetch(ndg_ctx_t *c, const char *what, void *dst, ui
     else if (w == "p") { src = c->p.p; bytes = c->n_a * 4; }
     else if (w == "v") { src = c->v.p; bytes = c->n_a * 4; }
     else if (w == "seg_start") { src = c->seg_start.p; bytes = c->n_seg * 4; }
+    else if (w == "ksw_p") { src = c->ksw_p.p; bytes = c->ksw_p.cap < (64u << 20) ? c->ksw_p.cap : (64u << 20); }
     else return fail(c, NDG_ERR_ARG, "unknown stage buffer '%s'", what);
     if (!dst) return (int64_t)bytes;
     if (bytes > cap) return fail(c, NDG_ERR_OVERFLOW, "buffer too small");
@@ -915,7 +917,7 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
             Tmax = std::max(Tmax, (k.tlen + 15) / 16 * 16); rmax = std::max(rmax, k.qlen + k.tlen); qmax = std::max(qmax, k.qlen);
         }
     }
-    const size_t state_bytes = ((size_t)9 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;   // cells 8T, sf T, qr
+    const size_t state_bytes = ((size_t)17 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;   // cells 8T, sf T, qr
     const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
     const size_t slot_bytes = state_bytes + h_bytes + off_bytes;
     const int blocks = std::min<int>(c->n_sm * 16, (n + NDK_WARPS - 1) / NDK_WARPS);
@@ -928,6 +930,10 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
     uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
     CK(cudaMemsetAsync(d_work, 0, 4, c->st));
     ndk_par P; P.m = m; memset(P.mat, 0, sizeof P.mat); memcpy(P.mat, mat, (size_t)m * m); P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
+    if (c->ksw_variant == 1)
+        KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
+                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));
+    else
     KLAUNCH("ksw_extd2", (k_ksw_extd2<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
                           c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));
     CK(cudaGetLastError());

@@ -62,7 +62,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant"]
 
 _lib = None
 
@@ -90,6 +90,7 @@ def load_library():
     L.ndg_set_opt.argtypes = [C.c_void_p, C.POINTER(_Opt)]
     L.ndg_set_limits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     L.ndg_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ndg_set_ksw_variant.argtypes = [C.c_void_p, C.c_int]
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
@@ -268,6 +269,9 @@ class Engine:
         return out
 
     # ---- base-level extension (ksw_extd2) ----------------------------------------------------
+    def set_ksw_variant(self, v):
+        self._ck(self.L.ndg_set_ksw_variant(self.h, v))
+
     def ksw_extd2_batch(self, calls, seqs, mat, q, e, q2, e2, m=5):
         """calls: structured array KSW_CALL_DTYPE; seqs: uint8 codes.  Returns (results KSW_RES_DTYPE, cigars list)."""
         n = calls.shape[0]

@@ -154,7 +154,8 @@ def test_cli_dropin_matches_reference_bytes(built, golden_dir, tmp_path):
     assert subprocess.run([exe, "--step", "1", "-c", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
 
 
-def test_ksw_extd2_batch_bit_exact(eng):
+@pytest.mark.parametrize("ksw_variant", [1, 0])
+def test_ksw_extd2_batch_bit_exact(eng, ksw_variant):
     """ndg_ksw_extd2_batch == ksw_extd2_sse (via the oracle restatement, and the compiled reference when present):
     score, max, end points, z-drop flag, reach_end and CIGAR, for every call of a mixed batch."""
     import sys
@@ -169,7 +170,9 @@ def test_ksw_extd2_batch_bit_exact(eng):
         calls[i] = (len(qs), len(ts), off, off + len(qs), w, zd, eb, flag)
         chunks += [qs, ts]; off += len(qs) + len(ts)
     seqs = np.concatenate(chunks)
+    eng.set_ksw_variant(ksw_variant)
     res, cigs = eng.ksw_extd2_batch(calls, seqs, mat, 4, 2, 24, 1)
+    eng.set_ksw_variant(1)
     L, R = oracle_lib(), ref_lib()
     names = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end")
     bad = []

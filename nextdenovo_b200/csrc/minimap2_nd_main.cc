@@ -4,7 +4,7 @@
 // Mirrors the parts of the reference's main() the NextDenovo pipeline drives for raw_align
 // (ref: nextDenovo:445-464): two-pass option handling (minimap2/main.c:177-363), index parts
 // (minimap2/index.c:284-288,353-358), query batches (minimap2/bseq.c:86-123), ordered .ovl output
-// (minimap2/map.c:1245-1352).  Input must be .2bit (what seq_dump writes, lib/bseq.c:93-139); other
+// (minimap2/map.c:1245-1352).  Input: .2bit (what seq_dump writes, lib/bseq.c:93-139) or FASTA/FASTQ[.gz] with decimal names; other
 // modes of the reference binary (-c, --step 2/3, PAF/SAM) are rejected, never approximated.
 #include <cstdio>
 #include <cstdlib>
@@ -13,11 +13,13 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <zlib.h>
 #include "ndgpu.h"
 
 struct Reads {
-    std::vector<uint32_t> words, len, id, hash;
+    std::vector<uint32_t> words, len, id, hash, nmask;   // nmask: 1 bit per base at nmask[word_off/2 + (i>>5)] (FASTA/Q input only)
     std::vector<uint64_t> word_off, key;
+    bool has_n = false;
     int n() const { return (int)len.size(); }
 };
 
@@ -45,7 +47,7 @@ static bool read_2bit(const char *fn, Reads &R)
     if (!fp) return false;
     uint8_t hdr[2];
     if (fread(hdr, 1, 2, fp) != 2 || !(hdr[0] == 0 || hdr[0] == 254)) {
-        fprintf(stderr, "[ERROR] '%s' is not a .2bit file; this build accepts the .2bit files written by seq_dump only\n", fn);
+        fprintf(stderr, "[ERROR] '%s' is not a .2bit file\n", fn);
         if (fp != stdin) fclose(fp);
         return false;
     }
@@ -64,9 +66,68 @@ static bool read_2bit(const char *fn, Reads &R)
     return true;
 }
 
+// FASTA/FASTQ[.gz] (ref: lib/mseq.h kseq; names must be decimal, ref: minimap2/map.c:1300 strtoul)
+static bool read_fastx(const char *fn, Reads &R)
+{
+    gzFile fp = strcmp(fn, "-") ? gzopen(fn, "rb") : gzdopen(0, "rb");
+    if (!fp) return false;
+    static unsigned char code[256]; static bool init = false;
+    if (!init) { memset(code, 4, 256); code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2; code['T'] = code['t'] = code['U'] = code['u'] = 3; init = true; }
+    std::vector<char> buf(1 << 16);
+    std::string line, seq, name;
+    bool have = false, fq = false, ok = true;
+    long qual_left = 0;
+    auto flush = [&]() {
+        if (!have) return;
+        char *end; unsigned long v = strtoul(name.c_str(), &end, 10);
+        if (name.empty() || *end) { fprintf(stderr, "[ERROR] read name '%s' is not a decimal integer; .ovl records store strtoul(name)\n", name.c_str()); ok = false; }
+        size_t L = seq.size(), nw = (L + 15) / 16; if (nw & 1) ++nw;
+        size_t o = R.words.size(); R.words.resize(o + nw, 0); R.nmask.resize((o + nw) / 2 + 1, 0);
+        for (size_t i = 0; i < L; ++i) {
+            unsigned c = code[(unsigned char)seq[i]];
+            if (c < 4) R.words[o + (i >> 4)] |= c << (30 - 2 * (i & 15));
+            else { R.nmask[o / 2 + (i >> 5)] |= 1u << (i & 31); R.has_n = true; }
+        }
+        uint64_t k; uint32_t h; name_fields((uint32_t)v, &k, &h);
+        R.id.push_back((uint32_t)v); R.len.push_back((uint32_t)L); R.key.push_back(k); R.hash.push_back(h);
+        R.word_off.push_back(R.words.size());
+        have = false; seq.clear();
+    };
+    R.word_off.push_back(0);
+    while (gzgets(fp, buf.data(), (int)buf.size())) {
+        line.assign(buf.data());
+        while (!line.empty() && line.back() != '\n' && gzgets(fp, buf.data(), (int)buf.size())) line += buf.data();
+        while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+        if (qual_left > 0) { qual_left -= (long)line.size(); continue; }
+        if (!line.empty() && (line[0] == '>' || (line[0] == '@' && (!have || fq)))) {
+            flush();
+            size_t e = 1; while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
+            name = line.substr(1, e - 1); have = true; fq = line[0] == '@';
+        } else if (!line.empty() && line[0] == '+' && have && fq) qual_left = (long)seq.size();
+        else if (have) seq += line;
+    }
+    flush();
+    gzclose(fp);
+    return ok;
+}
+
+// format sniffing as the reference (ref: lib/bseq.c:99-112): first byte 0 or 254 = .2bit
+static bool read_any(const char *fn, Reads &R)
+{
+    if (strcmp(fn, "-") != 0) {
+        FILE *fp = fopen(fn, "rb");
+        if (!fp) return false;
+        int c = fgetc(fp); fclose(fp);
+        if (c == 0 || c == 254) return read_2bit(fn, R);
+        return read_fastx(fn, R);
+    }
+    return read_2bit(fn, R);
+}
+
 static ndg_reads_t view(const Reads &R, int r0, int r1)
 {
     ndg_reads_t v; memset(&v, 0, sizeof v); v.name_id = R.id.data() + r0;
+    if (R.has_n) v.nmask = R.nmask.data();
     v.n_reads = r1 - r0; v.words = R.words.data(); v.word_off = R.word_off.data() + r0; v.len = R.len.data() + r0;
     v.name_key = R.key.data() + r0; v.name_hash = R.hash.data() + r0;
     return v;   // word_off entries are absolute into words[]; the library rebases them
@@ -138,7 +199,7 @@ int main(int argc, char **argv)
     if (!fo) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", out); return 1; }
 
     Reads T;
-    if (!read_2bit(pos[0], T)) { fprintf(stderr, "[ERROR] failed to open file '%s'\n", pos[0]); return 1; }
+    if (!read_any(pos[0], T)) { fprintf(stderr, "[ERROR] failed to open file '%s'\n", pos[0]); return 1; }
     ndg_ctx_t *g = nullptr;
     if (ndg_init(device, &g) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device); return 1; }
     ndg_set_opt(g, &o);
@@ -167,7 +228,7 @@ int main(int argc, char **argv)
         }
         for (size_t qf = 1; qf < pos.size(); ++qf) {
             Reads Qown; const Reads *Q = &T;
-            if (strcmp(pos[qf], pos[0]) != 0) { if (!read_2bit(pos[qf], Qown)) { fprintf(stderr, "ERROR: failed to open file '%s'\n", pos[qf]); return 1; } Q = &Qown; }
+            if (strcmp(pos[qf], pos[0]) != 0) { if (!read_any(pos[qf], Qown)) { fprintf(stderr, "ERROR: failed to open file '%s'\n", pos[qf]); return 1; } Q = &Qown; }
             int q_at = 0;
             while (q_at < Q->n()) {                             // bseq.c:86-123: a batch ends once >= chunk_size bases were read
                 int q0 = q_at; int64_t size = 0;

@@ -131,10 +131,11 @@ def _reads_struct(r: Reads):
     s = _Reads()
     s._keep = (np.ascontiguousarray(r.words, dtype=np.uint32), np.ascontiguousarray(r.word_off, dtype=np.uint64),
                np.ascontiguousarray(r.length, dtype=np.uint32), np.ascontiguousarray(r.name_key, dtype=np.uint64),
-               np.ascontiguousarray(r.name_hash, dtype=np.uint32), np.ascontiguousarray(r.ids, dtype=np.uint32))
+               np.ascontiguousarray(r.name_hash, dtype=np.uint32), np.ascontiguousarray(r.ids, dtype=np.uint32),
+               None if getattr(r, "nmask", None) is None else np.ascontiguousarray(r.nmask, dtype=np.uint32))
     s.n_reads = r.n
     s.words, s.word_off, s.len = _ptr(s._keep[0]), _ptr(s._keep[1]), _ptr(s._keep[2])
-    s.nmask = None
+    s.nmask = _ptr(s._keep[6])
     s.name_key, s.name_hash, s.name_id = _ptr(s._keep[3]), _ptr(s._keep[4]), _ptr(s._keep[5])
     return s
 

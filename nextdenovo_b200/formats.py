@@ -17,6 +17,7 @@ class Reads:
     ids: np.ndarray          # uint32 numeric names (strtoul of the name)
     name_key: np.ndarray     # uint64 strcmp-order-preserving key
     name_hash: np.ndarray    # uint32 X31 hash of the decimal name
+    nmask: np.ndarray = None # optional uint32: 1 bit per base (ambiguous), word i of read r at nmask[word_off[r]//2 + i]
 
     @property
     def n(self):
@@ -29,7 +30,8 @@ class Reads:
     def slice(self, r0, r1):
         w0, w1 = int(self.word_off[r0]), int(self.word_off[r1])
         return Reads(self.words[w0:w1], (self.word_off[r0:r1 + 1] - np.uint64(w0)).astype(np.uint64),
-                     self.length[r0:r1], self.ids[r0:r1], self.name_key[r0:r1], self.name_hash[r0:r1])
+                     self.length[r0:r1], self.ids[r0:r1], self.name_key[r0:r1], self.name_hash[r0:r1],
+                     None if self.nmask is None else self.nmask[w0 // 2:w1 // 2 + 1])
 
 
 def _ndigits(ids):
@@ -80,6 +82,83 @@ def make_reads(words_list, lengths, ids):
     words = np.concatenate(words_list).astype(np.uint32) if len(words_list) else np.zeros(0, np.uint32)
     assert words.shape[0] == int(off[-1])
     return Reads(np.ascontiguousarray(words), off, lengths, ids, name_keys(ids), x31_hash(ids))
+
+
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _c, _v in ((b"Aa", 0), (b"Cc", 1), (b"Gg", 2), (b"TtUu", 3)):
+    for _ch in _c:
+        _CODE[_ch] = _v
+
+
+def reads_from_ascii(seqs, ids):
+    """ASCII sequences (bytes) -> Reads with an ambiguity mask (any non-ACGTU base, ref: minimap2/sketch.c:9-26).
+    Each read occupies an even number of words so that the mask offset is word_off/2 (include/ndgpu.h)."""
+    words, masks, lens = [], [], []
+    any_n = False
+    for s in seqs:
+        c = _CODE[np.frombuffer(s, dtype=np.uint8)]
+        n = c.shape[0]
+        amb = c == 4
+        any_n |= bool(amb.any())
+        w = pack_bases(np.where(amb, 0, c).astype(np.uint8)) if n else np.zeros(0, np.uint32)
+        if w.shape[0] & 1:
+            w = np.concatenate([w, np.zeros(1, np.uint32)])
+        m = np.zeros(w.shape[0] // 2, dtype=np.uint32)
+        if n:
+            bits = np.zeros(m.shape[0] * 32, dtype=np.uint32); bits[:n] = amb
+            m = np.bitwise_or.reduce(bits.reshape(-1, 32) << np.arange(32, dtype=np.uint32), axis=1).astype(np.uint32)
+        words.append(w); masks.append(m); lens.append(n)
+    ids = np.asarray(ids, dtype=np.uint32)
+    lens = np.asarray(lens, dtype=np.uint32)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum([w.shape[0] for w in words], out=off[1:])
+    allw = np.concatenate(words).astype(np.uint32) if words else np.zeros(0, np.uint32)
+    allm = np.concatenate(masks + [np.zeros(2, np.uint32)]).astype(np.uint32)
+    return Reads(np.ascontiguousarray(allw), off, lens, ids, name_keys(ids), x31_hash(ids), allm)
+
+
+def read_fastx(path, max_reads=None):
+    """FASTA/FASTQ, optionally gzipped (ref: lib/mseq.h kseq, minimap2/bseq.c:39-49).  Names must be the decimal
+    integers seq_dump / the .ovl format work with (ref: minimap2/map.c:1300 strtoul)."""
+    import gzip
+    with open(path, "rb") as fh:
+        magic = fh.read(2)
+    op = gzip.open if magic == b"\x1f\x8b" else open
+    seqs, ids = [], []
+    with op(path, "rb") as fh:
+        name, chunks, mode = None, [], None
+        qual_left = 0
+        for line in fh:
+            line = line.rstrip(b"\r\n")
+            if qual_left > 0:
+                qual_left -= len(line)
+                continue
+            if line[:1] in (b">", b"@") and (mode != "fq_seq" or line[:1] == b"@") and not (mode == "fq_seq" and chunks == [] and False):
+                if name is not None:
+                    seqs.append(b"".join(chunks)); ids.append(name)
+                    if max_reads is not None and len(seqs) >= max_reads:
+                        name = None
+                        break
+                tok = line[1:].split()[0] if len(line) > 1 else b""
+                if not tok.isdigit():
+                    raise ValueError("read name %r is not a decimal integer (the .ovl format stores strtoul(name))" % tok)
+                name, chunks, mode = int(tok), [], ("fq_seq" if line[:1] == b"@" else "fa")
+            elif line[:1] == b"+" and mode == "fq_seq":
+                qual_left = sum(len(c) for c in chunks)
+            else:
+                chunks.append(line)
+        if name is not None:
+            seqs.append(b"".join(chunks)); ids.append(name)
+    return reads_from_ascii(seqs, ids)
+
+
+def read_seqfile(path, max_reads=None):
+    """format sniffing as the reference does (ref: lib/bseq.c:99-112: first byte 0 or 254 = .2bit)"""
+    with open(path, "rb") as fh:
+        b = fh.read(2)
+    if len(b) == 2 and b[0] in (0, 254):
+        return read_2bit(path, max_reads)
+    return read_fastx(path, max_reads)
 
 
 def read_2bit(path, max_reads=None):

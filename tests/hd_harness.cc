@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <string>
 #include "../nextdenovo_b200/csrc/nd_core.cuh"
 #include "../oracle/nd_oracle.h"
 
@@ -22,8 +23,50 @@ static std::vector<uint32_t> pack2bit(const char *s, int len)
     return w;
 }
 
+// ambiguous bases: chunked state machine with the 1-bit mask vs the oracle on ASCII with 'N'
+static int selftest_n()
+{
+    unsigned long long st = 88172645463325252ULL;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    long bad = 0, tot = 0;
+    const int cfg[][3] = { {5, 15, 0}, {10, 17, 0}, {7, 16, 0}, {5, 19, 1}, {3, 11, 1}, {1, 9, 0} };
+    for (int it = 0; it < 1500; ++it) {
+        int len = 1 + (int)(rnd() % 1200);
+        std::string s(len, 'A');
+        for (int i = 0; i < len; ++i) s[i] = "ACGT"[rnd() & 3];
+        int nN = (int)(rnd() % 6);
+        for (int j = 0; j < nN; ++j) { int p = (int)(rnd() % len), run = 1 + (int)(rnd() % (rnd() % 4 == 0 ? 40 : 3)); for (int q = p; q < len && q < p + run; ++q) s[q] = 'N'; }
+        if (it % 5 == 0) { int p = (int)(rnd() % len), run = (int)(rnd() % 60); for (int q = p; q < len && q < p + run; ++q) s[q] = 'A'; }
+        std::vector<uint32_t> words((len + 15) / 16 + 2, 0), mask((len + 31) / 32 + 2, 0);
+        for (int i = 0; i < len; ++i) {
+            int c = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : s[i] == 'T' ? 3 : 4;
+            if (c == 4) mask[i >> 5] |= 1u << (i & 31); else words[i >> 4] |= (uint32_t)c << (30 - 2 * (i & 15));
+        }
+        for (auto &c : cfg) {
+            std::vector<ndo_u128> ref(len + 1);
+            size_t n_ref = ndo_sketch(s.data(), len, c[0], c[1], 9, c[2], ref.data(), 0);
+            nd_seqview sv = { words.data(), mask.data(), len };
+            std::vector<nd_u128> got;
+            int cl = 16 + (int)(rnd() % 300);
+            for (int cs = 0; cs < len; cs += cl) {
+                int ce = cs + cl < len ? cs + cl : len;
+                std::vector<nd_u128> tmp(cl + c[0] + 8);
+                int n = nd_sketch_chunk<16>(sv, c[0], c[1], c[2], 9, cs, ce, tmp.data(), (int)tmp.size());
+                got.insert(got.end(), tmp.begin(), tmp.begin() + std::min<int>(n, (int)tmp.size()));
+            }
+            bool ok = got.size() == n_ref;
+            for (size_t i = 0; ok && i < n_ref; ++i) ok = got[i].x == ref[i].x && got[i].y == ref[i].y;
+            if (!ok) { if (bad < 5) fprintf(stderr, "N selftest mismatch it=%d len=%d w=%d k=%d hpc=%d: %zu vs %zu\n", it, len, c[0], c[1], c[2], got.size(), n_ref); ++bad; }
+            ++tot;
+        }
+    }
+    printf("selftest_n cases=%ld bad=%ld\n", tot, bad);
+    return bad != 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc == 2 && !strcmp(argv[1], "selftest_n")) return selftest_n();
     if (argc < 3) { fprintf(stderr, "usage: hd_harness reads.2bit preset [max_reads] [chunk]\n"); return 2; }
     ndo_reads *R = ndo_read_2bit(argv[1]);
     if (!R) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }

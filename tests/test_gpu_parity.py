@@ -218,3 +218,98 @@ def test_sketch_adversarial_reads(eng, w, k, hpc):
         want = oracle.sketch(bytes(lut[s]), w, k, rid=3 + r, hpc=hpc)
         got = xy[int(off[r]):int(off[r + 1])]
         assert got.shape == want.shape and (got == want).all(), "read %d len %d" % (r, len(s))
+
+
+def _oracle_ovl(tmp_path, T, Q, preset, **kw):
+    import nextdenovo_b200 as nd
+    from oracle import oracle
+    pt, pq = str(tmp_path / "t.2bit"), str(tmp_path / "q.2bit")
+    nd.write_2bit(pt, T)
+    nd.write_2bit(pq, Q)
+    o = oracle.make_opt(preset, **kw)
+    out = str(tmp_path / "o.ovl")
+    oracle.step1_files(pt, pt if Q is T else pq, o, out)
+    return open(out, "rb").read()
+
+
+def test_edge_cases_vs_oracle(eng, engine_mod, tmp_path):
+    """ragged and degenerate inputs: reads shorter than k / than one window, a zero-length read, exact duplicates
+    (every anchor tied), a 300 kb read, low-complexity reads, queries without any hit -- byte-equal to the oracle"""
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200 import synth
+    from nextdenovo_b200.formats import pack_bases, make_reads, unpack_bases
+    rng = np.random.default_rng(77)
+    g = synth.genome(400000, 5)
+    base = synth.reads(g, 60, 20000, seed=5)
+    seqs = []
+    for r in range(base.n):
+        w0, w1 = int(base.word_off[r]), int(base.word_off[r + 1])
+        seqs.append(unpack_bases(base.words[w0:w1], 20000))
+    seqs += [seqs[3].copy(), seqs[3].copy(), seqs[10][:9000].copy()]              # duplicates and a contained read
+    seqs += [rng.integers(0, 4, n).astype(np.uint8) for n in (1, 5, 14, 15, 18, 19, 20, 33, 600)]   # too short / unrelated
+    seqs.append(np.zeros(0, dtype=np.uint8))                                         # empty read
+    seqs.append(np.concatenate([g[1000:151000], g[160000:310000]]).astype(np.uint8))  # 300 kb read spanning many others
+    seqs.append(np.zeros(5000, dtype=np.uint8)); seqs.append(np.tile(np.array([0, 1], np.uint8), 3000))
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    ids = list(range(100, 100 + len(seqs)))                                         # names "100".."1xx": strcmp order != numeric for mixed widths
+    ids[5], ids[7] = 9, 1000
+    reads = make_reads([pack_bases(s) if len(s) else np.zeros(0, np.uint32) for s in seqs], [len(s) for s in seqs], ids)
+    for preset, kw in (("ava-ont", {}), ("ava-pb", {}), ("ava-ont", dict(k=17, w=10))):
+        io, mo = _opts(preset, kw.get("k"), kw.get("w"))
+        for variant in ((1, 1), (0, 0)):
+            eng.set_variant(*variant)
+            ovl, st = engine_mod.run_step1(eng, reads, reads, io, mo)
+            want = _oracle_ovl(tmp_path, reads, reads, preset, **kw)
+            assert ovl == want, "%s %s %s: %s" % (preset, kw, variant, _diff_msg(ovl, want))
+            assert st["records"] > 50
+    eng.set_variant(1, 1)
+    # queries that hit nothing
+    lonely = make_reads([pack_bases(rng.integers(0, 4, 3000).astype(np.uint8)) for _ in range(4)], [3000] * 4, [5000, 5001, 5002, 5003])
+    io, mo = _opts("ava-ont")
+    ovl, st = engine_mod.run_step1(eng, reads, lonely, io, mo)
+    assert ovl == b"" and st["records"] == 0
+
+
+def test_fastx_input_with_ambiguous_bases(built, engine_mod, eng, reads_sub, tmp_path):
+    """FASTA.gz input (decimal names, N runs, lower case): the drop-in executable and the Python path both equal the
+    unmodified reference run on the same file (ambiguous bases reset the sketch window, ref: minimap2/sketch.c:112)."""
+    import gzip
+    import subprocess
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200.formats import unpack_bases
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref", "minimap2-nd")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(4)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    fa = str(tmp_path / "r.fa.gz")
+    with gzip.open(fa, "wb") as fh:
+        for r in range(70):
+            w0, w1 = int(reads_sub.word_off[r]), int(reads_sub.word_off[r + 1])
+            s = bytearray(lut[unpack_bases(reads_sub.words[w0:w1], int(reads_sub.length[r]))].tobytes())
+            for _ in range(int(rng.integers(0, 6))):
+                p, ln = int(rng.integers(0, len(s))), int(rng.integers(1, 30))
+                s[p:p + ln] = b"N" * len(s[p:p + ln])
+            if r % 3 == 0:
+                s = bytearray(bytes(s).lower())
+            fh.write(b">%d some comment\n" % int(reads_sub.ids[r]))
+            for i in range(0, len(s), 70):
+                fh.write(bytes(s[i:i + 70]) + b"\n")
+    want_p = str(tmp_path / "ref.ovl"); got_p = str(tmp_path / "gpu.ovl")
+    subprocess.run([ref, "--step", "1", "-t", "8", "-x", "ava-ont", fa, fa, "-o", want_p], check=True, capture_output=True)
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    r = subprocess.run([exe, "--step", "1", "-t", "8", "-x", "ava-ont", fa, fa, "-o", got_p], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = open(want_p, "rb").read()
+    assert len(want) > 10000 and open(got_p, "rb").read() == want
+    reads = nd.read_seqfile(fa)
+    assert reads.nmask is not None and reads.n == 70
+    io, mo = _opts("ava-ont")
+    ovl, st = engine_mod.run_step1(eng, reads, reads, io, mo)
+    assert ovl == want, _diff_msg(ovl, want)
+    # a name that is not a decimal integer is an error, not garbage ids
+    bad = str(tmp_path / "bad.fa")
+    open(bad, "wb").write(b">read_x\nACGTACGTACGT\n")
+    assert subprocess.run([exe, "--step", "1", "-x", "ava-ont", bad, bad, "-o", got_p], capture_output=True).returncode == 1

@@ -17,8 +17,14 @@ def harness(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("preset,n,chunk", [("ava-ont", 30, 61), ("ava-pb", 30, 47), ("k17w10", 40, 512)])
+@pytest.mark.parametrize("preset,n,chunk", [("ava-ont", 30, 61), ("ava-pb", 30, 47), ("k17w10", 40, 512), ("k16w7", 25, 100)])
 def test_hd_blocks_match_oracle(harness, golden_dir, preset, n, chunk):
     out = subprocess.run([harness, os.path.join(golden_dir, "sub120.2bit"), preset, str(n), str(chunk)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "bad_sketch=0 bad_sort=0 bad_hits=0" in out.stdout
+
+
+def test_ambiguous_bases_chunked_sketch(harness):
+    """1500 random sequences with N runs x 6 (w,k,hpc) settings: chunked state machine with the 1-bit mask == oracle"""
+    out = subprocess.run([harness, "selftest_n"], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr

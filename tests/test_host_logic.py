@@ -91,3 +91,27 @@ def test_index_parts_and_query_batches():
     assert index_parts(r, io) == [(0, 10)]
     assert query_batches(r, 100) == [(0, 4), (4, 8), (8, 10)]
     assert shard_bounds(10, 4) == [0, 2, 5, 7, 10]
+
+
+def test_fastx_reader_and_mask(tmp_path):
+    """FASTA / FASTQ(.gz) parsing, ambiguity mask layout (bit i&31 of nmask[word_off/2 + i>>5]), format sniffing"""
+    import gzip
+    from nextdenovo_b200.formats import unpack_bases
+    fa = tmp_path / "t.fa"
+    fa.write_bytes(b">3 c\nACGTNN\nacgu\n>4\n\n>5\n" + b"N" * 40 + b"\n" + b"ACGT" * 20 + b"\n")
+    a = nd.read_seqfile(str(fa))
+    assert a.n == 3 and list(a.length) == [10, 0, 120] and list(a.ids) == [3, 4, 5]
+    assert (a.word_off % 2 == 0).all()
+    assert int(a.nmask[0]) == 0b110000 and int(a.nmask[int(a.word_off[2]) // 2]) == 0xffffffff and int(a.nmask[int(a.word_off[2]) // 2 + 1]) == 0xff
+    assert list(unpack_bases(a.words[:2], 10)) == [0, 1, 2, 3, 0, 0, 0, 1, 2, 3]
+    fq = tmp_path / "t.fq.gz"
+    with gzip.open(str(fq), "wb") as f:
+        f.write(b"@7\nACGTN\n+\nIIII@\n@8 x\nGGG\n+\n@@@\n")
+    b = nd.read_seqfile(str(fq))
+    assert b.n == 2 and list(b.length) == [5, 3] and list(b.ids) == [7, 8]
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">chr1\nACGT\n")
+    with pytest.raises(ValueError):
+        nd.read_seqfile(str(bad))
+    s = a.slice(2, 3)
+    assert s.n == 1 and int(s.nmask[0]) == 0xffffffff

@@ -26,6 +26,7 @@
 // ------------------------------------------------------------------------------------------------
 #define NDW_RING 256
 #define NDW_CHAIN_WARPS 4
+#define NDW_GAP_TAB 2048
 
 struct ndw_ring {
     uint32_t x[NDW_RING];
@@ -33,13 +34,22 @@ struct ndw_ring {
 };
 
 __global__ void __launch_bounds__(NDW_CHAIN_WARPS * 32)
-k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chain_par par, int max_span,
+k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chain_par par, int max_span, int uniform_span,
                   nd_chain_bufs B, uint32_t *work)
 {
     __shared__ ndw_ring rings[NDW_CHAIN_WARPS];
+    __shared__ int16_t s_gap[NDW_GAP_TAB];
     const int lane = threadIdx.x & 31;
     ndw_ring &R = rings[threadIdx.x >> 5];
     const nd_u64 mdx = (nd_u64)par.max_dist_x;
+    // Without HPC every anchor spans exactly k bases, so the average span (chain.c:41-42) is the same float for
+    // every read and the gap cost (chain.c:72) depends on the diagonal distance only: tabulate it once per block.
+    const bool use_tab = uniform_span > 0 && par.bw < NDW_GAP_TAB;
+    if (use_tab) {
+        const float avg_u = __fdiv_rn(__ull2float_rn((nd_u64)uniform_span), __ll2float_rn(1LL));
+        for (int d = threadIdx.x; d <= par.bw; d += blockDim.x) s_gap[d] = (int16_t)nd_gap_cost(d, avg_u);
+    }
+    __syncthreads();
 
     for (;;) {
         uint32_t s = 0;
@@ -50,6 +60,7 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
         if (!nd_seg_bounds(S, s, par, max_span, &b, &n)) continue;
         const int r = nd_find_owner(S.a_off, Q.n_reads, b);
         const float avg = avg_qspan[r];
+        const bool tab_ok = use_tab && avg == (float)uniform_span;   // (float)sum/n can differ from k once sum >= 2^24
         const nd_u128 *a = S.a + b;
         int32_t *f = B.f + b, *p = B.p + b, *v = B.v + b, *t = B.t + b;
 
@@ -95,7 +106,7 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
                         if (d <= (nd_i64)par.bw) {
                             int32_t m = (nd_i64)dq < (nd_i64)dr ? dq : (int32_t)dr;
                             if (m > q_span) m = q_span;
-                            sc = m - nd_gap_cost((int)d, avg) + fj;
+                            sc = m - (tab_ok ? (int)s_gap[(int)d] : nd_gap_cost((int)d, avg)) + fj;
                             cand = true;
                         }
                     }
@@ -233,10 +244,15 @@ k_rs_level(ndw_sort_bufs W, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_r
         // 1. digits + histogram
         for (int d = lane; d < 256; d += 32) head[d] = 0;
         __syncwarp();
-        for (uint32_t i = lane; i < n; i += 32) {
-            uint32_t d = (uint32_t)(in[i].x >> s & 255);
-            dig[i] = (uint8_t)d; src_of[i] = i;
-            atomicAdd(&head[d], 1u);
+        for (uint32_t i0 = lane; i0 < n; i0 += 128) {               // 4 independent loads in flight per lane
+            nd_u64 xv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint32_t i = i0 + 32 * k; xv[k] = i < n ? in[i].x : 0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = i0 + 32 * k;
+                if (i < n) { const uint32_t d = (uint32_t)(xv[k] >> s & 255); dig[i] = (uint8_t)d; src_of[i] = i; atomicAdd(&head[d], 1u); }
+            }
         }
         __syncwarp();
         uint32_t c[8], sum = 0, nonempty = 0, dmin = 256, dmax = 0;
@@ -270,18 +286,30 @@ k_rs_level(ndw_sort_bufs W, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_r
         if (nonempty == 2) {
             const uint32_t d0 = dmin, d1 = dmax, n0 = tail[d0];
             uint32_t K = 0;
-            for (uint32_t b0 = 0; b0 < n0; b0 += 32) {                // m list
-                uint32_t i = b0 + lane; bool fl = i < n0 && dig[i] == d1;
-                unsigned m = __ballot_sync(NDW_FULL, fl);
-                if (fl) tmp[K + __popc(m & lt)] = i;
-                K += __popc(m);
+            for (uint32_t b0 = 0; b0 < n0; b0 += 128) {               // m list
+                uint32_t dg[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const uint32_t i = b0 + 32 * k + lane; dg[k] = i < n0 ? dig[i] : 256u; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t i = b0 + 32 * k + lane; const bool fl = dg[k] == d1;
+                    const unsigned m = __ballot_sync(NDW_FULL, fl);
+                    if (fl) tmp[K + __popc(m & lt)] = i;
+                    K += __popc(m);
+                }
             }
             uint32_t K1 = 0;
-            for (uint32_t b0 = n0; b0 < n; b0 += 32) {                // z list
-                uint32_t i = b0 + lane; bool fl = i < n && dig[i] == d0;
-                unsigned m = __ballot_sync(NDW_FULL, fl);
-                if (fl) tmp[n0 + K1 + __popc(m & lt)] = i;
-                K1 += __popc(m);
+            for (uint32_t b0 = n0; b0 < n; b0 += 128) {               // z list
+                uint32_t dg[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const uint32_t i = b0 + 32 * k + lane; dg[k] = i < n ? dig[i] : 256u; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t i = b0 + 32 * k + lane; const bool fl = dg[k] == d0;
+                    const unsigned m = __ballot_sync(NDW_FULL, fl);
+                    if (fl) tmp[n0 + K1 + __popc(m & lt)] = i;
+                    K1 += __popc(m);
+                }
             }
             __syncwarp();
             if (K) {
@@ -327,9 +355,14 @@ k_rs_level(ndw_sort_bufs W, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_r
         __threadfence_block();
 
         // 3. gather into the other buffer
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint4 vv = *reinterpret_cast<const uint4 *>(in + src_of[i]);
-            *reinterpret_cast<uint4 *>(out + i) = vv;
+        for (uint32_t i0 = lane; i0 < n; i0 += 128) {
+            uint32_t sidx[4]; uint4 vv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint32_t i = i0 + 32 * k; sidx[k] = i < n ? src_of[i] : 0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vv[k] = *reinterpret_cast<const uint4 *>(in + sidx[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint32_t i = i0 + 32 * k; if (i < n) *reinterpret_cast<uint4 *>(out + i) = vv[k]; }
         }
         __syncwarp();
 
@@ -374,11 +407,11 @@ static inline void ndw_sort_launch(cudaStream_t st, ndw_sort_bufs W, const nd_u6
 }
 
 static inline void ndw_chain_fill_launch(cudaStream_t st, nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chain_par par,
-                                         int max_span, nd_chain_bufs B, uint32_t *work_counter, int n_sm)
+                                         int max_span, int uniform_span, nd_chain_bufs B, uint32_t *work_counter, int n_sm)
 {
     cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
     unsigned blocks = (unsigned)(n_sm * 8);
     unsigned need = (S.n_seg + NDW_CHAIN_WARPS - 1) / NDW_CHAIN_WARPS;
     if (need < blocks) blocks = need ? need : 1;
-    k_chain_fill_warp<<<blocks, NDW_CHAIN_WARPS * 32, 0, st>>>(S, Q, avg_qspan, par, max_span, B, work_counter);
+    k_chain_fill_warp<<<blocks, NDW_CHAIN_WARPS * 32, 0, st>>>(S, Q, avg_qspan, par, max_span, uniform_span, B, work_counter);
 }

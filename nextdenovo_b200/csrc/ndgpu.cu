@@ -26,7 +26,7 @@ struct DevBuf {
         if (bytes <= cap) return 0;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 2 + 256;      // generous slack: regrowth (cudaFree + cudaMalloc) stalls the stream for ~100 ms
         if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; } want = bytes; }
         cap = want;
         return 0;
@@ -623,7 +623,7 @@ int map_resident(ndg_ctx *c, int qidx_base)
     if (c->chain_variant == 0) {
         KLAUNCH("chain_fill_seq", (k_chain_fill_seq<<<nblk(c->n_seg, 64), 64, 0, c->st>>>(SV, V, c->avgq.as<float>(), par, max_span, B)));
     } else {
-        KLAUNCH("chain_fill_warp", ndw_chain_fill_launch(c->st, SV, V, c->avgq.as<float>(), par, max_span, B, c->scalars.as<uint32_t>() + 48, c->n_sm));
+        KLAUNCH("chain_fill_warp", ndw_chain_fill_launch(c->st, SV, V, c->avgq.as<float>(), par, max_span, o.hpc ? 0 : o.k, B, c->scalars.as<uint32_t>() + 48, c->n_sm));
     }
     CK(cudaGetLastError());
     KLAUNCH("chain_backtrack", (k_chain_backtrack<<<nblk(c->n_seg, 64), 64, 0, c->st>>>(SV, V, par, max_span, o.seed, B, c->hits.as<nd_hit>(), hit_cap, d_nh)));

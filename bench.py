@@ -238,6 +238,8 @@ def main_ours(a, rank, world, local_rank):
     import nextdenovo_b200 as nd
     from nextdenovo_b200 import engine
     dist = None
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)                                       # NCCL / torchrun banners go to stderr; stdout carries the JSON line only
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -269,13 +271,15 @@ def main_ours(a, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     t_index = time.time() - t0
 
-    # ---- query batches: rank r takes batches r, r+world, ... (no data-path collective)
+    # ---- query shards (no data-path collective).  Weak scaling needs every rank to do statistically identical
+    # work; with MM_F_NO_DUAL the number of records a read yields depends on where its *name* sorts (strcmp on
+    # decimal strings), so contiguous id ranges are not comparable.  Each rank therefore maps its own copy of the
+    # same K batches (rank r starts r batches further into the list, so ranks never work on the same batch at the
+    # same time).
     nb = a.warmup + a.steps
     B = a.batch_reads
-    batches = []
-    for i in range(nb):
-        q0 = ((i * world + rank) * B) % max(reads.n - B, 1)
-        batches.append(reads.slice(q0, q0 + B))
+    base_batches = [reads.slice((i * B) % max(reads.n - B, 1), (i * B) % max(reads.n - B, 1) + B) for i in range(nb)]
+    batches = base_batches[:a.warmup] + [base_batches[a.warmup + (i + rank) % a.steps] for i in range(a.steps)]
 
     def barrier():
         if dist is not None:
@@ -290,6 +294,7 @@ def main_ours(a, rank, world, local_rank):
     barrier()
     clk = ClockSampler(dev); clk.start()
     t_res = 0.0
+    t_dev_ms = 0.0
     rec = sq = n_mz = n_a = n_hits = 0
     state = np.zeros(2, dtype=np.uint32)
     for i in range(a.warmup, nb):
@@ -299,7 +304,7 @@ def main_ours(a, rank, world, local_rank):
         r = eng.map_resident()                          # all kernels of the step; internally event-timed per kernel
         torch.cuda.synchronize(dev)
         t_res += time.perf_counter() - e0
-        n_mz += r["n_minimizers"]; n_a += r["n_anchors"]; n_hits += r["n_hits"]
+        n_mz += r["n_minimizers"]; n_a += r["n_anchors"]; n_hits += r["n_hits"]; t_dev_ms += r["device_ms"]
         hits, _ = eng.map_download()
         out = bytearray()
         rr, ss = eng.emit_step1(hits, batches[i], state, out)
@@ -338,7 +343,7 @@ def main_ours(a, rank, world, local_rank):
     barrier()
 
     # ---- reduce over ranks: total units / max time
-    t_res_dev = dev_ms / 1e3
+    t_res_dev = t_dev_ms / 1e3                      # one CUDA-event pair around each step on the launching stream (gaps included)
     if dist is not None:
         tt = torch.tensor([t_res_dev, t_e2e, t_res], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -347,6 +352,8 @@ def main_ours(a, rank, world, local_rank):
         t_res_dev, t_e2e, t_res = [float(x) for x in tt.tolist()]
         rec, sq, rec_e, launches = [int(x) for x in cc.tolist()]
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         # dominant kernel + roofline (algorithmic bytes: DESIGN.md "Kernels and rooflines")
         top = max(prof.items(), key=lambda kv: kv[1][0])
@@ -387,8 +394,10 @@ def main_ours(a, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps},
+                         "traffic": None, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps,
+                         "note": "integer DP / hashing kernels: issue- and latency-bound, not HBM-bound (ncu: profiles/r01_summary.md)"},
             "cpu_baseline": cpu,
+            "kernel_sum_ms_per_step": dev_ms / a.steps,
             "work": {"records": rec, "sum_qspan": sq, "minimizers": n_mz, "anchors": n_a, "hits": n_hits, "host_wall_resident_s": t_res},
             "kernels_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "index": {"build_s": t_index, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"]},

@@ -80,6 +80,7 @@ typedef struct {
     const ndg_hit_t *hits;      /* pinned host memory owned by the context; sorted by qidx, then in the
                                    reference's per-query output order; valid until the next map call */
     uint64_t n_minimizers, n_anchors, n_segments;   /* work counters of this call */
+    double device_ms;           /* CUDA-event time from the first to the last kernel of the call (ndg_map_resident) */
 } ndg_map_result_t;
 
 typedef struct {

@@ -752,10 +752,15 @@ extern "C" int ndg_map_resident(ndg_ctx_t *c, ndg_map_result_t *out)
 {
     if (!c) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
+    cudaEvent_t e0 = ev_get(c), e1 = ev_get(c);
+    CK(cudaEventRecord(e0, c->st));
     int rc = map_resident(c, 0);
     if (rc) return rc;
+    CK(cudaEventRecord(e1, c->st));
     CK(cudaStreamSynchronize(c->st));
-    if (out) { out->n_hits = (int64_t)c->n_hits; out->hits = nullptr; out->n_minimizers = c->n_mz; out->n_anchors = c->n_a; out->n_segments = c->n_seg; }
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    c->ev_pool.push_back(e0); c->ev_pool.push_back(e1);
+    if (out) { out->n_hits = (int64_t)c->n_hits; out->hits = nullptr; out->n_minimizers = c->n_mz; out->n_anchors = c->n_a; out->n_segments = c->n_seg; out->device_ms = ms; }
     return NDG_OK;
 }
 

@@ -38,7 +38,7 @@ class _Reads(C.Structure):
 
 class _MapResult(C.Structure):
     _fields_ = [("n_hits", C.c_int64), ("hits", C.c_void_p),
-                ("n_minimizers", C.c_uint64), ("n_anchors", C.c_uint64), ("n_segments", C.c_uint64)]
+                ("n_minimizers", C.c_uint64), ("n_anchors", C.c_uint64), ("n_segments", C.c_uint64), ("device_ms", C.c_double)]
 
 
 class _IndexStat(C.Structure):
@@ -251,7 +251,7 @@ class Engine:
     def map_resident(self):
         res = _MapResult()
         self._ck(self.L.ndg_map_resident(self.h, C.byref(res)))
-        return dict(n_hits=res.n_hits, n_minimizers=res.n_minimizers, n_anchors=res.n_anchors, n_segments=res.n_segments)
+        return dict(n_hits=res.n_hits, n_minimizers=res.n_minimizers, n_anchors=res.n_anchors, n_segments=res.n_segments, device_ms=res.device_ms)
 
     def map_download(self):
         res = _MapResult()

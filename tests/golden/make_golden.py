@@ -8,6 +8,9 @@ oracle/_ref: `make -C oracle`).  Run from the repo root.  Committed outputs:
   G3_ava-pb.ovl             minimap2-nd --step 1 -x ava-pb               T T   (md5 7fb430f9...)
   sub120.2bit               first 120 reads of reads_test.seed.2bit
   S1_sub120_ava-ont.ovl, S3_sub120_ava-pb.ovl, S5_sub120_dual.ovl (sub120 x full with --dual=yes -I 20M: 2 index parts)
+  S6_sub120_ava-ont_c.ovl, S7_sub120_ava-pb_c.ovl   the same inputs with -c (base-level alignment, regime B)
+  S8_sub30_ava-ont_c.ovl    first 30 reads of sub120, -c -x ava-ont (CPU-sized case for the host alignment logic)
+  G4_ava-ont_c.ovl          minimap2-nd --step 1 -c -x ava-ont T T (md5 4c7e8525..., ~6 min on 8 threads)
 """
 import os, subprocess, sys, tempfile, hashlib
 sys.path.insert(0, os.getcwd())
@@ -39,6 +42,13 @@ def main():
     run(["-x", "ava-ont", S, S], G + "/S1_sub120_ava-ont.ovl")
     run(["-x", "ava-pb", S, S], G + "/S3_sub120_ava-pb.ovl")
     run(["--dual=yes", "-I", "20M", "-x", "ava-ont", T, S], G + "/S5_sub120_dual.ovl")
+    run(["-c", "-x", "ava-ont", S, S], G + "/S6_sub120_ava-ont_c.ovl")
+    run(["-c", "-x", "ava-pb", S, S], G + "/S7_sub120_ava-pb_c.ovl")
+    with tempfile.TemporaryDirectory() as td:
+        nd.write_2bit(td + "/sub30.2bit", nd.read_2bit(S, max_reads=30))
+        run(["-c", "-x", "ava-ont", td + "/sub30.2bit", td + "/sub30.2bit"], G + "/S8_sub30_ava-ont_c.ovl")
+    if "--full" in sys.argv:
+        run(["-c", "-x", "ava-ont", T, T], G + "/G4_ava-ont_c.ovl")
 
 
 if __name__ == "__main__":

@@ -101,6 +101,26 @@ int  ndg_set_variant(ndg_ctx_t *ctx, int sort_variant, int chain_variant);
 /* ksw_extd2 kernel generation: 0 = one cell per lane, 1 = two cells per lane in s16x2 (DPX) registers */
 int  ndg_set_ksw_variant(ndg_ctx_t *ctx, int variant);
 
+/* ---- regime B: base-level alignment of every chain (`-c`, MM_F_CIGAR) ---------------------------
+ * Replaces align_regs() -> mm_align_skeleton() (ref: minimap2/map.c:484-505, minimap2/align.c:857-913):
+ * once enabled, ndg_map_batch / ndg_map_batch_ovl return hits whose qs/qe/rs/re/mlen/blen are the
+ * ones of the gapped alignment (mm_update_extra, align.c:240-286), filtered by mm_filter_regs and ordered
+ * by mm_hit_sort (dp_max, ref: hit.c:169-201,257-276); ndg_hit_t.score then carries dp_max.
+ * The DP runs on the GPU (ksw_extd2 kernel, one launch per round of calls); which calls to make and the
+ * CIGAR stitching is host code (csrc/nd_align.hpp).  Must be set before ndg_index_add(): the library keeps a
+ * host copy of the 2-bit target reads (what mm_idx_t::S is for, ref: minimap2/index.c:152-162).
+ * Fields follow mm_mapopt_t (ref: minimap2/options.c:37-44): a,b match/mismatch; q,e,q2,e2 gap costs;
+ * sc_ambi; zdrop, zdrop_inv; end_bonus; min_dp_max; min_ksw_len; max_clip_ratio; no_end_flt = MM_F_NO_END_FLT.
+ * Requires q+e < q2+e2 or different (q,e)/(q2,e2) (the dual-affine kernel; q==q2&&e==e2 is rejected). */
+typedef struct {
+    int32_t a, b, q, e, q2, e2, sc_ambi, zdrop, zdrop_inv, end_bonus, min_dp_max, min_ksw_len, no_end_flt;
+    float max_clip_ratio;
+} ndg_aln_opt_t;
+int  ndg_set_aln_opt(ndg_ctx_t *ctx, const ndg_aln_opt_t *opt);      /* NULL switches regime B off */
+/* counters of the alignment stage since the last ndg_prof_reset(): chains, DP calls, GPU rounds/launches, sum(qlen*tlen), kernel ms */
+typedef struct { uint64_t n_chains, n_calls, n_rounds, n_launches, n_retries, rect_cells; double dp_ms, host_ms; } ndg_aln_stat_t;
+int  ndg_aln_stats(ndg_ctx_t *ctx, ndg_aln_stat_t *out);
+
 /* page-locked host memory for batch inputs (optional; lets the H2D copy run at full PCIe speed) */
 void *ndg_host_alloc(uint64_t bytes);
 void  ndg_host_free(void *p);

@@ -141,11 +141,13 @@ int main(int argc, char **argv)
     int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0;
     uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
     const char *out = nullptr; std::vector<const char *> pos;
-    bool cigar = false;
+    bool cigar = false, unsupported_out = false;
+    ndg_aln_opt_t ao = { 2, 4, 4, 2, 24, 1, 1, 400, 200, -1, 80, 200, 0, 1.0f };   // minimap2/options.c:37-44
     const double t0 = now();
     auto takes = [](const std::string &a) {
         static const char *t[] = { "-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen", "--maxhan1", "--maxhan2",
-                                   "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v", "--device", "-N", "-p", "-M", "-z", "-A", "-B", "-O", "-E", "-s" };
+                                   "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v", "--device", "-N", "-p", "-M", "-z", "-A", "-B", "-O", "-E", "-s",
+                                   "--min-dp-score", "--end-bonus", "--max-clip-ratio" };
         for (auto x : t) if (a == x) return true;
         return false;
     };
@@ -176,7 +178,15 @@ int main(int argc, char **argv)
         else if (k == "-n") o.min_cnt = atoi(v); else if (k == "-m") o.min_chain_score = atoi(v);
         else if (k == "-I") batch_size = (uint64_t)parse_num(v); else if (k == "-K") q_batch = parse_num(v);
         else if (k == "-D") o.flag_no_diag = 1; else if (k == "-X") o.flag_no_diag = o.flag_no_dual = 1;
-        else if (k == "-c" || k == "-a" || k == "--cs" || k == "-S") cigar = true;
+        else if (k == "-c") cigar = true;
+        else if (k == "-a" || k == "--cs" || k == "-S" || k == "--MD") unsupported_out = true;
+        else if (k == "-A") ao.a = atoi(v); else if (k == "-B") ao.b = atoi(v);
+        else if (k == "-s" || k == "--min-dp-score") ao.min_dp_max = atoi(v);
+        else if (k == "--end-bonus") ao.end_bonus = atoi(v); else if (k == "--max-clip-ratio") ao.max_clip_ratio = (float)atof(v);
+        else if (k == "--no-end-flt") ao.no_end_flt = 1;
+        else if (k == "-z") { char *e; ao.zdrop = ao.zdrop_inv = (int)strtol(v, &e, 10); if (*e == ',') ao.zdrop_inv = (int)strtol(e + 1, &e, 10); }
+        else if (k == "-O") { char *e; ao.q = ao.q2 = (int)strtol(v, &e, 10); if (*e == ',') ao.q2 = (int)strtol(e + 1, &e, 10); }
+        else if (k == "-E") { char *e; ao.e = ao.e2 = (int)strtol(v, &e, 10); if (*e == ',') ao.e2 = (int)strtol(e + 1, &e, 10); }
         else if (k == "--minlen") minlen = (int)parse_num(v); else if (k == "--maxhan1") maxhan1 = (int)parse_num(v);
         else if (k == "--maxhan2") maxhan2 = (int)parse_num(v); else if (k == "--dvt") dvt = 1;
         else if (k == "--seed") o.seed = atoi(v); else if (k == "--max-chain-skip") o.max_chain_skip = atoi(v);
@@ -191,9 +201,15 @@ int main(int argc, char **argv)
         fprintf(stderr, "Usage: minimap2-nd --step 1 [options] <target.2bit> <query.2bit> -o out.ovl\n");
         return 1;
     }
-    if (step != 1 || cigar || !out) {
-        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 ... -o FILE` without base-level alignment only\n");
+    if (step != 1 || unsupported_out || !out) {
+        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` (.ovl output) only\n");
         return 1;
+    }
+    if (cigar) {                                                // mm_check_opt, minimap2/options.c:190-213
+        if (ao.q <= 0 || ao.q2 <= 0 || ao.e <= 0 || ao.e2 <= 0) { fprintf(stderr, "[ERROR]\033[1;31m -O and -E must be positive\033[0m\n"); return 1; }
+        if ((ao.q != ao.q2 || ao.e != ao.e2) && !(ao.e > ao.e2 && ao.q + ao.e < ao.q2 + ao.e2)) { fprintf(stderr, "[ERROR]\033[1;31m dual gap penalties violating E1>E2 and O1+E1<O2+E2\033[0m\n"); return 1; }
+        if ((ao.q + ao.e) + (ao.q2 + ao.e2) > 127) { fprintf(stderr, "[ERROR]\033[1;31m scoring system violating ({-O}+{-E})+({-O2}+{-E2}) <= 127\033[0m\n"); return 1; }
+        if (ao.zdrop < ao.zdrop_inv) { fprintf(stderr, "[ERROR]\033[1;31m Z-drop should not be less than inversion-Z-drop\033[0m\n"); return 1; }
     }
     FILE *fo = fopen(out, "wb");                                // main.c:259-262 (freopen)
     if (!fo) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", out); return 1; }
@@ -203,6 +219,7 @@ int main(int argc, char **argv)
     ndg_ctx_t *g = nullptr;
     if (ndg_init(device, &g) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device); return 1; }
     ndg_set_opt(g, &o);
+    if (cigar && ndg_set_aln_opt(g, &ao)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
 
     uint32_t state[2] = { 0, 0 };
     uint64_t n_rec = 0, sum_qspan = 0;
@@ -245,6 +262,11 @@ int main(int argc, char **argv)
         }
     }
     if (fclose(fo) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+    if (verbose >= 3 && cigar) {
+        ndg_aln_stat_t as; ndg_aln_stats(g, &as);
+        fprintf(stderr, "[M::align] chains %llu; DP calls %llu in %llu rounds / %llu launches (%llu retried); DP kernels %.3f s; alignment stage %.3f s\n", (unsigned long long)as.n_chains,
+                (unsigned long long)as.n_calls, (unsigned long long)as.n_rounds, (unsigned long long)as.n_launches, (unsigned long long)as.n_retries, as.dp_ms / 1e3, as.host_ms / 1e3);
+    }
     if (verbose >= 3) {
         fprintf(stderr, "[M::main] Version: 2.17-r941-ndgpu (%s)\n[M::main] CMD:", ndg_version());
         for (int i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);

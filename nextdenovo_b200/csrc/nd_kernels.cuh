@@ -413,6 +413,31 @@ k_chain_backtrack(nd_seg_view S, nd_reads_dev Q, nd_chain_par par, int max_span,
                            });
 }
 
+// regime B hand-over: the anchors of every kept chain in chain order (what mm_chain_dp returns in b[],
+// ref: minimap2/chain.c:135-141) and the chain's peak score f[j_end] (its backtracking priority, :104).
+// One thread per hit; p[] is relative to the start of the segment the chain lives in.
+__global__ void k_hit_cnt(const nd_hit *hits, nd_u64 n, uint32_t *cnt)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = (uint32_t)hits[i].cnt;
+    if (i == n) cnt[i] = 0;
+}
+__global__ void k_chain_collect(const nd_hit *hits, nd_u64 n_hits, int qidx_base, const nd_u64 *a_off, const uint32_t *seg_start, uint32_t n_seg,
+                                const nd_u128 *a, const int32_t *p, const int32_t *f, const nd_u64 *dst_off, nd_u128 *out, int32_t *fend)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits) return;
+    const nd_hit h = hits[i];
+    const nd_u64 g = a_off[h.qidx - qidx_base] + (nd_u64)h.as;
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) { uint32_t mid = lo + (hi - lo) / 2; if ((nd_u64)seg_start[mid] <= g) lo = mid; else hi = mid; }
+    const nd_u64 b = seg_start[lo];
+    fend[i] = f[g];
+    int j = (int)(g - b);
+    nd_u128 *dst = out + dst_off[i];
+    for (int k = h.cnt - 1; k >= 0; --k) { dst[k] = a[b + j]; j = p[b + j]; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // hit ordering helpers
 // ------------------------------------------------------------------------------------------------

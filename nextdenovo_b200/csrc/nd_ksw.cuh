@@ -47,7 +47,9 @@ __device__ __forceinline__ bool ndk_zdrop(ndk_res &ez, int H, int r, int t, int 
 }
 
 // ref: ksw2.h:119-152, is_rot = 1, min_intron_len = 0 (lane 0)
-__device__ int ndk_backtrack(bool is_rev, const uint8_t *p, const int *off, const int *off_end, int n_col, int i0, int j0, uint32_t *cigar)
+// rowtab != 0: the backtrack matrix lives in 64-row chunks, rowtab[r >> 6] = byte offset of the chunk from p
+__device__ int ndk_backtrack(bool is_rev, const uint8_t *p, const int *off, const int *off_end, int n_col, int i0, int j0, uint32_t *cigar,
+                             const unsigned long long *rowtab = nullptr)
 {
     int n = 0, i = i0, j = j0, state = 0;
     while (i >= 0 && j >= 0) {
@@ -55,7 +57,7 @@ __device__ int ndk_backtrack(bool is_rev, const uint8_t *p, const int *off, cons
         int o = off[r];
         if (i < o) force = 2;
         if (i > off_end[r]) force = 1;
-        uint32_t tmp = force < 0 ? p[(size_t)r * n_col + i - o] : 0;
+        uint32_t tmp = force < 0 ? (rowtab ? p[rowtab[r >> 6] + (size_t)(r & 63) * n_col + i - o] : p[(size_t)r * n_col + i - o]) : 0;
         if (state == 0) state = tmp & 7;
         else if (!(tmp >> (state + 2) & 1)) state = 0;
         if (state == 0) state = tmp & 7;
@@ -318,6 +320,7 @@ k_ksw_extd2(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, 
 }
 
 
+
 // ------------------------------------------------------------------------------------------------
 // Packed generation: two adjacent target cells per lane in s16x2 registers, DPX integer SIMD
 // (VIADD.16x2, VIMNMX.S16x2 with predicate outputs, VIMNMX3.S16x2 on sm_100a).  64 cells per warp step.
@@ -368,13 +371,17 @@ __device__ __forceinline__ void ndk_pair(unsigned xt1, unsigned vt1, unsigned x2
 
 __global__ void __launch_bounds__(NDK_WARPS * 32)
 k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
-               uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work)
+               uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work,
+               unsigned long long *arena_cur = nullptr, unsigned long long arena_bytes = 0, size_t off_bytes = 0)
 {
+    // arena_cur != 0: backtrack rows are carved from pmat[0, arena_bytes) on demand, 64 rows at a time (a z-dropped
+    // extension touches a fraction of its worst-case matrix); a call that finds the arena full reports pad = 1 (retry)
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * NDK_WARPS + (threadIdx.x >> 5);
     uint8_t *base = scratch + (size_t)slot * slot_bytes;
     int32_t *H = reinterpret_cast<int32_t *>(base + state_bytes);
     int *off = reinterpret_cast<int *>(base + state_bytes + h_bytes);
+    unsigned long long *rowtab = arena_cur ? reinterpret_cast<unsigned long long *>(base + state_bytes + h_bytes + off_bytes) : nullptr;
 
     for (;;) {
         int ci = 0;
@@ -414,9 +421,11 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
         int16_t *h16 = reinterpret_cast<int16_t *>(base);
         uint8_t *sf = base + (size_t)16 * T, *qr = sf + T;
         int *off_end = off + qlen + tlen - 1;
-        uint8_t *p = pmat + c.p_off;
+        uint8_t *p = rowtab ? pmat : pmat + c.p_off;
         uint32_t *cigar = cigars + c.cigar_off;
         const unsigned Q = ndk_pk(q, q), Q2 = ndk_pk(q2, q2), NQE = ndk_pk(-qe, -qe), NQE2 = ndk_pk(-qe2, -qe2), SCM = ndk_pk(sc_mch, sc_mch);
+        bool arena_full = false;
+        uint8_t *chunk = nullptr;
 
         if (run) {
             const int qpad = ((qlen + 15) / 16 + 1) * 16 + 32;
@@ -457,8 +466,15 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
                 const int sc_end = st0 + (en0 - st0 + 16) / 16 * 16;
                 const bool generic = (flag & NDK_GENERIC_SC) != 0;
                 const int sc_hi = generic ? en0 + 1 : sc_end;           // scores rewritten on [st0, sc_hi)
+                if (rowtab && with_cigar && (r & 63) == 0) {
+                    unsigned long long o = 0;
+                    if (lane == 0) { o = atomicAdd(arena_cur, 64ull * (unsigned long long)n_col); rowtab[r >> 6] = o; }
+                    o = __shfl_sync(NDK_FULL, o, 0);
+                    if (o + 64ull * (unsigned long long)n_col > arena_bytes) { arena_full = true; break; }
+                    chunk = pmat + o;
+                }
                 {
-                    uint8_t *pr = p + (size_t)r * n_col - st;
+                    uint8_t *pr = (rowtab ? chunk + (size_t)(r & 63) * n_col : p + (size_t)r * n_col) - st;
                     for (int t0 = st; t0 <= en; t0 += 64) {
                         const int t = t0 + 2 * lane;
                         const bool act = t <= en;
@@ -556,18 +572,34 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
                 last_st = st; last_en = en;
             }
             __syncwarp();
-            if (with_cigar && lane == 0) {
+            if (arena_full) ez.pad = 1;
+            else if (with_cigar && lane == 0) {
                 const bool rev = (flag & NDK_REV_CIGAR) != 0;
                 if (!ez.zdropped && !(flag & NDK_EXTZ_ONLY))
-                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, tlen - 1, qlen - 1, cigar);
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, tlen - 1, qlen - 1, cigar, rowtab);
                 else if (!ez.zdropped && (flag & NDK_EXTZ_ONLY) && ez.mqe + c.end_bonus > ez.max) {
                     ez.reach_end = 1;
-                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.mqe_t, qlen - 1, cigar);
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.mqe_t, qlen - 1, cigar, rowtab);
                 } else if (ez.max_t >= 0 && ez.max_q >= 0)
-                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.max_t, ez.max_q, cigar);
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.max_t, ez.max_q, cigar, rowtab);
             }
         }
         if (lane == 0) res[ci] = ez;
         __syncwarp();
     }
+}
+
+// ---- compact CIGAR hand-back: per-call capacity buffers -> one dense array ---------------------------------
+__global__ void k_ksw_ncigar(const ndk_res *res, int n, uint32_t *ncig)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ncig[i] = (uint32_t)res[i].n_cigar;
+    if (i == n) ncig[i] = 0;
+}
+__global__ void k_ksw_cigar_gather(const ndk_call *calls, const ndk_res *res, const unsigned long long *dst_off, int n, const uint32_t *cigars, uint32_t *out)
+{
+    const int i = (int)((blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint32_t *src = cigars + calls[i].cigar_off; uint32_t *dst = out + dst_off[i];
+    for (int k = lane; k < res[i].n_cigar; k += 32) dst[k] = src[k];
 }

@@ -13,6 +13,8 @@
 #include "nd_kernels.cuh"
 #include "nd_warp.cuh"
 #include "nd_ksw.cuh"
+#include "nd_align.hpp"
+#include <omp.h>
 
 static_assert(sizeof(nd_hit) == sizeof(ndg_hit_t), "hit layout");
 static_assert(sizeof(nd_hit) == 56, "hit size");
@@ -106,6 +108,13 @@ struct ndg_ctx {
     int overflow_flag = 0;
     // upload staging
     HostBuf up;
+    // regime B (base-level alignment)
+    bool aln_on = false; ndal::Opt aln; ndg_aln_stat_t aln_stat = {};
+    std::vector<uint32_t> ht_words, ht_nmask; std::vector<uint64_t> ht_word_off; bool ht_has_n = false;
+    std::vector<ndg_hit_t> aln_hits;
+    DevBuf ksw_ncig, ksw_coff, ksw_cout, ch_cnt, ch_off, ch_a, ch_fend;
+    HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
+    uint64_t arena_want = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -294,10 +303,12 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
-                       &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars };
+                       &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
+                       &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend };
     for (auto b : bufs) b->release();
     c->q.release();
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
+    c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release();
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -344,6 +355,7 @@ extern "C" int ndg_prof_reset(ndg_ctx_t *c)
     if (!c) return NDG_ERR_ARG;
     prof_flush(c);
     for (auto &e : c->prof) { e.ms = 0; e.launches = 0; }
+    c->aln_stat = ndg_aln_stat_t();
     return NDG_OK;
 }
 
@@ -356,6 +368,7 @@ extern "C" int ndg_index_begin(ndg_ctx_t *c)
     cudaSetDevice(c->device);
     c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->t_has_id = true;
     c->index_ready = false; c->n_pos = 0;
+    c->ht_words.clear(); c->ht_nmask.clear(); c->ht_word_off.clear(); c->ht_has_n = false;
     return NDG_OK;
 }
 
@@ -392,6 +405,17 @@ extern "C" int ndg_index_add(ndg_ctx_t *c, const ndg_reads_t *T)
         if (int rc = sketch_reads(c, c->q, rid0 + r0, 1, c->tmz, c->n_tmz, true, nullptr, &n)) return rc;
         c->n_tmz += n;
         r0 = r1;
+    }
+    if (c->aln_on) {                    // regime B reads target bases on the host (ref: mm_idx_getseq, minimap2/index.c:152-162)
+        const uint64_t wb = T->word_off[0], nw = T->word_off[T->n_reads] - wb, w0 = c->ht_words.size();   // offsets may be absolute into a larger array
+        if (T->nmask && !c->ht_has_n) { c->ht_nmask.assign(w0 / 2, 0); c->ht_has_n = true; }
+        c->ht_words.insert(c->ht_words.end(), T->words + wb, T->words + wb + nw);
+        if (c->ht_words.size() & 1) c->ht_words.push_back(0);
+        if (c->ht_has_n) {
+            c->ht_nmask.resize(c->ht_words.size() / 2 + 1, 0);
+            if (T->nmask) memcpy(c->ht_nmask.data() + w0 / 2, T->nmask + wb / 2, (size_t)((nw + 1) / 2) * 4);
+        }
+        for (int i = 0; i < T->n_reads; ++i) c->ht_word_off.push_back(w0 + T->word_off[i] - wb);
     }
     return index_meta(c, T);
 }
@@ -708,12 +732,28 @@ int emit_resident(ndg_ctx *c, int qidx_base, const ndg_emit_opt_t *eo, uint32_t 
 }
 } // namespace
 
+namespace { int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1); }
+
 extern "C" int ndg_map_batch_ovl(ndg_ctx_t *c, const ndg_reads_t *Q, const ndg_emit_opt_t *eo, uint32_t state[2],
                                  const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work)
 {
     if (!c || !Q || !eo || !state || !ovl || !n_bytes || Q->n_reads <= 0) return NDG_ERR_ARG;
     if (!Q->name_id || !c->t_has_id) return fail(c, NDG_ERR_ARG, "ndg_map_batch_ovl needs name_id for targets and queries");
     cudaSetDevice(c->device);
+    if (c->aln_on) {                    // regime B: the aligned hits are on the host already; filter + encode there
+        ndg_map_result_t R;
+        if (int rc = ndg_map_batch(c, Q, &R)) return rc;
+        if (c->h_ovl.reserve((size_t)R.n_hits * 48 + 64)) return fail(c, NDG_ERR_NOMEM, "pinned .ovl buffer");
+        uint64_t rec = 0, sq = 0;
+        const int64_t nb = ndg_ovl_emit_step1(R.hits, R.n_hits, Q->name_id, Q->name_key, Q->len, c->h_tid.data(), c->h_tkey.data(), c->h_tlen.data(),
+                                              eo->minlen, eo->dvt, eo->maxhan1, eo->maxhan2, state, c->h_ovl.as<uint8_t>(), c->h_ovl.cap, &rec, &sq);
+        if (nb < 0) return fail(c, NDG_ERR_OVERFLOW, "ovl buffer");
+        *ovl = c->h_ovl.as<uint8_t>(); *n_bytes = (uint64_t)nb;
+        if (n_rec) *n_rec += rec;
+        if (sum_qspan) *sum_qspan += sq;
+        if (work) { *work = R; work->hits = nullptr; }
+        return NDG_OK;
+    }
     RSV(c->scalars, 1024);
     uint32_t *d_state = c->scalars.as<uint32_t>() + 168;
     CK(cudaMemcpyAsync(d_state, state, 8, cudaMemcpyHostToDevice, c->st));
@@ -780,6 +820,10 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
 {
     if (!c || !Q || !out || Q->n_reads <= 0) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
+    if (c->aln_on) {
+        if (c->ht_word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "regime B needs ndg_set_aln_opt() before ndg_index_add() (target bases are kept on the host)");
+        c->aln_hits.clear();
+    }
     uint64_t tot_hits = 0, tot_mz = 0, tot_a = 0, tot_seg = 0;
     int r0 = 0;
     uint64_t budget = c->sub_batch_bases;
@@ -790,6 +834,12 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
         int rc = map_resident(c, r0);
         if (rc == NDG_ERR_OVERFLOW && r1 - r0 > 1 && c->err.find("anchors") != std::string::npos) { budget = std::max<uint64_t>(bases / 2, 1); continue; }
         if (rc) return rc;
+        if (c->aln_on) {
+            if (int rc2 = align_resident(c, Q, r0, r1)) return rc2;
+            tot_mz += c->n_mz; tot_a += c->n_a; tot_seg += c->n_seg;
+            r0 = r1;
+            continue;
+        }
         if (c->h_hits.cap < (tot_hits + c->n_hits + 1) * sizeof(nd_hit)) {       // grow, preserving content
             HostBuf nb; if (nb.reserve((tot_hits + c->n_hits + 1) * sizeof(nd_hit) * 2)) return fail(c, NDG_ERR_NOMEM, "pinned hit buffer");
             if (tot_hits) memcpy(nb.p, c->h_hits.p, tot_hits * sizeof(nd_hit));
@@ -802,6 +852,246 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
     }
     out->n_hits = (int64_t)tot_hits; out->hits = c->h_hits.as<ndg_hit_t>();
     out->n_minimizers = tot_mz; out->n_anchors = tot_a; out->n_segments = tot_seg;
+    return NDG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// regime B: base-level alignment.  Host logic in nd_align.hpp; every DP call runs in k_ksw_extd2_px.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct GpuDp : ndal::Backend {
+    ndg_ctx *c; ndk_par P; int rc = 0;
+
+    static uint64_t p_need(const ndal::DpReq &k)
+    {
+        int w = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
+        int ncol = std::min(k.qlen, k.tlen); ncol = (std::min(ncol, w + 1) + 15) / 16 + 1;
+        const uint64_t rows = (uint64_t)(k.qlen + k.tlen - 1);
+        return ((rows + 63) / 64 * 64) * (uint64_t)ncol * 16;                 // whole 64-row chunks
+    }
+
+    int launch_group(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const uint32_t *ids, size_t n,
+                     std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars, std::vector<uint32_t> &retry)
+    {
+        std::vector<ndk_call> hc(n);
+        uint64_t seqb = 0, cig = 0; int Tmax = 16, rmax = 1, qmax = 1;
+        for (size_t i = 0; i < n; ++i) {
+            const ndal::DpReq &k = reqs[ids[i]]; ndk_call &d = hc[i];
+            d.qlen = k.qlen; d.tlen = k.tlen; d.q_off = seqb; d.t_off = seqb + (uint64_t)k.qlen; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag;
+            d.p_off = 0; d.cigar_off = cig;
+            seqb += (uint64_t)k.qlen + k.tlen; cig += (uint64_t)k.qlen + k.tlen + 2;
+            Tmax = std::max(Tmax, (k.tlen + 15) / 16 * 16); rmax = std::max(rmax, k.qlen + k.tlen); qmax = std::max(qmax, k.qlen);
+        }
+        if (c->h_kseq.reserve(seqb + 64)) return fail(c, NDG_ERR_NOMEM, "pinned sequence staging");
+        uint8_t *hs = c->h_kseq.as<uint8_t>();
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long long i = 0; i < (long long)n; ++i) ndal::materialize(reqs[ids[(size_t)i]], T, hs + hc[(size_t)i].q_off, hs + hc[(size_t)i].t_off);
+        const size_t state_bytes = ((size_t)17 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;
+        const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
+        const size_t tab_bytes = ((size_t)8 * ((size_t)(rmax >> 6) + 2) + 255) / 256 * 256;
+        const size_t slot_bytes = state_bytes + h_bytes + off_bytes + tab_bytes;
+        const int blocks = std::min<int>(c->n_sm * 16, (int)((n + NDK_WARPS - 1) / NDK_WARPS));
+        const size_t slots = (size_t)blocks * NDK_WARPS;
+        RSV(c->ksw_calls, n * sizeof(ndk_call)); RSV(c->ksw_seqs, seqb + 64); RSV(c->ksw_res, n * sizeof(ndk_res));
+        RSV(c->ksw_cig, (cig + 4) * 4); RSV(c->ksw_scratch, slots * slot_bytes); RSV(c->scalars, 1024);
+        RSV(c->ksw_ncig, (n + 1) * 4); RSV(c->ksw_coff, (n + 1) * 8);
+        CK(cudaMemcpyAsync(c->ksw_calls.p, hc.data(), n * sizeof(ndk_call), cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync(c->ksw_seqs.p, hs, seqb, cudaMemcpyHostToDevice, c->st));
+        uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
+        unsigned long long *d_cur = c->scalars.as<unsigned long long>() + 104;
+        CK(cudaMemsetAsync(d_work, 0, 4, c->st));
+        CK(cudaMemsetAsync(d_cur, 0, 8, c->st));
+        cudaEvent_t e0 = ev_get(c), e1 = ev_get(c);
+        CK(cudaEventRecord(e0, c->st));
+        KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), (int)n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
+                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work,
+                              d_cur, (unsigned long long)c->ksw_p.cap, off_bytes)));
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, c->st));
+        KLAUNCH("ksw_cigar", (k_ksw_ncigar<<<nblk(n + 1, 256), 256, 0, c->st>>>(c->ksw_res.as<ndk_res>(), (int)n, c->ksw_ncig.as<uint32_t>())));
+        if (int r2 = scan_u32_to_u64(c, c->ksw_ncig.as<uint32_t>(), c->ksw_coff.as<nd_u64>(), n)) return r2;
+        if (c->h_koff.reserve((n + 1) * 8) || c->h_kres.reserve(n * sizeof(ndk_res))) return fail(c, NDG_ERR_NOMEM, "pinned result staging");
+        CK(cudaMemcpyAsync(c->h_koff.p, c->ksw_coff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(c->h_kres.p, c->ksw_res.p, n * sizeof(ndk_res), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->aln_stat.dp_ms += ms; c->ev_pool.push_back(e0); c->ev_pool.push_back(e1); }
+        const uint64_t *koff = c->h_koff.as<uint64_t>(); const uint64_t tot = koff[n];
+        if (tot) {
+            RSV(c->ksw_cout, tot * 4);
+            if (c->h_kcig.reserve(tot * 4)) return fail(c, NDG_ERR_NOMEM, "pinned cigar staging");
+            KLAUNCH("ksw_cigar", (k_ksw_cigar_gather<<<nblk((uint64_t)n * 32, 256), 256, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), c->ksw_res.as<ndk_res>(),
+                                  (const unsigned long long *)c->ksw_coff.as<nd_u64>(), (int)n, c->ksw_cig.as<uint32_t>(), c->ksw_cout.as<uint32_t>())));
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(c->h_kcig.p, c->ksw_cout.p, tot * 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        const ndk_res *hr = c->h_kres.as<ndk_res>(); const uint32_t *hcg = c->h_kcig.as<uint32_t>();
+        const size_t base = cigars.size();
+        if (base + tot >= (1ull << 32)) return fail(c, NDG_ERR_OVERFLOW, "round produces more than 2^32 CIGAR operations; align fewer reads per batch");
+        cigars.resize(base + tot);
+        if (tot) memcpy(cigars.data() + base, hcg, tot * 4);
+        for (size_t i = 0; i < n; ++i) {
+            if (hr[i].pad) { retry.push_back(ids[i]); continue; }
+            ndal::DpRes &z = res[ids[i]];
+            z.max = hr[i].max; z.zdropped = hr[i].zdropped; z.max_q = hr[i].max_q; z.max_t = hr[i].max_t; z.mqe = hr[i].mqe; z.mqe_t = hr[i].mqe_t;
+            z.mte = hr[i].mte; z.mte_q = hr[i].mte_q; z.score = hr[i].score; z.n_cigar = hr[i].n_cigar; z.reach_end = hr[i].reach_end;
+            z.cig_off = (uint32_t)(base + koff[i]);
+        }
+        ++c->aln_stat.n_launches;
+        return 0;
+    }
+
+    int run_impl(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars)
+    {
+        const size_t n = reqs.size();
+        cudaSetDevice(c->device);
+        if (!c->ksw_p.p) {                          // backtrack arena: a fixed slice of HBM, reused by every launch
+            size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+            uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(24ull << 30, fr / 3);
+            if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
+            c->ksw_p.cap = want;
+        }
+        const uint64_t arena = c->ksw_p.cap;
+        std::vector<uint64_t> need(n);
+        std::vector<uint32_t> order(n);
+        for (size_t i = 0; i < n; ++i) { need[i] = p_need(reqs[i]); order[i] = (uint32_t)i; }
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return need[x] != need[y] ? need[x] > need[y] : x < y; });   // long calls first
+        std::vector<uint8_t> full(n, 0);            // 1: reserve the worst case (after a failed optimistic attempt)
+        std::vector<uint32_t> pending(order), group, retry;
+        const uint64_t SEQ_MAX = 768ull << 20, CIG_MAX = 768ull << 20; const size_t CNT_MAX = 4u << 20;
+        while (!pending.empty()) {
+            group.clear(); retry.clear();
+            uint64_t sum = 0, seqb = 0; size_t k = 0;
+            for (; k < pending.size(); ++k) {
+                const uint32_t id = pending[k]; const ndal::DpReq &q = reqs[id];
+                // an extension usually z-drops long before its worst-case matrix is written: reserve a fraction first
+                const uint64_t est = (full[id] || !(q.flag & NDK_EXTZ_ONLY)) ? need[id] : std::min<uint64_t>(need[id], (2ull << 20) + need[id] / 16);
+                const uint64_t sb = (uint64_t)q.qlen + q.tlen;
+                if (!group.empty() && (sum + est > arena - arena / 16 || seqb + sb > SEQ_MAX || seqb + sb + 2 * (group.size() + 1) > CIG_MAX || group.size() >= CNT_MAX)) break;
+                if (need[id] > arena) return fail(c, NDG_ERR_NOMEM, "one alignment needs a %llu-byte backtrack matrix, arena is %llu", (unsigned long long)need[id], (unsigned long long)arena);
+                group.push_back(id); sum += est; seqb += sb;
+            }
+            if (int r = launch_group(reqs, T, group.data(), group.size(), res, cigars, retry)) return r;
+            for (uint32_t id : retry) { if (full[id] && group.size() == 1) return fail(c, NDG_ERR_NOMEM, "backtrack arena exhausted by a single call"); full[id] = 1; }
+            c->aln_stat.n_retries += retry.size();
+            std::vector<uint32_t> rest(retry);
+            rest.insert(rest.end(), pending.begin() + (long)k, pending.end());
+            pending.swap(rest);
+        }
+        return 0;
+    }
+
+    void run(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars) override
+    {
+        res.assign(reqs.size(), ndal::DpRes()); cigars.clear();
+        if (rc) return;                             // after an error the tasks drain on default results; the caller reports rc
+        rc = run_impl(reqs, T, res, cigars);
+    }
+};
+
+// chains of the resident sub-batch -> host, alignment, final hits appended to c->aln_hits
+int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
+{
+    const uint64_t NH = c->n_hits;
+    if (NH == 0) return 0;
+    const double t_host0 = omp_get_wtime();
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    { ndal::Opt &A = c->aln; const ndg_opt_t &o = c->opt; A.k = o.k; A.hpc = o.hpc; A.bw = o.bw; A.max_gap = o.max_gap; A.min_cnt = o.min_cnt; A.min_chain_score = o.min_chain_score; }
+    RSV(c->ch_cnt, (NH + 1) * 4); RSV(c->ch_off, (NH + 1) * 8); RSV(c->ch_fend, NH * 4);
+    KLAUNCH("chain_collect", (k_hit_cnt<<<nblk(NH + 1, 256), 256, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, c->ch_cnt.as<uint32_t>())));
+    if (int rc = scan_u32_to_u64(c, c->ch_cnt.as<uint32_t>(), c->ch_off.as<nd_u64>(), NH)) return rc;
+    CK(cudaMemcpyAsync(h, c->ch_off.as<nd_u64>() + NH, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NCA = h[0];
+    RSV(c->ch_a, (NCA + 1) * 16);
+    KLAUNCH("chain_collect", (k_chain_collect<<<nblk(NH, 128), 128, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, r0, c->a_off.as<nd_u64>(), c->seg_start.as<uint32_t>(), (uint32_t)c->n_seg,
+                              c->a.as<nd_u128>(), c->p.as<int32_t>(), c->f.as<int32_t>(), c->ch_off.as<nd_u64>(), c->ch_a.as<nd_u128>(), c->ch_fend.as<int32_t>())));
+    CK(cudaGetLastError());
+    if (c->h_hits.reserve((NH + 1) * sizeof(nd_hit)) || c->h_cha.reserve((NCA + 1) * 16) || c->h_chf.reserve((NH + 1) * 4)) return fail(c, NDG_ERR_NOMEM, "pinned chain staging");
+    CK(cudaMemcpyAsync(c->h_hits.p, c->hits_sorted.p, NH * sizeof(nd_hit), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->h_cha.p, c->ch_a.p, NCA * 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->h_chf.p, c->ch_fend.p, NH * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const nd_hit *hh = c->h_hits.as<nd_hit>(); const nd_u128 *ha = c->h_cha.as<nd_u128>(); const int32_t *hf = c->h_chf.as<int32_t>();
+
+    ndal::SeqStore ST; ST.words = c->ht_words.data(); ST.word_off = c->ht_word_off.data(); ST.len = c->h_tlen.data(); ST.nmask = c->ht_has_n ? c->ht_nmask.data() : nullptr;
+    ndal::SeqStore SQ; SQ.words = Q->words; SQ.word_off = Q->word_off; SQ.len = Q->len; SQ.nmask = Q->nmask;
+    GpuDp be; be.c = c;
+    be.P.m = 5; memset(be.P.mat, 0, sizeof be.P.mat); ndal::simple_mat(be.P.mat, c->aln); be.P.q = c->aln.q; be.P.e = c->aln.e; be.P.q2 = c->aln.q2; be.P.e2 = c->aln.e2;
+
+    // reads are aligned in groups that bound the host memory held by one round of DP results
+    const uint64_t GROUP_CHAINS = 24000;
+    uint64_t hi = 0, aoff = 0;
+    int r = r0;
+    while (r < r1) {
+        const int g0 = r; const uint64_t h0 = hi, a0 = aoff;
+        uint64_t nch = 0;
+        std::vector<uint64_t> hbeg, abeg;
+        while (r < r1 && (r == g0 || nch < GROUP_CHAINS)) {
+            hbeg.push_back(hi); abeg.push_back(aoff);
+            while (hi < NH && hh[hi].qidx == r) { aoff += (uint64_t)hh[hi].cnt; ++hi; ++nch; }
+            ++r;
+        }
+        hbeg.push_back(hi); abeg.push_back(aoff);
+        (void)h0; (void)a0;
+        std::vector<ndal::ReadJob> jobs((size_t)(r - g0));
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int j = 0; j < r - g0; ++j) {
+            ndal::ReadJob &J = jobs[(size_t)j];
+            const int qi = g0 + j;
+            J.qid = qi; J.qlen = (int)Q->len[qi];
+            const uint64_t b = hbeg[(size_t)j], e = hbeg[(size_t)j + 1];
+            if (b == e) continue;
+            J.strands.resize((size_t)2 * J.qlen);
+            ndal::encode_strands(SQ, qi, J.qlen, J.strands.data(), J.strands.data() + J.qlen);
+            std::vector<ndal::ChainIn> ch((size_t)(e - b));
+            uint64_t ao = abeg[(size_t)j];
+            for (uint64_t k = b; k < e; ++k) {
+                ndal::ChainIn &x = ch[(size_t)(k - b)];
+                x.zkey = hh[k].zkey; x.score = hh[k].score; x.cnt = hh[k].cnt; x.fend = hf[k]; x.jend = hh[k].as; x.anchors = ha + ao;
+                ao += (uint64_t)hh[k].cnt;
+            }
+            ndal::build_read_job(J, ch);
+        }
+        ndal::Stats st;
+        ndal::align_batch(c->aln, ST, jobs, be, &st);
+        if (be.rc) return be.rc;
+        c->aln_stat.n_chains += st.n_tasks; c->aln_stat.n_calls += st.n_calls; c->aln_stat.n_rounds += st.n_rounds; c->aln_stat.rect_cells += st.cells;
+        for (size_t j = 0; j < jobs.size(); ++j)
+            for (const ndal::Reg &x : jobs[j].regs) {
+                ndg_hit_t o; memset(&o, 0, sizeof o);
+                o.zkey = (uint64_t)(uint32_t)(x.has_p ? x.dp_max : x.score) << 32 | x.hash;
+                o.qidx = jobs[j].qid; o.rid = x.rid; o.qs = x.qs; o.qe = x.qe; o.rs = x.rs; o.re = x.re; o.mlen = x.mlen; o.blen = x.blen;
+                o.score = x.has_p ? x.dp_max : x.score; o.cnt = x.cnt; o.rev = x.rev; o.as = x.as;
+                c->aln_hits.push_back(o);
+            }
+    }
+    c->aln_stat.host_ms += (omp_get_wtime() - t_host0) * 1e3;
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ndg_set_aln_opt(ndg_ctx_t *c, const ndg_aln_opt_t *o)
+{
+    if (!c) return NDG_ERR_ARG;
+    if (!o) { c->aln_on = false; return NDG_OK; }
+    if (o->q == o->q2 && o->e == o->e2) return fail(c, NDG_ERR_ARG, "single-affine gap costs (q==q2, e==e2) select ksw_extz2 in the reference; only the dual-affine kernel is built");
+    if (o->a <= 0 || o->b < 0 || o->q <= 0 || o->e <= 0 || o->q2 <= 0 || o->e2 <= 0 || (o->q + o->e) + (o->q2 + o->e2) > 127 || o->a + o->b > 127 - 0)
+        return fail(c, NDG_ERR_ARG, "scoring out of the int8 range the reference accepts (ref: minimap2/options.c:199-207)");
+    ndal::Opt &A = c->aln;
+    A.a = o->a; A.b = o->b; A.q = o->q; A.e = o->e; A.q2 = o->q2; A.e2 = o->e2; A.sc_ambi = o->sc_ambi; A.zdrop = o->zdrop; A.zdrop_inv = o->zdrop_inv;
+    A.end_bonus = o->end_bonus; A.min_dp_max = o->min_dp_max; A.min_ksw_len = o->min_ksw_len; A.no_end_flt = o->no_end_flt; A.max_clip_ratio = o->max_clip_ratio;
+    c->aln_on = true;
+    return NDG_OK;
+}
+
+extern "C" int ndg_aln_stats(ndg_ctx_t *c, ndg_aln_stat_t *out)
+{
+    if (!c || !out) return NDG_ERR_ARG;
+    *out = c->aln_stat;
     return NDG_OK;
 }
 

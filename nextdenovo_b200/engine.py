@@ -8,7 +8,7 @@ import ctypes as C
 import os
 import numpy as np
 from .formats import Reads
-from .options import IdxOpt, MapOpt, MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_I_HPC
+from .options import IdxOpt, MapOpt, MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_F_NO_END_FLT, MM_I_HPC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -29,6 +29,16 @@ class _Opt(C.Structure):
                 ("max_chain_skip", C.c_int32), ("max_chain_iter", C.c_int32),
                 ("seed", C.c_int32), ("mid_occ_frac", C.c_float),
                 ("mid_occ", C.c_int32), ("min_mid_occ", C.c_int32)]
+
+
+class _AlnOpt(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("a", "b", "q", "e", "q2", "e2", "sc_ambi", "zdrop", "zdrop_inv", "end_bonus", "min_dp_max",
+                                         "min_ksw_len", "no_end_flt")] + [("max_clip_ratio", C.c_float)]
+
+
+class _AlnStat(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_chains", "n_calls", "n_rounds", "n_launches", "n_retries", "rect_cells")] + \
+               [("dp_ms", C.c_double), ("host_ms", C.c_double)]
 
 
 class _Reads(C.Structure):
@@ -62,7 +72,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats"]
 
 _lib = None
 
@@ -91,6 +101,8 @@ def load_library():
     L.ndg_set_limits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     L.ndg_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ndg_set_ksw_variant.argtypes = [C.c_void_p, C.c_int]
+    L.ndg_set_aln_opt.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndg_aln_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
@@ -170,9 +182,14 @@ class Engine:
             raise NdgError("libndgpu error %d: %s" % (rc, self.L.ndg_last_error(self.h).decode()))
 
     def set_options(self, io: IdxOpt, mo: MapOpt):
-        if mo.flag & MM_F_CIGAR:
-            raise NdgError("-c (base-level extension) is not available through this entry point")
         self.io, self.mo = io, mo
+        if mo.flag & MM_F_CIGAR:                        # regime B (ref: minimap2/map.c:484-505)
+            ao = _AlnOpt(a=mo.a, b=mo.b, q=mo.q, e=mo.e, q2=mo.q2, e2=mo.e2, sc_ambi=mo.sc_ambi, zdrop=mo.zdrop, zdrop_inv=mo.zdrop_inv,
+                         end_bonus=mo.end_bonus, min_dp_max=mo.min_dp_max, min_ksw_len=mo.min_ksw_len,
+                         no_end_flt=1 if mo.flag & MM_F_NO_END_FLT else 0, max_clip_ratio=mo.max_clip_ratio)
+            self._ck(self.L.ndg_set_aln_opt(self.h, C.byref(ao)))
+        else:
+            self._ck(self.L.ndg_set_aln_opt(self.h, None))
         o = _Opt(k=io.k, w=io.w, hpc=1 if io.flag & MM_I_HPC else 0,
                  flag_no_diag=1 if mo.flag & MM_F_NO_DIAG else 0, flag_no_dual=1 if mo.flag & MM_F_NO_DUAL else 0,
                  min_cnt=mo.min_cnt, min_chain_score=mo.min_chain_score, bw=mo.bw, max_gap=mo.max_gap,
@@ -270,6 +287,11 @@ class Engine:
         return out
 
     # ---- base-level extension (ksw_extd2) ----------------------------------------------------
+    def aln_stats(self):
+        st = _AlnStat()
+        self._ck(self.L.ndg_aln_stats(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _AlnStat._fields_}
+
     def set_ksw_variant(self, v):
         self._ck(self.L.ndg_set_ksw_variant(self.h, v))
 

@@ -10,6 +10,7 @@ MM_F_NO_DUAL = 0x002
 MM_F_CIGAR = 0x004
 MM_F_NO_LJOIN = 0x400
 MM_F_ALL_CHAINS = 0x800000
+MM_F_NO_END_FLT = 0x10000000
 MM_I_HPC = 0x1
 
 
@@ -45,6 +46,20 @@ class MapOpt:                       # subset of mm_mapopt_t, minimap2/minimap.h:
     maxhan2: int = 500
     dvt: int = 0
     n_threads: int = 3
+    # base-level alignment (-c), minimap2/options.c:37-44
+    a: int = 2
+    b: int = 4
+    q: int = 4
+    e: int = 2
+    q2: int = 24
+    e2: int = 1
+    sc_ambi: int = 1
+    zdrop: int = 400
+    zdrop_inv: int = 200
+    end_bonus: int = -1
+    min_dp_max: int = 80
+    min_ksw_len: int = 200
+    max_clip_ratio: float = 1.0
     extra: dict = field(default_factory=dict)
 
 
@@ -88,7 +103,8 @@ def parse_args(argv):
     (ref: nextDenovo:445-464, lib/config_parser.py:191-217).  Returns (io, mo, out, positional)."""
     io, mo = IdxOpt(), MapOpt()
     takes = {"-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen",
-             "--maxhan1", "--maxhan2", "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v"}
+             "--maxhan1", "--maxhan2", "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v",
+             "-A", "-B", "-O", "-E", "-z", "-s", "--min-dp-score", "--end-bonus", "--max-clip-ratio"}
     toks, pos, i = [], [], 0
     while i < len(argv):
         a = argv[i]
@@ -133,6 +149,24 @@ def parse_args(argv):
         elif k == "-P": mo.flag |= MM_F_ALL_CHAINS
         elif k == "-X": mo.flag |= MM_F_ALL_CHAINS | MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_NO_LJOIN
         elif k == "-c": mo.flag |= MM_F_CIGAR
+        elif k == "-A": mo.a = int(v)
+        elif k == "-B": mo.b = int(v)
+        elif k in ("-s", "--min-dp-score"): mo.min_dp_max = int(v)
+        elif k == "--end-bonus": mo.end_bonus = int(v)
+        elif k == "--max-clip-ratio": mo.max_clip_ratio = float(v)
+        elif k == "--no-end-flt": mo.flag |= MM_F_NO_END_FLT
+        elif k == "-z":
+            z = v.split(",")
+            mo.zdrop = mo.zdrop_inv = int(z[0])
+            if len(z) > 1: mo.zdrop_inv = int(z[1])
+        elif k == "-O":
+            z = v.split(",")
+            mo.q = mo.q2 = int(z[0])
+            if len(z) > 1: mo.q2 = int(z[1])
+        elif k == "-E":
+            z = v.split(",")
+            mo.e = mo.e2 = int(z[0])
+            if len(z) > 1: mo.e2 = int(z[1])
         elif k == "--minlen": mo.minlen = parse_num(v)
         elif k == "--maxhan1": mo.maxhan1 = parse_num(v)
         elif k == "--maxhan2": mo.maxhan2 = parse_num(v)

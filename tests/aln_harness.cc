@@ -29,6 +29,19 @@ struct CpuBackend : ndal::Backend {
     void run(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars) override
     {
         const size_t n = reqs.size();
+        if (getenv("ALN_PSTAT")) {
+            static const double edges[] = {1<<16, 1<<18, 1<<20, 1<<22, 1<<24, 1<<26, 1e18};
+            double cnt[7] = {0}, vol[7] = {0}, cells[7] = {0};
+            for (const ndal::DpReq &c : reqs) {
+                int w = c.w < 0 ? std::max(c.qlen, c.tlen) : c.w; int ncol = std::min(c.qlen, c.tlen); ncol = (std::min(ncol, w + 1) + 15) / 16 + 1;
+                double pb = ((double)(c.qlen + c.tlen - 1) * ncol + 1) * 16;
+                int b = 0; while (pb > edges[b]) ++b;
+                cnt[b] += 1; vol[b] += pb; cells[b] += pb;
+            }
+            fprintf(stderr, "[pstat] round n=%zu:", n);
+            for (int b = 0; b < 7; ++b) fprintf(stderr, " <=%.0e: %.0f calls %.2f GB |", edges[b], cnt[b], vol[b] / 1e9);
+            fprintf(stderr, "\n");
+        }
         res.assign(n, ndal::DpRes());
         std::vector<std::vector<uint32_t> > cg(n);
 #pragma omp parallel

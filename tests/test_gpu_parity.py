@@ -151,7 +151,39 @@ def test_cli_dropin_matches_reference_bytes(built, golden_dir, tmp_path):
     assert r.returncode == 0, r.stderr
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "S5_sub120_dual.ovl"), "rb").read()
     assert subprocess.run([exe, "--step", "1", "-x", "nope", src, src, "-o", out], capture_output=True).returncode == 1
-    assert subprocess.run([exe, "--step", "1", "-c", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--step", "2", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--step", "1", "-c", "-O", "4,2", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+
+
+@pytest.mark.parametrize("preset,gold", [("ava-ont", "S6_sub120_ava-ont_c.ovl"), ("ava-pb", "S7_sub120_ava-pb_c.ovl")])
+def test_step1_cigar_sub120(eng, engine_mod, reads_sub, golden_dir, preset, gold):
+    """regime B (`-c`): chains -> ksw_extd2 on the GPU -> stitched alignments; the .ovl bytes (coordinates and match counts of the
+    gapped alignments, hit order by dp_max) equal the reference's (ref: minimap2/align.c:565-913, map.c:484-505)."""
+    from nextdenovo_b200.options import MM_F_CIGAR
+    io, mo = _opts(preset)
+    mo.flag |= MM_F_CIGAR
+    eng.set_variant(1, 1)
+    eng.set_limits(64 << 20, 0)
+    ovl, st = engine_mod.run_step1(eng, reads_sub, reads_sub, io, mo)
+    mo.flag &= ~MM_F_CIGAR
+    eng.set_options(io, mo)                      # switch regime B off again for the tests that follow
+    want = open(os.path.join(golden_dir, gold), "rb").read()
+    assert ovl == want, _diff_msg(ovl, want)
+    s = eng.aln_stats()
+    assert s["n_chains"] > 7000 and s["n_calls"] > 300000 and s["n_launches"] >= s["n_rounds"]
+
+
+def test_cli_cigar_matches_reference_bytes(built, golden_dir, tmp_path):
+    """bin/minimap2-nd --step 1 -c: same bytes as the reference binary (golden S6)"""
+    import subprocess
+    root = os.path.dirname(golden_dir.rstrip("/")).rsplit("/tests", 1)[0]
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "sub120.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([exe, "--step", "1", "-t", "8", "-c", "-x", "ava-ont", src, src, "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S6_sub120_ava-ont_c.ovl"), "rb").read()
+    assert "DP calls" in r.stderr
 
 
 @pytest.mark.parametrize("ksw_variant", [1, 0])

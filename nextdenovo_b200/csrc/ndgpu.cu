@@ -851,6 +851,7 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
         r0 = r1;
     }
     out->n_hits = (int64_t)tot_hits; out->hits = c->h_hits.as<ndg_hit_t>();
+    if (c->aln_on) { out->n_hits = (int64_t)c->aln_hits.size(); out->hits = c->aln_hits.data(); }
     out->n_minimizers = tot_mz; out->n_anchors = tot_a; out->n_segments = tot_seg;
     return NDG_OK;
 }
@@ -915,8 +916,15 @@ struct GpuDp : ndal::Backend {
         if (c->h_koff.reserve((n + 1) * 8) || c->h_kres.reserve(n * sizeof(ndk_res))) return fail(c, NDG_ERR_NOMEM, "pinned result staging");
         CK(cudaMemcpyAsync(c->h_koff.p, c->ksw_coff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(c->h_kres.p, c->ksw_res.p, n * sizeof(ndk_res), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(c->h_scalars.as<uint64_t>() + 8, d_cur, 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->aln_stat.dp_ms += ms; c->ev_pool.push_back(e0); c->ev_pool.push_back(e1); }
+        last_used = c->h_scalars.as<uint64_t>()[8];
+        { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->aln_stat.dp_ms += ms; c->ev_pool.push_back(e0); c->ev_pool.push_back(e1);
+          if (getenv("NDG_ALN_DEBUG")) {
+              double cells = 0; for (size_t i = 0; i < n; ++i) cells += (double)hc[i].qlen * hc[i].tlen;
+              fprintf(stderr, "[ndg::dp] launch %llu: %zu calls, longest %dx%d, rect cells %.3g, seq %.1f MB, kernel %.1f ms, arena used %.2f GB, ext_frac %.4f\n", (unsigned long long)c->aln_stat.n_launches, n,
+                      hc[0].qlen, hc[0].tlen, cells, seqb / 1e6, ms, c->h_scalars.as<uint64_t>()[8] / 1e9, ext_frac);
+          } }
         const uint64_t *koff = c->h_koff.as<uint64_t>(); const uint64_t tot = koff[n];
         if (tot) {
             RSV(c->ksw_cout, tot * 4);
@@ -943,42 +951,57 @@ struct GpuDp : ndal::Backend {
         return 0;
     }
 
+    double ext_frac = 1.0 / 16;                     // share of an extension's worst-case matrix that gets written (adapted from the arena cursor)
+    uint64_t last_used = 0;
+
     int run_impl(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars)
     {
         const size_t n = reqs.size();
         cudaSetDevice(c->device);
         if (!c->ksw_p.p) {                          // backtrack arena: a fixed slice of HBM, reused by every launch
             size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
-            uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(24ull << 30, fr / 3);
+            uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(64ull << 30, (uint64_t)(fr * 0.45));
             if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
             c->ksw_p.cap = want;
         }
-        const uint64_t arena = c->ksw_p.cap;
+        const uint64_t arena = c->ksw_p.cap, arena_eff = arena - arena / 16;
         std::vector<uint64_t> need(n);
-        std::vector<uint32_t> order(n);
-        for (size_t i = 0; i < n; ++i) { need[i] = p_need(reqs[i]); order[i] = (uint32_t)i; }
-        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return need[x] != need[y] ? need[x] > need[y] : x < y; });   // long calls first
+        std::vector<uint32_t> pending(n);
+        for (size_t i = 0; i < n; ++i) { need[i] = p_need(reqs[i]); pending[i] = (uint32_t)i; if (need[i] > arena_eff) return fail(c, NDG_ERR_NOMEM, "one alignment needs a %llu-byte backtrack matrix, arena is %llu", (unsigned long long)need[i], (unsigned long long)arena); }
+        std::sort(pending.begin(), pending.end(), [&](uint32_t x, uint32_t y) { return need[x] != need[y] ? need[x] > need[y] : x < y; });   // long calls first
         std::vector<uint8_t> full(n, 0);            // 1: reserve the worst case (after a failed optimistic attempt)
-        std::vector<uint32_t> pending(order), group, retry;
-        const uint64_t SEQ_MAX = 768ull << 20, CIG_MAX = 768ull << 20; const size_t CNT_MAX = 4u << 20;
+        std::vector<uint32_t> group, rest, retry;
+        const uint64_t SEQ_MAX = 768ull << 20; const size_t CNT_MAX = 4u << 20;
+        auto est_of = [&](uint32_t id) -> uint64_t {
+            // an extension usually z-drops long before its worst-case matrix is written: reserve a fraction first
+            if (full[id] || !(reqs[id].flag & NDK_EXTZ_ONLY)) return need[id];
+            return std::min<uint64_t>(need[id], (1ull << 20) + (uint64_t)(need[id] * ext_frac));
+        };
         while (!pending.empty()) {
-            group.clear(); retry.clear();
-            uint64_t sum = 0, seqb = 0; size_t k = 0;
-            for (; k < pending.size(); ++k) {
-                const uint32_t id = pending[k]; const ndal::DpReq &q = reqs[id];
-                // an extension usually z-drops long before its worst-case matrix is written: reserve a fraction first
-                const uint64_t est = (full[id] || !(q.flag & NDK_EXTZ_ONLY)) ? need[id] : std::min<uint64_t>(need[id], (2ull << 20) + need[id] / 16);
-                const uint64_t sb = (uint64_t)q.qlen + q.tlen;
-                if (!group.empty() && (sum + est > arena - arena / 16 || seqb + sb > SEQ_MAX || seqb + sb + 2 * (group.size() + 1) > CIG_MAX || group.size() >= CNT_MAX)) break;
-                if (need[id] > arena) return fail(c, NDG_ERR_NOMEM, "one alignment needs a %llu-byte backtrack matrix, arena is %llu", (unsigned long long)need[id], (unsigned long long)arena);
-                group.push_back(id); sum += est; seqb += sb;
+            // every launch takes each L-th call of the size-ordered list: the same mix of long and short calls in every launch, long ones first
+            uint64_t s_est = 0, s_seq = 0;
+            for (uint32_t id : pending) { s_est += est_of(id); s_seq += (uint64_t)reqs[id].qlen + reqs[id].tlen + 2; }
+            size_t L = (size_t)std::max<uint64_t>(std::max<uint64_t>((s_est + arena_eff - 1) / arena_eff, (s_seq + SEQ_MAX - 1) / SEQ_MAX), (pending.size() + CNT_MAX - 1) / CNT_MAX);
+            if (L < 1) L = 1;
+            group.clear(); rest.clear(); retry.clear();
+            uint64_t sum = 0, seqb = 0, fixed = 0, ext_need = 0;
+            for (size_t k = 0; k < pending.size(); ++k) {
+                const uint32_t id = pending[k]; const uint64_t e = est_of(id), sb = (uint64_t)reqs[id].qlen + reqs[id].tlen + 2;
+                if (k % L == 0 && (group.empty() || (sum + e <= arena_eff && seqb + sb <= SEQ_MAX))) {
+                    group.push_back(id); sum += e; seqb += sb;
+                    if (e == need[id]) fixed += e; else ext_need += need[id];
+                } else rest.push_back(id);
             }
             if (int r = launch_group(reqs, T, group.data(), group.size(), res, cigars, retry)) return r;
+            if (ext_need > 0 && retry.empty()) {    // what the optimistic calls really wrote
+                const double used = last_used > fixed ? (double)(last_used - fixed) : 0.0;
+                ext_frac = std::min(1.0, std::max(1.0 / 256, 0.5 * ext_frac + 0.5 * 1.5 * used / (double)ext_need));
+            } else if (!retry.empty()) ext_frac = std::min(1.0, ext_frac * 2);
             for (uint32_t id : retry) { if (full[id] && group.size() == 1) return fail(c, NDG_ERR_NOMEM, "backtrack arena exhausted by a single call"); full[id] = 1; }
             c->aln_stat.n_retries += retry.size();
-            std::vector<uint32_t> rest(retry);
-            rest.insert(rest.end(), pending.begin() + (long)k, pending.end());
-            pending.swap(rest);
+            // retried calls go first (they are long); the list stays size-ordered otherwise
+            pending.assign(retry.begin(), retry.end());
+            pending.insert(pending.end(), rest.begin(), rest.end());
         }
         return 0;
     }
@@ -1022,7 +1045,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
     be.P.m = 5; memset(be.P.mat, 0, sizeof be.P.mat); ndal::simple_mat(be.P.mat, c->aln); be.P.q = c->aln.q; be.P.e = c->aln.e; be.P.q2 = c->aln.q2; be.P.e2 = c->aln.e2;
 
     // reads are aligned in groups that bound the host memory held by one round of DP results
-    const uint64_t GROUP_CHAINS = 24000;
+    const uint64_t GROUP_CHAINS = 400000;
     uint64_t hi = 0, aoff = 0;
     int r = r0;
     while (r < r1) {

@@ -473,19 +473,39 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
                     if (o + 64ull * (unsigned long long)n_col > arena_bytes) { arena_full = true; break; }
                     chunk = pmat + o;
                 }
+                const bool exact_h = !approx_max && r > 0;             // exact maximum: H[t] += v[t] fused into the sweep below
+                const int en1 = st0 + (en0 - st0) / 4 * 4;
+                long long best = (long long)0x8000000000000000ULL;
                 {
                     uint8_t *pr = (rowtab ? chunk + (size_t)(r & 63) * n_col : p + (size_t)r * n_col) - st;
+                    int ch = (exact_h && st > 0) ? H[st - 1] : 0;        // old H of the cell left of the sweep (for H[en0], ref :352)
+                    // software pipeline: the state of the next 64 cells is requested before the current 64 are computed
+                    uint4 A = make_uint4(0, 0, 0, 0), Bw = make_uint4(0, 0, 0, 0); unsigned sq2 = 0; int sr0 = 0, sr1 = 0; int2 hh = make_int2(0, 0);
+                    {
+                        const int t = st + 2 * lane;
+                        if (t <= en) {
+                            A = pairw[t]; Bw = pairw[t + 1];
+                            if (t + 1 >= st0 && t < sc_hi) { sq2 = *reinterpret_cast<const uint16_t *>(sf + t); sr0 = qrr[t]; sr1 = qrr[t + 1]; }
+                            if (exact_h) hh = *reinterpret_cast<const int2 *>(H + t);
+                        }
+                    }
                     for (int t0 = st; t0 <= en; t0 += 64) {
                         const int t = t0 + 2 * lane;
                         const bool act = t <= en;
-                        uint4 A = make_uint4(0, 0, 0, 0), Bw = make_uint4(0, 0, 0, 0);
+                        uint4 An = make_uint4(0, 0, 0, 0), Bn = make_uint4(0, 0, 0, 0); unsigned sq2n = 0; int sr0n = 0, sr1n = 0; int2 hhn = make_int2(0, 0);
+                        {
+                            const int tn = t + 64;
+                            if (tn <= en) {
+                                An = pairw[tn]; Bn = pairw[tn + 1];
+                                if (tn + 1 >= st0 && tn < sc_hi) { sq2n = *reinterpret_cast<const uint16_t *>(sf + tn); sr0n = qrr[tn]; sr1n = qrr[tn + 1]; }
+                                if (exact_h) hhn = *reinterpret_cast<const int2 *>(H + tn);
+                            }
+                        }
                         unsigned z = 0;
                         if (act) {
-                            A = pairw[t]; Bw = pairw[t + 1];            // pair index t/2 -> words 2*(t/2), 2*(t/2)+1
                             int zl = (int)(int16_t)(Bw.z & 0xffffu), zh = (int)Bw.z >> 16;
                             if (t + 1 >= st0 && t < sc_hi) {
-                                const unsigned sq2 = *reinterpret_cast<const uint16_t *>(sf + t);
-                                const int sq0 = sq2 & 255, sq1 = sq2 >> 8, sr0 = qrr[t], sr1 = qrr[t + 1];
+                                const int sq0 = sq2 & 255, sq1 = sq2 >> 8;
                                 if (t >= st0) {
                                     if (generic) zl = P.mat[sq0 * m + sr0];
                                     else { zl = sq0 == sr0 ? sc_mch : sc_mis; if (sq0 == m - 1 || sr0 == m - 1) zl = sc_N; }
@@ -510,6 +530,42 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
                             pairw[t + 1] = make_uint4(yn, y2n, zkeep, 0u);
                             if (with_cigar) *reinterpret_cast<uint16_t *>(pr + t) = (uint16_t)d;
                         }
+                        if (exact_h) {                                  // ref: ksw2_extd2_sse.c:346-371 (H update + SIMD-ordered maximum)
+                            int ph = __shfl_up_sync(NDK_FULL, hh.y, 1);
+                            if (lane == 0) ph = ch;
+                            ch = __shfl_sync(NDK_FULL, hh.y, 31);
+                            if (act && t + 1 >= st0 && t <= en0) {
+                                const int v0 = (int)(int16_t)(vn & 0xffffu), v1 = (int)vn >> 16, u0 = (int)(int16_t)(un & 0xffffu), u1 = (int)un >> 16;
+                                int h0 = hh.x, h1 = hh.y;
+                                if (t >= st0) {
+                                    if (t < en0) {
+                                        h0 = hh.x + v0;
+                                        const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2) : 1u + (4u << 20) + (unsigned)(t - en1);
+                                        const long long key = ((long long)h0 << 32) | (long long)(0xffffffffu - rank);
+                                        best = key > best ? key : best;
+                                    } else {                            // t == en0
+                                        h0 = en0 > 0 ? ph + u0 : hh.x + v0;
+                                        const long long key = ((long long)h0 << 32) | 0xffffffffLL;
+                                        best = key > best ? key : best;
+                                    }
+                                }
+                                if (t + 1 <= en0) {
+                                    if (t + 1 < en0) {
+                                        h1 = hh.y + v1;
+                                        const int tt = t + 1;
+                                        const unsigned rank = tt < en1 ? 1u + ((unsigned)((tt - st0) & 3) << 20) + (unsigned)((tt - st0) >> 2) : 1u + (4u << 20) + (unsigned)(tt - en1);
+                                        const long long key = ((long long)h1 << 32) | (long long)(0xffffffffu - rank);
+                                        best = key > best ? key : best;
+                                    } else {                            // t + 1 == en0 (> 0): H[en0] = H[en0-1] + u[en0], H[en0-1] being this lane's old low cell
+                                        h1 = hh.x + u1;
+                                        const long long key = ((long long)h1 << 32) | 0xffffffffLL;
+                                        best = key > best ? key : best;
+                                    }
+                                }
+                                *reinterpret_cast<int2 *>(H + t) = make_int2(h0, h1);
+                            }
+                        }
+                        A = An; Bw = Bn; sq2 = sq2n; sr0 = sr0n; sr1 = sr1n; hh = hhn;
                     }
                     if (!generic && sc_end - 1 > en) {                  // score cells past the rounded band end (spill into sf[] beyond T)
                         const int t = en + 1 + lane;
@@ -527,21 +583,6 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
                 if (!approx_max) {
                     int max_H, max_t;
                     if (r > 0) {
-                        const int en1 = st0 + (en0 - st0) / 4 * 4;
-                        const int Hlast = en0 > 0 ? H[en0 - 1] + NDK_H16(en0, 3) : H[en0] + NDK_H16(en0, 1);
-                        __syncwarp();
-                        long long best = ((long long)Hlast << 32) | 0xffffffffLL;
-                        for (int t0 = st0; t0 <= en0; t0 += 32) {
-                            const int t = t0 + lane;
-                            if (t < en0) {
-                                const int h = H[t] + NDK_H16(t, 1);
-                                H[t] = h;
-                                const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2)
-                                                              : 1u + (4u << 20) + (unsigned)(t - en1);
-                                const long long key = ((long long)h << 32) | (long long)(0xffffffffu - rank);
-                                best = key > best ? key : best;
-                            } else if (t == en0) H[t] = Hlast;
-                        }
 #pragma unroll
                         for (int o = 16; o; o >>= 1) { long long y2k = __shfl_xor_sync(NDK_FULL, best, o); best = y2k > best ? y2k : best; }
                         max_H = (int)(best >> 32);

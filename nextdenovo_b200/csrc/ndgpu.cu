@@ -893,7 +893,8 @@ struct GpuDp : ndal::Backend {
         const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
         const size_t tab_bytes = ((size_t)8 * ((size_t)(rmax >> 6) + 2) + 255) / 256 * 256;
         const size_t slot_bytes = state_bytes + h_bytes + off_bytes + tab_bytes;
-        const int blocks = std::min<int>(c->n_sm * 16, (int)((n + NDK_WARPS - 1) / NDK_WARPS));
+        static const int bps = getenv("NDG_KSW_BPS") ? atoi(getenv("NDG_KSW_BPS")) : 16;
+        const int blocks = std::min<int>(c->n_sm * bps, (int)((n + NDK_WARPS - 1) / NDK_WARPS));
         const size_t slots = (size_t)blocks * NDK_WARPS;
         RSV(c->ksw_calls, n * sizeof(ndk_call)); RSV(c->ksw_seqs, seqb + 64); RSV(c->ksw_res, n * sizeof(ndk_res));
         RSV(c->ksw_cig, (cig + 4) * 4); RSV(c->ksw_scratch, slots * slot_bytes); RSV(c->scalars, 1024);
@@ -978,20 +979,18 @@ struct GpuDp : ndal::Backend {
             return std::min<uint64_t>(need[id], (1ull << 20) + (uint64_t)(need[id] * ext_frac));
         };
         while (!pending.empty()) {
-            // every launch takes each L-th call of the size-ordered list: the same mix of long and short calls in every launch, long ones first
-            uint64_t s_est = 0, s_seq = 0;
-            for (uint32_t id : pending) { s_est += est_of(id); s_seq += (uint64_t)reqs[id].qlen + reqs[id].tlen + 2; }
-            size_t L = (size_t)std::max<uint64_t>(std::max<uint64_t>((s_est + arena_eff - 1) / arena_eff, (s_seq + SEQ_MAX - 1) / SEQ_MAX), (pending.size() + CNT_MAX - 1) / CNT_MAX);
-            if (L < 1) L = 1;
+            // a launch takes a run of the size-ordered list: calls of similar length share a launch, so no launch waits on one
+            // call that is far longer than the rest (a lone warp advances ~0.1 G cells/s; the GPU as a whole ~200 G cells/s)
             group.clear(); rest.clear(); retry.clear();
             uint64_t sum = 0, seqb = 0, fixed = 0, ext_need = 0;
-            for (size_t k = 0; k < pending.size(); ++k) {
+            size_t k = 0;
+            for (; k < pending.size(); ++k) {
                 const uint32_t id = pending[k]; const uint64_t e = est_of(id), sb = (uint64_t)reqs[id].qlen + reqs[id].tlen + 2;
-                if (k % L == 0 && (group.empty() || (sum + e <= arena_eff && seqb + sb <= SEQ_MAX))) {
-                    group.push_back(id); sum += e; seqb += sb;
-                    if (e == need[id]) fixed += e; else ext_need += need[id];
-                } else rest.push_back(id);
+                if (!group.empty() && (sum + e > arena_eff || seqb + sb > SEQ_MAX || group.size() >= CNT_MAX)) break;
+                group.push_back(id); sum += e; seqb += sb;
+                if (e == need[id]) fixed += e; else ext_need += need[id];
             }
+            rest.assign(pending.begin() + (long)k, pending.end());
             if (int r = launch_group(reqs, T, group.data(), group.size(), res, cigars, retry)) return r;
             if (ext_need > 0 && retry.empty()) {    // what the optimistic calls really wrote
                 const double used = last_used > fixed ? (double)(last_used - fixed) : 0.0;

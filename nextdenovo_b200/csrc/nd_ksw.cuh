@@ -630,6 +630,288 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cooperative generation for wide bands (extensions with w = 1.5*bw+1, long joins): the same cell code, one call per block.
+// A lone warp advances a 3000-cell diagonal in 47 dependent round trips to its L2-resident state; eight warps do it in 6.
+// ------------------------------------------------------------------------------------------------
+#define NDK_COOP_WARPS 8
+__global__ void __launch_bounds__(NDK_COOP_WARPS * 32)
+k_ksw_extd2_coop(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
+               uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work,
+               unsigned long long *arena_cur = nullptr, unsigned long long arena_bytes = 0, size_t off_bytes = 0)
+{
+    // One call per BLOCK: every anti-diagonal is cut into NDK_COOP_WARPS runs of 64-cell steps, one run per warp.  The only
+    // values a run needs from its left neighbour are last diagonal's x, v, x2 (and H) of the cell just before it; they are read
+    // before the first barrier, the in-place sweeps happen between the two barriers of a diagonal.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gtid = threadIdx.x;
+    const int slot = blockIdx.x;
+    __shared__ long long s_best[NDK_COOP_WARPS];
+    __shared__ unsigned long long s_o;
+    __shared__ int s_ci;
+    uint8_t *base = scratch + (size_t)slot * slot_bytes;
+    int32_t *H = reinterpret_cast<int32_t *>(base + state_bytes);
+    int *off = reinterpret_cast<int *>(base + state_bytes + h_bytes);
+    unsigned long long *rowtab = arena_cur ? reinterpret_cast<unsigned long long *>(base + state_bytes + h_bytes + off_bytes) : nullptr;
+
+    for (;;) {
+        if (gtid == 0) s_ci = (int)atomicAdd(work, 1u);
+        __syncthreads();
+        const int ci = s_ci;
+        __syncthreads();
+        if (ci >= n_calls) break;
+        const ndk_call c = calls[ci];
+        const int qlen = c.qlen, tlen = c.tlen, flag = c.flag, zdrop = c.zdrop;
+        const uint8_t *query = seqs + c.q_off, *target = seqs + c.t_off;
+        const bool with_cigar = !(flag & NDK_SCORE_ONLY), approx_max = (flag & NDK_APPROX_MAX) != 0, right = with_cigar && (flag & NDK_RIGHT);
+        ndk_res ez;
+        ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1; ez.max = 0; ez.score = ez.mqe = ez.mte = NDK_NEG_INF;
+        ez.n_cigar = 0; ez.zdropped = 0; ez.reach_end = 0; ez.pad = 0;
+        int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
+        const int qe0 = q + e;
+        const int m = P.m;
+        bool run = !(m <= 1 || qlen <= 0 || tlen <= 0);
+        if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+        const int qe = q + e, qe2 = q2 + e2;
+        const int sc_mch = P.mat[0], sc_mis = P.mat[1], sc_N = P.mat[m * m - 1] == 0 ? -e2 : P.mat[m * m - 1];
+        int w = c.w;
+        if (w < 0) w = tlen > qlen ? tlen : qlen;
+        const int T = (tlen + 15) / 16 * 16;
+        int n_col_ = qlen < tlen ? qlen : tlen;
+        n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+        const int n_col = n_col_ * 16;
+        {
+            int min_sc = P.mat[1];
+            for (int t = 1; t < m * m; ++t) min_sc = min_sc < P.mat[t] ? min_sc : P.mat[t];
+            if (-min_sc > 2 * (q + e)) run = false;
+        }
+        int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+        if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+        const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+
+        uint4 *pairw = reinterpret_cast<uint4 *>(base);                 // 2 x uint4 per pair of cells
+        int16_t *h16 = reinterpret_cast<int16_t *>(base);
+        uint8_t *sf = base + (size_t)16 * T, *qr = sf + T;
+        int *off_end = off + qlen + tlen - 1;
+        uint8_t *p = rowtab ? pmat : pmat + c.p_off;
+        uint32_t *cigar = cigars + c.cigar_off;
+        const unsigned Q = ndk_pk(q, q), Q2 = ndk_pk(q2, q2), NQE = ndk_pk(-qe, -qe), NQE2 = ndk_pk(-qe2, -qe2), SCM = ndk_pk(sc_mch, sc_mch);
+        bool arena_full = false;
+        uint8_t *chunk = nullptr;
+
+        if (run) {
+            const int qpad = ((qlen + 15) / 16 + 1) * 16 + 32;
+            {
+                const unsigned i1 = ndk_pk(-q - e, -q - e), i2 = ndk_pk(-q2 - e2, -q2 - e2);
+                for (int j = gtid; j < T / 2; j += NDK_COOP_WARPS * 32) {
+                    pairw[2 * j] = make_uint4(i1, i1, i2, i1);          // x v x2 u
+                    pairw[2 * j + 1] = make_uint4(i1, i2, 0u, 0u);      // y y2 s -
+                }
+                for (int t = gtid; t < T; t += NDK_COOP_WARPS * 32) {
+                    sf[t] = t < tlen ? target[t] : 0;
+                    if (!approx_max) H[t] = NDK_NEG_INF;
+                }
+            }
+            for (int t = gtid; t < qpad; t += NDK_COOP_WARPS * 32) qr[t] = t < qlen ? query[qlen - 1 - t] : 0;
+            __syncthreads();
+
+            int last_st = -1, last_en = -1, H0 = 0, last_H0_t = 0;
+            for (int r = 0; r < qlen + tlen - 1; ++r) {
+                int st = 0, en = tlen - 1;
+                if (st < r - qlen + 1) st = r - qlen + 1;
+                if (en > r) en = r;
+                if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+                if (en > (r + w) >> 1) en = (r + w) >> 1;
+                if (st > en) { ez.zdropped = 1; break; }
+                const int st0 = st, en0 = en;
+                st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+                const int vb = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+                const int n_steps = (en - st) / 64 + 1, spw = (n_steps + NDK_COOP_WARPS - 1) / NDK_COOP_WARPS;
+                const int lo = st + 64 * spw * wid;                     // this warp sweeps [lo, my_en]
+                const int my_en = en < lo + 64 * spw - 1 ? en : lo + 64 * spw - 1;
+                unsigned cx, cv, cx2;                                   // previous-diagonal x, v, x2 of cell lo-1, in the HIGH halves
+                if (lo > st) {
+                    if (lo <= en) { cx = (unsigned)NDK_H16(lo - 1, 0) << 16; cv = (unsigned)NDK_H16(lo - 1, 1) << 16; cx2 = (unsigned)NDK_H16(lo - 1, 2) << 16; }
+                    else { cx = cv = cx2 = 0; }
+                } else if (st > 0) {
+                    if (st - 1 >= last_st && st - 1 <= last_en) { cx = (unsigned)NDK_H16(st - 1, 0) << 16; cv = (unsigned)NDK_H16(st - 1, 1) << 16; cx2 = (unsigned)NDK_H16(st - 1, 2) << 16; }
+                    else { cx = (unsigned)(-q - e) << 16; cv = cx; cx2 = (unsigned)(-q2 - e2) << 16; }
+                } else { cx = (unsigned)(-q - e) << 16; cv = (unsigned)vb << 16; cx2 = (unsigned)(-q2 - e2) << 16; }
+                if (en >= r && gtid == 0) { NDK_H16(r, 4) = (int16_t)(-q - e); NDK_H16(r, 5) = (int16_t)(-q2 - e2); NDK_H16(r, 3) = (int16_t)vb; }
+                if (with_cigar && gtid == 0) { off[r] = st; off_end[r] = en; }
+                const bool exact_h = !approx_max && r > 0;             // exact maximum: H[t] += v[t] fused into the sweep below
+                int ch = (exact_h && lo > 0 && lo <= en) ? H[lo - 1] : 0;   // old H of the cell left of this warp's run (for H[en0], ref :352)
+                const uint8_t *qrr = qr + (qlen - 1 - r);
+                const int sc_end = st0 + (en0 - st0 + 16) / 16 * 16;
+                const bool generic = (flag & NDK_GENERIC_SC) != 0;
+                const int sc_hi = generic ? en0 + 1 : sc_end;           // scores rewritten on [st0, sc_hi)
+                if (rowtab && with_cigar && (r & 63) == 0 && gtid == 0) {
+                    const unsigned long long o = atomicAdd(arena_cur, 64ull * (unsigned long long)n_col);
+                    rowtab[r >> 6] = o; s_o = o;
+                }
+                __syncthreads();                                        // barrier 1: boundary values read, cell r initialised
+                if (rowtab && with_cigar && (r & 63) == 0) {
+                    const unsigned long long o = s_o;
+                    if (o + 64ull * (unsigned long long)n_col > arena_bytes) { arena_full = true; break; }
+                    chunk = pmat + o;
+                }
+                const int en1 = st0 + (en0 - st0) / 4 * 4;
+                long long best = (long long)0x8000000000000000ULL;
+                {
+                    uint8_t *pr = (rowtab ? chunk + (size_t)(r & 63) * n_col : p + (size_t)r * n_col) - st;
+                    // software pipeline: the state of the next 64 cells is requested before the current 64 are computed
+                    uint4 A = make_uint4(0, 0, 0, 0), Bw = make_uint4(0, 0, 0, 0); unsigned sq2 = 0; int sr0 = 0, sr1 = 0; int2 hh = make_int2(0, 0);
+                    {
+                        const int t = lo + 2 * lane;
+                        if (t <= my_en) {
+                            A = pairw[t]; Bw = pairw[t + 1];
+                            if (t + 1 >= st0 && t < sc_hi) { sq2 = *reinterpret_cast<const uint16_t *>(sf + t); sr0 = qrr[t]; sr1 = qrr[t + 1]; }
+                            if (exact_h) hh = *reinterpret_cast<const int2 *>(H + t);
+                        }
+                    }
+                    for (int t0 = lo; t0 <= my_en; t0 += 64) {
+                        const int t = t0 + 2 * lane;
+                        const bool act = t <= en;
+                        uint4 An = make_uint4(0, 0, 0, 0), Bn = make_uint4(0, 0, 0, 0); unsigned sq2n = 0; int sr0n = 0, sr1n = 0; int2 hhn = make_int2(0, 0);
+                        {
+                            const int tn = t + 64;
+                            if (tn <= my_en) {
+                                An = pairw[tn]; Bn = pairw[tn + 1];
+                                if (tn + 1 >= st0 && tn < sc_hi) { sq2n = *reinterpret_cast<const uint16_t *>(sf + tn); sr0n = qrr[tn]; sr1n = qrr[tn + 1]; }
+                                if (exact_h) hhn = *reinterpret_cast<const int2 *>(H + tn);
+                            }
+                        }
+                        unsigned z = 0;
+                        if (act) {
+                            int zl = (int)(int16_t)(Bw.z & 0xffffu), zh = (int)Bw.z >> 16;
+                            if (t + 1 >= st0 && t < sc_hi) {
+                                const int sq0 = sq2 & 255, sq1 = sq2 >> 8;
+                                if (t >= st0) {
+                                    if (generic) zl = P.mat[sq0 * m + sr0];
+                                    else { zl = sq0 == sr0 ? sc_mch : sc_mis; if (sq0 == m - 1 || sr0 == m - 1) zl = sc_N; }
+                                }
+                                if (t + 1 < sc_hi) {
+                                    if (generic) zh = P.mat[sq1 * m + sr1];
+                                    else { zh = sq1 == sr1 ? sc_mch : sc_mis; if (sq1 == m - 1 || sr1 == m - 1) zh = sc_N; }
+                                }
+                            }
+                            z = ndk_pk(zl, zh);
+                        }
+                        const unsigned zkeep = z;
+                        unsigned px = __shfl_up_sync(NDK_FULL, A.x, 1), pv = __shfl_up_sync(NDK_FULL, A.y, 1), px2 = __shfl_up_sync(NDK_FULL, A.z, 1);
+                        if (lane == 0) { px = cx; pv = cv; px2 = cx2; }
+                        cx = __shfl_sync(NDK_FULL, A.x, 31); cv = __shfl_sync(NDK_FULL, A.y, 31); cx2 = __shfl_sync(NDK_FULL, A.z, 31);
+                        const unsigned xt1 = __byte_perm(px, A.x, 0x5432), vt1 = __byte_perm(pv, A.y, 0x5432), x2t1 = __byte_perm(px2, A.z, 0x5432);
+                        unsigned un, vn, xn, yn, x2n, y2n, d;
+                        if (right) ndk_pair<true>(xt1, vt1, x2t1, A.w, Bw.x, Bw.y, z, Q, Q2, NQE, NQE2, SCM, un, vn, xn, yn, x2n, y2n, d);
+                        else ndk_pair<false>(xt1, vt1, x2t1, A.w, Bw.x, Bw.y, z, Q, Q2, NQE, NQE2, SCM, un, vn, xn, yn, x2n, y2n, d);
+                        if (act) {
+                            pairw[t] = make_uint4(xn, vn, x2n, un);
+                            pairw[t + 1] = make_uint4(yn, y2n, zkeep, 0u);
+                            if (with_cigar) *reinterpret_cast<uint16_t *>(pr + t) = (uint16_t)d;
+                        }
+                        if (exact_h) {                                  // ref: ksw2_extd2_sse.c:346-371 (H update + SIMD-ordered maximum)
+                            int ph = __shfl_up_sync(NDK_FULL, hh.y, 1);
+                            if (lane == 0) ph = ch;
+                            ch = __shfl_sync(NDK_FULL, hh.y, 31);
+                            if (act && t + 1 >= st0 && t <= en0) {
+                                const int v0 = (int)(int16_t)(vn & 0xffffu), v1 = (int)vn >> 16, u0 = (int)(int16_t)(un & 0xffffu), u1 = (int)un >> 16;
+                                int h0 = hh.x, h1 = hh.y;
+                                if (t >= st0) {
+                                    if (t < en0) {
+                                        h0 = hh.x + v0;
+                                        const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2) : 1u + (4u << 20) + (unsigned)(t - en1);
+                                        const long long key = ((long long)h0 << 32) | (long long)(0xffffffffu - rank);
+                                        best = key > best ? key : best;
+                                    } else {                            // t == en0
+                                        h0 = en0 > 0 ? ph + u0 : hh.x + v0;
+                                        const long long key = ((long long)h0 << 32) | 0xffffffffLL;
+                                        best = key > best ? key : best;
+                                    }
+                                }
+                                if (t + 1 <= en0) {
+                                    if (t + 1 < en0) {
+                                        h1 = hh.y + v1;
+                                        const int tt = t + 1;
+                                        const unsigned rank = tt < en1 ? 1u + ((unsigned)((tt - st0) & 3) << 20) + (unsigned)((tt - st0) >> 2) : 1u + (4u << 20) + (unsigned)(tt - en1);
+                                        const long long key = ((long long)h1 << 32) | (long long)(0xffffffffu - rank);
+                                        best = key > best ? key : best;
+                                    } else {                            // t + 1 == en0 (> 0): H[en0] = H[en0-1] + u[en0], H[en0-1] being this lane's old low cell
+                                        h1 = hh.x + u1;
+                                        const long long key = ((long long)h1 << 32) | 0xffffffffLL;
+                                        best = key > best ? key : best;
+                                    }
+                                }
+                                *reinterpret_cast<int2 *>(H + t) = make_int2(h0, h1);
+                            }
+                        }
+                        A = An; Bw = Bn; sq2 = sq2n; sr0 = sr0n; sr1 = sr1n; hh = hhn;
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { long long y2k = __shfl_xor_sync(NDK_FULL, best, o); best = y2k > best ? y2k : best; }
+                    if (lane == 0) s_best[wid] = best;
+                    __syncthreads();                                    // barrier 2: every run of this diagonal is written
+                    if (wid == 0 && !generic && sc_end - 1 > en) {      // score cells past the rounded band end (spill into sf[] beyond T)
+                        const int t = en + 1 + lane;
+                        int zz = 0;
+                        const bool on = t < sc_end;
+                        if (on) {
+                            const int sq = t < T ? sf[t] : qr[t - T], sr = qrr[t];
+                            zz = sq == sr ? sc_mch : sc_mis; if (sq == m - 1 || sr == m - 1) zz = sc_N;
+                        }
+                        __syncwarp();
+                        if (on) { if (t < T) NDK_H16(t, 6) = (int16_t)zz; else sf[t - T] = (uint8_t)zz; }
+                    }
+                }
+                if (!approx_max) {
+                    int max_H, max_t;
+                    if (r > 0) {
+                        best = s_best[0];
+#pragma unroll
+                        for (int o = 1; o < NDK_COOP_WARPS; ++o) best = s_best[o] > best ? s_best[o] : best;
+                        max_H = (int)(best >> 32);
+                        const unsigned rank = 0xffffffffu - (unsigned)(best & 0xffffffffLL);
+                        if (rank == 0) max_t = en0;
+                        else if (rank - 1 < (4u << 20)) max_t = st0 + (int)((rank - 1) & 0xfffff) * 4 + (int)((rank - 1) >> 20);
+                        else max_t = en1 + (int)(rank - 1 - (4u << 20));
+                    } else {
+                        if (gtid == 0) H[0] = NDK_H16(0, 1) - qe0;
+                        max_H = NDK_H16(0, 1) - qe0; max_t = 0;
+                    }
+                    if (en0 == tlen - 1) { int h = r == 0 ? max_H : H[en0]; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
+                    if (r - st0 == qlen - 1) { int h = r == 0 ? max_H : H[st0]; if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; } }
+                    if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = r == 0 ? max_H : H[tlen - 1];
+                } else {
+                    if (r > 0) {
+                        if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+                            int d0 = NDK_H16(last_H0_t, 1), d1 = NDK_H16(last_H0_t + 1, 3);
+                            if (d0 > d1) H0 += d0; else { H0 += d1; ++last_H0_t; }
+                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += NDK_H16(last_H0_t, 1);
+                        else { ++last_H0_t; H0 += NDK_H16(last_H0_t, 3); }
+                    } else { H0 = NDK_H16(0, 1) - qe0; last_H0_t = 0; }
+                    if ((flag & NDK_APPROX_DROP) && ndk_zdrop(ez, H0, r, last_H0_t, zdrop, (int)(int8_t)e2)) break;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+                }
+                last_st = st; last_en = en;
+            }
+            __syncthreads();
+            if (arena_full) ez.pad = 1;
+            else if (with_cigar && gtid == 0) {
+                const bool rev = (flag & NDK_REV_CIGAR) != 0;
+                if (!ez.zdropped && !(flag & NDK_EXTZ_ONLY))
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, tlen - 1, qlen - 1, cigar, rowtab);
+                else if (!ez.zdropped && (flag & NDK_EXTZ_ONLY) && ez.mqe + c.end_bonus > ez.max) {
+                    ez.reach_end = 1;
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.mqe_t, qlen - 1, cigar, rowtab);
+                } else if (ez.max_t >= 0 && ez.max_q >= 0)
+                    ez.n_cigar = ndk_backtrack(rev, p, off, off_end, n_col, ez.max_t, ez.max_q, cigar, rowtab);
+            }
+        }
+        if (gtid == 0) res[ci] = ez;
+        __syncthreads();
+    }
+}
+
 // ---- compact CIGAR hand-back: per-call capacity buffers -> one dense array ---------------------------------
 __global__ void k_ksw_ncigar(const ndk_res *res, int n, uint32_t *ncig)
 {

@@ -115,6 +115,7 @@ struct ndg_ctx {
     DevBuf ksw_ncig, ksw_coff, ksw_cout, ch_cnt, ch_off, ch_a, ch_fend;
     HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
     uint64_t arena_want = 0;
+    cudaStream_t st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -309,6 +310,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     c->q.release();
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
     c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release();
+    if (c->st2) { cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); }
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -873,9 +875,22 @@ struct GpuDp : ndal::Backend {
         return ((rows + 63) / 64 * 64) * (uint64_t)ncol * 16;                 // whole 64-row chunks
     }
 
-    int launch_group(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const uint32_t *ids, size_t n,
+    int launch_group(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const uint32_t *ids_in, size_t n,
                      std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars, std::vector<uint32_t> &retry)
     {
+        // calls whose anti-diagonals are wide go to the block-per-call kernel (first in the array), the rest to the warp-per-call one
+        static const int coop_min = getenv("NDG_COOP_MIN") ? atoi(getenv("NDG_COOP_MIN")) : 1024;
+        std::vector<uint32_t> idv; idv.reserve(n);
+        size_t nb = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t i = 0; i < n; ++i) {
+                const ndal::DpReq &k = reqs[ids_in[i]];
+                const int wd = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
+                const bool big = std::min(std::min(k.qlen, k.tlen), wd + 1) >= coop_min;
+                if (big == (pass == 0)) idv.push_back(ids_in[i]);
+                if (pass == 0 && big) ++nb;
+            }
+        const uint32_t *ids = idv.data();
         std::vector<ndk_call> hc(n);
         uint64_t seqb = 0, cig = 0; int Tmax = 16, rmax = 1, qmax = 1;
         for (size_t i = 0; i < n; ++i) {
@@ -894,23 +909,39 @@ struct GpuDp : ndal::Backend {
         const size_t tab_bytes = ((size_t)8 * ((size_t)(rmax >> 6) + 2) + 255) / 256 * 256;
         const size_t slot_bytes = state_bytes + h_bytes + off_bytes + tab_bytes;
         static const int bps = getenv("NDG_KSW_BPS") ? atoi(getenv("NDG_KSW_BPS")) : 16;
-        const int blocks = std::min<int>(c->n_sm * bps, (int)((n + NDK_WARPS - 1) / NDK_WARPS));
-        const size_t slots = (size_t)blocks * NDK_WARPS;
+        const size_t ns = n - nb;
+        const int blocks = ns ? std::min<int>(c->n_sm * bps, (int)((ns + NDK_WARPS - 1) / NDK_WARPS)) : 0;
+        const int cblocks = nb ? (int)std::min<size_t>((size_t)c->n_sm * 2, nb) : 0;
+        const size_t slots = (size_t)blocks * NDK_WARPS + (size_t)cblocks;
         RSV(c->ksw_calls, n * sizeof(ndk_call)); RSV(c->ksw_seqs, seqb + 64); RSV(c->ksw_res, n * sizeof(ndk_res));
         RSV(c->ksw_cig, (cig + 4) * 4); RSV(c->ksw_scratch, slots * slot_bytes); RSV(c->scalars, 1024);
         RSV(c->ksw_ncig, (n + 1) * 4); RSV(c->ksw_coff, (n + 1) * 8);
+        if (!c->st2) { CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming)); }
         CK(cudaMemcpyAsync(c->ksw_calls.p, hc.data(), n * sizeof(ndk_call), cudaMemcpyHostToDevice, c->st));
         CK(cudaMemcpyAsync(c->ksw_seqs.p, hs, seqb, cudaMemcpyHostToDevice, c->st));
         uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
         unsigned long long *d_cur = c->scalars.as<unsigned long long>() + 104;
-        CK(cudaMemsetAsync(d_work, 0, 4, c->st));
+        CK(cudaMemsetAsync(d_work, 0, 8, c->st));
         CK(cudaMemsetAsync(d_cur, 0, 8, c->st));
         cudaEvent_t e0 = ev_get(c), e1 = ev_get(c);
         CK(cudaEventRecord(e0, c->st));
-        KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), (int)n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
-                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work,
-                              d_cur, (unsigned long long)c->ksw_p.cap, off_bytes)));
-        CK(cudaGetLastError());
+        if (nb) {                                   // second stream: both kernels share the SMs and the arena
+            CK(cudaEventRecord(c->ev_a, c->st));
+            CK(cudaStreamWaitEvent(c->st2, c->ev_a, 0));
+            k_ksw_extd2_coop<<<cblocks, NDK_COOP_WARPS * 32, 0, c->st2>>>(c->ksw_calls.as<ndk_call>(), (int)nb, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
+                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work + 1,
+                              d_cur, (unsigned long long)c->ksw_p.cap, off_bytes);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->ev_b, c->st2));
+            ++c->launches;
+        }
+        if (ns) {
+            KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>() + nb, (int)ns, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>() + nb,
+                                  c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>() + (size_t)cblocks * slot_bytes, slot_bytes, state_bytes, h_bytes, d_work,
+                                  d_cur, (unsigned long long)c->ksw_p.cap, off_bytes)));
+            CK(cudaGetLastError());
+        }
+        if (nb) CK(cudaStreamWaitEvent(c->st, c->ev_b, 0));
         CK(cudaEventRecord(e1, c->st));
         KLAUNCH("ksw_cigar", (k_ksw_ncigar<<<nblk(n + 1, 256), 256, 0, c->st>>>(c->ksw_res.as<ndk_res>(), (int)n, c->ksw_ncig.as<uint32_t>())));
         if (int r2 = scan_u32_to_u64(c, c->ksw_ncig.as<uint32_t>(), c->ksw_coff.as<nd_u64>(), n)) return r2;
@@ -923,7 +954,7 @@ struct GpuDp : ndal::Backend {
         { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->aln_stat.dp_ms += ms; c->ev_pool.push_back(e0); c->ev_pool.push_back(e1);
           if (getenv("NDG_ALN_DEBUG")) {
               double cells = 0; for (size_t i = 0; i < n; ++i) cells += (double)hc[i].qlen * hc[i].tlen;
-              fprintf(stderr, "[ndg::dp] launch %llu: %zu calls, longest %dx%d, rect cells %.3g, seq %.1f MB, kernel %.1f ms, arena used %.2f GB, ext_frac %.4f\n", (unsigned long long)c->aln_stat.n_launches, n,
+              fprintf(stderr, "[ndg::dp] launch %llu: %zu calls (%zu wide), longest %dx%d, rect cells %.3g, seq %.1f MB, kernel %.1f ms, arena used %.2f GB, ext_frac %.4f\n", (unsigned long long)c->aln_stat.n_launches, n, nb,
                       hc[0].qlen, hc[0].tlen, cells, seqb / 1e6, ms, c->h_scalars.as<uint64_t>()[8] / 1e9, ext_frac);
           } }
         const uint64_t *koff = c->h_koff.as<uint64_t>(); const uint64_t tot = koff[n];
@@ -1247,7 +1278,12 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
     uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
     CK(cudaMemsetAsync(d_work, 0, 4, c->st));
     ndk_par P; P.m = m; memset(P.mat, 0, sizeof P.mat); memcpy(P.mat, mat, (size_t)m * m); P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
-    if (c->ksw_variant == 1)
+    if (c->ksw_variant == 2) {                       // block-per-call generation (wide bands)
+        const int cb = std::min<int>(c->n_sm * 2, n);
+        RSV(c->ksw_scratch, (size_t)cb * slot_bytes);
+        KLAUNCH("ksw_extd2", (k_ksw_extd2_coop<<<cb, NDK_COOP_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
+                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));
+    } else if (c->ksw_variant == 1)
         KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
                               c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));
     else

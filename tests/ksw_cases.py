@@ -86,3 +86,24 @@ def random_cases(n, seed=5, max_len=1500):
         out.append((np.ascontiguousarray(qv), np.ascontiguousarray(t), int(rng.choice([-1, 3001, 751, 100, 20, 5, 0])),
                     int(rng.choice([400, 200, 50, -1])), int(rng.choice([-1, 5, 50])), int(rng.choice(FLAGS))))
     return out
+
+
+def wide_cases(n, seed=11):
+    """long pairs with wide bands (the extension / long-join calls of mm_align1): 2-6 kb, w in {3001, 751, -1}"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.choice([1100, 2500, 4000, 6000]))
+        t = rng.integers(0, 4, L).astype(np.uint8)
+        rate = float(rng.choice([0.05, 0.15, 0.3]))
+        u = rng.random(L)
+        keep = u >= rate * 0.3
+        qv = np.where((u >= rate * 0.6) & (u < rate), (t + 1 + rng.integers(0, 3, L)) % 4, t).astype(np.uint8)[keep]
+        ins = rng.random(qv.shape[0]) < rate * 0.3
+        qv = np.insert(qv, np.nonzero(ins)[0], rng.integers(0, 4, int(ins.sum())).astype(np.uint8))
+        if rng.random() < 0.5:                  # unrelated tail: the extension z-drops inside it
+            cut = int(rng.integers(L // 4, L))
+            qv = np.concatenate([qv[:cut], rng.integers(0, 4, int(rng.integers(500, 3000))).astype(np.uint8)])
+        out.append((np.ascontiguousarray(qv), np.ascontiguousarray(t), int(rng.choice([3001, 751, -1, 1500])),
+                    int(rng.choice([400, 200])), int(rng.choice([-1, 5])), int(rng.choice([0x40 | 0x02 | 0x80, 0x40, 0x08, 0]))))
+    return out

@@ -186,7 +186,35 @@ def test_cli_cigar_matches_reference_bytes(built, golden_dir, tmp_path):
     assert "DP calls" in r.stderr
 
 
-@pytest.mark.parametrize("ksw_variant", [1, 0])
+@pytest.mark.parametrize("ksw_variant", [1, 2])
+def test_ksw_extd2_wide_bands_bit_exact(eng, ksw_variant):
+    """long calls with wide bands through the warp-per-call (1) and the block-per-call (2) kernels == the reference function"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from ksw_cases import simple_mat, oracle_lib, oracle_call, ref_lib, ref_call, wide_cases
+    from nextdenovo_b200.engine import KSW_CALL_DTYPE
+    mat = simple_mat()
+    cases = wide_cases(48)
+    calls = np.zeros(len(cases), dtype=KSW_CALL_DTYPE)
+    chunks, off = [], 0
+    for i, (qs, ts, w, zd, eb, flag) in enumerate(cases):
+        calls[i] = (len(qs), len(ts), off, off + len(qs), w, zd, eb, flag)
+        chunks += [qs, ts]; off += len(qs) + len(ts)
+    eng.set_ksw_variant(ksw_variant)
+    res, cigs = eng.ksw_extd2_batch(calls, np.concatenate(chunks), mat, 4, 2, 24, 1)
+    eng.set_ksw_variant(1)
+    L, R = oracle_lib(), ref_lib()
+    names = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end")
+    bad = []
+    for i, (qs, ts, w, zd, eb, flag) in enumerate(cases):
+        want = ref_call(R, qs, ts, mat, 4, 2, 24, 1, w, zd, eb, flag) if R is not None else oracle_call(L, qs, ts, mat, 4, 2, 24, 1, w, zd, eb, flag)
+        got = (tuple(int(res[n][i]) for n in names), [int(x) for x in cigs[i]])
+        if got != want:
+            bad.append((i, len(qs), len(ts), w, hex(flag), got[0], want[0]))
+    assert not bad, "%d/%d calls differ; first: %s" % (len(bad), len(cases), bad[:3])
+
+
+@pytest.mark.parametrize("ksw_variant", [1, 0, 2])
 def test_ksw_extd2_batch_bit_exact(eng, ksw_variant):
     """ndg_ksw_extd2_batch == ksw_extd2_sse (via the oracle restatement, and the compiled reference when present):
     score, max, end points, z-drop flag, reach_end and CIGAR, for every call of a mixed batch."""

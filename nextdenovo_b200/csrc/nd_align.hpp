@@ -23,11 +23,21 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <stdio.h>
 #include <vector>
 #include <algorithm>
 #include "nd_core.cuh"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace ndal {
+
+#ifdef _OPENMP
+inline double wall() { return omp_get_wtime(); }
+#else
+inline double wall() { return 0; }
+#endif
 
 static const uint64_t SEED_LONG_JOIN = 1ULL << 40, SEED_IGNORE = 1ULL << 41;     // ref: minimap2/mmpriv.h:18-21
 static const uint64_t SEED_TANDEM = 1ULL << 42, SEED_SELF = 1ULL << 43;
@@ -57,11 +67,33 @@ struct SeqStore {                                  // 2-bit words as in the .2bi
     }
     void get(int rid, int st, int en, uint8_t *dst) const            // mm_idx_getseq, ref: minimap2/index.c:152-162
     {
-        for (int i = st; i < en; ++i) dst[i - st] = base(rid, (uint32_t)i);
+        const uint32_t *w = words + word_off[rid];
+        int i = st;
+        for (; i < en && (i & 15); ++i) dst[i - st] = (uint8_t)(w[i >> 4] >> (30 - 2 * (i & 15)) & 3);
+        for (; i + 16 <= en; i += 16) {
+            const uint32_t x = w[i >> 4]; uint8_t *d = dst + (i - st);
+            for (int k = 0; k < 16; ++k) d[k] = (uint8_t)(x >> (30 - 2 * k) & 3);
+        }
+        for (; i < en; ++i) dst[i - st] = (uint8_t)(w[i >> 4] >> (30 - 2 * (i & 15)) & 3);
+        if (nmask) {
+            const uint32_t *m = nmask + word_off[rid] / 2;
+            for (i = st; i < en; ++i) if (m[i >> 5] >> (i & 31) & 1) dst[i - st] = 4;
+        }
     }
     void get_reversed(int rid, int st, int en, uint8_t *dst) const   // the same followed by mm_seq_rev (align.c:25-31)
     {
-        for (int i = st; i < en; ++i) dst[en - 1 - i] = base(rid, (uint32_t)i);
+        const uint32_t *w = words + word_off[rid];
+        int i = st;
+        for (; i < en && (i & 15); ++i) dst[en - 1 - i] = (uint8_t)(w[i >> 4] >> (30 - 2 * (i & 15)) & 3);
+        for (; i + 16 <= en; i += 16) {
+            const uint32_t x = w[i >> 4]; uint8_t *d = dst + (en - 1 - i);
+            for (int k = 0; k < 16; ++k) d[-k] = (uint8_t)(x >> (30 - 2 * k) & 3);
+        }
+        for (; i < en; ++i) dst[en - 1 - i] = (uint8_t)(w[i >> 4] >> (30 - 2 * (i & 15)) & 3);
+        if (nmask) {
+            const uint32_t *m = nmask + word_off[rid] / 2;
+            for (i = st; i < en; ++i) if (m[i >> 5] >> (i & 31) & 1) dst[en - 1 - i] = 4;
+        }
     }
 };
 
@@ -165,33 +197,36 @@ struct LocalSW {
                     prof[((size_t)c * slen + i) * 8 + l] = k >= ql ? 0 : mat[c * 5 + query[k]];
                 }
     }
-    static inline int16_t adds(int16_t x, int16_t y) { int v = (int)x + y; return (int16_t)(v > 32767 ? 32767 : v < -32768 ? -32768 : v); }
-    static inline int16_t subu(int16_t x, int16_t y) { int v = (int)(uint16_t)x - (int)(uint16_t)y; return (int16_t)(uint16_t)(v < 0 ? 0 : v); }
+    // All running values are in [0, 32767] (E and F never go below 0, so H = max(H_diag + s, E, F) >= 0): the unsigned saturating
+    // subtractions of the striped kernel are max(x - y, 0) and its signed saturating add is min(x + y, 32767).  Lane loops are
+    // written for the vectoriser.
     int run(int tlen, const uint8_t *target, int gapo, int gape, int *qe, int *te)
     {
         int gmax = 0;
-        const int16_t goe = (int16_t)(gapo + gape), ge = (int16_t)gape;
+        const int goe = gapo + gape, ge = gape;
         *qe = *te = -1;
         H0.assign((size_t)slen * 8, 0); H1.assign((size_t)slen * 8, 0); E.assign((size_t)slen * 8, 0); Hmax.assign((size_t)slen * 8, 0);
-        int16_t *h0 = H0.data(), *h1 = H1.data();
+        int16_t *h0 = H0.data(), *h1 = H1.data(), *Ev = E.data();
         for (int i = 0; i < tlen; ++i) {
-            int16_t h[8], f[8], mx[8], e[8];
+            int16_t h[8], f[8], mx[8];
             const int16_t *S = &prof[(size_t)target[i] * slen * 8];
             for (int l = 0; l < 8; ++l) { f[l] = 0; mx[l] = 0; }
             h[0] = 0; for (int l = 1; l < 8; ++l) h[l] = h0[(size_t)(slen - 1) * 8 + l - 1];
             for (int j = 0; j < slen; ++j) {
+                const int16_t *Sj = S + (size_t)j * 8, *H0j = h0 + (size_t)j * 8; int16_t *Ej = Ev + (size_t)j * 8, *H1j = h1 + (size_t)j * 8;
+#pragma omp simd
                 for (int l = 0; l < 8; ++l) {
-                    int16_t hh = adds(h[l], S[(size_t)j * 8 + l]);
-                    e[l] = E[(size_t)j * 8 + l];
-                    if (e[l] > hh) hh = e[l];
-                    if (f[l] > hh) hh = f[l];
-                    if (hh > mx[l]) mx[l] = hh;
-                    h1[(size_t)j * 8 + l] = hh;
-                    hh = subu(hh, goe);
-                    e[l] = subu(e[l], ge); if (hh > e[l]) e[l] = hh;
-                    E[(size_t)j * 8 + l] = e[l];
-                    f[l] = subu(f[l], ge); if (hh > f[l]) f[l] = hh;
-                    h[l] = h0[(size_t)j * 8 + l];
+                    int hh = (int)h[l] + Sj[l]; hh = hh > 32767 ? 32767 : hh;
+                    const int e = Ej[l];
+                    hh = hh > e ? hh : e; hh = hh > f[l] ? hh : f[l];
+                    mx[l] = (int16_t)(mx[l] > hh ? mx[l] : hh);
+                    H1j[l] = (int16_t)hh;
+                    const int h2 = hh - goe > 0 ? hh - goe : 0;
+                    int e2 = e - ge > 0 ? e - ge : 0; e2 = e2 > h2 ? e2 : h2;
+                    Ej[l] = (int16_t)e2;
+                    int f2 = f[l] - ge > 0 ? f[l] - ge : 0; f2 = f2 > h2 ? f2 : h2;
+                    f[l] = (int16_t)f2;
+                    h[l] = H0j[l];
                 }
             }
             bool stop = false;
@@ -199,14 +234,15 @@ struct LocalSW {
                 for (int l = 7; l > 0; --l) f[l] = f[l - 1];
                 f[0] = 0;
                 for (int j = 0; j < slen && !stop; ++j) {
-                    bool any = false;
+                    int16_t *H1j = h1 + (size_t)j * 8; int any = 0;
+#pragma omp simd reduction(|:any)
                     for (int l = 0; l < 8; ++l) {
-                        int16_t hh = h1[(size_t)j * 8 + l];
-                        if (f[l] > hh) hh = f[l];
-                        h1[(size_t)j * 8 + l] = hh;
-                        hh = subu(hh, goe);
-                        f[l] = subu(f[l], ge);
-                        if (f[l] > hh) any = true;
+                        int hh = H1j[l]; hh = hh > f[l] ? hh : f[l];
+                        H1j[l] = (int16_t)hh;
+                        const int h2 = hh - goe > 0 ? hh - goe : 0;
+                        const int f2 = f[l] - ge > 0 ? f[l] - ge : 0;
+                        f[l] = (int16_t)f2;
+                        any |= f2 > h2;
                     }
                     if (!any) stop = true;
                 }
@@ -577,6 +613,9 @@ struct Ctx {
     const Opt *o; const SeqStore *T; int8_t mat[25];
 };
 
+struct WalkProf { double t_plan = 0, t_zdrop = 0, t_extra = 0, t_task_max = 0; long n_zdrop = 0, n_extra = 0, n_inv = 0; };
+inline WalkProf *&walk_prof() { static thread_local WalkProf *p = 0; return p; }
+
 struct Walker {                                    // one attempt at mm_align1 / mm_align1_inv for the current hit of a task
     const Ctx &C; ReadJob &J; Task &K; int task_id; std::vector<DpReq> &reqs; std::vector<uint8_t> &tbuf; std::vector<int> &scratch;
     bool missing = false;
@@ -605,7 +644,7 @@ struct Walker {                                    // one attempt at mm_align1 /
         const Opt &o = *C.o; const SeqStore &T = *C.T;
         r2.cnt = 0;
         if (r.cnt == 0) return true;
-        if (!K.planned) { plan_windows(o, T, J, r, K.W, scratch); K.planned = true; }
+        if (!K.planned) { const double tp = walk_prof() ? wall() : 0; plan_windows(o, T, J, r, K.W, scratch); K.planned = true; if (walk_prof()) walk_prof()->t_plan += wall() - tp; }
         const Windows &W = K.W;
         const nd_u128 *a = J.a.data();
         const int qlen = J.qlen, rid = W.rid, rev = W.rev, as1 = W.as1, cnt1 = W.cnt1, bw = W.bw;
@@ -641,7 +680,9 @@ struct Walker {                                    // one attempt at mm_align1 /
                         if (tbuf.size() < (size_t)(re - rs) + 1) tbuf.resize((size_t)(re - rs) + 1);
                         T.get(rid, rs, re, tbuf.data());
                     }
+                    const double tz = walk_prof() ? wall() : 0;
                     z->zcode = test_zdrop(o, qstrand + qs, tbuf.data(), z->n_cigar, K.cigpool.data() + z->cig_off, C.mat);
+                    if (walk_prof()) { walk_prof()->t_zdrop += wall() - tz; ++walk_prof()->n_zdrop; if (z->zcode == 2) ++walk_prof()->n_inv; }
                 }
                 const int zcode = z->zcode;
                 if (zcode != 0) {
@@ -679,11 +720,13 @@ struct Walker {                                    // one attempt at mm_align1 /
         w.rs = rs1; w.re = re1;
         if (rev) { w.qs = qlen - qe1; w.qe = qlen - qs1; } else { w.qs = qs1; w.qe = qe1; }
         if (w.has_p) {
+            const double tx = walk_prof() ? wall() : 0;
             if (tbuf.size() < (size_t)(re1 - rs1) + 1) tbuf.resize((size_t)(re1 - rs1) + 1);
             T.get(rid, rs1, re1, tbuf.data());
             update_extra(w, J.strand(w.rev) + qs1, tbuf.data(), C.mat, o.q, o.e);
+            if (walk_prof()) { walk_prof()->t_extra += wall() - tx; ++walk_prof()->n_extra; }
         }
-        r = w; r2 = w2;
+        r = std::move(w); r2 = std::move(w2);
         return true;
     }
 
@@ -791,7 +834,7 @@ struct Backend {                                   // runs ksw_extd2 for a list 
     virtual ~Backend() {}
 };
 
-struct Stats { uint64_t n_tasks = 0, n_calls = 0, n_rounds = 0, cells = 0; };
+struct Stats { uint64_t n_tasks = 0, n_calls = 0, n_rounds = 0, cells = 0; double t_walk = 0, t_dp = 0, t_hand = 0, t_finish = 0; };
 
 // jobs[r].regs are replaced by the aligned, filtered and ordered hits (what mm_align_skeleton returns)
 inline void align_batch(const Opt &o, const SeqStore &T, std::vector<ReadJob> &jobs, Backend &be, Stats *st)
@@ -809,24 +852,43 @@ inline void align_batch(const Opt &o, const SeqStore &T, std::vector<ReadJob> &j
     std::vector<DpReq> reqs; std::vector<DpRes> res; std::vector<uint32_t> cigs;
     while (!active.empty()) {
         reqs.clear();
+        double t0 = wall();
+        const bool dbg = getenv("NDAL_DEBUG") != 0;
+        WalkProf tot; double busy_sum = 0, busy_max = 0; int n_thr = 0;
 #pragma omp parallel
         {
             std::vector<DpReq> mine; std::vector<uint8_t> tbuf; std::vector<int> scratch;
-#pragma omp for schedule(dynamic, 16) nowait
+            WalkProf wp; if (dbg) walk_prof() = &wp;
+            double busy = 0;
+#pragma omp for schedule(dynamic, 1) nowait
             for (long long k = 0; k < (long long)active.size(); ++k) {
                 Task &K = tasks[(size_t)active[(size_t)k]];
+                const double ta = dbg ? wall() : 0;
                 advance(C, jobs[(size_t)K.read], K, active[(size_t)k], mine, tbuf, scratch);
+                if (dbg) { const double d = wall() - ta; busy += d; if (d > wp.t_task_max) wp.t_task_max = d; }
             }
+            walk_prof() = 0;
 #pragma omp critical
-            reqs.insert(reqs.end(), mine.begin(), mine.end());
+            {
+                reqs.insert(reqs.end(), mine.begin(), mine.end());
+                if (dbg) { tot.t_plan += wp.t_plan; tot.t_zdrop += wp.t_zdrop; tot.t_extra += wp.t_extra; tot.n_zdrop += wp.n_zdrop; tot.n_extra += wp.n_extra; tot.n_inv += wp.n_inv;
+                           if (wp.t_task_max > tot.t_task_max) tot.t_task_max = wp.t_task_max; busy_sum += busy; if (busy > busy_max) busy_max = busy; ++n_thr; }
+            }
         }
+        if (dbg) fprintf(stderr, "[ndal] walk detail: %d threads, busy sum %.2f s (max thread %.2f s, slowest task %.3f s); plan %.2f s, zdrop tests %ld in %.2f s (%ld inversion candidates), update_extra %ld in %.2f s\n",
+                         n_thr, busy_sum, busy_max, tot.t_task_max, tot.t_plan, tot.n_zdrop, tot.t_zdrop, tot.n_inv, tot.n_extra, tot.t_extra);
         std::vector<int> next;
         for (size_t k = 0; k < active.size(); ++k) if (!tasks[(size_t)active[k]].done) next.push_back(active[k]);
         active.swap(next);
+        if (st) st->t_walk += wall() - t0;
+        if (getenv("NDAL_DEBUG")) fprintf(stderr, "[ndal] round: %zu active tasks walked in %.3f s -> %zu calls\n", active.size() + 0, wall() - t0, reqs.size());
         if (reqs.empty()) break;
         if (st) { st->n_calls += reqs.size(); ++st->n_rounds; for (const DpReq &q : reqs) st->cells += (uint64_t)q.qlen * q.tlen; }
         res.clear(); cigs.clear();
+        t0 = wall();
         be.run(reqs, T, res, cigs);
+        if (st) st->t_dp += wall() - t0;
+        t0 = wall();
         // hand results to their tasks; the calls of one task are contiguous in reqs
         std::vector<size_t> runs;
         for (size_t i = 0; i < reqs.size(); ++i) if (i == 0 || reqs[i].task != reqs[i - 1].task) runs.push_back(i);
@@ -842,7 +904,9 @@ inline void align_batch(const Opt &o, const SeqStore &T, std::vector<ReadJob> &j
                 K.memo.push_back(std::make_pair(reqs[i].key, z));
             }
         }
+        if (st) st->t_hand += wall() - t0;
     }
+    const double t1 = wall();
     size_t t = 0;
     for (size_t r = 0; r < jobs.size(); ++r) {
         const size_t n0 = jobs[r].regs.size();
@@ -852,6 +916,7 @@ inline void align_batch(const Opt &o, const SeqStore &T, std::vector<ReadJob> &j
     }
 #pragma omp parallel for schedule(dynamic, 4)
     for (long long r = 0; r < (long long)jobs.size(); ++r) finish_read(o, jobs[(size_t)r].qlen, jobs[(size_t)r].regs);
+    if (st) st->t_finish += wall() - t1;
 }
 
 // chains of one read as the GPU path hands them over -> chain array + hits in the reference's order

@@ -15,6 +15,8 @@
 #include "nd_ksw.cuh"
 #include "nd_align.hpp"
 #include <omp.h>
+#include <parallel/algorithm>
+#include <omp.h>
 
 static_assert(sizeof(nd_hit) == sizeof(ndg_hit_t), "hit layout");
 static_assert(sizeof(nd_hit) == 56, "hit size");
@@ -116,10 +118,29 @@ struct ndg_ctx {
     HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
     uint64_t arena_want = 0;
     cudaStream_t st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int n_threads = 1;                            // host threads of the alignment stage
 };
 
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// CPUs this process may really use: the affinity mask, capped by a cgroup CPU quota when there is one (a container that shows
+// 128 logical CPUs may be allowed 16 CPUs' worth of time; oversubscribing it makes every OpenMP region slower)
+int usable_cpus()
+{
+    int n = omp_get_num_procs();
+    long quota = -1, period = 0;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {                       // cgroup v2
+        char a[64];
+        if (fscanf(f, "%63s %ld", a, &period) == 2 && strcmp(a, "max") != 0) quota = atol(a);
+        fclose(f);
+    } else {                                                                    // cgroup v1
+        if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(g, "%ld", &quota) != 1) quota = -1; fclose(g); }
+        if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(g, "%ld", &period) != 1) period = 0; fclose(g); }
+    }
+    if (quota > 0 && period > 0) { int q = (int)((quota + period - 1) / period); if (q >= 1 && q < n) n = q; }
+    return n < 1 ? 1 : n;
+}
 
 int fail(ndg_ctx *c, int code, const char *fmt, ...)
 {
@@ -289,6 +310,7 @@ extern "C" int ndg_init(int device, ndg_ctx_t **out)
     c->opt.k = 15; c->opt.w = 10; c->opt.min_cnt = 3; c->opt.min_chain_score = 40; c->opt.bw = 500; c->opt.max_gap = 5000;
     c->opt.max_chain_skip = 25; c->opt.max_chain_iter = 5000; c->opt.seed = 11; c->opt.mid_occ_frac = 2e-4f;
     if (c->h_scalars.reserve(4096)) { delete c; return NDG_ERR_NOMEM; }
+    c->n_threads = usable_cpus();
     c->n_sm = prop.multiProcessorCount;
     cudaDeviceSetLimit(cudaLimitStackSize, 8192);
     *out = c;
@@ -864,8 +886,29 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// One launch of the DP kernels with everything it owns; two of them are in flight at a time so that staging the next launch
+// (sequence bytes, call table) and collecting the previous one overlap the kernels.
+struct DpLaunch {
+    HostBuf h_seq, h_res, h_cig, h_off;
+    DevBuf calls, seqs, res, cig, scratch, ncig, coff, cout, tmp, cur;
+    cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr, e0 = nullptr, e1 = nullptr;
+    std::vector<ndk_call> hc; std::vector<uint32_t> ids;
+    size_t n = 0, nb = 0; uint64_t seqb = 0, cig_cap = 0, fixed = 0, ext_need = 0;
+    int Tmax = 16, rmax = 1, qmax = 1;
+    bool busy = false;
+    void release() {
+        h_seq.release(); h_res.release(); h_cig.release(); h_off.release();
+        DevBuf *d[] = { &calls, &seqs, &res, &cig, &scratch, &ncig, &coff, &cout, &tmp, &cur };
+        for (auto x : d) x->release();
+        if (st) { cudaStreamDestroy(st); cudaStreamDestroy(st2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(e0); cudaEventDestroy(e1); st = nullptr; }
+    }
+};
+
 struct GpuDp : ndal::Backend {
     ndg_ctx *c; ndk_par P; int rc = 0;
+    DpLaunch L[2];
+    double ext_frac = 1.0 / 16;                     // share of an extension's worst-case matrix that gets written (adapted from the arena cursor)
+    ~GpuDp() { for (auto &l : L) l.release(); }
 
     static uint64_t p_need(const ndal::DpReq &k)
     {
@@ -875,106 +918,149 @@ struct GpuDp : ndal::Backend {
         return ((rows + 63) / 64 * 64) * (uint64_t)ncol * 16;                 // whole 64-row chunks
     }
 
-    int launch_group(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const uint32_t *ids_in, size_t n,
-                     std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars, std::vector<uint32_t> &retry)
+    // host side of a launch: order the calls (wide ones first: they go to the block-per-call kernel), write the sequence bytes
+    int prepare(DpLaunch &B, const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const std::vector<uint32_t> &ids_in)
     {
-        // calls whose anti-diagonals are wide go to the block-per-call kernel (first in the array), the rest to the warp-per-call one
         static const int coop_min = getenv("NDG_COOP_MIN") ? atoi(getenv("NDG_COOP_MIN")) : 1024;
-        std::vector<uint32_t> idv; idv.reserve(n);
-        size_t nb = 0;
+        const size_t n = ids_in.size();
+        B.ids.clear(); B.ids.reserve(n); B.nb = 0;
         for (int pass = 0; pass < 2; ++pass)
             for (size_t i = 0; i < n; ++i) {
                 const ndal::DpReq &k = reqs[ids_in[i]];
                 const int wd = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
                 const bool big = std::min(std::min(k.qlen, k.tlen), wd + 1) >= coop_min;
-                if (big == (pass == 0)) idv.push_back(ids_in[i]);
-                if (pass == 0 && big) ++nb;
+                if (big == (pass == 0)) B.ids.push_back(ids_in[i]);
+                if (pass == 0 && big) ++B.nb;
             }
-        const uint32_t *ids = idv.data();
-        std::vector<ndk_call> hc(n);
-        uint64_t seqb = 0, cig = 0; int Tmax = 16, rmax = 1, qmax = 1;
+        B.n = n; B.hc.resize(n);
+        uint64_t seqb = 0, cig = 0; B.Tmax = 16; B.rmax = 1; B.qmax = 1;
         for (size_t i = 0; i < n; ++i) {
-            const ndal::DpReq &k = reqs[ids[i]]; ndk_call &d = hc[i];
+            const ndal::DpReq &k = reqs[B.ids[i]]; ndk_call &d = B.hc[i];
             d.qlen = k.qlen; d.tlen = k.tlen; d.q_off = seqb; d.t_off = seqb + (uint64_t)k.qlen; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag;
             d.p_off = 0; d.cigar_off = cig;
             seqb += (uint64_t)k.qlen + k.tlen; cig += (uint64_t)k.qlen + k.tlen + 2;
-            Tmax = std::max(Tmax, (k.tlen + 15) / 16 * 16); rmax = std::max(rmax, k.qlen + k.tlen); qmax = std::max(qmax, k.qlen);
+            B.Tmax = std::max(B.Tmax, (k.tlen + 15) / 16 * 16); B.rmax = std::max(B.rmax, k.qlen + k.tlen); B.qmax = std::max(B.qmax, k.qlen);
         }
-        if (c->h_kseq.reserve(seqb + 64)) return fail(c, NDG_ERR_NOMEM, "pinned sequence staging");
-        uint8_t *hs = c->h_kseq.as<uint8_t>();
+        B.seqb = seqb; B.cig_cap = cig;
+        if (B.h_seq.reserve(seqb + 64)) return fail(c, NDG_ERR_NOMEM, "pinned sequence staging");
+        uint8_t *hs = B.h_seq.as<uint8_t>();
 #pragma omp parallel for schedule(dynamic, 256)
-        for (long long i = 0; i < (long long)n; ++i) ndal::materialize(reqs[ids[(size_t)i]], T, hs + hc[(size_t)i].q_off, hs + hc[(size_t)i].t_off);
-        const size_t state_bytes = ((size_t)17 * Tmax + ((size_t)(qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;
-        const size_t h_bytes = ((size_t)4 * Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * rmax + 255) / 256 * 256;
-        const size_t tab_bytes = ((size_t)8 * ((size_t)(rmax >> 6) + 2) + 255) / 256 * 256;
+        for (long long i = 0; i < (long long)n; ++i) ndal::materialize(reqs[B.ids[(size_t)i]], T, hs + B.hc[(size_t)i].q_off, hs + B.hc[(size_t)i].t_off);
+        return 0;
+    }
+
+    // enqueue the input copies of a prepared launch (they do not touch the arena, so they overlap the previous launch's kernels)
+    int submit_copies(DpLaunch &B)
+    {
+        const size_t n = B.n;
+        if (!B.st) {
+            CK(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&B.st2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&B.ev_a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&B.ev_b, cudaEventDisableTiming));
+            CK(cudaEventCreate(&B.e0)); CK(cudaEventCreate(&B.e1));
+        }
+        RSV(B.calls, n * sizeof(ndk_call)); RSV(B.seqs, B.seqb + 64); RSV(B.res, n * sizeof(ndk_res));
+        RSV(B.cig, (B.cig_cap + 4) * 4); RSV(B.cur, 256);
+        RSV(B.ncig, (n + 1) * 4); RSV(B.coff, (n + 1) * 8);
+        if (B.h_off.reserve((n + 2) * 8) || B.h_res.reserve(n * sizeof(ndk_res))) return fail(c, NDG_ERR_NOMEM, "pinned result staging");
+        CK(cudaMemcpyAsync(B.calls.p, B.hc.data(), n * sizeof(ndk_call), cudaMemcpyHostToDevice, B.st));
+        CK(cudaMemcpyAsync(B.seqs.p, B.h_seq.p, B.seqb, cudaMemcpyHostToDevice, B.st));
+        return 0;
+    }
+
+    // enqueue the kernels of a launch; the arena must be free (previous launch's kernels finished)
+    int submit_kernels(DpLaunch &B, uint8_t *arena, uint64_t arena_bytes)
+    {
+        const size_t n = B.n, nb = B.nb, ns = n - nb;
+        const size_t state_bytes = ((size_t)17 * B.Tmax + ((size_t)(B.qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;
+        const size_t h_bytes = ((size_t)4 * B.Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * B.rmax + 255) / 256 * 256;
+        const size_t tab_bytes = ((size_t)8 * ((size_t)(B.rmax >> 6) + 2) + 255) / 256 * 256;
         const size_t slot_bytes = state_bytes + h_bytes + off_bytes + tab_bytes;
         static const int bps = getenv("NDG_KSW_BPS") ? atoi(getenv("NDG_KSW_BPS")) : 16;
-        const size_t ns = n - nb;
         const int blocks = ns ? std::min<int>(c->n_sm * bps, (int)((ns + NDK_WARPS - 1) / NDK_WARPS)) : 0;
         const int cblocks = nb ? (int)std::min<size_t>((size_t)c->n_sm * 2, nb) : 0;
         const size_t slots = (size_t)blocks * NDK_WARPS + (size_t)cblocks;
-        RSV(c->ksw_calls, n * sizeof(ndk_call)); RSV(c->ksw_seqs, seqb + 64); RSV(c->ksw_res, n * sizeof(ndk_res));
-        RSV(c->ksw_cig, (cig + 4) * 4); RSV(c->ksw_scratch, slots * slot_bytes); RSV(c->scalars, 1024);
-        RSV(c->ksw_ncig, (n + 1) * 4); RSV(c->ksw_coff, (n + 1) * 8);
-        if (!c->st2) { CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming)); }
-        CK(cudaMemcpyAsync(c->ksw_calls.p, hc.data(), n * sizeof(ndk_call), cudaMemcpyHostToDevice, c->st));
-        CK(cudaMemcpyAsync(c->ksw_seqs.p, hs, seqb, cudaMemcpyHostToDevice, c->st));
-        uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
-        unsigned long long *d_cur = c->scalars.as<unsigned long long>() + 104;
-        CK(cudaMemsetAsync(d_work, 0, 8, c->st));
-        CK(cudaMemsetAsync(d_cur, 0, 8, c->st));
-        cudaEvent_t e0 = ev_get(c), e1 = ev_get(c);
-        CK(cudaEventRecord(e0, c->st));
+        RSV(c->ksw_scratch, slots * slot_bytes);    // shared: launches never run their kernels at the same time
+        DevBuf &scr = c->ksw_scratch;
+        unsigned long long *d_cur = B.cur.as<unsigned long long>();           // [0] arena cursor, [1] two work counters
+        uint32_t *d_work = reinterpret_cast<uint32_t *>(d_cur + 1);
+        CK(cudaMemsetAsync(d_cur, 0, 16, B.st));
+        CK(cudaEventRecord(B.e0, B.st));
         if (nb) {                                   // second stream: both kernels share the SMs and the arena
-            CK(cudaEventRecord(c->ev_a, c->st));
-            CK(cudaStreamWaitEvent(c->st2, c->ev_a, 0));
-            k_ksw_extd2_coop<<<cblocks, NDK_COOP_WARPS * 32, 0, c->st2>>>(c->ksw_calls.as<ndk_call>(), (int)nb, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
-                              c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work + 1,
-                              d_cur, (unsigned long long)c->ksw_p.cap, off_bytes);
+            CK(cudaEventRecord(B.ev_a, B.st));
+            CK(cudaStreamWaitEvent(B.st2, B.ev_a, 0));
+            k_ksw_extd2_coop<<<cblocks, NDK_COOP_WARPS * 32, 0, B.st2>>>(B.calls.as<ndk_call>(), (int)nb, B.seqs.as<uint8_t>(), P, B.res.as<ndk_res>(),
+                              arena, B.cig.as<uint32_t>(), scr.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work + 1, d_cur, arena_bytes, off_bytes);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(c->ev_b, c->st2));
+            CK(cudaEventRecord(B.ev_b, B.st2));
             ++c->launches;
         }
         if (ns) {
-            KLAUNCH("ksw_extd2", (k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>() + nb, (int)ns, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>() + nb,
-                                  c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>() + (size_t)cblocks * slot_bytes, slot_bytes, state_bytes, h_bytes, d_work,
-                                  d_cur, (unsigned long long)c->ksw_p.cap, off_bytes)));
+            k_ksw_extd2_px<<<blocks, NDK_WARPS * 32, 0, B.st>>>(B.calls.as<ndk_call>() + nb, (int)ns, B.seqs.as<uint8_t>(), P, B.res.as<ndk_res>() + nb,
+                              arena, B.cig.as<uint32_t>(), scr.as<uint8_t>() + (size_t)cblocks * slot_bytes, slot_bytes, state_bytes, h_bytes, d_work, d_cur, arena_bytes, off_bytes);
             CK(cudaGetLastError());
+            ++c->launches;
         }
-        if (nb) CK(cudaStreamWaitEvent(c->st, c->ev_b, 0));
-        CK(cudaEventRecord(e1, c->st));
-        KLAUNCH("ksw_cigar", (k_ksw_ncigar<<<nblk(n + 1, 256), 256, 0, c->st>>>(c->ksw_res.as<ndk_res>(), (int)n, c->ksw_ncig.as<uint32_t>())));
-        if (int r2 = scan_u32_to_u64(c, c->ksw_ncig.as<uint32_t>(), c->ksw_coff.as<nd_u64>(), n)) return r2;
-        if (c->h_koff.reserve((n + 1) * 8) || c->h_kres.reserve(n * sizeof(ndk_res))) return fail(c, NDG_ERR_NOMEM, "pinned result staging");
-        CK(cudaMemcpyAsync(c->h_koff.p, c->ksw_coff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(c->h_kres.p, c->ksw_res.p, n * sizeof(ndk_res), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(c->h_scalars.as<uint64_t>() + 8, d_cur, 8, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        last_used = c->h_scalars.as<uint64_t>()[8];
-        { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->aln_stat.dp_ms += ms; c->ev_pool.push_back(e0); c->ev_pool.push_back(e1);
-          if (getenv("NDG_ALN_DEBUG")) {
-              double cells = 0; for (size_t i = 0; i < n; ++i) cells += (double)hc[i].qlen * hc[i].tlen;
-              fprintf(stderr, "[ndg::dp] launch %llu: %zu calls (%zu wide), longest %dx%d, rect cells %.3g, seq %.1f MB, kernel %.1f ms, arena used %.2f GB, ext_frac %.4f\n", (unsigned long long)c->aln_stat.n_launches, n, nb,
-                      hc[0].qlen, hc[0].tlen, cells, seqb / 1e6, ms, c->h_scalars.as<uint64_t>()[8] / 1e9, ext_frac);
-          } }
-        const uint64_t *koff = c->h_koff.as<uint64_t>(); const uint64_t tot = koff[n];
+        if (nb) CK(cudaStreamWaitEvent(B.st, B.ev_b, 0));
+        CK(cudaEventRecord(B.e1, B.st));
+        k_ksw_ncigar<<<nblk(n + 1, 256), 256, 0, B.st>>>(B.res.as<ndk_res>(), (int)n, B.ncig.as<uint32_t>());
+        {
+            size_t tmp = 0;
+            auto it = cub::TransformInputIterator<nd_u64, cub::CastOp<nd_u64>, const uint32_t *>(B.ncig.as<uint32_t>(), cub::CastOp<nd_u64>());
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, B.coff.as<nd_u64>(), (long long)(n + 1), B.st));
+            RSV(B.tmp, tmp);
+            CK(cub::DeviceScan::ExclusiveSum(B.tmp.p, tmp, it, B.coff.as<nd_u64>(), (long long)(n + 1), B.st));
+        }
+        CK(cudaMemcpyAsync(B.h_off.p, B.coff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, B.st));
+        CK(cudaMemcpyAsync(B.h_off.as<uint64_t>() + n + 1, d_cur, 8, cudaMemcpyDeviceToHost, B.st));
+        CK(cudaMemcpyAsync(B.h_res.p, B.res.p, n * sizeof(ndk_res), cudaMemcpyDeviceToHost, B.st));
+        B.busy = true;
+        return 0;
+    }
+
+    // wait for the kernels of a launch: calls that found the arena full go to retry; the CIGAR gather is queued behind
+    int collect_a(DpLaunch &B, std::vector<uint32_t> &retry, size_t *n_retry_out)
+    {
+        const size_t n = B.n;
+        CK(cudaStreamSynchronize(B.st));
+        { float ms = 0; cudaEventElapsedTime(&ms, B.e0, B.e1); c->aln_stat.dp_ms += ms;
+          if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::dp] launch %llu: %zu calls (%zu wide), longest %dx%d, seq %.1f MB, kernels %.1f ms, arena used %.2f GB, ext_frac %.4f\n",
+                                               (unsigned long long)c->aln_stat.n_launches, n, B.nb, B.hc[0].qlen, B.hc[0].tlen, B.seqb / 1e6, ms, B.h_off.as<uint64_t>()[n + 1] / 1e9, ext_frac); }
+        const uint64_t *koff = B.h_off.as<uint64_t>(); const uint64_t tot = koff[n], used = koff[n + 1];
+        const ndk_res *hr = B.h_res.as<ndk_res>();
+        size_t n_retry = 0;
+        for (size_t i = 0; i < n; ++i) if (hr[i].pad) { retry.push_back(B.ids[i]); ++n_retry; }
+        if (B.ext_need > 0 && n_retry == 0) {       // what the optimistic calls really wrote
+            const double u = used > B.fixed ? (double)(used - B.fixed) : 0.0;
+            ext_frac = std::min(1.0, std::max(1.0 / 256, 0.5 * ext_frac + 0.5 * 1.5 * u / (double)B.ext_need));
+        } else if (n_retry) ext_frac = std::min(1.0, ext_frac * 2);
+        c->aln_stat.n_retries += n_retry; *n_retry_out = n_retry;
         if (tot) {
-            RSV(c->ksw_cout, tot * 4);
-            if (c->h_kcig.reserve(tot * 4)) return fail(c, NDG_ERR_NOMEM, "pinned cigar staging");
-            KLAUNCH("ksw_cigar", (k_ksw_cigar_gather<<<nblk((uint64_t)n * 32, 256), 256, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), c->ksw_res.as<ndk_res>(),
-                                  (const unsigned long long *)c->ksw_coff.as<nd_u64>(), (int)n, c->ksw_cig.as<uint32_t>(), c->ksw_cout.as<uint32_t>())));
+            RSV(B.cout, tot * 4);
+            if (B.h_cig.reserve(tot * 4)) return fail(c, NDG_ERR_NOMEM, "pinned cigar staging");
+            k_ksw_cigar_gather<<<nblk((uint64_t)n * 32, 256), 256, 0, B.st>>>(B.calls.as<ndk_call>(), B.res.as<ndk_res>(), (const unsigned long long *)B.coff.as<nd_u64>(), (int)n,
+                                                                                 B.cig.as<uint32_t>(), B.cout.as<uint32_t>());
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(c->h_kcig.p, c->ksw_cout.p, tot * 4, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
+            CK(cudaMemcpyAsync(B.h_cig.p, B.cout.p, tot * 4, cudaMemcpyDeviceToHost, B.st));
         }
-        const ndk_res *hr = c->h_kres.as<ndk_res>(); const uint32_t *hcg = c->h_kcig.as<uint32_t>();
+        return 0;
+    }
+
+    // CIGARs of a launch have arrived: hand the results over (overlaps the next launch's kernels)
+    int collect_b(DpLaunch &B, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars)
+    {
+        const size_t n = B.n;
+        CK(cudaStreamSynchronize(B.st));
+        B.busy = false;
+        const uint64_t *koff = B.h_off.as<uint64_t>(); const uint64_t tot = koff[n];
+        const ndk_res *hr = B.h_res.as<ndk_res>();
         const size_t base = cigars.size();
         if (base + tot >= (1ull << 32)) return fail(c, NDG_ERR_OVERFLOW, "round produces more than 2^32 CIGAR operations; align fewer reads per batch");
         cigars.resize(base + tot);
-        if (tot) memcpy(cigars.data() + base, hcg, tot * 4);
-        for (size_t i = 0; i < n; ++i) {
-            if (hr[i].pad) { retry.push_back(ids[i]); continue; }
-            ndal::DpRes &z = res[ids[i]];
+        if (tot) memcpy(cigars.data() + base, B.h_cig.p, tot * 4);
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; ++i) {
+            if (hr[i].pad) continue;
+            ndal::DpRes &z = res[B.ids[(size_t)i]];
             z.max = hr[i].max; z.zdropped = hr[i].zdropped; z.max_q = hr[i].max_q; z.max_t = hr[i].max_t; z.mqe = hr[i].mqe; z.mqe_t = hr[i].mqe_t;
             z.mte = hr[i].mte; z.mte_q = hr[i].mte_q; z.score = hr[i].score; z.n_cigar = hr[i].n_cigar; z.reach_end = hr[i].reach_end;
             z.cig_off = (uint32_t)(base + koff[i]);
@@ -982,9 +1068,6 @@ struct GpuDp : ndal::Backend {
         ++c->aln_stat.n_launches;
         return 0;
     }
-
-    double ext_frac = 1.0 / 16;                     // share of an extension's worst-case matrix that gets written (adapted from the arena cursor)
-    uint64_t last_used = 0;
 
     int run_impl(const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, std::vector<ndal::DpRes> &res, std::vector<uint32_t> &cigars)
     {
@@ -996,42 +1079,51 @@ struct GpuDp : ndal::Backend {
             if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
             c->ksw_p.cap = want;
         }
-        const uint64_t arena = c->ksw_p.cap, arena_eff = arena - arena / 16;
+        const uint64_t arena = c->ksw_p.cap & ~(uint64_t)255, arena_eff = arena - arena / 16;
         std::vector<uint64_t> need(n);
         std::vector<uint32_t> pending(n);
-        for (size_t i = 0; i < n; ++i) { need[i] = p_need(reqs[i]); pending[i] = (uint32_t)i; if (need[i] > arena_eff) return fail(c, NDG_ERR_NOMEM, "one alignment needs a %llu-byte backtrack matrix, arena is %llu", (unsigned long long)need[i], (unsigned long long)arena); }
-        std::sort(pending.begin(), pending.end(), [&](uint32_t x, uint32_t y) { return need[x] != need[y] ? need[x] > need[y] : x < y; });   // long calls first
+        for (size_t i = 0; i < n; ++i) { need[i] = p_need(reqs[i]); pending[i] = (uint32_t)i; if (need[i] > arena_eff) return fail(c, NDG_ERR_NOMEM, "one alignment needs a %llu-byte backtrack matrix, the arena is %llu", (unsigned long long)need[i], (unsigned long long)arena); }
+        __gnu_parallel::sort(pending.begin(), pending.end(), [&](uint32_t x, uint32_t y) { return need[x] != need[y] ? need[x] > need[y] : x < y; });   // long calls first
         std::vector<uint8_t> full(n, 0);            // 1: reserve the worst case (after a failed optimistic attempt)
-        std::vector<uint32_t> group, rest, retry;
+        std::vector<uint32_t> group, retry;
         const uint64_t SEQ_MAX = 768ull << 20; const size_t CNT_MAX = 4u << 20;
         auto est_of = [&](uint32_t id) -> uint64_t {
             // an extension usually z-drops long before its worst-case matrix is written: reserve a fraction first
             if (full[id] || !(reqs[id].flag & NDK_EXTZ_ONLY)) return need[id];
             return std::min<uint64_t>(need[id], (1ull << 20) + (uint64_t)(need[id] * ext_frac));
         };
-        while (!pending.empty()) {
-            // a launch takes a run of the size-ordered list: calls of similar length share a launch, so no launch waits on one
-            // call that is far longer than the rest (a lone warp advances ~0.1 G cells/s; the GPU as a whole ~200 G cells/s)
-            group.clear(); rest.clear(); retry.clear();
-            uint64_t sum = 0, seqb = 0, fixed = 0, ext_need = 0;
-            size_t k = 0;
-            for (; k < pending.size(); ++k) {
-                const uint32_t id = pending[k]; const uint64_t e = est_of(id), sb = (uint64_t)reqs[id].qlen + reqs[id].tlen + 2;
-                if (!group.empty() && (sum + e > arena_eff || seqb + sb > SEQ_MAX || group.size() >= CNT_MAX)) break;
-                group.push_back(id); sum += e; seqb += sb;
-                if (e == need[id]) fixed += e; else ext_need += need[id];
+        size_t head = 0, rhead = 0; int cur = -1, nxt = 0;
+        // A launch takes a run of the size-ordered list: calls of similar length share a launch, so no launch waits on one call that is
+        // far longer than the rest.  While the kernels of one launch run, the next one is staged (sequence bytes, call table, copies)
+        // and the previous one's results are handed over; kernels of different launches never overlap (they share the arena).
+        for (;;) {
+            const bool more = head < pending.size() || rhead < retry.size();
+            if (more) {
+                DpLaunch &B = L[nxt];
+                group.clear();
+                uint64_t sum = 0, seqb = 0; B.fixed = 0; B.ext_need = 0;
+                auto take = [&](uint32_t id) -> bool {
+                    const uint64_t e = est_of(id), sb = (uint64_t)reqs[id].qlen + reqs[id].tlen + 2;
+                    if (!group.empty() && (sum + e > arena_eff || seqb + sb > SEQ_MAX || group.size() >= CNT_MAX)) return false;
+                    group.push_back(id); sum += e; seqb += sb;
+                    if (e == need[id]) B.fixed += e; else B.ext_need += need[id];
+                    return true;
+                };
+                while (rhead < retry.size() && take(retry[rhead])) ++rhead;           // retried calls first (they are long)
+                if (rhead >= retry.size()) while (head < pending.size() && take(pending[head])) ++head;
+                if (int r = prepare(B, reqs, T, group)) return r;
+                if (int r = submit_copies(B)) return r;
             }
-            rest.assign(pending.begin() + (long)k, pending.end());
-            if (int r = launch_group(reqs, T, group.data(), group.size(), res, cigars, retry)) return r;
-            if (ext_need > 0 && retry.empty()) {    // what the optimistic calls really wrote
-                const double used = last_used > fixed ? (double)(last_used - fixed) : 0.0;
-                ext_frac = std::min(1.0, std::max(1.0 / 256, 0.5 * ext_frac + 0.5 * 1.5 * used / (double)ext_need));
-            } else if (!retry.empty()) ext_frac = std::min(1.0, ext_frac * 2);
-            for (uint32_t id : retry) { if (full[id] && group.size() == 1) return fail(c, NDG_ERR_NOMEM, "backtrack arena exhausted by a single call"); full[id] = 1; }
-            c->aln_stat.n_retries += retry.size();
-            // retried calls go first (they are long); the list stays size-ordered otherwise
-            pending.assign(retry.begin(), retry.end());
-            pending.insert(pending.end(), rest.begin(), rest.end());
+            if (cur >= 0) {
+                const size_t r0 = retry.size(); size_t nr = 0;
+                if (int r = collect_a(L[cur], retry, &nr)) return r;
+                for (size_t i = r0; i < retry.size(); ++i) { if (full[retry[i]] && L[cur].n == 1) return fail(c, NDG_ERR_NOMEM, "backtrack arena exhausted by a single call"); full[retry[i]] = 1; }
+            }
+            if (more) { if (int r = submit_kernels(L[nxt], c->ksw_p.as<uint8_t>(), arena)) return r; L[nxt].busy = true; }
+            if (cur >= 0) { if (int r = collect_b(L[cur], res, cigars)) return r; }
+            if (more) { cur = nxt; nxt ^= 1; }
+            else if (cur >= 0) cur = -1;            // the last launch is in; retried calls may have appeared
+            else break;
         }
         return 0;
     }
@@ -1040,7 +1132,10 @@ struct GpuDp : ndal::Backend {
     {
         res.assign(reqs.size(), ndal::DpRes()); cigars.clear();
         if (rc) return;                             // after an error the tasks drain on default results; the caller reports rc
+        const double t0 = omp_get_wtime();
         rc = run_impl(reqs, T, res, cigars);
+        if (rc) for (auto &l : L) if (l.busy) { cudaStreamSynchronize(l.st); l.busy = false; }
+        c->aln_stat.dp_wall_ms += (omp_get_wtime() - t0) * 1e3;
     }
 };
 
@@ -1050,6 +1145,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
     const uint64_t NH = c->n_hits;
     if (NH == 0) return 0;
     const double t_host0 = omp_get_wtime();
+    omp_set_num_threads(c->n_threads);
     uint64_t *h = c->h_scalars.as<uint64_t>();
     { ndal::Opt &A = c->aln; const ndg_opt_t &o = c->opt; A.k = o.k; A.hpc = o.hpc; A.bw = o.bw; A.max_gap = o.max_gap; A.min_cnt = o.min_cnt; A.min_chain_score = o.min_chain_score; }
     RSV(c->ch_cnt, (NH + 1) * 4); RSV(c->ch_off, (NH + 1) * 8); RSV(c->ch_fend, NH * 4);
@@ -1109,8 +1205,11 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
             ndal::build_read_job(J, ch);
         }
         ndal::Stats st;
+        const double tb0 = omp_get_wtime();
         ndal::align_batch(c->aln, ST, jobs, be, &st);
         if (be.rc) return be.rc;
+        if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::aln] group of %zu reads: prepare %.2f s, walk %.2f s, dp (host wall) %.2f s, hand-back %.2f s, finish %.2f s, total %.2f s\n", jobs.size(),
+                                             tb0 - t_host0, st.t_walk, st.t_dp, st.t_hand, st.t_finish, omp_get_wtime() - tb0);
         c->aln_stat.n_chains += st.n_tasks; c->aln_stat.n_calls += st.n_calls; c->aln_stat.n_rounds += st.n_rounds; c->aln_stat.rect_cells += st.cells;
         for (size_t j = 0; j < jobs.size(); ++j)
             for (const ndal::Reg &x : jobs[j].regs) {
@@ -1139,6 +1238,13 @@ extern "C" int ndg_set_aln_opt(ndg_ctx_t *c, const ndg_aln_opt_t *o)
     A.end_bonus = o->end_bonus; A.min_dp_max = o->min_dp_max; A.min_ksw_len = o->min_ksw_len; A.no_end_flt = o->no_end_flt; A.max_clip_ratio = o->max_clip_ratio;
     c->aln_on = true;
     return NDG_OK;
+}
+
+extern "C" int ndg_set_threads(ndg_ctx_t *c, int n)
+{
+    if (!c) return NDG_ERR_ARG;
+    c->n_threads = n > 0 ? n : usable_cpus();
+    return c->n_threads;
 }
 
 extern "C" int ndg_aln_stats(ndg_ctx_t *c, ndg_aln_stat_t *out)

@@ -38,7 +38,7 @@ class _AlnOpt(C.Structure):
 
 class _AlnStat(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_chains", "n_calls", "n_rounds", "n_launches", "n_retries", "rect_cells")] + \
-               [("dp_ms", C.c_double), ("host_ms", C.c_double)]
+               [("dp_ms", C.c_double), ("host_ms", C.c_double), ("dp_wall_ms", C.c_double)]
 
 
 class _Reads(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads"]
 
 _lib = None
 
@@ -103,6 +103,7 @@ def load_library():
     L.ndg_set_ksw_variant.argtypes = [C.c_void_p, C.c_int]
     L.ndg_set_aln_opt.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_aln_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndg_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
@@ -287,6 +288,9 @@ class Engine:
         return out
 
     # ---- base-level extension (ksw_extd2) ----------------------------------------------------
+    def set_threads(self, n=0):
+        return self.L.ndg_set_threads(self.h, n)
+
     def aln_stats(self):
         st = _AlnStat()
         self._ck(self.L.ndg_aln_stats(self.h, C.byref(st)))

@@ -156,6 +156,7 @@ int main(int argc, char **argv)
     ndal::align_batch(ao, ST, jobs, be, &st);
     fprintf(stderr, "[aln_harness] tasks=%llu calls=%llu rounds=%llu cells=%.3g\n", (unsigned long long)st.n_tasks, (unsigned long long)st.n_calls,
             (unsigned long long)st.n_rounds, (double)st.cells);
+    fprintf(stderr, "[aln_harness] walk %.2f s, dp %.2f s, hand-back %.2f s, finish %.2f s\n", st.t_walk, st.t_dp, st.t_hand, st.t_finish);
 
     FILE *fo = fopen(argv[7], "wb");
     uint32_t state[2] = {0, 0}; long n_rec = 0;

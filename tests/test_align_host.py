@@ -16,7 +16,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libminimap2_ref.so")
 def harness(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("aln") / "aln_harness")
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libnd_oracle.so"])
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "aln_harness.cc"),
+    subprocess.check_call(["g++", "-O3", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "aln_harness.cc"),
                            "-L" + os.path.join(ROOT, "oracle"), "-lnd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-ldl"])
     return exe
 

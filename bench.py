@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="1,1")
     ap.add_argument("--no-ksw", action="store_true", help="skip the regime-B (ksw_extd2) kernel measurement")
+    ap.add_argument("--no-regime-b", action="store_true", help="skip the regime-B (-c) whole-step measurement")
+    ap.add_argument("--regime-b-full", action="store_true", help="regime B on all 997 reads of the reference's test data (GPU ~1 min, reference ~4 min)")
     return ap.parse_args()
 
 
@@ -135,6 +137,68 @@ def run_reference(reads, threads):
     return recs, sq, (t_map - t_idx) if (t_idx is not None and t_map is not None) else total, total
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (same rule as libndgpu's ndg_set_threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):
+            q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, -(-int(q) // int(per))))
+        else:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and per > 0:
+                n = min(n, max(1, -(-q // per)))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+def regime_b_bench(eng, engine_mod, with_reference=True, full=False):
+    """Regime B (`-c`, base-level alignment of every chain) on real reads: tests/golden/sub120.2bit (120 reads of the reference's
+    test_data, 7346 overlaps; --regime-b-full: all 997 reads, 133100 overlaps) self-overlap with -x ava-ont.  Whole step through the
+    public API (index build + mapping + alignment + .ovl bytes), checked against the golden bytes, next to the unmodified reference
+    binary on the host cores for the same input."""
+    import hashlib
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200.options import MM_F_CIGAR
+    g = os.path.join(ROOT, "tests", "golden")
+    src = os.path.join(g, "reads_test.seed.2bit" if full else "sub120.2bit")
+    gold = os.path.join(g, "G4_ava-ont_c.ovl" if full else "S6_sub120_ava-ont_c.ovl")
+    reads = nd.read_2bit(src)
+    io, mo = nd.IdxOpt(), nd.MapOpt()
+    nd.set_opt("ava-ont", io, mo)
+    mo.step, mo.minlen = 1, 500
+    mo.flag |= MM_F_CIGAR
+    eng.set_limits(64 << 20, 0)
+    thr = eng.set_threads(0)
+    out = {"workload": "%s self-overlap, --step 1 -c -x ava-ont (%d reads)" % (os.path.basename(src), reads.n), "host_threads": thr}
+    for rep in range(2):                                    # first pass warms allocations (arena, pinned buffers)
+        eng.prof_reset()
+        t0 = time.time()
+        ovl, st = engine_mod.run_step1(eng, reads, reads, io, mo)
+        dt = time.time() - t0
+    s = eng.aln_stats()
+    out.update({"seconds": dt, "records": int(st["records"]), "overlaps_per_s": st["records"] / dt, "bytes_identical_to_reference": ovl == open(gold, "rb").read(),
+                "md5": hashlib.md5(ovl).hexdigest(), "chains": s["n_chains"], "dp_calls": s["n_calls"], "rounds": s["n_rounds"], "launches": s["n_launches"],
+                "cells": s["p_bytes"], "dp_kernel_s": s["dp_ms"] / 1e3, "dp_backend_wall_s": s["dp_wall_ms"] / 1e3, "alignment_stage_s": s["host_ms"] / 1e3,
+                "gcups_kernels": s["p_bytes"] / max(s["dp_ms"], 1e-9) / 1e6, "gcups_stage": s["p_bytes"] / max(s["host_ms"], 1e-9) / 1e6})
+    mo.flag &= ~MM_F_CIGAR
+    eng.set_options(io, mo)
+    if with_reference:
+        exe = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+        with tempfile.TemporaryDirectory() as td:
+            o = os.path.join(td, "r.ovl")
+            t0 = time.time()
+            subprocess.run([exe, "--step", "1", "-c", "-t", str(usable_cpus()), "-x", "ava-ont", src, src, "-o", o], stderr=subprocess.DEVNULL, check=True)
+            rt = time.time() - t0
+            same = open(o, "rb").read() == ovl
+        out["reference"] = {"seconds": rt, "threads": usable_cpus(), "same_bytes": same, "overlaps_per_s": st["records"] / rt}
+        out["speedup_vs_reference"] = rt / dt
+    return out
+
+
 def cpu_sample(n):
     genome_bp = max(int(n * READ_LEN / DEPTH), 200000)
     return make_reads(n, genome_bp), "%d reads x %d bp at %dx depth (genome %d bp), self-overlap, mapping phase only" % (n, READ_LEN, DEPTH, genome_bp)
@@ -213,7 +277,7 @@ def ksw_bench(eng, n_calls=20000, L=413, seed=SEED):
 def main_reference(a, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     reads, desc = cpu_sample(a.cpu_sample_reads)
     rec = sq = 0
     tsum = 0.0
@@ -366,7 +430,7 @@ def main_ours(a, rank, world, local_rank):
         if not a.no_cpu_baseline:
             try:
                 sample, desc = cpu_sample(a.cpu_sample_reads)
-                threads = os.cpu_count() or 1
+                threads = usable_cpus()
                 r_, s_, tm, tot = run_reference(sample, threads)
                 cpu = {"value": r_ / tm, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": desc,
                        "aligned_gbp_per_s": s_ / tm / 1e9, "mapping_s": tm, "process_s": tot}
@@ -379,6 +443,12 @@ def main_ours(a, rank, world, local_rank):
                 ksw["roofline_frac_hbm"] = ksw["achieved_GBps"] / hbm_peak
             except Exception as ex:  # noqa: BLE001
                 ksw = {"error": repr(ex)}
+        rb = None
+        if not a.no_regime_b and world == 1:
+            try:
+                rb = regime_b_bench(eng, engine, with_reference=not a.no_cpu_baseline, full=a.regime_b_full)
+            except Exception as ex:  # noqa: BLE001
+                rb = {"error": repr(ex)}
         line = {
             "metric": "overlaps/sec", "value": rec / t_res_dev, "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * t_res_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -403,6 +473,7 @@ def main_ours(a, rank, world, local_rank):
             "index": {"build_s": t_index, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"]},
             "gen_s": t_gen,
             "ksw2_extd2": ksw,
+            "regime_b": rb,
         }
         print(json.dumps(line))
     eng.close()

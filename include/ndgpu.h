@@ -121,9 +121,10 @@ int  ndg_set_aln_opt(ndg_ctx_t *ctx, const ndg_aln_opt_t *opt);      /* NULL swi
  * (affinity mask capped by the cgroup CPU quota).  Returns the number in effect. */
 int  ndg_set_threads(ndg_ctx_t *ctx, int n);
 /* counters of the alignment stage since the last ndg_prof_reset(): chains, DP calls, GPU rounds/launches, sum(qlen*tlen);
+ * p_bytes = backtrack bytes written = DP cells computed (1 byte per cell, 64-row granularity);
  * dp_ms = sum of per-launch kernel times (two launches overlap, so it can exceed dp_wall_ms = wall time spent in the DP backend);
  * host_ms = wall time of the whole alignment stage */
-typedef struct { uint64_t n_chains, n_calls, n_rounds, n_launches, n_retries, rect_cells; double dp_ms, host_ms, dp_wall_ms; } ndg_aln_stat_t;
+typedef struct { uint64_t n_chains, n_calls, n_rounds, n_launches, n_retries, rect_cells, p_bytes; double dp_ms, host_ms, dp_wall_ms; } ndg_aln_stat_t;
 int  ndg_aln_stats(ndg_ctx_t *ctx, ndg_aln_stat_t *out);
 
 /* page-locked host memory for batch inputs (optional; lets the H2D copy run at full PCIe speed) */

@@ -265,8 +265,8 @@ int main(int argc, char **argv)
     if (fclose(fo) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
     if (verbose >= 3 && cigar) {
         ndg_aln_stat_t as; ndg_aln_stats(g, &as);
-        fprintf(stderr, "[M::align] chains %llu; DP calls %llu in %llu rounds / %llu launches (%llu retried); DP kernels %.3f s (backend wall %.3f s); alignment stage %.3f s\n", (unsigned long long)as.n_chains,
-                (unsigned long long)as.n_calls, (unsigned long long)as.n_rounds, (unsigned long long)as.n_launches, (unsigned long long)as.n_retries, as.dp_ms / 1e3, as.dp_wall_ms / 1e3, as.host_ms / 1e3);
+        fprintf(stderr, "[M::align] chains %llu; DP calls %llu in %llu rounds / %llu launches (%llu retried); %.3g cells; DP kernels %.3f s (backend wall %.3f s); alignment stage %.3f s on %d host threads\n", (unsigned long long)as.n_chains,
+                (unsigned long long)as.n_calls, (unsigned long long)as.n_rounds, (unsigned long long)as.n_launches, (unsigned long long)as.n_retries, (double)as.p_bytes, as.dp_ms / 1e3, as.dp_wall_ms / 1e3, as.host_ms / 1e3, n_threads);
     }
     if (verbose >= 3) {
         fprintf(stderr, "[M::main] Version: 2.17-r941-ndgpu (%s)\n[M::main] CMD:", ndg_version());

@@ -1033,7 +1033,7 @@ struct GpuDp : ndal::Backend {
             const double u = used > B.fixed ? (double)(used - B.fixed) : 0.0;
             ext_frac = std::min(1.0, std::max(1.0 / 256, 0.5 * ext_frac + 0.5 * 1.5 * u / (double)B.ext_need));
         } else if (n_retry) ext_frac = std::min(1.0, ext_frac * 2);
-        c->aln_stat.n_retries += n_retry; *n_retry_out = n_retry;
+        c->aln_stat.n_retries += n_retry; *n_retry_out = n_retry; c->aln_stat.p_bytes += std::min<uint64_t>(used, c->ksw_p.cap);
         if (tot) {
             RSV(B.cout, tot * 4);
             if (B.h_cig.reserve(tot * 4)) return fail(c, NDG_ERR_NOMEM, "pinned cigar staging");
@@ -1075,6 +1075,7 @@ struct GpuDp : ndal::Backend {
         cudaSetDevice(c->device);
         if (!c->ksw_p.p) {                          // backtrack arena: a fixed slice of HBM, reused by every launch
             size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+            if (!c->arena_want && getenv("NDG_ARENA_GB")) c->arena_want = (uint64_t)(atof(getenv("NDG_ARENA_GB")) * (1ull << 30));
             uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(64ull << 30, (uint64_t)(fr * 0.45));
             if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
             c->ksw_p.cap = want;

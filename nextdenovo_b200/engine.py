@@ -37,7 +37,7 @@ class _AlnOpt(C.Structure):
 
 
 class _AlnStat(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("n_chains", "n_calls", "n_rounds", "n_launches", "n_retries", "rect_cells")] + \
+    _fields_ = [(n, C.c_uint64) for n in ("n_chains", "n_calls", "n_rounds", "n_launches", "n_retries", "rect_cells", "p_bytes")] + \
                [("dp_ms", C.c_double), ("host_ms", C.c_double), ("dp_wall_ms", C.c_double)]
 
 

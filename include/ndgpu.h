@@ -60,6 +60,9 @@ typedef struct {
     const uint64_t *name_key;
     const uint32_t *name_hash;
     const uint32_t *name_id;    /* optional: strtoul(name) (ref: minimap2/map.c:1300-1301); needed by ndg_map_batch_ovl */
+    const uint32_t *tag;        /* optional: group tag (> 0) per read.  Index reads and query reads only see each other when their tags
+                                 * are equal: one launch then serves many throw-away mini indexes (the per-query indexes of --step 2,
+                                 * ref: minimap2/map.c:1046-1125).  NULL = one shared index. */
 } ndg_reads_t;
 
 /* One chain-derived hit: the fields of mm_reg1_t (ref: minimap2/minimap.h:84-99) that leave the
@@ -163,6 +166,20 @@ int ndg_map_batch_ovl(ndg_ctx_t *ctx, const ndg_reads_t *queries, const ndg_emit
 int ndg_map_upload(ndg_ctx_t *ctx, const ndg_reads_t *queries);      /* H2D only (single sub-batch) */
 int ndg_map_resident(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* kernels only; hits stay on device */
 int ndg_map_download(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* D2H of the hits */
+
+/* ---- `--step 2` (cns_align): first-pass mapping, per-query re-mapping of the dovetail candidates against throw-away mini
+ * indexes, 10-field records after the contained/dovetail bookkeeping, `.bl` side file.
+ * Replaces the step-2 branch of worker_for() and of the writer (ref: minimap2/map.c:988-1128,1305-1328, lib/ovl.c:205-253,339-361,
+ * 449-563).  Every mapping (first pass and the re-mappings: each candidate target against a (kn,wn) index of the query, or the
+ * query against groups of cn targets) runs through the same GPU pipeline; the re-mappings of a whole batch share one tagged index.
+ * Call order: ndg_step2_begin() once, before the first ndg_index_add(); ndg_step2_map_batch() per query batch (records appended
+ * to the stream, the first call also returns the 2-byte header of the 10-field flavour); ndg_step2_finish() for the .bl text.
+ * mode: 0 = no re-mapping, 2 = the default re-mapping (modes 1 and 3 are rejected). */
+typedef struct { int32_t minlen, maxhan1, maxhan2, minmatch, mode, cn, kn, wn, outctn; float minide; } ndg_step2_opt_t;
+int ndg_step2_begin(ndg_ctx_t *ctx, const ndg_step2_opt_t *opt);
+int ndg_step2_map_batch(ndg_ctx_t *ctx, const ndg_reads_t *queries, const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan,
+                        ndg_map_result_t *work);
+int ndg_step2_finish(ndg_ctx_t *ctx, const char **bl_text, uint64_t *bl_bytes);
 
 /* ---- sketch only, for tests: replaces mm_sketch (ref: minimap2/sketch.c:358-361) ----------- */
 /* returns minimizers of all reads, concatenated; off has n_reads+1 entries */

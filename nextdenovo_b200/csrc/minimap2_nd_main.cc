@@ -142,12 +142,13 @@ int main(int argc, char **argv)
     uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
     const char *out = nullptr; std::vector<const char *> pos;
     bool cigar = false, unsupported_out = false;
+    ndg_step2_opt_t s2 = { 2000, 5000, 500, 100, 2, 20, 17, 10, 0, 0.05f };   // minimap2/main.c:194-198, options.c:50-62
     ndg_aln_opt_t ao = { 2, 4, 4, 2, 24, 1, 1, 400, 200, -1, 80, 200, 0, 1.0f };   // minimap2/options.c:37-44
     const double t0 = now();
     auto takes = [](const std::string &a) {
         static const char *t[] = { "-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen", "--maxhan1", "--maxhan2",
                                    "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v", "--device", "-N", "-p", "-M", "-z", "-A", "-B", "-O", "-E", "-s",
-                                   "--min-dp-score", "--end-bonus", "--max-clip-ratio" };
+                                   "--min-dp-score", "--end-bonus", "--max-clip-ratio", "--minide", "--minmatch", "--mode", "--kn", "--wn", "--cn" };
         for (auto x : t) if (a == x) return true;
         return false;
     };
@@ -168,6 +169,7 @@ int main(int argc, char **argv)
         } else if (kv.first == "--step") {
             step = atoi(kv.second.c_str());
             if (step == 1) minlen = 500; else if (step == 2 || step == 3) minlen = 2000;
+            if (step == 2) { maxhan1 = 5000; maxhan2 = 500; s2.minide = 0.05f; s2.minmatch = 100; s2.kn = 17; s2.wn = 10; s2.cn = 20; }
             else { fprintf(stderr, "[ERROR] unknown preset step '%s'\n", kv.second.c_str()); return 1; }
         }
     }
@@ -184,6 +186,9 @@ int main(int argc, char **argv)
         else if (k == "-s" || k == "--min-dp-score") ao.min_dp_max = atoi(v);
         else if (k == "--end-bonus") ao.end_bonus = atoi(v); else if (k == "--max-clip-ratio") ao.max_clip_ratio = (float)atof(v);
         else if (k == "--no-end-flt") ao.no_end_flt = 1;
+        else if (k == "--minide") s2.minide = (float)atof(v); else if (k == "--minmatch") s2.minmatch = (int)parse_num(v);
+        else if (k == "--mode") s2.mode = atoi(v); else if (k == "--kn") s2.kn = atoi(v); else if (k == "--wn") s2.wn = atoi(v);
+        else if (k == "--cn") s2.cn = atoi(v); else if (k == "--outctn") s2.outctn = 1;
         else if (k == "-z") { char *e; ao.zdrop = ao.zdrop_inv = (int)strtol(v, &e, 10); if (*e == ',') ao.zdrop_inv = (int)strtol(e + 1, &e, 10); }
         else if (k == "-O") { char *e; ao.q = ao.q2 = (int)strtol(v, &e, 10); if (*e == ',') ao.q2 = (int)strtol(e + 1, &e, 10); }
         else if (k == "-E") { char *e; ao.e = ao.e2 = (int)strtol(v, &e, 10); if (*e == ',') ao.e2 = (int)strtol(e + 1, &e, 10); }
@@ -201,10 +206,11 @@ int main(int argc, char **argv)
         fprintf(stderr, "Usage: minimap2-nd --step 1 [options] <target.2bit> <query.2bit> -o out.ovl\n");
         return 1;
     }
-    if (step != 1 || unsupported_out || !out) {
-        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` (.ovl output) only\n");
+    if ((step != 1 && step != 2) || unsupported_out || !out || (step == 2 && cigar)) {
+        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` and `--step 2 ... -o FILE` (.ovl output) only\n");
         return 1;
     }
+    if (step == 2 && s2.mode != 0 && s2.mode != 2) { fprintf(stderr, "[ERROR] --mode %d is not built (0 and 2 are)\n", s2.mode); return 1; }
     if (cigar) {                                                // mm_check_opt, minimap2/options.c:190-213
         if (ao.q <= 0 || ao.q2 <= 0 || ao.e <= 0 || ao.e2 <= 0) { fprintf(stderr, "[ERROR]\033[1;31m -O and -E must be positive\033[0m\n"); return 1; }
         if ((ao.q != ao.q2 || ao.e != ao.e2) && !(ao.e > ao.e2 && ao.q + ao.e < ao.q2 + ao.e2)) { fprintf(stderr, "[ERROR]\033[1;31m dual gap penalties violating E1>E2 and O1+E1<O2+E2\033[0m\n"); return 1; }
@@ -213,6 +219,11 @@ int main(int argc, char **argv)
     }
     FILE *fo = fopen(out, "wb");                                // main.c:259-262 (freopen)
     if (!fo) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", out); return 1; }
+    FILE *fbl = nullptr;
+    if (step == 2) {                                            // main.c:263-272: FILE.bl next to the records
+        std::string bn = std::string(out) + ".bl";
+        if (!(fbl = fopen(bn.c_str(), "w"))) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", bn.c_str()); return 1; }
+    }
 
     Reads T;
     if (!read_any(pos[0], T)) { fprintf(stderr, "[ERROR] failed to open file '%s'\n", pos[0]); return 1; }
@@ -220,6 +231,7 @@ int main(int argc, char **argv)
     if (ndg_init(device, &g) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device); return 1; }
     ndg_set_opt(g, &o);
     if (cigar && ndg_set_aln_opt(g, &ao)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+    if (step == 2) { s2.minlen = minlen; s2.maxhan1 = maxhan1; s2.maxhan2 = maxhan2; if (ndg_step2_begin(g, &s2)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; } }
     n_threads = ndg_set_threads(g, n_threads);                  // -t: host threads (only the -c stage has host-side work worth threading)
 
     uint32_t state[2] = { 0, 0 };
@@ -256,11 +268,17 @@ int main(int argc, char **argv)
                 ndg_emit_opt_t eo = { minlen, dvt, maxhan1, maxhan2 };
                 const uint8_t *bytes = nullptr; uint64_t nb = 0;
                 // mapping + output stage (filter, delta/varint records) on the GPU; only the .ovl bytes come back
-                if (ndg_map_batch_ovl(g, &qv, &eo, state, &bytes, &nb, &n_rec, &sum_qspan, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+                if (step == 2 ? ndg_step2_map_batch(g, &qv, &bytes, &nb, &n_rec, &sum_qspan, &R)
+                              : ndg_map_batch_ovl(g, &qv, &eo, state, &bytes, &nb, &n_rec, &sum_qspan, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
                 if (nb && fwrite(bytes, 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
                 if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, q_at - q0);
             }
         }
+    }
+    if (fbl) {                                                  // main.c:522-526 (out_bl)
+        const char *bl = nullptr; uint64_t nbl = 0;
+        if (ndg_step2_finish(g, &bl, &nbl)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+        if ((nbl && fwrite(bl, 1, (size_t)nbl, fbl) != (size_t)nbl) || fclose(fbl) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
     }
     if (fclose(fo) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
     if (verbose >= 3 && cigar) {

@@ -53,6 +53,7 @@ struct nd_reads_dev {
     const nd_u64 *name_key;
     const uint32_t *name_hash;
     const uint32_t *name_id;
+    const uint32_t *tag;           // optional group tag per read
     int n_reads;
 };
 
@@ -168,12 +169,15 @@ __global__ void k_gather_off(const nd_u64 *pos, const nd_u64 *chunk_off, int n_p
 // index build helpers
 // ------------------------------------------------------------------------------------------------
 
-__global__ void k_split_xy(const nd_u128 *mz, nd_u64 n, nd_u64 *key, nd_u64 *val)
+// index key = minimizer hash, optionally with the group tag of the read it came from above the 2k hash bits
+__global__ void k_split_xy(const nd_u128 *mz, nd_u64 n, nd_u64 *key, nd_u64 *val, const uint32_t *t_tag, int tag_shift)
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     nd_u128 m = mz[i];
-    key[i] = m.x >> 8; val[i] = m.y;
+    nd_u64 k = m.x >> 8;
+    if (t_tag) k |= (nd_u64)t_tag[m.y >> 32] << tag_shift;
+    key[i] = k; val[i] = m.y;
 }
 
 __global__ void k_count_heads(const nd_u64 *key, nd_u64 n, nd_u64 *n_distinct)
@@ -232,6 +236,7 @@ struct nd_seed_par {
     const nd_u64 *pos;                 // index position lists
     const nd_u64 *t_key; const uint32_t *t_len;
     int mid_occ, no_diag, no_dual;
+    int tag_shift;                     // > 0: probe key = hash | tag(read) << tag_shift
 };
 
 __device__ __forceinline__ bool nd_skip_seed(const nd_seed_par &P, nd_u64 r, uint32_t q_pos, nd_u64 qkey, uint32_t qlen, int *is_self)
@@ -258,8 +263,10 @@ k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz
     if (m >= n_mz) return;
     nd_u128 z = mz[m];
     nd_u64 off = 0; uint32_t n = 0, keep = 0;
-    if (nd_ht_lookup(P.tab, P.log2cap, z.x >> 8, &off, &n) && n < (uint32_t)P.mid_occ) {
-        int r = nd_find_owner(mz_off, Q.n_reads, m);
+    nd_u64 key = z.x >> 8; int r = -1;
+    if (P.tag_shift > 0) { r = nd_find_owner(mz_off, Q.n_reads, m); key |= (nd_u64)Q.tag[r] << P.tag_shift; }
+    if (nd_ht_lookup(P.tab, P.log2cap, key, &off, &n) && n < (uint32_t)P.mid_occ) {
+        if (r < 0) r = nd_find_owner(mz_off, Q.n_reads, m);
         nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y;
         for (uint32_t kk = 0; kk < n; ++kk) {
             int self;

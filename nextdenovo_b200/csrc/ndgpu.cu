@@ -14,6 +14,7 @@
 #include "nd_warp.cuh"
 #include "nd_ksw.cuh"
 #include "nd_align.hpp"
+#include "nd_step2.hpp"
 #include <omp.h>
 #include <parallel/algorithm>
 #include <omp.h>
@@ -67,16 +68,16 @@ struct ProfEntry { std::string name; double ms = 0; uint64_t launches = 0; };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
 struct ReadsDev {            // a batch of reads resident on the device
-    DevBuf words, word_off, len, nmask, name_key, name_hash, name_id, chunk_off;
+    DevBuf words, word_off, len, nmask, name_key, name_hash, name_id, chunk_off, tag; bool has_tag = false;
     int n_reads = 0; uint64_t n_words = 0, n_chunks = 0, n_bases = 0; bool has_nmask = false;
     nd_reads_dev view() const {
         nd_reads_dev v;
         v.words = words.as<uint32_t>(); v.word_off = word_off.as<nd_u64>(); v.len = len.as<uint32_t>();
         v.nmask = has_nmask ? nmask.as<uint32_t>() : nullptr;
-        v.name_key = name_key.as<nd_u64>(); v.name_hash = name_hash.as<uint32_t>(); v.name_id = name_id.as<uint32_t>(); v.n_reads = n_reads;
+        v.name_key = name_key.as<nd_u64>(); v.name_hash = name_hash.as<uint32_t>(); v.name_id = name_id.as<uint32_t>(); v.tag = has_tag ? tag.as<uint32_t>() : nullptr; v.n_reads = n_reads;
         return v;
     }
-    void release() { words.release(); word_off.release(); len.release(); nmask.release(); name_key.release(); name_hash.release(); name_id.release(); chunk_off.release(); }
+    void release() { words.release(); word_off.release(); len.release(); nmask.release(); name_key.release(); name_hash.release(); name_id.release(); chunk_off.release(); tag.release(); }
 };
 
 } // namespace
@@ -96,7 +97,7 @@ struct ndg_ctx {
     std::vector<ProfEntry> prof; std::vector<ProfPending> pending; std::vector<cudaEvent_t> ev_pool;
     // index
     DevBuf tmz; uint64_t n_tmz = 0;               // raw target minimizers (x,y)
-    DevBuf t_key, t_len, t_id; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen, h_tid; bool t_has_id = true;
+    DevBuf t_key, t_len, t_id, t_tag; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen, h_tid, h_ttag; bool t_has_id = true, t_has_tag = false; int tag_shift = 0;
     DevBuf em_keep, em_kidx, em_len, em_off, em_out; HostBuf h_ovl; uint32_t n_targets = 0; uint64_t t_sum_len = 0;
     DevBuf idx_pos, idx_tab; int log2cap = 0; uint64_t n_pos = 0; bool index_ready = false;
     int mid_occ = 0;
@@ -119,6 +120,9 @@ struct ndg_ctx {
     uint64_t arena_want = 0;
     cudaStream_t st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int n_threads = 1;                            // host threads of the alignment stage
+    // --step 2
+    bool s2_on = false; nds2::Opt s2; nds2::Writer s2w; size_t s2_emitted = 0; std::string s2_bl; ndg_ctx *remap = nullptr;
+    uint64_t s2_remaps = 0, s2_groups = 0; double s2_remap_ms = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -231,6 +235,8 @@ int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
         RSV(D.nmask, (nw / 2 + 4) * 4);
         CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, (nw / 2 + 1) * 4, cudaMemcpyHostToDevice, c->st));
     }
+    D.has_tag = R->tag != nullptr;
+    if (R->tag) { RSV(D.tag, (size_t)n * 4); CK(cudaMemcpyAsync(D.tag.p, R->tag + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->st)); }
     CK(cudaStreamSynchronize(c->st));   // staging buffer is reused by the next call
     return 0;
 }
@@ -327,11 +333,12 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
-                       &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend };
+                       &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag };
     for (auto b : bufs) b->release();
     c->q.release();
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
     c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release();
+    if (c->remap) { ndg_destroy(c->remap); c->remap = nullptr; }
     if (c->st2) { cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); }
     cudaStreamDestroy(c->st);
     delete c;
@@ -390,7 +397,7 @@ extern "C" int ndg_index_begin(ndg_ctx_t *c)
 {
     if (!c) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
-    c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->t_has_id = true;
+    c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->h_ttag.clear(); c->t_has_id = true; c->t_has_tag = false; c->tag_shift = 0;
     c->index_ready = false; c->n_pos = 0;
     c->ht_words.clear(); c->ht_nmask.clear(); c->ht_word_off.clear(); c->ht_has_n = false;
     return NDG_OK;
@@ -402,8 +409,10 @@ static int index_meta(ndg_ctx *c, const ndg_reads_t *T)
         c->h_tkey.push_back(T->name_key ? T->name_key[i] : (uint64_t)(c->n_targets + i));
         c->h_tlen.push_back(T->len[i]);
         c->h_tid.push_back(T->name_id ? T->name_id[i] : 0);
+        c->h_ttag.push_back(T->tag ? T->tag[i] : 0);
         c->t_sum_len += T->len[i];
     }
+    if (T->tag) c->t_has_tag = true;
     if (!T->name_id) c->t_has_id = false;
     c->n_targets += T->n_reads;
     return 0;
@@ -430,7 +439,7 @@ extern "C" int ndg_index_add(ndg_ctx_t *c, const ndg_reads_t *T)
         c->n_tmz += n;
         r0 = r1;
     }
-    if (c->aln_on) {                    // regime B reads target bases on the host (ref: mm_idx_getseq, minimap2/index.c:152-162)
+    if (c->aln_on || c->s2_on) {        // regime B and step 2 read target bases on the host (ref: mm_idx_getseq, minimap2/index.c:152-162)
         const uint64_t wb = T->word_off[0], nw = T->word_off[T->n_reads] - wb, w0 = c->ht_words.size();   // offsets may be absolute into a larger array
         if (T->nmask && !c->ht_has_n) { c->ht_nmask.assign(w0 / 2, 0); c->ht_has_n = true; }
         c->ht_words.insert(c->ht_words.end(), T->words + wb, T->words + wb + nw);
@@ -483,9 +492,19 @@ extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
     DevBuf key_in, val_in, key_out;
     if (key_in.reserve(n * 8) || val_in.reserve(n * 8) || key_out.reserve(n * 8)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "index sort buffers"); }
     RSV(c->idx_pos, n * 8);
-    KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, key_in.as<nd_u64>(), val_in.as<nd_u64>())));
-    size_t tmp = 0;
     int end_bit = 2 * c->opt.k; if (end_bit > 64) end_bit = 64;
+    const uint32_t *d_ttag = nullptr;
+    if (c->t_has_tag) {                                  // tagged index: group tag above the 2k hash bits
+        uint32_t mx = 0; for (uint32_t t : c->h_ttag) mx = std::max(mx, t);
+        int tb = 1; while (tb < 32 && (mx >> tb)) ++tb;
+        if (2 * c->opt.k + tb > 64) return fail(c, NDG_ERR_ARG, "group tags up to %u do not fit above %d hash bits", mx, 2 * c->opt.k);
+        c->tag_shift = 2 * c->opt.k; end_bit = c->tag_shift + tb;
+        RSV(c->t_tag, (size_t)c->n_targets * 4 + 4);
+        CK(cudaMemcpyAsync(c->t_tag.p, c->h_ttag.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
+        d_ttag = c->t_tag.as<uint32_t>();
+    }
+    KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, key_in.as<nd_u64>(), val_in.as<nd_u64>(), d_ttag, c->tag_shift)));
+    size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in.as<nd_u64>(), key_out.as<nd_u64>(), val_in.as<nd_u64>(), c->idx_pos.as<nd_u64>(), (long long)n, 0, end_bit, c->st);
     if (c->cubtmp.reserve(tmp)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "cub temp"); }
     {
@@ -602,6 +621,8 @@ int map_resident(ndg_ctx *c, int qidx_base)
     // 2. probe + count
     nd_seed_par P; P.tab = c->idx_tab.as<nd_ht_slot>(); P.log2cap = c->log2cap; P.pos = c->idx_pos.as<nd_u64>();
     P.t_key = c->t_key.as<nd_u64>(); P.t_len = c->t_len.as<uint32_t>(); P.mid_occ = c->mid_occ; P.no_diag = o.flag_no_diag; P.no_dual = o.flag_no_dual;
+    P.tag_shift = c->tag_shift;
+    if (c->tag_shift > 0 && !Q.has_tag) return fail(c, NDG_ERR_ARG, "the index is tagged: query reads need tags too");
     nd_reads_dev V = Q.view();
     RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8);
     CK(cudaMemsetAsync(c->m_keep.as<uint32_t>() + M, 0, 4, c->st));
@@ -1252,6 +1273,157 @@ extern "C" int ndg_aln_stats(ndg_ctx_t *c, ndg_aln_stat_t *out)
 {
     if (!c || !out) return NDG_ERR_ARG;
     *out = c->aln_stat;
+    return NDG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// --step 2.  Host logic in nd_step2.hpp; every mapping runs through the GPU pipeline above.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct ReadGather {                                // a read batch assembled from pieces of other batches (2-bit words verbatim)
+    std::vector<uint32_t> words, len, nmask, hash, id, tag; std::vector<uint64_t> word_off, key; bool has_n = false;
+    void add(const uint32_t *w, const uint64_t off, uint32_t L, const uint32_t *nm, uint32_t tg)
+    {
+        const size_t nw = (L + 15) / 16, w0 = words.size();
+        word_off.push_back(w0);
+        words.insert(words.end(), w + off, w + off + nw);
+        if (words.size() & 1) words.push_back(0);
+        if (has_n) {
+            nmask.resize(words.size() / 2 + 1, 0);
+            if (nm) memcpy(nmask.data() + w0 / 2, nm + off / 2, ((nw + 1) / 2) * 4);
+        }
+        len.push_back(L); hash.push_back(0); id.push_back((uint32_t)len.size() - 1); key.push_back(len.size()); tag.push_back(tg);
+    }
+    ndg_reads_t view()
+    {
+        ndg_reads_t v; memset(&v, 0, sizeof v);
+        word_off.push_back(words.size());
+        v.n_reads = (int32_t)len.size(); v.words = words.data(); v.word_off = word_off.data(); v.len = len.data(); v.nmask = has_n ? nmask.data() : nullptr;
+        v.name_key = key.data(); v.name_hash = hash.data(); v.name_id = id.data(); v.tag = tag.data();
+        return v;
+    }
+};
+
+// all re-mappings of a query batch in one tagged index + one mapping pass of the auxiliary context
+int step2_remap(ndg_ctx *c, const ndg_reads_t *Q, std::vector<nds2::QueryJob> &jobs, std::vector<nds2::Remap> &reqs)
+{
+    if (reqs.empty()) return 0;
+    const double t0 = omp_get_wtime();
+    if (!c->remap) { if (int rc = ndg_init(c->device, &c->remap)) return fail(c, rc, "cannot create the re-mapping context"); }
+    ndg_ctx *R = c->remap;
+    const uint64_t launches0 = ndg_kernel_launches(R);
+    ndg_opt_t o2 = c->opt; o2.k = c->s2.kn; o2.w = c->s2.wn; o2.flag_no_diag = 0; o2.flag_no_dual = 0; o2.mid_occ = c->mid_occ; o2.min_mid_occ = 0;
+    if (int rc = ndg_set_opt(R, &o2)) return fail(c, rc, "%s", ndg_last_error(R));
+    ndg_set_limits(R, c->sub_batch_bases, c->max_anchors);
+    const bool any_n = Q->nmask || c->ht_has_n;
+    ReadGather IX, MP; IX.has_n = MP.has_n = any_n;
+    const uint32_t *tn = c->ht_has_n ? c->ht_nmask.data() : nullptr;
+    std::vector<uint32_t> qtag(jobs.size(), 0), qslot(jobs.size(), 0), base(reqs.size(), 0);
+    uint32_t next_tag = 1;
+    for (size_t x = 0; x < reqs.size(); ++x) {
+        nds2::Remap &m = reqs[x];
+        if (m.query_is_index) {
+            if (!qtag[(size_t)m.query]) {           // the query becomes a one-read mini index (ref: map.c:1047)
+                qtag[(size_t)m.query] = next_tag++;
+                qslot[(size_t)m.query] = (uint32_t)IX.len.size();
+                IX.add(Q->words, Q->word_off[m.query], Q->len[m.query], Q->nmask, qtag[(size_t)m.query]);
+            }
+            base[x] = qslot[(size_t)m.query];
+            MP.add(c->ht_words.data(), c->ht_word_off[(size_t)m.mapped_rid], c->h_tlen[(size_t)m.mapped_rid], tn, qtag[(size_t)m.query]);
+        } else {                                    // up to cn targets form the mini index, the query is mapped (ref: map.c:1085-1125)
+            const uint32_t tg = next_tag++;
+            base[x] = (uint32_t)IX.len.size();
+            for (int32_t rid : m.group_rids) IX.add(c->ht_words.data(), c->ht_word_off[(size_t)rid], c->h_tlen[(size_t)rid], tn, tg);
+            MP.add(Q->words, Q->word_off[m.query], Q->len[m.query], Q->nmask, tg);
+            ++c->s2_groups;
+        }
+    }
+    ndg_reads_t iv = IX.view(), mv = MP.view();
+    ndg_index_stat_t st;
+    if (ndg_index_begin(R) || ndg_index_add(R, &iv) || ndg_index_finalize(R, &st)) return fail(c, NDG_ERR_STATE, "re-mapping index: %s", ndg_last_error(R));
+    ndg_map_result_t res;
+    if (int rc = ndg_map_batch(R, &mv, &res)) return fail(c, rc, "re-mapping: %s", ndg_last_error(R));
+    size_t h = 0;
+    for (size_t x = 0; x < reqs.size(); ++x) {
+        nds2::Remap &m = reqs[x];
+        m.result.clear();
+        while (h < (size_t)res.n_hits && res.hits[h].qidx == (int32_t)x) {
+            const ndg_hit_t &g = res.hits[h++];
+            nds2::Reg z; z.rid = g.rid - (int32_t)base[x]; z.rev = g.rev; z.qs = g.qs; z.qe = g.qe; z.rs = g.rs; z.re = g.re; z.mlen = g.mlen; z.blen = g.blen; z.score = g.score; z.cnt = g.cnt;
+            m.result.push_back(z);
+        }
+    }
+    c->s2_remaps += reqs.size(); c->launches += ndg_kernel_launches(R) - launches0; c->s2_remap_ms += (omp_get_wtime() - t0) * 1e3;
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ndg_step2_begin(ndg_ctx_t *c, const ndg_step2_opt_t *o)
+{
+    if (!c) return NDG_ERR_ARG;
+    if (!o) { c->s2_on = false; return NDG_OK; }
+    if (o->mode != 0 && o->mode != 2) return fail(c, NDG_ERR_ARG, "--mode %d is not built (0 and 2 are)", o->mode);
+    if (o->kn < 1 || o->kn > 28 || o->wn < 1 || o->wn > 255 || o->cn < 1) return fail(c, NDG_ERR_ARG, "kn/wn/cn out of range");
+    nds2::Opt &S = c->s2;
+    S.minlen = o->minlen; S.maxhan1 = o->maxhan1; S.maxhan2 = o->maxhan2; S.minmatch = o->minmatch; S.mode = o->mode; S.cn = o->cn; S.kn = o->kn; S.wn = o->wn; S.outctn = o->outctn; S.minide = o->minide;
+    c->s2w = nds2::Writer(); c->s2w.begin(); c->s2_emitted = 0; c->s2_on = true; c->s2_remaps = c->s2_groups = 0; c->s2_remap_ms = 0;
+    return NDG_OK;
+}
+
+extern "C" int ndg_step2_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan,
+                                   ndg_map_result_t *work)
+{
+    if (!c || !Q || !ovl || !n_bytes || Q->n_reads <= 0) return NDG_ERR_ARG;
+    if (!c->s2_on) return fail(c, NDG_ERR_STATE, "ndg_step2_begin() was not called");
+    if (c->aln_on) return fail(c, NDG_ERR_STATE, "--step 2 with base-level alignment is not built");
+    if (!Q->name_id || !c->t_has_id) return fail(c, NDG_ERR_ARG, "step 2 needs name_id for targets and queries");
+    if (c->ht_word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "step 2 needs ndg_step2_begin() before ndg_index_add() (target bases are kept on the host)");
+    omp_set_num_threads(c->n_threads);
+    ndg_map_result_t R;
+    if (int rc = ndg_map_batch(c, Q, &R)) return rc;
+    const int nq = Q->n_reads;
+    std::vector<nds2::QueryJob> jobs((size_t)nq);
+    {
+        int64_t h = 0;
+        for (int q = 0; q < nq; ++q) {
+            nds2::QueryJob &J = jobs[(size_t)q];
+            J.qlen = Q->len[q]; J.qkey = Q->name_key ? Q->name_key[q] : (uint64_t)q;
+            while (h < R.n_hits && R.hits[h].qidx == q) {
+                const ndg_hit_t &g = R.hits[h++];
+                nds2::Reg z; z.rid = g.rid; z.rev = g.rev; z.qs = g.qs; z.qe = g.qe; z.rs = g.rs; z.re = g.re; z.mlen = g.mlen; z.blen = g.blen; z.score = g.score; z.cnt = g.cnt;
+                J.regs.push_back(z);
+            }
+        }
+    }
+    std::vector<nds2::Remap> reqs; std::vector<size_t> rbeg((size_t)nq + 1, 0);
+    for (int q = 0; q < nq; ++q) {
+        nds2::mark_candidates(c->s2, jobs[(size_t)q], c->h_tkey.data(), c->h_tlen.data());
+        rbeg[(size_t)q] = reqs.size();
+        nds2::plan_remaps(c->s2, q, jobs[(size_t)q], reqs);
+    }
+    rbeg[(size_t)nq] = reqs.size();
+    if (int rc = step2_remap(c, Q, jobs, reqs)) return rc;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int q = 0; q < nq; ++q) nds2::apply_remaps(c->s2, jobs[(size_t)q], reqs, rbeg[(size_t)q], rbeg[(size_t)q + 1], c->h_tlen.data());
+    uint64_t rec = 0, sq = 0;
+    for (int q = 0; q < nq; ++q)
+        c->s2w.emit_query(c->s2, jobs[(size_t)q].regs, Q->name_id[q], jobs[(size_t)q].qkey, Q->len[q], c->h_tid.data(), c->h_tkey.data(), c->h_tlen.data(), &rec, &sq);
+    *ovl = c->s2w.out.data() + c->s2_emitted; *n_bytes = c->s2w.out.size() - c->s2_emitted; c->s2_emitted = c->s2w.out.size();
+    if (n_rec) *n_rec += rec;
+    if (sum_qspan) *sum_qspan += sq;
+    if (work) { *work = R; work->hits = nullptr; }
+    return NDG_OK;
+}
+
+extern "C" int ndg_step2_finish(ndg_ctx_t *c, const char **bl, uint64_t *n)
+{
+    if (!c || !bl || !n) return NDG_ERR_ARG;
+    if (!c->s2_on) return fail(c, NDG_ERR_STATE, "ndg_step2_begin() was not called");
+    c->s2_bl = c->s2w.bl_text();
+    *bl = c->s2_bl.c_str(); *n = c->s2_bl.size();
     return NDG_OK;
 }
 

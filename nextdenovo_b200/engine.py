@@ -36,6 +36,10 @@ class _AlnOpt(C.Structure):
                                          "min_ksw_len", "no_end_flt")] + [("max_clip_ratio", C.c_float)]
 
 
+class _Step2Opt(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("minlen", "maxhan1", "maxhan2", "minmatch", "mode", "cn", "kn", "wn", "outctn")] + [("minide", C.c_float)]
+
+
 class _AlnStat(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_chains", "n_calls", "n_rounds", "n_launches", "n_retries", "rect_cells", "p_bytes")] + \
                [("dp_ms", C.c_double), ("host_ms", C.c_double), ("dp_wall_ms", C.c_double)]
@@ -43,7 +47,7 @@ class _AlnStat(C.Structure):
 
 class _Reads(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
-                ("nmask", C.c_void_p), ("name_key", C.c_void_p), ("name_hash", C.c_void_p), ("name_id", C.c_void_p)]
+                ("nmask", C.c_void_p), ("name_key", C.c_void_p), ("name_hash", C.c_void_p), ("name_id", C.c_void_p), ("tag", C.c_void_p)]
 
 
 class _MapResult(C.Structure):
@@ -72,7 +76,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish"]
 
 _lib = None
 
@@ -104,6 +108,9 @@ def load_library():
     L.ndg_set_aln_opt.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_aln_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.ndg_step2_begin.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndg_step2_map_batch.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.ndg_step2_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
@@ -288,6 +295,28 @@ class Engine:
         return out
 
     # ---- base-level extension (ksw_extd2) ----------------------------------------------------
+    # ---- --step 2 -----------------------------------------------------------------------------
+    def step2_begin(self, mo: MapOpt):
+        o = _Step2Opt(minlen=mo.minlen, maxhan1=mo.maxhan1, maxhan2=mo.maxhan2, minmatch=mo.minmatch, mode=mo.mode, cn=mo.cn, kn=mo.kn, wn=mo.wn,
+                      outctn=mo.outctn, minide=mo.minide)
+        self._ck(self.L.ndg_step2_begin(self.h, C.byref(o)))
+
+    def step2_end(self):
+        self._ck(self.L.ndg_step2_begin(self.h, None))
+
+    def step2_map_batch(self, queries: Reads):
+        s = _reads_struct(queries)
+        ptr, nb, nrec, sq = C.c_void_p(), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        res = _MapResult()
+        self._ck(self.L.ndg_step2_map_batch(self.h, C.byref(s), C.byref(ptr), C.byref(nb), C.byref(nrec), C.byref(sq), C.byref(res)))
+        data = C.string_at(ptr.value, nb.value) if nb.value else b""
+        return data, dict(records=nrec.value, sum_qspan=sq.value, n_hits=res.n_hits, n_minimizers=res.n_minimizers, n_anchors=res.n_anchors)
+
+    def step2_finish(self):
+        ptr, nb = C.c_char_p(), C.c_uint64(0)
+        self._ck(self.L.ndg_step2_finish(self.h, C.byref(ptr), C.byref(nb)))
+        return C.string_at(ptr, nb.value) if nb.value else b""
+
     def set_threads(self, n=0):
         return self.L.ndg_set_threads(self.h, n)
 
@@ -440,6 +469,25 @@ def query_batches(queries: Reads, mini_batch_size):
                 break
         out.append((start, r))
     return out
+
+
+def run_step2(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: MapOpt):
+    """`minimap2-nd --step 2 ... TARGET QUERY -o OUT` (ref: minimap2/main.c:452-526).  Returns (ovl_bytes, bl_text, stats)."""
+    engine.set_options(io, mo)
+    engine.step2_begin(mo)
+    out = bytearray()
+    n_rec = 0
+    try:
+        for (t0, t1) in index_parts(targets, io):
+            engine.build_index(targets.slice(t0, t1))
+            for (q0, q1) in query_batches(queries, mo.mini_batch_size):
+                data, st = engine.step2_map_batch(queries.slice(q0, q1))
+                out += data
+                n_rec += st["records"]
+        bl = engine.step2_finish()
+    finally:
+        engine.step2_end()
+    return bytes(out), bl, dict(records=n_rec)
 
 
 def run_step1(engine: Engine, targets: Reads, queries: Reads, io: IdxOpt, mo: MapOpt, same_file=False, device_emit=True):

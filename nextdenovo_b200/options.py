@@ -60,6 +60,14 @@ class MapOpt:                       # subset of mm_mapopt_t, minimap2/minimap.h:
     min_dp_max: int = 80
     min_ksw_len: int = 200
     max_clip_ratio: float = 1.0
+    # --step 2 (minimap2/options.c:50-62, main.c:194-198)
+    minide: float = 0.05
+    minmatch: int = 100
+    mode: int = 2
+    cn: int = 20
+    kn: int = 17
+    wn: int = 10
+    outctn: int = 0
     extra: dict = field(default_factory=dict)
 
 
@@ -104,7 +112,8 @@ def parse_args(argv):
     io, mo = IdxOpt(), MapOpt()
     takes = {"-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen",
              "--maxhan1", "--maxhan2", "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v",
-             "-A", "-B", "-O", "-E", "-z", "-s", "--min-dp-score", "--end-bonus", "--max-clip-ratio"}
+             "-A", "-B", "-O", "-E", "-z", "-s", "--min-dp-score", "--end-bonus", "--max-clip-ratio",
+             "--minide", "--minmatch", "--mode", "--kn", "--wn", "--cn"}
     toks, pos, i = [], [], 0
     while i < len(argv):
         a = argv[i]
@@ -131,6 +140,8 @@ def parse_args(argv):
                 mo.minlen = 500
             elif mo.step in (2, 3):
                 mo.minlen = 2000
+                if mo.step == 2:
+                    mo.minide, mo.maxhan1, mo.maxhan2, mo.minmatch, mo.kn, mo.wn, mo.cn = 0.05, 5000, 500, 100, 17, 10, 20
             else:
                 raise ValueError("[ERROR] unknown preset step '%s'" % v)
     out = None
@@ -171,6 +182,13 @@ def parse_args(argv):
         elif k == "--maxhan1": mo.maxhan1 = parse_num(v)
         elif k == "--maxhan2": mo.maxhan2 = parse_num(v)
         elif k == "--dvt": mo.dvt = 1
+        elif k == "--minide": mo.minide = float(v)
+        elif k == "--minmatch": mo.minmatch = parse_num(v)
+        elif k == "--mode": mo.mode = int(v)
+        elif k == "--kn": mo.kn = int(v)
+        elif k == "--wn": mo.wn = int(v)
+        elif k == "--cn": mo.cn = int(v)
+        elif k == "--outctn": mo.outctn = 1
         elif k == "--seed": mo.seed = int(v)
         elif k == "--max-chain-skip": mo.max_chain_skip = int(v)
         elif k == "--max-chain-iter": mo.max_chain_iter = int(v)

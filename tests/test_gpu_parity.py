@@ -151,7 +151,7 @@ def test_cli_dropin_matches_reference_bytes(built, golden_dir, tmp_path):
     assert r.returncode == 0, r.stderr
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "S5_sub120_dual.ovl"), "rb").read()
     assert subprocess.run([exe, "--step", "1", "-x", "nope", src, src, "-o", out], capture_output=True).returncode == 1
-    assert subprocess.run([exe, "--step", "2", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--step", "3", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
     assert subprocess.run([exe, "--step", "1", "-c", "-O", "4,2", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
 
 
@@ -373,3 +373,41 @@ def test_fastx_input_with_ambiguous_bases(built, engine_mod, eng, reads_sub, tmp
     bad = str(tmp_path / "bad.fa")
     open(bad, "wb").write(b">read_x\nACGTACGTACGT\n")
     assert subprocess.run([exe, "--step", "1", "-x", "ava-ont", bad, bad, "-o", got_p], capture_output=True).returncode == 1
+
+
+def _step2_opts():
+    from nextdenovo_b200.options import parse_args
+    io, mo, out, pos = parse_args(["--step", "2", "-t", "8", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000", "a", "b", "-o", "x"])
+    return io, mo
+
+
+@pytest.mark.parametrize("src,gold", [("sub120.2bit", "S9_sub120_step2.ovl"), ("reads_test.seed.2bit", "G5_step2.ovl")])
+def test_step2_matches_reference(eng, engine_mod, golden_dir, src, gold):
+    """--step 2 (cns_align): first pass, re-mapping of every dovetail candidate against a (17,10) mini index of the query (all mini
+    indexes of a batch share one tagged GPU index), 10-field records and the .bl text == the reference's bytes
+    (ref: minimap2/map.c:988-1128,1305-1328; lib/ovl.c:339-361,449-563)."""
+    import nextdenovo_b200 as nd
+    reads = nd.read_2bit(os.path.join(golden_dir, src))
+    io, mo = _step2_opts()
+    eng.set_variant(1, 1)
+    eng.set_limits(64 << 20, 0)
+    ovl, bl, st = engine_mod.run_step2(eng, reads, reads, io, mo)
+    want = open(os.path.join(golden_dir, gold), "rb").read()
+    assert ovl == want, "records %d; %d vs %d bytes" % (st["records"], len(ovl), len(want))
+    assert bl == open(os.path.join(golden_dir, gold + ".bl"), "rb").read()
+    io1, mo1 = _opts("ava-ont")
+    eng.set_options(io1, mo1)
+
+
+def test_cli_step2_matches_reference_bytes(built, golden_dir, tmp_path):
+    import subprocess
+    root = os.path.dirname(golden_dir.rstrip("/")).rsplit("/tests", 1)[0]
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "sub120.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([exe, "-I", "6G", "--step", "2", "-t", "8", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000", src, src, "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl"), "rb").read()
+    assert open(out + ".bl", "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl.bl"), "rb").read()
+    assert subprocess.run([exe, "--step", "2", "--mode", "1", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1

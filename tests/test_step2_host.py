@@ -1,0 +1,27 @@
+"""Host side of `--step 2` (nextdenovo_b200/csrc/nd_step2.hpp: candidate marking, re-mapping plan and update rules, 10-field writer with
+its order-dependent contained/dovetail bookkeeping, `.bl` text in klib bucket order) with the oracle as the mapping backend, against the
+bytes the unmodified reference writes (tests/golden/S9_*, minted by make_golden.py).  CPU only."""
+import os
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("s2") / "step2_harness")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libnd_oracle.so"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "step2_harness.cc"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-lnd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    return exe
+
+
+def test_step2_logic_sub120_matches_reference(harness, golden_dir, tmp_path):
+    src = os.path.join(golden_dir, "sub120.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([harness, "ava-ont", "17", "17", "2000", "5000", src, src, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl"), "rb").read()
+    assert open(out + ".bl", "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl.bl"), "rb").read()
+    assert "records=148" in r.stderr

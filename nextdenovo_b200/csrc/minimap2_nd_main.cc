@@ -168,8 +168,9 @@ int main(int argc, char **argv)
             else { fprintf(stderr, "[ERROR] unknown preset '%s'\n", kv.second.c_str()); return 1; }
         } else if (kv.first == "--step") {
             step = atoi(kv.second.c_str());
-            if (step == 1) minlen = 500; else if (step == 2 || step == 3) minlen = 2000;
-            if (step == 2) { maxhan1 = 5000; maxhan2 = 500; s2.minide = 0.05f; s2.minmatch = 100; s2.kn = 17; s2.wn = 10; s2.cn = 20; }
+            if (step == 1) minlen = 500;
+            else if (step == 2) { minlen = 2000; maxhan1 = 5000; maxhan2 = 500; s2.minide = 0.05f; s2.minmatch = 100; s2.kn = 17; s2.wn = 10; s2.cn = 20; }
+            else if (step == 3) minlen = 2000;
             else { fprintf(stderr, "[ERROR] unknown preset step '%s'\n", kv.second.c_str()); return 1; }
         }
     }

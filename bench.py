@@ -199,6 +199,35 @@ def regime_b_bench(eng, engine_mod, with_reference=True, full=False):
     return out
 
 
+def step2_bench(eng, engine_mod, with_reference=True):
+    """`--step 2` (cns_align) on the reference's test data (997 reads, self-overlap, the pipeline's options -k 17 -w 17 --minlen 2000
+    --maxhan1 5000): whole step through the public API, .ovl and .bl checked against the golden bytes, next to the reference binary."""
+    import nextdenovo_b200 as nd
+    from nextdenovo_b200.options import parse_args
+    g = os.path.join(ROOT, "tests", "golden")
+    src = os.path.join(g, "reads_test.seed.2bit")
+    reads = nd.read_2bit(src)
+    args = ["-I", "6G", "--step", "2", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000"]
+    io, mo, _, _ = parse_args(args + ["a", "b", "-o", "x"])
+    eng.set_limits(64 << 20, 0)
+    for rep in range(2):
+        t0 = time.time()
+        ovl, bl, st = engine_mod.run_step2(eng, reads, reads, io, mo)
+        dt = time.time() - t0
+    out = {"workload": "reads_test.seed.2bit self-overlap, " + " ".join(args), "seconds": dt, "records": st["records"],
+           "bytes_identical_to_reference": ovl == open(os.path.join(g, "G5_step2.ovl"), "rb").read() and bl == open(os.path.join(g, "G5_step2.ovl.bl"), "rb").read()}
+    if with_reference:
+        exe = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+        with tempfile.TemporaryDirectory() as td:
+            o = os.path.join(td, "r.ovl")
+            t0 = time.time()
+            subprocess.run([exe] + args + ["-t", str(usable_cpus()), src, src, "-o", o], stderr=subprocess.DEVNULL, check=True)
+            rt = time.time() - t0
+        out["reference"] = {"seconds": rt, "threads": usable_cpus()}
+        out["speedup_vs_reference"] = rt / dt
+    return out
+
+
 def cpu_sample(n):
     genome_bp = max(int(n * READ_LEN / DEPTH), 200000)
     return make_reads(n, genome_bp), "%d reads x %d bp at %dx depth (genome %d bp), self-overlap, mapping phase only" % (n, READ_LEN, DEPTH, genome_bp)
@@ -449,6 +478,12 @@ def main_ours(a, rank, world, local_rank):
                 rb = regime_b_bench(eng, engine, with_reference=not a.no_cpu_baseline, full=a.regime_b_full)
             except Exception as ex:  # noqa: BLE001
                 rb = {"error": repr(ex)}
+        s2 = None
+        if not a.no_regime_b and world == 1:
+            try:
+                s2 = step2_bench(eng, engine, with_reference=not a.no_cpu_baseline)
+            except Exception as ex:  # noqa: BLE001
+                s2 = {"error": repr(ex)}
         line = {
             "metric": "overlaps/sec", "value": rec / t_res_dev, "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * t_res_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -474,6 +509,7 @@ def main_ours(a, rank, world, local_rank):
             "gen_s": t_gen,
             "ksw2_extd2": ksw,
             "regime_b": rb,
+            "step2": s2,
         }
         print(json.dumps(line))
     eng.close()

@@ -11,6 +11,7 @@ oracle/_ref: `make -C oracle`).  Run from the repo root.  Committed outputs:
   S6_sub120_ava-ont_c.ovl, S7_sub120_ava-pb_c.ovl   the same inputs with -c (base-level alignment, regime B)
   S8_sub30_ava-ont_c.ovl    first 30 reads of sub120, -c -x ava-ont (CPU-sized case for the host alignment logic)
   G4_ava-ont_c.ovl          minimap2-nd --step 1 -c -x ava-ont T T (md5 4c7e8525..., ~6 min on 8 threads)
+  S9_sub120_step2.ovl(.bl), G5_step2.ovl(.bl)   minimap2-nd -I 6G --step 2 -x ava-ont -k 17 -w 17 --minlen 2000 --maxhan1 5000 (sub120 / T)
 """
 import os, subprocess, sys, tempfile, hashlib
 sys.path.insert(0, os.getcwd())
@@ -47,6 +48,10 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         nd.write_2bit(td + "/sub30.2bit", nd.read_2bit(S, max_reads=30))
         run(["-c", "-x", "ava-ont", td + "/sub30.2bit", td + "/sub30.2bit"], G + "/S8_sub30_ava-ont_c.ovl")
+    a2 = ["-I", "6G", "--step", "2", "-t", "8", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000"]
+    for src, dst in ((S, "S9_sub120_step2.ovl"), (T, "G5_step2.ovl")):      # --step 2 writes DST and DST.bl
+        subprocess.check_call([REF + "/minimap2-nd"] + a2 + [src, src, "-o", G + "/" + dst], stderr=subprocess.DEVNULL)
+        print(dst, hashlib.md5(open(G + "/" + dst, "rb").read()).hexdigest())
     if "--full" in sys.argv:
         run(["-c", "-x", "ava-ont", T, T], G + "/G4_ava-ont_c.ovl")
 

@@ -411,3 +411,47 @@ def test_cli_step2_matches_reference_bytes(built, golden_dir, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl"), "rb").read()
     assert open(out + ".bl", "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl.bl"), "rb").read()
     assert subprocess.run([exe, "--step", "2", "--mode", "1", "-x", "ava-ont", src, src, "-o", out], capture_output=True).returncode == 1
+
+
+@pytest.mark.parametrize("args", [
+    ["--step", "1", "-c", "-x", "ava-ont"],
+    ["--step", "1", "-c", "--dual=yes", "-I", "300k", "-x", "ava-ont"],
+    ["--step", "1", "-c", "-x", "ava-pb"],
+    ["--step", "1", "-c", "-z", "200,100", "-s", "40", "--end-bonus", "5", "-x", "ava-ont"],
+    ["-I", "6G", "--step", "2", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000"],
+    ["-I", "400k", "--step", "2", "--dual=yes", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "1000", "--maxhan1", "3000", "--minide", "0.03"],
+    ["--step", "2", "--mode", "0", "-x", "ava-ont", "-k", "17", "-w", "17"],
+    ["--step", "2", "--outctn", "--cn", "7", "-K", "200k", "-x", "ava-ont", "-k", "15", "-w", "10", "--minlen", "500"],
+], ids=["c", "c-dual-parts", "c-hpc", "c-scoring", "step2", "step2-parts-dual", "step2-mode0", "step2-outctn-batches"])
+def test_cli_equals_reference_on_fastx_with_n(built, reads_sub, tmp_path, args):
+    """the drop-in executable and the unmodified reference run side by side on a FASTA file with N runs and lower case (40 reads):
+    regime B and step 2, index parts, query batches, --dual, non-default scoring: same .ovl (and .bl) bytes"""
+    import subprocess
+    from nextdenovo_b200.formats import unpack_bases
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref", "minimap2-nd")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(9)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    fa = str(tmp_path / "r.fa")
+    with open(fa, "wb") as fh:
+        for r in range(40):
+            w0, w1 = int(reads_sub.word_off[r]), int(reads_sub.word_off[r + 1])
+            s = bytearray(lut[unpack_bases(reads_sub.words[w0:w1], int(reads_sub.length[r]))].tobytes())
+            for _ in range(int(rng.integers(0, 5))):
+                p, ln = int(rng.integers(0, len(s))), int(rng.integers(1, 40))
+                s[p:p + ln] = b"N" * len(s[p:p + ln])
+            if r % 4 == 0:
+                s = bytearray(bytes(s).lower())
+            fh.write(b">%d\n" % int(reads_sub.ids[r]) + bytes(s) + b"\n")
+    want_p, got_p = str(tmp_path / "ref.ovl"), str(tmp_path / "gpu.ovl")
+    subprocess.run([ref] + args + ["-t", "8", fa, fa, "-o", want_p], check=True, capture_output=True)
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    r = subprocess.run([exe] + args + ["-t", "8", fa, fa, "-o", got_p], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = open(want_p, "rb").read()
+    assert len(want) > 100 and open(got_p, "rb").read() == want
+    if "2" in args[:4] and "--step" in args:
+        if os.path.exists(want_p + ".bl"):
+            assert open(got_p + ".bl", "rb").read() == open(want_p + ".bl", "rb").read()

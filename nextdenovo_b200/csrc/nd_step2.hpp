@@ -262,6 +262,8 @@ struct Writer {
 // A re-mapping request: map `mapped` against the mini index made of `group`.  In the common branch the group is the query
 // itself and the mapped sequences are its candidate targets (ref: map.c:1046-1084); with >= 200 candidates the group is a
 // batch of up to cn targets and the query is mapped (ref: map.c:1085-1125).
+// Ambiguous bases: a target mapped against the query's mini index has them turned into A (the reference passes "ACGT"[code]
+// characters, code 4 is the terminator byte, and its base table maps byte 0 to A); index reads and a mapped query keep them.
 struct Remap {
     int query = 0;                                  // batch-local query index this request belongs to
     bool query_is_index = true;

@@ -1284,16 +1284,18 @@ namespace {
 
 struct ReadGather {                                // a read batch assembled from pieces of other batches (2-bit words verbatim)
     std::vector<uint32_t> words, len, nmask, hash, id, tag; std::vector<uint64_t> word_off, key; bool has_n = false;
-    void add(const uint32_t *w, const uint64_t off, uint32_t L, const uint32_t *nm, uint32_t tg)
+    // n_to_a: ambiguous bases become 'A'.  The reference hands a re-mapped target over as "ACGT"[code] characters, code 4 gives the
+    // string terminator, and seq_nt4_table[0] is 0 = A (ref: minimap2/map.c:1041-1045, minimap2/sketch.c:8).
+    void add(const uint32_t *w, const uint64_t off, uint32_t L, const uint32_t *nm, uint32_t tg, bool n_to_a = false)
     {
         const size_t nw = (L + 15) / 16, w0 = words.size();
         word_off.push_back(w0);
         words.insert(words.end(), w + off, w + off + nw);
         if (words.size() & 1) words.push_back(0);
-        if (has_n) {
-            nmask.resize(words.size() / 2 + 1, 0);
-            if (nm) memcpy(nmask.data() + w0 / 2, nm + off / 2, ((nw + 1) / 2) * 4);
-        }
+        if (has_n) nmask.resize(words.size() / 2 + 1, 0);
+        if (nm && n_to_a) {
+            for (uint32_t i = 0; i < L; ++i) if (nm[off / 2 + (i >> 5)] >> (i & 31) & 1) words[w0 + (i >> 4)] &= ~(3u << (30 - 2 * (i & 15)));
+        } else if (has_n && nm) memcpy(nmask.data() + w0 / 2, nm + off / 2, ((nw + 1) / 2) * 4);
         len.push_back(L); hash.push_back(0); id.push_back((uint32_t)len.size() - 1); key.push_back(len.size()); tag.push_back(tg);
     }
     ndg_reads_t view()
@@ -1331,7 +1333,7 @@ int step2_remap(ndg_ctx *c, const ndg_reads_t *Q, std::vector<nds2::QueryJob> &j
                 IX.add(Q->words, Q->word_off[m.query], Q->len[m.query], Q->nmask, qtag[(size_t)m.query]);
             }
             base[x] = qslot[(size_t)m.query];
-            MP.add(c->ht_words.data(), c->ht_word_off[(size_t)m.mapped_rid], c->h_tlen[(size_t)m.mapped_rid], tn, qtag[(size_t)m.query]);
+            MP.add(c->ht_words.data(), c->ht_word_off[(size_t)m.mapped_rid], c->h_tlen[(size_t)m.mapped_rid], tn, qtag[(size_t)m.query], true);
         } else {                                    // up to cn targets form the mini index, the query is mapped (ref: map.c:1085-1125)
             const uint32_t tg = next_tag++;
             base[x] = (uint32_t)IX.len.size();

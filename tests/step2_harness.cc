@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <string>
 #include "../oracle/nd_oracle.h"
 #include "../nextdenovo_b200/csrc/nd_step2.hpp"
 
@@ -16,6 +17,24 @@ static void to_regs(const ndo_reg *r, int n, std::vector<nds2::Reg> &out)
     for (int i = 0; i < n; ++i) { nds2::Reg &z = out[(size_t)i]; z.rid = r[i].rid; z.rev = r[i].rev; z.qs = r[i].qs; z.qe = r[i].qe; z.rs = r[i].rs; z.re = r[i].re; z.mlen = r[i].mlen; z.blen = r[i].blen; z.score = r[i].score; z.cnt = r[i].cnt; }
 }
 
+// minimal FASTA reader (one line per sequence or wrapped; decimal names) into the oracle's read container
+static ndo_reads *read_fasta(const char *fn)
+{
+    FILE *f = fopen(fn, "r"); if (!f) return 0;
+    ndo_reads *R = (ndo_reads *)calloc(1, sizeof(ndo_reads));
+    std::vector<std::string> names, seqs; char *line = 0; size_t cap = 0; ssize_t n;
+    while ((n = getline(&line, &cap, f)) > 0) {
+        while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+        if (line[0] == '>') { std::string nm(line + 1); nm = nm.substr(0, nm.find_first_of(" \t")); names.push_back(nm); seqs.push_back(""); }
+        else if (!seqs.empty()) seqs.back() += line;
+    }
+    free(line); fclose(f);
+    R->n = (int)names.size(); R->seq = (char **)calloc(R->n, sizeof(char *)); R->name = (char **)calloc(R->n, sizeof(char *)); R->len = (int *)calloc(R->n, sizeof(int)); R->id = (uint32_t *)calloc(R->n, 4);
+    for (int i = 0; i < R->n; ++i) { R->seq[i] = strdup(seqs[i].c_str()); R->name[i] = strdup(names[i].c_str()); R->len[i] = (int)seqs[i].size(); R->id[i] = (uint32_t)strtoul(names[i].c_str(), 0, 10); }
+    return R;
+}
+static ndo_reads *read_any(const char *fn) { size_t L = strlen(fn); return (L > 3 && !strcmp(fn + L - 3, ".fa")) ? read_fasta(fn) : ndo_read_2bit(fn); }
+
 int main(int argc, char **argv)
 {
     if (argc != 9) { fprintf(stderr, "usage: step2_harness <preset> <k> <w> <minlen> <maxhan1> target.2bit query.2bit out.ovl\n"); return 2; }
@@ -23,8 +42,8 @@ int main(int argc, char **argv)
     if (atoi(argv[2]) > 0) o.k = atoi(argv[2]);
     if (atoi(argv[3]) > 0) o.w = atoi(argv[3]);
     nds2::Opt so; so.minlen = atoi(argv[4]); so.maxhan1 = atoi(argv[5]);
-    ndo_reads *T = ndo_read_2bit(argv[6]);
-    ndo_reads *Q = strcmp(argv[6], argv[7]) ? ndo_read_2bit(argv[7]) : T;
+    ndo_reads *T = read_any(argv[6]);
+    ndo_reads *Q = strcmp(argv[6], argv[7]) ? read_any(argv[7]) : T;
     if (!T || !Q) { fprintf(stderr, "cannot read input\n"); return 1; }
     ndo_index *idx = ndo_index_build(T->n, (const char *const *)T->seq, T->len, (const char *const *)T->name, o.w, o.k, o.hpc);
     const int mid_occ = o.mid_occ > 0 ? o.mid_occ : ndo_index_mid_occ(idx, o.mid_occ_frac);
@@ -47,7 +66,10 @@ int main(int argc, char **argv)
             const char *qs = Q->seq[i]; int ql = Q->len[i]; const char *nm = "q";
             ndo_index *mini = ndo_index_build(1, &qs, &ql, &nm, so.wn, so.kn, o.hpc);
             for (nds2::Remap &m : reqs[(size_t)i]) {
-                int nn = 0; ndo_reg *x = ndo_map_read(mini, &o, mid_occ, NULL, T->seq[m.mapped_rid], T->len[m.mapped_rid], &nn);
+                // the reference re-maps "ACGT"[code] characters: an ambiguous base becomes '\0', which its base table reads as A (map.c:1041-1045)
+                std::string ts(T->seq[m.mapped_rid], (size_t)T->len[m.mapped_rid]);
+                for (char &ch : ts) if (!strchr("ACGTUacgtu", ch)) ch = 'A';
+                int nn = 0; ndo_reg *x = ndo_map_read(mini, &o, mid_occ, NULL, ts.c_str(), T->len[m.mapped_rid], &nn);
                 to_regs(x, nn, m.result); free(x); ++n_remap;
             }
             ndo_index_free(mini);

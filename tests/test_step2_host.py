@@ -25,3 +25,20 @@ def test_step2_logic_sub120_matches_reference(harness, golden_dir, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl"), "rb").read()
     assert open(out + ".bl", "rb").read() == open(os.path.join(golden_dir, "S9_sub120_step2.ovl.bl"), "rb").read()
     assert "records=148" in r.stderr
+
+
+def test_step2_logic_with_ambiguous_bases_matches_reference_run(harness, tmp_path):
+    """40 reads with N runs and lower case in FASTA: the reference binary (when oracle/_ref is present) and the host logic + oracle
+    mapping agree on .ovl and .bl; pins the N -> A reading of re-mapped targets (ref: minimap2/map.c:1041-1045)"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not present")
+    fa = str(tmp_path / "r.fa")
+    subprocess.check_call(["python", os.path.join(ROOT, "tools", "mkfa_n.py"), fa], cwd=ROOT)
+    want, got = str(tmp_path / "ref.ovl"), str(tmp_path / "mine.ovl")
+    subprocess.run([ref, "-I", "6G", "--step", "2", "-t", "4", "-x", "ava-ont", "-k", "17", "-w", "17", "--minlen", "2000", "--maxhan1", "5000", fa, fa, "-o", want],
+                   check=True, capture_output=True)
+    r = subprocess.run([harness, "ava-ont", "17", "17", "2000", "5000", fa, fa, got], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(got, "rb").read() == open(want, "rb").read()
+    assert open(got + ".bl", "rb").read() == open(want + ".bl", "rb").read()

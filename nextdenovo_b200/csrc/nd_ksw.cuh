@@ -634,7 +634,9 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
 // Cooperative generation for wide bands (extensions with w = 1.5*bw+1, long joins): the same cell code, one call per block.
 // A lone warp advances a 3000-cell diagonal in 47 dependent round trips to its L2-resident state; eight warps do it in 6.
 // ------------------------------------------------------------------------------------------------
+#ifndef NDK_COOP_WARPS
 #define NDK_COOP_WARPS 8
+#endif
 __global__ void __launch_bounds__(NDK_COOP_WARPS * 32)
 k_ksw_extd2_coop(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
                uint8_t *scratch, size_t slot_bytes, size_t state_bytes, size_t h_bytes, uint32_t *work,

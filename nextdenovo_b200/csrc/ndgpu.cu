@@ -998,7 +998,7 @@ struct GpuDp : ndal::Backend {
         const size_t slot_bytes = state_bytes + h_bytes + off_bytes + tab_bytes;
         static const int bps = getenv("NDG_KSW_BPS") ? atoi(getenv("NDG_KSW_BPS")) : 16;
         const int blocks = ns ? std::min<int>(c->n_sm * bps, (int)((ns + NDK_WARPS - 1) / NDK_WARPS)) : 0;
-        const int cblocks = nb ? (int)std::min<size_t>((size_t)c->n_sm * 2, nb) : 0;
+        const int cblocks = nb ? (int)std::min<size_t>((size_t)c->n_sm * (16 / NDK_COOP_WARPS), nb) : 0;
         const size_t slots = (size_t)blocks * NDK_WARPS + (size_t)cblocks;
         RSV(c->ksw_scratch, slots * slot_bytes);    // shared: launches never run their kernels at the same time
         DevBuf &scr = c->ksw_scratch;
@@ -1560,7 +1560,7 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
     CK(cudaMemsetAsync(d_work, 0, 4, c->st));
     ndk_par P; P.m = m; memset(P.mat, 0, sizeof P.mat); memcpy(P.mat, mat, (size_t)m * m); P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
     if (c->ksw_variant == 2) {                       // block-per-call generation (wide bands)
-        const int cb = std::min<int>(c->n_sm * 2, n);
+        const int cb = std::min<int>(c->n_sm * (16 / NDK_COOP_WARPS), n);
         RSV(c->ksw_scratch, (size_t)cb * slot_bytes);
         KLAUNCH("ksw_extd2", (k_ksw_extd2_coop<<<cb, NDK_COOP_WARPS * 32, 0, c->st>>>(c->ksw_calls.as<ndk_call>(), n, c->ksw_seqs.as<uint8_t>(), P, c->ksw_res.as<ndk_res>(),
                               c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), c->ksw_scratch.as<uint8_t>(), slot_bytes, state_bytes, h_bytes, d_work)));

@@ -118,7 +118,6 @@ struct ndg_ctx {
     DevBuf ksw_ncig, ksw_coff, ksw_cout, ch_cnt, ch_off, ch_a, ch_fend;
     HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
     uint64_t arena_want = 0;
-    cudaStream_t st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int n_threads = 1;                            // host threads of the alignment stage
     // --step 2
     bool s2_on = false; nds2::Opt s2; nds2::Writer s2w; size_t s2_emitted = 0; std::string s2_bl; ndg_ctx *remap = nullptr;
@@ -339,7 +338,6 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
     c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release();
     if (c->remap) { ndg_destroy(c->remap); c->remap = nullptr; }
-    if (c->st2) { cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); }
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -1197,7 +1195,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
     uint64_t hi = 0, aoff = 0;
     int r = r0;
     while (r < r1) {
-        const int g0 = r; const uint64_t h0 = hi, a0 = aoff;
+        const int g0 = r;
         uint64_t nch = 0;
         std::vector<uint64_t> hbeg, abeg;
         while (r < r1 && (r == g0 || nch < GROUP_CHAINS)) {
@@ -1206,7 +1204,6 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
             ++r;
         }
         hbeg.push_back(hi); abeg.push_back(aoff);
-        (void)h0; (void)a0;
         std::vector<ndal::ReadJob> jobs((size_t)(r - g0));
 #pragma omp parallel for schedule(dynamic, 1)
         for (int j = 0; j < r - g0; ++j) {
@@ -1531,8 +1528,6 @@ extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, in
     cudaSetDevice(c->device);
     std::vector<ndk_call> hc((size_t)n);
     uint64_t p_total = 0; int Tmax = 16, rmax = 1, qmax = 1;
-    int qq = q, ee = e, qq2 = q2, ee2 = e2;
-    (void)qq; (void)ee; (void)qq2; (void)ee2;
     for (int i = 0; i < n; ++i) {
         const ndg_ksw_call_t &k = calls[i];
         if (k.qlen < 0 || k.tlen < 0 || k.q_off + (uint64_t)k.qlen > seq_bytes || k.t_off + (uint64_t)k.tlen > seq_bytes) return fail(c, NDG_ERR_ARG, "ksw call %d out of range", i);

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=100000, help="reads in the index (configs[1]: 100k)")
     ap.add_argument("--batch-reads", type=int, default=3000, help="query reads per step")
+    ap.add_argument("--sub-batch-mbp", type=int, default=64, help="device sub-batch limit in Mbp (a step must fit one sub-batch)")
     ap.add_argument("--cpu-sample-reads", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="1,1")
@@ -371,6 +372,7 @@ def main_ours(a, rank, world, local_rank):
     # same time).
     nb = a.warmup + a.steps
     B = a.batch_reads
+    eng.set_limits(a.sub_batch_mbp << 20, 0)
     base_batches = [reads.slice((i * B) % max(reads.n - B, 1), (i * B) % max(reads.n - B, 1) + B) for i in range(nb)]
     batches = base_batches[:a.warmup] + [base_batches[a.warmup + (i + rank) % a.steps] for i in range(a.steps)]
 

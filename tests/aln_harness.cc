@@ -74,21 +74,40 @@ struct CpuBackend : ndal::Backend {
     }
 };
 
-struct Packed { std::vector<uint32_t> words, len; std::vector<uint64_t> word_off; };
+struct Packed { std::vector<uint32_t> words, len, nmask; std::vector<uint64_t> word_off; };
 static void pack(const ndo_reads *R, Packed &P)
 {
     P.word_off.assign(1, 0);
     for (int r = 0; r < R->n; ++r) {
         const int L = R->len[r]; const size_t nw = ((size_t)(L + 15) / 16 + 1) & ~(size_t)1;
         const size_t w0 = P.words.size();
-        P.words.resize(w0 + nw, 0);
+        P.words.resize(w0 + nw, 0); P.nmask.resize((w0 + nw) / 2 + 1, 0);
         for (int i = 0; i < L; ++i) {
-            int c = R->seq[r][i]; c = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
-            P.words[w0 + (i >> 4)] |= (uint32_t)c << (30 - 2 * (i & 15));
+            int c = R->seq[r][i]; c = (c == 'A' || c == 'a') ? 0 : (c == 'C' || c == 'c') ? 1 : (c == 'G' || c == 'g') ? 2 : (c == 'T' || c == 't' || c == 'U' || c == 'u') ? 3 : 4;
+            if (c < 4) P.words[w0 + (i >> 4)] |= (uint32_t)c << (30 - 2 * (i & 15));
+            else P.nmask[w0 / 2 + (i >> 5)] |= 1u << (i & 31);
         }
         P.len.push_back((uint32_t)L); P.word_off.push_back(P.words.size());
     }
 }
+
+// minimal FASTA reader (decimal names) into the oracle's read container
+static ndo_reads *read_fasta(const char *fn)
+{
+    FILE *f = fopen(fn, "r"); if (!f) return 0;
+    ndo_reads *R = (ndo_reads *)calloc(1, sizeof(ndo_reads));
+    std::vector<std::string> names, seqs; char *line = 0; size_t cap = 0; ssize_t n;
+    while ((n = getline(&line, &cap, f)) > 0) {
+        while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+        if (line[0] == '>') { std::string nm(line + 1); nm = nm.substr(0, nm.find_first_of(" \t")); names.push_back(nm); seqs.push_back(""); }
+        else if (!seqs.empty()) seqs.back() += line;
+    }
+    free(line); fclose(f);
+    R->n = (int)names.size(); R->seq = (char **)calloc(R->n, sizeof(char *)); R->name = (char **)calloc(R->n, sizeof(char *)); R->len = (int *)calloc(R->n, sizeof(int)); R->id = (uint32_t *)calloc(R->n, 4);
+    for (int i = 0; i < R->n; ++i) { R->seq[i] = strdup(seqs[i].c_str()); R->name[i] = strdup(names[i].c_str()); R->len[i] = (int)seqs[i].size(); R->id[i] = (uint32_t)strtoul(names[i].c_str(), 0, 10); }
+    return R;
+}
+static ndo_reads *read_any(const char *fn) { size_t L = strlen(fn); return (L > 3 && !strcmp(fn + L - 3, ".fa")) ? read_fasta(fn) : ndo_read_2bit(fn); }
 
 int main(int argc, char **argv)
 {
@@ -96,16 +115,16 @@ int main(int argc, char **argv)
     ndo_opt o; ndo_opt_preset(&o, NULL); ndo_opt_preset(&o, argv[2]);
     if (atoi(argv[3]) > 0) o.k = atoi(argv[3]);
     if (atoi(argv[4]) > 0) o.w = atoi(argv[4]);
-    ndo_reads *T = ndo_read_2bit(argv[5]);
-    ndo_reads *Q = strcmp(argv[5], argv[6]) ? ndo_read_2bit(argv[6]) : T;
+    ndo_reads *T = read_any(argv[5]);
+    ndo_reads *Q = strcmp(argv[5], argv[6]) ? read_any(argv[6]) : T;
     if (!T || !Q) { fprintf(stderr, "cannot read input\n"); return 1; }
     ndo_index *idx = ndo_index_build(T->n, (const char *const *)T->seq, T->len, (const char *const *)T->name, o.w, o.k, o.hpc);
     const int mid_occ = o.mid_occ > 0 ? o.mid_occ : ndo_index_mid_occ(idx, o.mid_occ_frac);
 
     ndal::Opt ao; ao.k = o.k; ao.hpc = o.hpc; ao.bw = o.bw; ao.max_gap = o.max_gap; ao.min_cnt = o.min_cnt; ao.min_chain_score = o.min_chain_score;
     Packed PT, PQ; pack(T, PT); if (Q != T) pack(Q, PQ);
-    ndal::SeqStore ST; ST.words = PT.words.data(); ST.word_off = PT.word_off.data(); ST.len = PT.len.data();
-    ndal::SeqStore SQ = ST; if (Q != T) { SQ.words = PQ.words.data(); SQ.word_off = PQ.word_off.data(); SQ.len = PQ.len.data(); }
+    ndal::SeqStore ST; ST.words = PT.words.data(); ST.word_off = PT.word_off.data(); ST.len = PT.len.data(); ST.nmask = PT.nmask.data();
+    ndal::SeqStore SQ = ST; if (Q != T) { SQ.words = PQ.words.data(); SQ.word_off = PQ.word_off.data(); SQ.len = PQ.len.data(); SQ.nmask = PQ.nmask.data(); }
 
     CpuBackend be; be.o = &ao; ndal::simple_mat(be.mat, ao);
     if (!strcmp(argv[1], "ref")) {

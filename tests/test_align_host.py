@@ -43,3 +43,17 @@ def test_align_logic_tiny_with_oracle_dp(harness, golden_dir, tmp_path):
         r2 = subprocess.run([harness, "ref", "ava-ont", "0", "0", sub, sub, b], capture_output=True, text=True, cwd=ROOT)
         assert r2.returncode == 0, r2.stderr
         assert open(a, "rb").read() == open(b, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (make -C oracle ref)")
+def test_align_logic_with_ambiguous_bases_matches_reference_run(harness, tmp_path):
+    """40 reads with N runs and lower case in FASTA: a live run of the reference with -c and the host logic (+ reference ksw as the
+    DP checker, oracle chains) write the same bytes"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+    fa = str(tmp_path / "r.fa")
+    subprocess.check_call(["python", os.path.join(ROOT, "tools", "mkfa_n.py"), fa], cwd=ROOT)
+    want, got = str(tmp_path / "ref.ovl"), str(tmp_path / "mine.ovl")
+    subprocess.run([ref, "--step", "1", "-c", "-t", "8", "-x", "ava-ont", fa, fa, "-o", want], check=True, capture_output=True)
+    r = subprocess.run([harness, "ref", "ava-ont", "0", "0", fa, fa, got], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    assert open(got, "rb").read() == open(want, "rb").read()

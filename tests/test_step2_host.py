@@ -42,3 +42,13 @@ def test_step2_logic_with_ambiguous_bases_matches_reference_run(harness, tmp_pat
     assert r.returncode == 0, r.stderr
     assert open(got, "rb").read() == open(want, "rb").read()
     assert open(got + ".bl", "rb").read() == open(want + ".bl", "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/util/khash.h"), reason="reference tree not present")
+def test_ktable_bucket_layout_equals_klib(tmp_path):
+    """the table behind the .bl line order against the reference's own khash.h: same buckets after the same insertions
+    (66 cases: sequential ids, colliding low bits, random keys, repeats; 1 to 40000 keys, i.e. through 14 growth steps)"""
+    exe = str(tmp_path / "ktable_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I/root/reference/util", "-o", exe, os.path.join(ROOT, "tests", "ktable_check.cc")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr

@@ -148,6 +148,11 @@ int ndg_index_clear_minimizers(ndg_ctx_t *ctx);
 /* device-to-device copy on the context's stream, synchronous (glue for torch.distributed buffers) */
 int ndg_copy_d2d(ndg_ctx_t *ctx, void *dst_dev, const void *src_dev, uint64_t bytes);
 int ndg_index_finalize(ndg_ctx_t *ctx, ndg_index_stat_t *stat);
+/* Let ctx borrow the finalized index of src (same device; no counterpart in the reference, where worker threads share `mi`):
+ * several contexts, each with its own stream and workspace, can then map batches concurrently against one copy of the index.
+ * src must stay alive and keep its index while ctx uses it; ndg_index_begin()/ndg_destroy() on ctx drop the loan. */
+int ndg_index_share(ndg_ctx_t *ctx, ndg_ctx_t *src);
+
 /* point query, for tests: replaces mm_idx_get (ref: minimap2/index.c:81-98). positions copied to host */
 int ndg_index_get(ndg_ctx_t *ctx, uint64_t minier, uint64_t *pos, int cap, int *n);
 

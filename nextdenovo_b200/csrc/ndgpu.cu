@@ -119,6 +119,7 @@ struct ndg_ctx {
     HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
     uint64_t arena_want = 0;
     int n_threads = 1;                            // host threads of the alignment stage
+    bool idx_borrowed = false;                    // index buffers belong to another context (ndg_index_share)
     // --step 2
     bool s2_on = false; nds2::Opt s2; nds2::Writer s2w; size_t s2_emitted = 0; std::string s2_bl; ndg_ctx *remap = nullptr;
     uint64_t s2_remaps = 0, s2_groups = 0; double s2_remap_ms = 0;
@@ -322,11 +323,20 @@ extern "C" int ndg_init(int device, ndg_ctx_t **out)
     return NDG_OK;
 }
 
+static void drop_index_loan(ndg_ctx *c)
+{
+    if (!c->idx_borrowed) return;
+    DevBuf *b[] = { &c->idx_pos, &c->idx_tab, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
+    for (auto x : b) { x->p = nullptr; x->cap = 0; }
+    c->idx_borrowed = false; c->index_ready = false;
+}
+
 extern "C" void ndg_destroy(ndg_ctx_t *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    drop_index_loan(c);
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
@@ -395,6 +405,7 @@ extern "C" int ndg_index_begin(ndg_ctx_t *c)
 {
     if (!c) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
+    drop_index_loan(c);
     c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->h_ttag.clear(); c->t_has_id = true; c->t_has_tag = false; c->tag_shift = 0;
     c->index_ready = false; c->n_pos = 0;
     c->ht_words.clear(); c->ht_nmask.clear(); c->ht_word_off.clear(); c->ht_has_n = false;
@@ -467,6 +478,24 @@ extern "C" int ndg_copy_d2d(ndg_ctx_t *c, void *dst, const void *src, uint64_t b
     CK(cudaStreamSynchronize(c->st));
     return NDG_OK;
 }
+extern "C" int ndg_index_share(ndg_ctx_t *c, ndg_ctx_t *src)
+{
+    if (!c || !src || c == src) return NDG_ERR_ARG;
+    if (!src->index_ready) return fail(c, NDG_ERR_STATE, "the source context has no finalized index");
+    if (c->device != src->device) return fail(c, NDG_ERR_ARG, "contexts are on different devices");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(src->st);
+    drop_index_loan(c);
+    DevBuf *own[] = { &c->idx_pos, &c->idx_tab, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
+    DevBuf *from[] = { &src->idx_pos, &src->idx_tab, &src->t_key, &src->t_len, &src->t_id, &src->t_tag };
+    for (int i = 0; i < 6; ++i) { own[i]->release(); own[i]->p = from[i]->p; own[i]->cap = from[i]->cap; }
+    c->log2cap = src->log2cap; c->n_pos = src->n_pos; c->mid_occ = src->mid_occ; c->tag_shift = src->tag_shift;
+    c->n_targets = src->n_targets; c->t_sum_len = src->t_sum_len; c->t_has_id = src->t_has_id; c->t_has_tag = src->t_has_tag;
+    c->h_tkey = src->h_tkey; c->h_tlen = src->h_tlen; c->h_tid = src->h_tid; c->h_ttag = src->h_ttag;
+    c->idx_borrowed = true; c->index_ready = true;
+    return NDG_OK;
+}
+
 extern "C" int ndg_index_clear_minimizers(ndg_ctx_t *c) { if (!c) return NDG_ERR_ARG; c->n_tmz = 0; return NDG_OK; }
 
 extern "C" int ndg_index_import(ndg_ctx_t *c, const void *dev, uint64_t n)

@@ -76,7 +76,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish", "ndg_index_share"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library():
     L.ndg_set_aln_opt.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_aln_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.ndg_index_share.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_step2_begin.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_step2_map_batch.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.ndg_step2_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -217,6 +218,11 @@ class Engine:
         s = _reads_struct(targets)
         self._ck(self.L.ndg_index_add(self.h, C.byref(s)))
         return self.finalize_index(targets)
+
+    def share_index_of(self, other):
+        """borrow the finalized index of another Engine on the same device (ndg_index_share)"""
+        self._ck(self.L.ndg_index_share(self.h, other.h))
+        self.targets, self.stat = other.targets, other.stat
 
     def finalize_index(self, targets: Reads):
         st = _IndexStat()

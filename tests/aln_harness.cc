@@ -121,7 +121,11 @@ int main(int argc, char **argv)
     ndo_index *idx = ndo_index_build(T->n, (const char *const *)T->seq, T->len, (const char *const *)T->name, o.w, o.k, o.hpc);
     const int mid_occ = o.mid_occ > 0 ? o.mid_occ : ndo_index_mid_occ(idx, o.mid_occ_frac);
 
+    // optional overrides (test sweeps): ALN_BW, ALN_MAXGAP, ALN_MINCNT, ALN_MINSC (chaining, as -r -g -n -m), ALN_ZDROP, ALN_ZDROP_INV, ALN_MINDP, ALN_ENDBONUS
+    auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
+    o.bw = envi("ALN_BW", o.bw); o.max_gap = envi("ALN_MAXGAP", o.max_gap); o.min_cnt = envi("ALN_MINCNT", o.min_cnt); o.min_chain_score = envi("ALN_MINSC", o.min_chain_score);
     ndal::Opt ao; ao.k = o.k; ao.hpc = o.hpc; ao.bw = o.bw; ao.max_gap = o.max_gap; ao.min_cnt = o.min_cnt; ao.min_chain_score = o.min_chain_score;
+    ao.zdrop = envi("ALN_ZDROP", ao.zdrop); ao.zdrop_inv = envi("ALN_ZDROP_INV", ao.zdrop_inv); ao.min_dp_max = envi("ALN_MINDP", ao.min_dp_max); ao.end_bonus = envi("ALN_ENDBONUS", ao.end_bonus);
     Packed PT, PQ; pack(T, PT); if (Q != T) pack(Q, PQ);
     ndal::SeqStore ST; ST.words = PT.words.data(); ST.word_off = PT.word_off.data(); ST.len = PT.len.data(); ST.nmask = PT.nmask.data();
     ndal::SeqStore SQ = ST; if (Q != T) { SQ.words = PQ.words.data(); SQ.word_off = PQ.word_off.data(); SQ.len = PQ.len.data(); SQ.nmask = PQ.nmask.data(); }

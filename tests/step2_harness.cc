@@ -42,6 +42,10 @@ int main(int argc, char **argv)
     if (atoi(argv[2]) > 0) o.k = atoi(argv[2]);
     if (atoi(argv[3]) > 0) o.w = atoi(argv[3]);
     nds2::Opt so; so.minlen = atoi(argv[4]); so.maxhan1 = atoi(argv[5]);
+    // optional overrides (test sweeps): S2_MAXHAN2, S2_MINMATCH, S2_CN, S2_OUTCTN, S2_MINIDE (x1000), S2_MODE
+    { auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
+      so.maxhan2 = envi("S2_MAXHAN2", so.maxhan2); so.minmatch = envi("S2_MINMATCH", so.minmatch); so.cn = envi("S2_CN", so.cn); so.outctn = envi("S2_OUTCTN", so.outctn);
+      so.minide = envi("S2_MINIDE", (int)(so.minide * 1000 + .5)) / 1000.f; so.mode = envi("S2_MODE", so.mode); }
     ndo_reads *T = read_any(argv[6]);
     ndo_reads *Q = strcmp(argv[6], argv[7]) ? read_any(argv[7]) : T;
     if (!T || !Q) { fprintf(stderr, "cannot read input\n"); return 1; }

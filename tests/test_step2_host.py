@@ -52,3 +52,23 @@ def test_ktable_bucket_layout_equals_klib(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I/root/reference/util", "-o", exe, os.path.join(ROOT, "tests", "ktable_check.cc")])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("preset,k,w,minlen,maxhan1,extra,env", [
+    ("ava-ont", 15, 10, 500, 3000, [], {}),
+    ("ava-ont", 15, 5, 500, 5000, ["--outctn", "--minide", "0.02"], {"S2_OUTCTN": "1", "S2_MINIDE": "20"}),
+    ("ava-pb", 19, 10, 1000, 5000, [], {}),
+    ("ava-ont", 15, 5, 300, 5000, ["--cn", "5", "--minide", "0.01", "--minmatch", "30"], {"S2_CN": "5", "S2_MINIDE": "10", "S2_MINMATCH": "30"}),
+], ids=["k15w10", "outctn", "hpc", "cn5"])
+def test_step2_logic_option_sweep_against_reference_run(harness, golden_dir, tmp_path, preset, k, w, minlen, maxhan1, extra, env):
+    ref = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not present")
+    src = os.path.join(golden_dir, "sub120.2bit")
+    want, got = str(tmp_path / "ref.ovl"), str(tmp_path / "mine.ovl")
+    subprocess.run([ref, "-I", "6G", "--step", "2", "-t", "4", "-x", preset, "-k", str(k), "-w", str(w), "--minlen", str(minlen), "--maxhan1", str(maxhan1)] + extra +
+                   [src, src, "-o", want], check=True, capture_output=True)
+    r = subprocess.run([harness, preset, str(k), str(w), str(minlen), str(maxhan1), src, src, got], capture_output=True, text=True, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr
+    assert open(got, "rb").read() == open(want, "rb").read()
+    assert open(got + ".bl", "rb").read() == open(want + ".bl", "rb").read()

@@ -456,6 +456,9 @@ def main_ours(a, rank, world, local_rank):
                      "sort_perm": 32 * n_a, "chain_backtrack": 16 * n_a + 56 * n_hits, "sketch": READ_LEN / 4 * B * a.steps + 16 * n_mz,
                      "probe_count": 32 * n_mz + 8 * n_a, "fill_anchors": 16 * n_mz + 8 * n_a + 16 * n_a}
         alg = float(bytes_per.get(top[0], 32 * n_a))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the ncu --set full capture
+        # profiles/r01d_chain_fill_warp_ncu_full_raw.csv (65.36 MB + 21.61 MB); only quoted for that kernel and that workload
+        ncu_traffic = {"chain_fill_warp": 86.97e6} if (a.reads == 100000 and B == 3000) else {}
         achieved = alg / (top[1][0] / 1e3) / 1e9 if top[1][0] > 0 else 0.0
         cpu = None
         if not a.no_cpu_baseline:
@@ -501,7 +504,7 @@ def main_ours(a, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps,
+                         "traffic": ncu_traffic.get(top[0]), "algorithmic_bytes_per_launch": alg / a.steps, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps,
                          "note": "integer DP / hashing kernels: issue- and latency-bound, not HBM-bound (ncu: profiles/r01_summary.md)"},
             "cpu_baseline": cpu,
             "kernel_sum_ms_per_step": dev_ms / a.steps,

@@ -632,10 +632,11 @@ k_ksw_extd2_px(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par 
 
 // ------------------------------------------------------------------------------------------------
 // Cooperative generation for wide bands (extensions with w = 1.5*bw+1, long joins): the same cell code, one call per block.
-// A lone warp advances a 3000-cell diagonal in 47 dependent round trips to its L2-resident state; eight warps do it in 6.
+// A lone warp advances a 3000-cell diagonal in 47 dependent round trips to its L2-resident state; four warps do it in 12 (8 warps
+// per call were measured too: faster for a single call, 17 % slower for the full test set, where thousands of calls are in flight).
 // ------------------------------------------------------------------------------------------------
 #ifndef NDK_COOP_WARPS
-#define NDK_COOP_WARPS 8
+#define NDK_COOP_WARPS 4
 #endif
 __global__ void __launch_bounds__(NDK_COOP_WARPS * 32)
 k_ksw_extd2_coop(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,

@@ -1121,12 +1121,15 @@ struct GpuDp : ndal::Backend {
     {
         const size_t n = reqs.size();
         cudaSetDevice(c->device);
-        if (!c->ksw_p.p) {                          // backtrack arena: a fixed slice of HBM, reused by every launch
-            size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+        {                                           // backtrack arena: a fixed slice of HBM, reused by every launch
             if (!c->arena_want && getenv("NDG_ARENA_GB")) c->arena_want = (uint64_t)(atof(getenv("NDG_ARENA_GB")) * (1ull << 30));
-            uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(64ull << 30, (uint64_t)(fr * 0.45));
-            if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
-            c->ksw_p.cap = want;
+            size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+            const uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(64ull << 30, (uint64_t)((fr + c->ksw_p.cap) * 0.45));
+            if (c->ksw_p.cap < want - want / 8) {   // also replaces a smaller buffer left by ndg_ksw_extd2_batch()
+                c->ksw_p.release();
+                if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }
+                c->ksw_p.cap = want;
+            }
         }
         const uint64_t arena = c->ksw_p.cap & ~(uint64_t)255, arena_eff = arena - arena / 16;
         std::vector<uint64_t> need(n);

@@ -956,6 +956,7 @@ struct GpuDp : ndal::Backend {
     ndg_ctx *c; ndk_par P; int rc = 0;
     DpLaunch L[2];
     double ext_frac = 1.0 / 16;                     // share of an extension's worst-case matrix that gets written (adapted from the arena cursor)
+    double t_prepare = 0, t_wait = 0, t_hand = 0, t_plan = 0;   // host phases of the back end (NDG_ALN_DEBUG)
     ~GpuDp() { for (auto &l : L) l.release(); }
 
     static uint64_t p_need(const ndal::DpReq &k)
@@ -1131,6 +1132,7 @@ struct GpuDp : ndal::Backend {
                 c->ksw_p.cap = want;
             }
         }
+        const double t_plan0 = omp_get_wtime();
         const uint64_t arena = c->ksw_p.cap & ~(uint64_t)255, arena_eff = arena - arena / 16;
         std::vector<uint64_t> need(n);
         std::vector<uint32_t> pending(n);
@@ -1144,6 +1146,7 @@ struct GpuDp : ndal::Backend {
             if (full[id] || !(reqs[id].flag & NDK_EXTZ_ONLY)) return need[id];
             return std::min<uint64_t>(need[id], (1ull << 20) + (uint64_t)(need[id] * ext_frac));
         };
+        t_plan += omp_get_wtime() - t_plan0;
         size_t head = 0, rhead = 0; int cur = -1, nxt = 0;
         // A launch takes a run of the size-ordered list: calls of similar length share a launch, so no launch waits on one call that is
         // far longer than the rest.  While the kernels of one launch run, the next one is staged (sequence bytes, call table, copies)
@@ -1163,16 +1166,20 @@ struct GpuDp : ndal::Backend {
                 };
                 while (rhead < retry.size() && take(retry[rhead])) ++rhead;           // retried calls first (they are long)
                 if (rhead >= retry.size()) while (head < pending.size() && take(pending[head])) ++head;
+                const double tp = omp_get_wtime();
                 if (int r = prepare(B, reqs, T, group)) return r;
                 if (int r = submit_copies(B)) return r;
+                t_prepare += omp_get_wtime() - tp;
             }
             if (cur >= 0) {
                 const size_t r0 = retry.size(); size_t nr = 0;
+                const double tw = omp_get_wtime();
                 if (int r = collect_a(L[cur], retry, &nr)) return r;
+                t_wait += omp_get_wtime() - tw;
                 for (size_t i = r0; i < retry.size(); ++i) { if (full[retry[i]] && L[cur].n == 1) return fail(c, NDG_ERR_NOMEM, "backtrack arena exhausted by a single call"); full[retry[i]] = 1; }
             }
             if (more) { if (int r = submit_kernels(L[nxt], c->ksw_p.as<uint8_t>(), arena)) return r; L[nxt].busy = true; }
-            if (cur >= 0) { if (int r = collect_b(L[cur], res, cigars)) return r; }
+            if (cur >= 0) { const double th = omp_get_wtime(); if (int r = collect_b(L[cur], res, cigars)) return r; t_hand += omp_get_wtime() - th; }
             if (more) { cur = nxt; nxt ^= 1; }
             else if (cur >= 0) cur = -1;            // the last launch is in; retried calls may have appeared
             else break;
@@ -1259,6 +1266,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
         const double tb0 = omp_get_wtime();
         ndal::align_batch(c->aln, ST, jobs, be, &st);
         if (be.rc) return be.rc;
+        if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::dp] back end host phases: order+estimate %.2f s, prepare+copies %.2f s, waiting for kernels %.2f s, hand-back %.2f s\n", be.t_plan, be.t_prepare, be.t_wait, be.t_hand);
         if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::aln] group of %zu reads: prepare %.2f s, walk %.2f s, dp (host wall) %.2f s, hand-back %.2f s, finish %.2f s, total %.2f s\n", jobs.size(),
                                              tb0 - t_host0, st.t_walk, st.t_dp, st.t_hand, st.t_finish, omp_get_wtime() - tb0);
         c->aln_stat.n_chains += st.n_tasks; c->aln_stat.n_calls += st.n_calls; c->aln_stat.n_rounds += st.n_rounds; c->aln_stat.rect_cells += st.cells;

@@ -1125,7 +1125,7 @@ struct GpuDp : ndal::Backend {
         {                                           // backtrack arena: a fixed slice of HBM, reused by every launch
             if (!c->arena_want && getenv("NDG_ARENA_GB")) c->arena_want = (uint64_t)(atof(getenv("NDG_ARENA_GB")) * (1ull << 30));
             size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
-            const uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(64ull << 30, (uint64_t)((fr + c->ksw_p.cap) * 0.45));
+            const uint64_t want = c->arena_want ? c->arena_want : std::min<uint64_t>(96ull << 30, (uint64_t)((fr + c->ksw_p.cap) * 0.45));
             if (c->ksw_p.cap < want - want / 8) {   // also replaces a smaller buffer left by ndg_ksw_extd2_batch()
                 c->ksw_p.release();
                 if (cudaMalloc(&c->ksw_p.p, want) != cudaSuccess) { cudaGetLastError(); c->ksw_p.p = nullptr; return fail(c, NDG_ERR_NOMEM, "backtrack arena of %llu bytes", (unsigned long long)want); }

@@ -5,11 +5,11 @@ library ``libndgpu.so`` (hand-written sm_100a CUDA).  There is no CPU compute pa
 compute API without the built library, or running it without a B200, raises.
 """
 from .options import IdxOpt, MapOpt, set_opt, parse_num  # noqa: F401
-from .formats import (read_2bit, write_2bit, read_fastx, read_seqfile, reads_from_ascii, Reads, decode_ovl8, encode_ovl8_py,
+from .formats import (read_2bit, write_2bit, read_fastx, read_seqfile, reads_from_ascii, Reads, decode_ovl8, decode_ovl10, encode_ovl8_py,
                       name_keys, x31_hash)  # noqa: F401
 
 __all__ = ["IdxOpt", "MapOpt", "set_opt", "parse_num", "read_2bit", "write_2bit", "Reads",
-           "decode_ovl8", "encode_ovl8_py", "name_keys", "x31_hash", "Engine", "lib_path"]
+           "decode_ovl8", "decode_ovl10", "encode_ovl8_py", "name_keys", "x31_hash", "Engine", "lib_path"]
 
 
 def __getattr__(name):          # lazy: the ctypes binding loads the CUDA library on first use

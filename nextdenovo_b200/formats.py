@@ -246,6 +246,43 @@ def decode_ovl8(buf):
     return out.astype(np.uint32)
 
 
+def decode_ovl10(buf):
+    """Decode a 10-field .ovl stream (`--step 2`; starts with the bytes 0, 255) to an (n, 10) uint32 array in ovl_cvt column order:
+    qname rev qs qe tname ts te qlen tlen identity (ref: lib/ovl.c:150-203 decode_ovl with n = 10, util/ovl_cvt.c:33-50: a zero
+    length means "same read as the previous record")."""
+    b = np.frombuffer(buf, dtype=np.uint8)
+    if b.shape[0] < 2 or b[0] != 0 or b[1] != 255:
+        raise ValueError("not a 10-field .ovl stream (header bytes 0, 255 missing)")
+    b = b[2:]
+    ends = np.nonzero(b < 128)[0]
+    starts = np.concatenate(([0], ends[:-1] + 1)) if ends.shape[0] else ends
+    nv = ends.shape[0]
+    if nv % 10:
+        raise ValueError("truncated .ovl stream")
+    vals = np.zeros(nv, dtype=np.uint64)
+    ln = ends - starts + 1
+    for k in range(int(ln.max()) if nv else 0):
+        sel = ln > k
+        vals[sel] = (vals[sel] << np.uint64(7)) | (b[starts[sel] + k] & 127).astype(np.uint64)
+    v = vals.reshape(-1, 10).astype(np.int64)
+    flags = v[:, 1]
+    out = np.zeros((v.shape[0], 10), dtype=np.int64)
+    out[:, 0] = np.cumsum(np.where(flags & 2, -v[:, 0], v[:, 0]))
+    out[:, 4] = np.cumsum(np.where(flags & 4, -v[:, 4], v[:, 4]))
+    out[:, 1] = flags & 1
+    out[:, 2] = v[:, 2]
+    out[:, 3] = v[:, 2] + v[:, 3]
+    out[:, 5] = v[:, 5]
+    out[:, 6] = np.where(flags & 8, v[:, 5] + v[:, 3] + v[:, 6], v[:, 5] + v[:, 3] - v[:, 6])
+    for col in (7, 8):                                  # lengths: carried forward while zero
+        x = v[:, col]
+        idx = np.where(x != 0, np.arange(x.shape[0]), 0)
+        np.maximum.accumulate(idx, out=idx)
+        out[:, col] = x[idx] if x.shape[0] else x
+    out[:, 9] = v[:, 9]
+    return out.astype(np.uint32)
+
+
 def encode_ovl8_py(records):
     """Pure-Python reference encoder for small cases (tests).  records: iterable of 8-tuples in
     ovl_cvt column order.  ref: lib/ovl.c:109-150."""

@@ -115,3 +115,21 @@ def test_fastx_reader_and_mask(tmp_path):
         nd.read_seqfile(str(bad))
     s = a.slice(2, 3)
     assert s.n == 1 and int(s.nmask[0]) == 0xffffffff
+
+
+def test_decode_ovl10_matches_ovl_cvt(golden_dir):
+    """10-field records of --step 2 (ref: lib/ovl.c:150-253, util/ovl_cvt.c:33-50) decoded by formats.decode_ovl10 == ovl_cvt -m 1"""
+    import os
+    import subprocess
+    import numpy as np
+    import nextdenovo_b200 as nd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cvt = os.path.join(root, "oracle", "_ref", "ovl_cvt")
+    f = os.path.join(golden_dir, "G5_step2.ovl")
+    a = nd.decode_ovl10(open(f, "rb").read())
+    assert a.shape == (7635, 10)
+    assert a[0].tolist() == [0, 0, 1929, 67698, 1, 31, 67777, 0, 85492, 2178]   # qlen 0: read 0 equals the initial "previous" name
+    if os.path.exists(cvt):
+        txt = subprocess.run([cvt, "-m", "1", f], capture_output=True, text=True).stdout
+        b = np.array([[int(x) for x in line.split("\t")] for line in txt.strip().split("\n")], dtype=np.uint32)
+        assert (a == b).all()

@@ -215,6 +215,12 @@ int ndg_ksw_extd2_batch(ndg_ctx_t *ctx, const ndg_ksw_call_t *calls, int32_t n_c
                         int32_t m, const int8_t *mat, int32_t q, int32_t e, int32_t q2, int32_t e2,
                         ndg_ksw_result_t *res, uint32_t *cigar, const uint64_t *cigar_off);
 
+/* Stitching batches that were encoded independently (e.g. by several contexts, see ndg_index_share): a batch encoded from
+ * state (0,0) starts with absolute names; this rewrites its FIRST 8-field record onto the true previous (qname, tname) of the
+ * stream (ref: lib/ovl.c:109-150, the delta/flag rules of encode_ovl).  dst receives the replacement bytes (at most 48),
+ * *skip the length of the original first record; returns the replacement length, or <0 on a truncated stream. */
+int ndg_ovl_rebase_first(const uint8_t *ovl, uint64_t n_bytes, const uint32_t prev[2], uint8_t *dst, uint32_t *skip);
+
 /* Step-1 emitter: applies the reference's output filter (ref: minimap2/map.c:1297-1304: drop hits whose
  * target is the query itself, keep qe-qs >= minlen, optional --dvt test :804-821) to a sorted hit list
  * and appends 8-field records.  q_id/q_key/q_len are indexed by hit.qidx, t_id/t_key/t_len by hit.rid

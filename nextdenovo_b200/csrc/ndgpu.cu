@@ -1517,6 +1517,27 @@ extern "C" int ndg_ovl_encode8(uint8_t *dst, uint32_t state[2], int rev, uint32_
 }
 
 // ref: minimap2/map.c:804-821 (check_realign_nextdenovo), used by --dvt at map.c:1302
+extern "C" int ndg_ovl_rebase_first(const uint8_t *ovl, uint64_t n, const uint32_t prev[2], uint8_t *dst, uint32_t *skip)
+{
+    if (!ovl || !prev || !dst || !skip) return NDG_ERR_ARG;
+    uint32_t v[8]; uint64_t p = 0;
+    for (int f = 0; f < 8; ++f) {                    // big-endian base-128 groups, continuation bit on all but the last byte
+        uint64_t x = 0; int nb = 0;
+        for (;;) { if (p >= n || ++nb > 5) return NDG_ERR_ARG; const uint8_t b = ovl[p++]; x = x << 7 | (b & 127); if (b < 128) break; }
+        v[f] = (uint32_t)x;
+    }
+    *skip = (uint32_t)p;
+    // encoded from state (0,0): the name fields are absolute and their "decreased" flags are clear
+    const uint32_t qname = v[0], tname = v[4];
+    uint32_t flags = v[1] & ~6u;
+    if (qname >= prev[0]) v[0] = qname - prev[0]; else { flags |= 2; v[0] = prev[0] - qname; }
+    if (tname >= prev[1]) v[4] = tname - prev[1]; else { flags |= 4; v[4] = prev[1] - tname; }
+    v[1] = flags;
+    int m = 0;
+    for (int f = 0; f < 8; ++f) m += ndg_put_varint(dst + m, v[f]);
+    return m;
+}
+
 static inline int ndg_check_dovetail(int rev, uint32_t qs, uint32_t qe, uint32_t qlen, uint32_t ts, uint32_t te, uint32_t tlen,
                                      int32_t maxhan1, int32_t maxhan2)
 {

@@ -63,3 +63,27 @@ def test_emit_step1_filter(engine_mod):
     rec = nd.decode_ovl8(dst[:nb].tobytes())
     assert nrec.value == 1 and sq.value == 690
     assert [int(x) for x in rec[0]] == [5, 0, 10, 700, 6, 1, 650, 300]
+
+
+def test_rebase_first_record_stitches_independent_batches(engine_mod, golden_dir):
+    """ndg_ovl_rebase_first: a batch encoded from state (0,0) is rebased onto the stream's true previous (qname, tname); splitting the
+    golden G1 stream at several records and stitching gives back the reference's bytes (ref: lib/ovl.c:109-150)."""
+    import ctypes as C
+    import os
+    import numpy as np
+    import nextdenovo_b200 as nd
+    L = engine_mod.load_library()
+    L.ndg_ovl_rebase_first.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    buf = open(os.path.join(golden_dir, "G1_ava-ont.ovl"), "rb").read()
+    rec = nd.decode_ovl8(buf)
+    for cut in (1, 777, 65000, 130000):
+        tup = [tuple(int(x) for x in r) for r in rec[:cut + 500]]
+        first, second0, want = nd.encode_ovl8_py(tup[:cut]), nd.encode_ovl8_py(tup[cut:]), nd.encode_ovl8_py(tup)
+        prev = np.array([rec[cut - 1][0], rec[cut - 1][4]], dtype=np.uint32)
+        dst = np.zeros(48, dtype=np.uint8)
+        skip = C.c_uint32(0)
+        sb = np.frombuffer(bytes(second0), dtype=np.uint8)
+        m = L.ndg_ovl_rebase_first(sb.ctypes.data, len(second0), prev.ctypes.data, dst.ctypes.data, C.byref(skip))
+        assert m > 0
+        assert bytes(first) + bytes(dst[:m]) + bytes(second0[skip.value:]) == bytes(want) == buf[:len(want)]
+    assert L.ndg_ovl_rebase_first(sb.ctypes.data, 3, prev.ctypes.data, dst.ctypes.data, C.byref(skip)) < 0      # truncated

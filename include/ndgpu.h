@@ -139,15 +139,32 @@ void  ndg_host_free(void *p);
 int ndg_index_begin(ndg_ctx_t *ctx);
 /* register target metadata (len, name_key) and sketch the targets on this GPU; rid continues */
 int ndg_index_add(ndg_ctx_t *ctx, const ndg_reads_t *targets);
-/* register metadata only (targets sketched on another GPU, see ndg_index_import) */
+/* register metadata only (targets sketched on another GPU, see ndg_index_shard_*) */
 int ndg_index_add_meta(ndg_ctx_t *ctx, const ndg_reads_t *targets);
-/* multi-GPU: raw (x,y) minimizers sketched so far, device pointer; and the converse */
-int ndg_index_export(ndg_ctx_t *ctx, const void **dev_minimizers, uint64_t *n);
-int ndg_index_import(ndg_ctx_t *ctx, const void *dev_minimizers, uint64_t n);
-int ndg_index_clear_minimizers(ndg_ctx_t *ctx);
-/* device-to-device copy on the context's stream, synchronous (glue for torch.distributed buffers) */
-int ndg_copy_d2d(ndg_ctx_t *ctx, void *dst_dev, const void *src_dev, uint64_t bytes);
 int ndg_index_finalize(ndg_ctx_t *ctx, ndg_index_stat_t *stat);
+/* N-GPU build of one index part (no counterpart in the reference, whose index is built by one process; the collectives are the
+ * caller's: NCCL from one process per GPU, or peer copies between contexts of one process).  The table is range-partitioned by
+ * minimizer: rank r builds slice r from the minimizers of its key range and the finished slices are all-gathered, so the sort is
+ * sharded N ways instead of replicated.  Call order on every rank r (target order = rank order: ndg_index_add_meta() for the reads
+ * of ranks < r, ndg_index_add() for the own ones, ndg_index_add_meta() for ranks > r):
+ *   split(N, counts)          own minimizers sorted and cut into the N key ranges; counts[j] pairs go to rank j
+ *   bucket(j, &k, &v, &n)     device pointers of those pairs (two u64 arrays)          -> all-to-all, received in rank order
+ *   recv_reserve(total,&k,&v) device buffers for everything destined for this rank
+ *   sort(&n_distinct)         received pairs sorted, run lengths taken
+ *   place(r, max_nd, hist)    max_nd = max over ranks of n_distinct: common slice size; slice r built; hist[65536] = run-length histogram
+ *   table_slice(j, &p, &b)    where slice j lives (equal sizes)                        -> all-gather in place
+ *   pos_reserve(r, n[N], seg) n[j] = pairs sorted on rank j; position list allocated; seg[j] = device pointer of segment j -> broadcast each
+ *   finish(hist_sum, nd_sum)  global histogram / distinct count (mid_occ, ref: minimap2/index.c:164-185 needs the whole part) */
+/* host helper: the slice (= rank) the minimizer key (hash, < 4^k) belongs to in an n_slices-way build */
+int32_t ndg_index_key_slice(uint64_t key, int32_t k, int32_t n_slices);
+int ndg_index_shard_split(ndg_ctx_t *ctx, int32_t n_slices, uint64_t *counts);
+int ndg_index_shard_bucket(ndg_ctx_t *ctx, int32_t j, const void **dev_keys, const void **dev_vals, uint64_t *n);
+int ndg_index_shard_recv_reserve(ndg_ctx_t *ctx, uint64_t total, void **dev_keys, void **dev_vals);
+int ndg_index_shard_sort(ndg_ctx_t *ctx, uint64_t *n_distinct);
+int ndg_index_shard_place(ndg_ctx_t *ctx, int32_t my_slice, uint64_t max_distinct_per_slice, uint32_t *hist65536);
+int ndg_index_shard_table_slice(ndg_ctx_t *ctx, int32_t j, void **dev, uint64_t *bytes);
+int ndg_index_shard_pos_reserve(ndg_ctx_t *ctx, int32_t my_slice, const uint64_t *n_pos_per_slice, void **dev_segments);
+int ndg_index_shard_finish(ndg_ctx_t *ctx, const uint32_t *hist65536, uint64_t n_distinct, ndg_index_stat_t *stat);
 /* Let ctx borrow the finalized index of src (same device; no counterpart in the reference, where worker threads share `mi`):
  * several contexts, each with its own stream and workspace, can then map batches concurrently against one copy of the index.
  * src must stay alive and keep its index while ctx uses it; ndg_index_begin()/ndg_destroy() on ctx drop the loan. */

@@ -5,7 +5,8 @@
 // (ref: nextDenovo:445-464): two-pass option handling (minimap2/main.c:177-363), index parts
 // (minimap2/index.c:284-288,353-358), query batches (minimap2/bseq.c:86-123), ordered .ovl output
 // (minimap2/map.c:1245-1352).  Input: .2bit (what seq_dump writes, lib/bseq.c:93-139) or FASTA/FASTQ[.gz] with decimal names; other
-// modes of the reference binary (-c, --step 2/3, PAF/SAM) are rejected, never approximated.
+// modes of the reference binary (--step 3, PAF/SAM, chain selection without MM_F_ALL_CHAINS) are rejected by name, never approximated;
+// unknown options are an error as in the reference.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -141,30 +142,72 @@ int main(int argc, char **argv)
     int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0, n_threads = 0;
     uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
     const char *out = nullptr; std::vector<const char *> pos;
-    bool cigar = false, unsupported_out = false;
+    bool cigar = false;
     ndg_step2_opt_t s2 = { 2000, 5000, 500, 100, 2, 20, 17, 10, 0, 0.05f };   // minimap2/main.c:194-198, options.c:50-62
     ndg_aln_opt_t ao = { 2, 4, 4, 2, 24, 1, 1, 400, 200, -1, 80, 200, 0, 1.0f };   // minimap2/options.c:37-44
     const double t0 = now();
-    auto takes = [](const std::string &a) {
-        static const char *t[] = { "-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen", "--maxhan1", "--maxhan2",
-                                   "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v", "--device", "-N", "-p", "-M", "-z", "-A", "-B", "-O", "-E", "-s",
-                                   "--min-dp-score", "--end-bonus", "--max-clip-ratio", "--minide", "--minmatch", "--mode", "--kn", "--wn", "--cn" };
-        for (auto x : t) if (a == x) return true;
-        return false;
-    };
+    // Option grammar of the reference (ref: minimap2/main.c:31-100 long_options, :162 opt_str; ketopt permutes positional arguments).
+    // Every option of the reference is known here with its arity; what this build does not implement is refused by name, and an
+    // option the reference does not know is an error, as in its '?' branch (main.c:186-188).
+    static const char *short_spec = "2aSDw:k:K:t:r:f:Vv:g:G:I:d:XT:s:x:Hcp:M:n:z:A:B:O:E:m:N:Qu:R:hF:LC:yYPo:";
+    struct LongOpt { const char *name; int has_arg; const char *canon; };          // has_arg: 0 none, 1 required, 2 optional (=value only)
+    static const LongOpt long_spec[] = {
+        {"bucket-bits",1,0},{"mb-size",1,"-K"},{"seed",1,0},{"no-kalloc",0,0},{"print-qname",0,0},{"no-self",0,"-D"},{"print-seeds",0,0},
+        {"max-chain-skip",1,0},{"min-dp-len",1,0},{"print-aln-seq",0,0},{"splice",0,0},{"cost-non-gt-ag",1,"-C"},{"no-long-join",0,0},{"sr",0,0},
+        {"frag",1,0},{"secondary",1,0},{"cs",2,0},{"end-bonus",1,0},{"no-pairing",0,0},{"splice-flank",1,0},{"idx-no-seq",0,0},{"end-seed-pen",1,0},
+        {"for-only",0,0},{"rev-only",0,0},{"heap-sort",1,0},{"all-chain",0,"-P"},{"dual",1,0},{"max-clip-ratio",1,0},{"min-occ-floor",1,0},{"MD",0,0},
+        {"lj-min-ratio",1,0},{"score-N",1,0},{"eqx",0,0},{"paf-no-hit",0,0},{"split-prefix",1,0},{"no-end-flt",0,0},{"hard-mask-level",0,0},
+        {"cap-sw-mem",1,0},{"max-qlen",1,0},{"max-chain-iter",1,0},{"junc-bed",1,0},{"junc-bonus",1,0},{"sam-hit-only",0,0},{"help",0,"-h"},
+        {"max-intron-len",1,"-G"},{"version",0,"-V"},{"min-count",1,"-n"},{"min-chain-score",1,"-m"},{"mask-level",1,"-M"},{"min-dp-score",1,"-s"},{"sam",0,"-a"},
+        {"step",1,0},{"minlen",1,0},{"minide",1,0},{"maxhan1",1,0},{"maxhan2",1,0},{"outraw",0,0},{"minmatch",1,0},{"mode",1,0},{"kn",1,0},{"wn",1,0},{"cn",1,0},
+        {"outctn",0,0},{"df",1,0},{"dvt",0,0},
+        {"device",1,0},{"gpus",1,0},                                                 // this build only: which GPU(s) to run on
+        {0,0,0} };
     std::vector<std::pair<std::string, std::string>> tok;
     for (int i = 1; i < argc; ++i) {
-        std::string a = argv[i];
-        size_t eq;
-        if (a.rfind("--", 0) == 0 && (eq = a.find('=')) != std::string::npos) tok.push_back({ a.substr(0, eq), a.substr(eq + 1) });
-        else if (takes(a)) { if (i + 1 >= argc) { fprintf(stderr, "[ERROR] missing option argument\n"); return 1; } tok.push_back({ a, argv[++i] }); }
-        else if (a.size() > 1 && a[0] == '-') tok.push_back({ a, "" });
-        else pos.push_back(argv[i]);
+        const std::string a = argv[i];
+        if (a == "-" || a.empty() || a[0] != '-') { pos.push_back(argv[i]); continue; }
+        if (a == "--") { for (++i; i < argc; ++i) pos.push_back(argv[i]); break; }
+        if (a[1] == '-') {                                      // long option
+            const size_t eq = a.find('=');
+            const std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            const LongOpt *lo = nullptr;
+            for (const LongOpt *x = long_spec; x->name; ++x) if (name == x->name) { lo = x; break; }
+            if (!lo) { fprintf(stderr, "[ERROR] unknown option in \"%s\"\n", argv[i]); return 1; }
+            std::string val;
+            if (eq != std::string::npos) val = a.substr(eq + 1);
+            else if (lo->has_arg == 1) { if (i + 1 >= argc) { fprintf(stderr, "[ERROR] missing option argument\n"); return 1; } val = argv[++i]; }
+            tok.push_back({ lo->canon ? std::string(lo->canon) : "--" + name, val });
+        } else {                                                // short option(s), possibly bundled / with an attached argument
+            for (size_t j = 1; j < a.size(); ++j) {
+                const char *sp = strchr(short_spec, a[j]);
+                if (!sp || a[j] == ':') { fprintf(stderr, "[ERROR] unknown option in \"%s\"\n", argv[i]); return 1; }
+                std::string key = std::string("-") + a[j];
+                if (sp[1] == ':') {
+                    std::string val;
+                    if (j + 1 < a.size()) val = a.substr(j + 1);
+                    else { if (i + 1 >= argc) { fprintf(stderr, "[ERROR] missing option argument\n"); return 1; } val = argv[++i]; }
+                    tok.push_back({ key, val });
+                    break;
+                }
+                tok.push_back({ key, "" });
+            }
+        }
+    }
+    bool all_chains = false;
+    {
+        // options that change results but are not built here: refuse by name instead of mapping something else
+        static const char *not_built[] = { "-a", "-S", "--cs", "--MD", "--eqx", "-Y", "-L", "-Q", "-y", "-R", "--splice", "--sr", "--frag", "--no-pairing", "--splice-flank",
+            "-u", "-C", "-G", "-F", "--heap-sort", "--for-only", "--rev-only", "--end-seed-pen", "--lj-min-ratio", "--split-prefix", "--junc-bed", "--junc-bonus",
+            "--sam-hit-only", "--paf-no-hit", "--secondary", "-T", "-d", "--bucket-bits", "--idx-no-seq", "--cap-sw-mem", "--max-qlen", "--print-seeds", "--print-aln-seq",
+            "--print-qname", "--df", "--outraw", "--hard-mask-level", 0 };
+        for (auto &kv : tok) for (const char **x = not_built; *x; ++x) if (kv.first == *x) {
+            fprintf(stderr, "[ERROR] option '%s' is not built in this GPU build (it implements `--step 1 [-c]` and `--step 2` with .ovl output)\n", kv.first.c_str()); return 1; }
     }
     for (auto &kv : tok) {                                      // pass 1: presets (main.c:177-205)
         if (kv.first == "-x") {
-            if (kv.second == "ava-ont") { o.hpc = 0; o.k = 15; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; o.bw = 2000; }
-            else if (kv.second == "ava-pb") { o.hpc = 1; o.k = 19; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; }
+            if (kv.second == "ava-ont") { all_chains = true; o.hpc = 0; o.k = 15; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; o.bw = 2000; }
+            else if (kv.second == "ava-pb") { all_chains = true; o.hpc = 1; o.k = 19; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; }
             else { fprintf(stderr, "[ERROR] unknown preset '%s'\n", kv.second.c_str()); return 1; }
         } else if (kv.first == "--step") {
             step = atoi(kv.second.c_str());
@@ -180,9 +223,10 @@ int main(int argc, char **argv)
         else if (k == "-r") o.bw = (int)parse_num(v); else if (k == "-g") o.max_gap = (int)parse_num(v);
         else if (k == "-n") o.min_cnt = atoi(v); else if (k == "-m") o.min_chain_score = atoi(v);
         else if (k == "-I") batch_size = (uint64_t)parse_num(v); else if (k == "-K") q_batch = parse_num(v);
-        else if (k == "-D") o.flag_no_diag = 1; else if (k == "-X") o.flag_no_diag = o.flag_no_dual = 1;
+        else if (k == "-D") o.flag_no_diag = 1; else if (k == "-X") { o.flag_no_diag = o.flag_no_dual = 1; all_chains = true; }
+        else if (k == "-P") all_chains = true;
         else if (k == "-c") cigar = true;
-        else if (k == "-a" || k == "--cs" || k == "-S" || k == "--MD") unsupported_out = true;
+        else if (k == "--min-dp-len") ao.min_ksw_len = atoi(v); else if (k == "--score-N") ao.sc_ambi = atoi(v);
         else if (k == "-A") ao.a = atoi(v); else if (k == "-B") ao.b = atoi(v);
         else if (k == "-s" || k == "--min-dp-score") ao.min_dp_max = atoi(v);
         else if (k == "--end-bonus") ao.end_bonus = atoi(v); else if (k == "--max-clip-ratio") ao.max_clip_ratio = (float)atof(v);
@@ -207,7 +251,11 @@ int main(int argc, char **argv)
         fprintf(stderr, "Usage: minimap2-nd --step 1 [options] <target.2bit> <query.2bit> -o out.ovl\n");
         return 1;
     }
-    if ((step != 1 && step != 2) || unsupported_out || !out || (step == 2 && cigar)) {
+    if (!all_chains) {          // the library keeps every chain (no mm_set_parent / mm_select_sub / best_n / pri_ratio, ref: minimap2/map.c:250-259)
+        fprintf(stderr, "[ERROR] this GPU build maps in all-chain mode only (MM_F_ALL_CHAINS): use -x ava-ont|ava-pb, -X or -P\n");
+        return 1;
+    }
+    if ((step != 1 && step != 2) || !out || (step == 2 && cigar)) {
         fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` and `--step 2 ... -o FILE` (.ovl output) only\n");
         return 1;
     }

@@ -57,6 +57,29 @@ ND_HD nd_u64 nd_mix64(nd_u64 key)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ordered index table: where a key belongs (layout and rationale: nd_kernels.cuh).  key * key_mul is a 64-bit fixed-point
+// fraction in [0, 1), monotone in the key; its integer part after scaling by n_slices is the slice, the rest the ideal slot.
+// ------------------------------------------------------------------------------------------------
+// Minimizer keys are NOT uniform (a minimizer is the minimum hash of its window, so keys crowd towards 0): the table is ordered
+// by a second bijective mix of the key on key_bits bits (odd multiplier mod 2^key_bits), which spreads any key set evenly.
+ND_HD nd_u64 nd_idx_mix(nd_u64 key, int key_bits) { return (key * 0x9E3779B97F4A7C15ULL) & ((1ULL << key_bits) - 1); }
+
+ND_HD nd_u64 nd_mulhi64(nd_u64 a, nd_u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (nd_u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+ND_HD uint32_t nd_idx_slice(nd_u64 key, nd_u64 key_mul, uint32_t n_slices) { return (uint32_t)nd_mulhi64(key * key_mul, (nd_u64)n_slices); }
+ND_HD nd_u64 nd_idx_ideal(nd_u64 key, nd_u64 key_mul, uint32_t n_slices, nd_u64 slice_cap)   // slice-local ideal slot
+{
+    const nd_u64 t = key * key_mul;
+    return nd_mulhi64(t * (nd_u64)n_slices, slice_cap);        // t * n_slices (mod 2^64) = position inside the slice as a fraction
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2-bit packed reads: 16 bases per u32, first base in the top two bits (ref: lib/bseq.c:114-139);
 // optional ambiguity mask, one bit per base (bit (i&31) of nmask[i>>5]), for FASTA input with N.
 // ------------------------------------------------------------------------------------------------

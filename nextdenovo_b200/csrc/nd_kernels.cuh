@@ -20,24 +20,50 @@ __device__ __forceinline__ int nd_find_owner(const nd_u64 *off, int n, nd_u64 v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// index hash table: open addressing, linear probing.  key = minimizer hash (< 2^56),
-// val = offset<<24 | min(count, 2^24-1).  ref: replaces khash buckets of minimap2/index.c:191-243
+// index table.  Replaces the khash buckets of minimap2/index.c:191-243 (and mm_idx_get, :81-98).
+//
+// Every key (minimizer hash, group tag above it for a tagged index) is first mixed bijectively on key_bits bits (nd_idx_mix:
+// minimizer hashes themselves crowd towards 0, being window minima), so mixed keys are spread uniformly over [0, 2^key_bits).
+// The table is ORDERED by mixed key: slot(key) = ideal(key) + displacement, with ideal() monotone and keys stored in increasing
+// order ("sorted array with gaps", load ~0.7).  Consequences:
+//   * it is built from the sorted keys without atomics: slot_i = i + max_{j<=i}(ideal_j - j), one prefix-max scan;
+//   * a lookup reads consecutive 16-byte slots from ideal(key) until it meets a key >= its own (empty slots hold the maximum
+//     key), so hits and misses both cost ~2 slots of one or two adjacent 32-byte sectors;
+//   * it is range-partitioned: slice r holds the keys with mulhi(key * key_mul, n_slices) == r in its own contiguous slot range
+//     (slice_cap ideal slots + a pad for the displaced tail), so N GPUs build one slice each and all-gather equal-sized pieces.
+// Slot value: a minimizer that occurs once carries its position inline (bit 63 set; rid < 2^31 keeps that bit free, as in the
+// reference's singleton trick, index.c:91-93,223-226); otherwise off << 24 | min(n, 2^24-1) into the slice's position list.
 // ------------------------------------------------------------------------------------------------
 struct nd_ht_slot { nd_u64 key, val; };
 #define ND_HT_EMPTY ND_U64_MAX
+#define ND_HT_INLINE (1ULL << 63)
+#define ND_HT_PAD 4096ULL
 
-__device__ __forceinline__ nd_u64 nd_ht_hash(nd_u64 key) { return key * 0x9E3779B97F4A7C15ULL; }
+struct nd_idx_view {
+    const nd_ht_slot *tab;         // n_slices * slice_slots slots
+    const nd_u64 *pos;             // position lists (sorted by key, ascending position inside a key: index.c:230)
+    const nd_u64 *pos_base;        // n_slices entries: where slice r's list starts in pos[]
+    nd_u64 slice_cap, slice_slots; // ideal slots per slice; slice_slots = slice_cap + ND_HT_PAD
+    nd_u64 key_mul;                // floor((2^64 - 1) / 2^key_bits): key * key_mul is a 64-bit fixed-point fraction in [0, 1)
+    uint32_t n_slices; int key_bits;
+};
 
-__device__ __forceinline__ bool nd_ht_lookup(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u64 *off, uint32_t *n)
+// returns n (0 = absent); *v = inline position (n == 1 && *inl) or offset into pos[]
+__device__ __forceinline__ uint32_t nd_idx_lookup(const nd_idx_view &I, nd_u64 raw_key, nd_u64 *v, bool *inl)
 {
-    const nd_u64 maskc = (1ULL << log2cap) - 1;
-    nd_u64 s = nd_ht_hash(key) >> (64 - log2cap);
+    const nd_u64 key = nd_idx_mix(raw_key, I.key_bits);
+    const nd_u64 t = key * I.key_mul;
+    const uint32_t sl = (uint32_t)__umul64hi(t, (nd_u64)I.n_slices);
+    const nd_ht_slot *p = I.tab + (nd_u64)sl * I.slice_slots + __umul64hi(t * (nd_u64)I.n_slices, I.slice_cap);
     for (;;) {
-        // 16-byte vector load of the slot
-        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(tab + s));
-        if (e.x == key) { *off = e.y >> 24; *n = (uint32_t)(e.y & 0xffffff); return true; }
-        if (e.x == ND_HT_EMPTY) return false;
-        s = (s + 1) & maskc;
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+        if (e.x >= key) {
+            if (e.x != key) return 0;
+            if (e.y & ND_HT_INLINE) { *v = e.y & ~ND_HT_INLINE; *inl = true; return 1; }
+            *v = I.pos_base[sl] + (e.y >> 24); *inl = false;
+            return (uint32_t)(e.y & 0xffffff);
+        }
+        ++p;
     }
 }
 
@@ -170,61 +196,66 @@ __global__ void k_gather_off(const nd_u64 *pos, const nd_u64 *chunk_off, int n_p
 // ------------------------------------------------------------------------------------------------
 
 // index key = minimizer hash, optionally with the group tag of the read it came from above the 2k hash bits
-__global__ void k_split_xy(const nd_u128 *mz, nd_u64 n, nd_u64 *key, nd_u64 *val, const uint32_t *t_tag, int tag_shift)
+__global__ void k_split_xy(const nd_u128 *mz, nd_u64 n, nd_u64 *key, nd_u64 *val, const uint32_t *t_tag, int tag_shift, int key_bits)
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     nd_u128 m = mz[i];
     nd_u64 k = m.x >> 8;
     if (t_tag) k |= (nd_u64)t_tag[m.y >> 32] << tag_shift;
-    key[i] = k; val[i] = m.y;
+    key[i] = nd_idx_mix(k, key_bits); val[i] = m.y;
 }
 
-__global__ void k_count_heads(const nd_u64 *key, nd_u64 n, nd_u64 *n_distinct)
+// per distinct key i (sorted): d[i] = ideal(key_i) - i, the quantity whose running maximum gives the displacement
+__global__ void k_index_ideal(const nd_u64 *ukey, nd_u64 n_distinct, nd_u64 key_mul, uint32_t n_slices, nd_u64 slice_cap, nd_i64 *d)
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool head = i < n && (i == 0 || key[i] != key[i - 1]);
-    unsigned m = __ballot_sync(0xffffffffu, head);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_distinct, (nd_u64)__popc(m));
+    if (i < n_distinct) d[i] = (nd_i64)nd_idx_ideal(ukey[i], key_mul, n_slices, slice_cap) - (nd_i64)i;
 }
 
-// per run head: run length by galloping search, insert into the table, histogram of run lengths
-// (small run lengths are histogrammed per block in shared memory: almost every run has length 1)
+// place the distinct keys of one slice: slot_i = i + running_max_i; value = inline position or (run start, count); histogram of
+// run lengths (small ones per block in shared memory: almost every run has length 1).  overflow: a key displaced beyond the pad.
 __global__ void __launch_bounds__(256)
-k_index_table(const nd_u64 *key, nd_u64 n, nd_ht_slot *tab, int log2cap, uint32_t *hist, int hist_bins)
+k_index_place(const nd_u64 *ukey, const uint32_t *cnt, const nd_u64 *start, const nd_i64 *dmax, nd_u64 n_distinct, const nd_u64 *vals,
+              nd_ht_slot *slice, nd_u64 slice_slots, uint32_t *hist, int hist_bins, int *overflow)
 {
     __shared__ uint32_t sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool head = false; nd_u64 kx = 0;
-    if (i < n) { kx = key[i]; head = i == 0 || key[i - 1] != kx; }
-    if (head) {
-        nd_u64 lo = i, hi;
-        nd_u64 step = 1;
-        while (lo + step < n && key[lo + step] == kx) { lo += step; step <<= 1; }
-        hi = lo + step < n ? lo + step : n;
-        while (hi - lo > 1) { nd_u64 mid = (lo + hi) >> 1; if (key[mid] == kx) lo = mid; else hi = mid; }
-        nd_u64 cnt = hi - i;
-        const nd_u64 maskc = (1ULL << log2cap) - 1;
-        nd_u64 s = nd_ht_hash(kx) >> (64 - log2cap);
-        for (;;) {
-            nd_u64 prev = atomicCAS(&tab[s].key, ND_HT_EMPTY, kx);
-            if (prev == ND_HT_EMPTY) { tab[s].val = i << 24 | (cnt < 0xffffffULL ? cnt : 0xffffffULL); break; }
-            s = (s + 1) & maskc;
+    if (i < n_distinct) {
+        const nd_u64 slot = (nd_u64)((nd_i64)i + dmax[i]);
+        const uint32_t c = cnt[i];
+        if (slot >= slice_slots - 1) atomicExch(overflow, 1);     // the last slot stays empty: it ends every scan
+        else {
+            nd_ht_slot e; e.key = ukey[i];
+            const nd_u64 st = start[i];
+            e.val = c == 1 ? (ND_HT_INLINE | vals[st]) : (st << 24 | (nd_u64)(c < 0xffffffu ? c : 0xffffffu));
+            *reinterpret_cast<ulonglong2 *>(slice + slot) = make_ulonglong2(e.key, e.val);
         }
-        if (cnt < 256) atomicAdd(&sh[cnt], 1u);
-        else atomicAdd(&hist[cnt < (nd_u64)hist_bins - 1 ? cnt : (nd_u64)hist_bins - 1], 1u);
+        if (c < 256) atomicAdd(&sh[c], 1u);
+        else atomicAdd(&hist[c < (uint32_t)hist_bins - 1 ? c : (uint32_t)hist_bins - 1], 1u);
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void k_index_get(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u64 *out)
+// which slice each sorted key falls into: bounds[r] = first index whose slice is >= r (n_slices + 1 entries)
+__global__ void k_index_slice_bounds(const nd_u64 *key_sorted, nd_u64 n, nd_u64 key_mul, uint32_t n_slices, nd_u64 *bounds)
 {
-    nd_u64 off = 0; uint32_t n = 0;
-    nd_ht_lookup(tab, log2cap, key, &off, &n);
-    out[0] = off; out[1] = n;
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const uint32_t cur = i < n ? nd_idx_slice(key_sorted[i], key_mul, n_slices) : n_slices;
+    const uint32_t prev = i > 0 ? nd_idx_slice(key_sorted[i - 1], key_mul, n_slices) : 0;
+    if (i == 0) { for (uint32_t r = 0; r <= cur; ++r) bounds[r] = 0; }
+    else for (uint32_t r = prev + 1; r <= cur; ++r) bounds[r] = i;
+}
+
+__global__ void k_index_get(nd_idx_view I, nd_u64 key, nd_u64 *out)
+{
+    nd_u64 v = 0; bool inl = false;
+    const uint32_t n = nd_idx_lookup(I, key, &v, &inl);
+    out[0] = v; out[1] = n; out[2] = inl ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -232,8 +263,7 @@ __global__ void k_index_get(const nd_ht_slot *tab, int log2cap, nd_u64 key, nd_u
 // ------------------------------------------------------------------------------------------------
 
 struct nd_seed_par {
-    const nd_ht_slot *tab; int log2cap;
-    const nd_u64 *pos;                 // index position lists
+    nd_idx_view idx;
     const nd_u64 *t_key; const uint32_t *t_len;
     int mid_occ, no_diag, no_dual;
     int tag_shift;                     // > 0: probe key = hash | tag(read) << tag_shift
@@ -262,18 +292,18 @@ k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz
     nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_mz) return;
     nd_u128 z = mz[m];
-    nd_u64 off = 0; uint32_t n = 0, keep = 0;
+    nd_u64 off = 0; uint32_t n = 0, keep = 0; bool inl = false;
     nd_u64 key = z.x >> 8; int r = -1;
     if (P.tag_shift > 0) { r = nd_find_owner(mz_off, Q.n_reads, m); key |= (nd_u64)Q.tag[r] << P.tag_shift; }
-    if (nd_ht_lookup(P.tab, P.log2cap, key, &off, &n) && n < (uint32_t)P.mid_occ) {
+    n = nd_idx_lookup(P.idx, key, &off, &inl);
+    if (n && n < (uint32_t)P.mid_occ) {
         if (r < 0) r = nd_find_owner(mz_off, Q.n_reads, m);
         nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y;
-        for (uint32_t kk = 0; kk < n; ++kk) {
-            int self;
-            keep += !nd_skip_seed(P, __ldg(P.pos + off + kk), q_pos, qkey, qlen, &self);
-        }
+        int self;
+        if (inl) keep = !nd_skip_seed(P, off, q_pos, qkey, qlen, &self);
+        else for (uint32_t kk = 0; kk < n; ++kk) keep += !nd_skip_seed(P, __ldg(P.idx.pos + off + kk), q_pos, qkey, qlen, &self);
     } else n = 0;
-    m_off[m] = off; m_n[m] = n; m_keep[m] = keep;
+    m_off[m] = off; m_n[m] = inl ? (n | 0x80000000u) : n; m_keep[m] = keep;     // top bit: m_off is the position itself
 }
 
 __global__ void __launch_bounds__(256)
@@ -290,9 +320,10 @@ k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *m
     if (m > mz_off[r] && (mz[m - 1].x >> 8) == (z.x >> 8)) tandem = true;
     if (m + 1 < mz_off[r + 1] && (mz[m + 1].x >> 8) == (z.x >> 8)) tandem = true;
     nd_u64 off = m_off[m]; uint32_t n = m_n[m];
+    const bool inl = (n & 0x80000000u) != 0; n &= 0x7fffffffu;
     nd_u128 *dst = a + a_pos[m];
     for (uint32_t kk = 0; kk < n; ++kk) {
-        nd_u64 rr = __ldg(P.pos + off + kk);
+        nd_u64 rr = inl ? off : __ldg(P.idx.pos + off + kk);
         int self;
         if (nd_skip_seed(P, rr, q_pos, qkey, qlen, &self)) continue;
         nd_u128 o;

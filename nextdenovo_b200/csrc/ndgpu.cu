@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <string>
 #include <vector>
+#include <memory>
 #include <algorithm>
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
@@ -64,6 +65,10 @@ struct HostBuf {   // pinned
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostTargets {         // 2-bit target reads kept on the host for regime B / step 2 (what mm_idx_t::S is for, ref: minimap2/index.c:152-162)
+    std::vector<uint32_t> words, nmask; std::vector<uint64_t> word_off; bool has_n = false;
+};
+
 struct ProfEntry { std::string name; double ms = 0; uint64_t launches = 0; };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
@@ -99,8 +104,17 @@ struct ndg_ctx {
     DevBuf tmz; uint64_t n_tmz = 0;               // raw target minimizers (x,y)
     DevBuf t_key, t_len, t_id, t_tag; std::vector<uint64_t> h_tkey; std::vector<uint32_t> h_tlen, h_tid, h_ttag; bool t_has_id = true, t_has_tag = false; int tag_shift = 0;
     DevBuf em_keep, em_kidx, em_len, em_off, em_out; HostBuf h_ovl; uint32_t n_targets = 0; uint64_t t_sum_len = 0;
-    DevBuf idx_pos, idx_tab; int log2cap = 0; uint64_t n_pos = 0; bool index_ready = false;
-    int mid_occ = 0;
+    DevBuf idx_pos, idx_tab, idx_pos_base; uint64_t n_pos = 0; bool index_ready = false;
+    uint32_t n_slices = 1; uint64_t slice_cap = 0, slice_slots = 0, key_mul = 0; int key_bits = 0;      // geometry of the ordered table (nd_kernels.cuh)
+    // transient buffers of an index build (ndg_index_finalize / ndg_index_shard_*)
+    DevBuf ib_lkey, ib_lval, ib_rkey, ib_rval, ib_skey, ib_sval, ib_ukey, ib_cnt, ib_start, ib_d;
+    uint64_t ib_n_local = 0, ib_n_recv = 0, ib_n_sorted = 0, ib_n_distinct = 0; std::vector<uint64_t> ib_bounds;
+    // occurrence cutoff (ref: minimap2/options.c:66-76): a user value (-f >= 1) wins; otherwise the value derived from the FIRST index
+    // part finalized after ndg_set_opt() is kept for the later parts of the run.  idx_hist/idx_distinct describe the current index,
+    // so the derivation can be redone (a borrower calling ndg_set_opt() after ndg_index_share()).
+    int mid_occ_user = 0, mid_occ_run = 0; bool opt_fresh = true;
+    std::vector<uint32_t> idx_hist; uint64_t idx_distinct = 0;
+    int mid_occ() const { return mid_occ_user > 0 ? mid_occ_user : mid_occ_run; }
     // mapping workspace
     ReadsDev q;
     DevBuf staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
@@ -113,7 +127,7 @@ struct ndg_ctx {
     HostBuf up;
     // regime B (base-level alignment)
     bool aln_on = false; ndal::Opt aln; ndg_aln_stat_t aln_stat = {};
-    std::vector<uint32_t> ht_words, ht_nmask; std::vector<uint64_t> ht_word_off; bool ht_has_n = false;
+    std::shared_ptr<HostTargets> ht = std::make_shared<HostTargets>();   // host copy of the target bases (shared with borrowers of the index)
     std::vector<ndg_hit_t> aln_hits;
     DevBuf ksw_ncig, ksw_coff, ksw_cout, ch_cnt, ch_off, ch_a, ch_fend;
     HostBuf h_kseq, h_kres, h_kcig, h_koff, h_cha, h_chf;
@@ -231,9 +245,9 @@ int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
     CK(cudaMemcpyAsync(D.name_hash.p, h_hash, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(D.name_id.p, h_id, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     if (R->nmask) {
-        if ((w0 & 1) != 0) return fail(c, NDG_ERR_ARG, "nmask requires even word offsets");
+        for (int i = 0; i <= n; ++i) if (R->word_off[r0 + i] & 1) return fail(c, NDG_ERR_ARG, "nmask requires an even word offset for every read (read %d)", r0 + i);
         RSV(D.nmask, (nw / 2 + 4) * 4);
-        CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, (nw / 2 + 1) * 4, cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, ((nw + 1) / 2) * 4, cudaMemcpyHostToDevice, c->st));   // exactly the mask words the slice covers
     }
     D.has_tag = R->tag != nullptr;
     if (R->tag) { RSV(D.tag, (size_t)n * 4); CK(cudaMemcpyAsync(D.tag.p, R->tag + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->st)); }
@@ -292,6 +306,26 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     return 0;
 }
 
+// ref: minimap2/index.c:164-185 (mm_idx_cal_max_occ) + minimap2/options.c:66-76: value at rank (1-f)*n_distinct of the
+// per-minimizer occurrence counts, +1, floored by --min-occ-floor.  idx_hist[c] = number of distinct minimizers occurring c times.
+int derive_mid_occ(ndg_ctx *c, int *out)
+{
+    int v;
+    if (c->opt.mid_occ_frac <= 0.f) v = INT32_MAX;
+    else {
+        const int HB = (int)c->idx_hist.size();
+        if (HB == 0) return fail(c, NDG_ERR_STATE, "no index statistics to derive mid_occ from");
+        uint32_t kth = (uint32_t)((1. - c->opt.mid_occ_frac) * c->idx_distinct);
+        uint64_t acc = 0; int vbin = -1;
+        for (int b = 0; b < HB; ++b) { acc += c->idx_hist[b]; if (acc > kth) { vbin = b; break; } }
+        if (vbin < 0 || vbin == HB - 1) return fail(c, NDG_ERR_OVERFLOW, "mid_occ order statistic beyond histogram range");
+        v = vbin + 1;
+    }
+    if (v < c->opt.min_mid_occ) v = c->opt.min_mid_occ;
+    *out = v;
+    return 0;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -326,9 +360,10 @@ extern "C" int ndg_init(int device, ndg_ctx_t **out)
 static void drop_index_loan(ndg_ctx *c)
 {
     if (!c->idx_borrowed) return;
-    DevBuf *b[] = { &c->idx_pos, &c->idx_tab, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
+    DevBuf *b[] = { &c->idx_pos, &c->idx_tab, &c->idx_pos_base, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
     for (auto x : b) { x->p = nullptr; x->cap = 0; }
     c->idx_borrowed = false; c->index_ready = false;
+    c->ht = std::make_shared<HostTargets>();
 }
 
 extern "C" void ndg_destroy(ndg_ctx_t *c)
@@ -339,7 +374,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     drop_index_loan(c);
     prof_flush(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
+    DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->idx_pos_base, &c->ib_lkey, &c->ib_lval, &c->ib_rkey, &c->ib_rval, &c->ib_skey, &c->ib_sval, &c->ib_ukey, &c->ib_cnt, &c->ib_start, &c->ib_d, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
                        &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag };
@@ -362,7 +397,11 @@ extern "C" int ndg_set_opt(ndg_ctx_t *c, const ndg_opt_t *o)
 {
     if (!c || !o) return NDG_ERR_ARG;
     c->opt = *o;
-    c->mid_occ = o->mid_occ > 0 ? o->mid_occ : 0;   // <=0: derived from the first index part built after this call
+    c->mid_occ_user = o->mid_occ > 0 ? o->mid_occ : 0;
+    // the derived cutoff belongs to a run: the first index part finalized after this call sets it anew; if an index is
+    // already in place (finalized or borrowed) it is re-derived from that index right away, so mapping never sees 0
+    c->mid_occ_run = 0; c->opt_fresh = true;
+    if (c->index_ready && derive_mid_occ(c, &c->mid_occ_run)) return NDG_ERR_OVERFLOW;
     return NDG_OK;
 }
 extern "C" int ndg_set_limits(ndg_ctx_t *c, uint64_t sub_batch_bases, uint64_t max_anchors)
@@ -408,7 +447,7 @@ extern "C" int ndg_index_begin(ndg_ctx_t *c)
     drop_index_loan(c);
     c->n_tmz = 0; c->n_targets = 0; c->t_sum_len = 0; c->h_tkey.clear(); c->h_tlen.clear(); c->h_tid.clear(); c->h_ttag.clear(); c->t_has_id = true; c->t_has_tag = false; c->tag_shift = 0;
     c->index_ready = false; c->n_pos = 0;
-    c->ht_words.clear(); c->ht_nmask.clear(); c->ht_word_off.clear(); c->ht_has_n = false;
+    c->ht = std::make_shared<HostTargets>();          // never clear in place: a borrower may still hold the previous store
     return NDG_OK;
 }
 
@@ -436,6 +475,8 @@ extern "C" int ndg_index_add_meta(ndg_ctx_t *c, const ndg_reads_t *T)
 extern "C" int ndg_index_add(ndg_ctx_t *c, const ndg_reads_t *T)
 {
     if (!c || !T || T->n_reads <= 0) return NDG_ERR_ARG;
+    if (c->idx_borrowed) return fail(c, NDG_ERR_STATE, "this context borrows another context's index: call ndg_index_begin() before building its own");
+    if (T->nmask) for (int i = 0; i <= T->n_reads; ++i) if (T->word_off[i] & 1) return fail(c, NDG_ERR_ARG, "nmask requires an even word offset for every read (read %d)", i);
     cudaSetDevice(c->device);
     uint32_t rid0 = c->n_targets;
     int r0 = 0;
@@ -449,35 +490,304 @@ extern "C" int ndg_index_add(ndg_ctx_t *c, const ndg_reads_t *T)
         r0 = r1;
     }
     if (c->aln_on || c->s2_on) {        // regime B and step 2 read target bases on the host (ref: mm_idx_getseq, minimap2/index.c:152-162)
-        const uint64_t wb = T->word_off[0], nw = T->word_off[T->n_reads] - wb, w0 = c->ht_words.size();   // offsets may be absolute into a larger array
-        if (T->nmask && !c->ht_has_n) { c->ht_nmask.assign(w0 / 2, 0); c->ht_has_n = true; }
-        c->ht_words.insert(c->ht_words.end(), T->words + wb, T->words + wb + nw);
-        if (c->ht_words.size() & 1) c->ht_words.push_back(0);
-        if (c->ht_has_n) {
-            c->ht_nmask.resize(c->ht_words.size() / 2 + 1, 0);
-            if (T->nmask) memcpy(c->ht_nmask.data() + w0 / 2, T->nmask + wb / 2, (size_t)((nw + 1) / 2) * 4);
+        const uint64_t wb = T->word_off[0], nw = T->word_off[T->n_reads] - wb, w0 = c->ht->words.size();   // offsets may be absolute into a larger array
+        if (T->nmask && !c->ht->has_n) { c->ht->nmask.assign(w0 / 2, 0); c->ht->has_n = true; }
+        c->ht->words.insert(c->ht->words.end(), T->words + wb, T->words + wb + nw);
+        if (c->ht->words.size() & 1) c->ht->words.push_back(0);
+        if (c->ht->has_n) {
+            c->ht->nmask.resize(c->ht->words.size() / 2 + 1, 0);
+            if (T->nmask) memcpy(c->ht->nmask.data() + w0 / 2, T->nmask + wb / 2, (size_t)((nw + 1) / 2) * 4);
         }
-        for (int i = 0; i < T->n_reads; ++i) c->ht_word_off.push_back(w0 + T->word_off[i] - wb);
+        for (int i = 0; i < T->n_reads; ++i) c->ht->word_off.push_back(w0 + T->word_off[i] - wb);
     }
     return index_meta(c, T);
 }
 
-extern "C" int ndg_index_export(ndg_ctx_t *c, const void **dev, uint64_t *n)
+// ------------------------------------------------------------------------------------------------
+// index build: sort by minimizer -> run lengths -> ordered table (nd_kernels.cuh).  The same stages serve one GPU (one slice)
+// and N GPUs (slice r built on rank r from the keys of its range, finished slices all-gathered): ndg_index_shard_*.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+void idx_stage_release(ndg_ctx *c)
 {
-    if (!c || !dev || !n) return NDG_ERR_ARG;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
-    *dev = c->tmz.p; *n = c->n_tmz;
-    return NDG_OK;
+    DevBuf *b[] = { &c->ib_lkey, &c->ib_lval, &c->ib_rkey, &c->ib_rval, &c->ib_skey, &c->ib_sval, &c->ib_ukey, &c->ib_cnt, &c->ib_start, &c->ib_d };
+    for (auto x : b) x->release();
+    c->ib_n_local = c->ib_n_recv = c->ib_n_sorted = c->ib_n_distinct = 0;
 }
-extern "C" int ndg_copy_d2d(ndg_ctx_t *c, void *dst, const void *src, uint64_t bytes)
+
+// key geometry of the part being built: keys are < key_range (2k hash bits, group tags above them for a tagged index)
+int idx_key_geometry(ndg_ctx *c)
 {
-    if (!c || (bytes && (!dst || !src))) return NDG_ERR_ARG;
-    cudaSetDevice(c->device);
-    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->st));
+    int bits = 2 * c->opt.k;
+    c->tag_shift = 0;
+    if (c->t_has_tag) {
+        uint32_t mx = 0; for (uint32_t t : c->h_ttag) mx = std::max(mx, t);
+        int tb = 1; while (tb < 32 && (mx >> tb)) ++tb;
+        if (bits + tb > 63) return fail(c, NDG_ERR_ARG, "group tags up to %u do not fit above %d hash bits", mx, bits);
+        c->tag_shift = bits; bits += tb;
+        RSV(c->t_tag, (size_t)c->n_targets * 4 + 4);
+        CK(cudaMemcpyAsync(c->t_tag.p, c->h_ttag.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
+    }
+    c->key_bits = bits; c->key_mul = ~0ull / (1ull << bits);
+    return 0;
+}
+
+// (key, val) pairs sorted by key on key_bits bits; stable LSD radix => ascending position inside a key (ref: index.c:230)
+int idx_sort(ndg_ctx *c, const nd_u64 *kin, const nd_u64 *vin, uint64_t n, nd_u64 *kout, nd_u64 *vout)
+{
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (long long)n, 0, c->key_bits, c->st));
+    RSV(c->cubtmp, tmp);
+    KLAUNCH("index_sort", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, kin, kout, vin, vout, (long long)n, 0, c->key_bits, c->st)));
+    return 0;
+}
+
+// distinct keys, their counts and run starts of a sorted key array
+int idx_runs(ndg_ctx *c, const nd_u64 *skey, uint64_t n)
+{
+    RSV(c->ib_ukey, (n + 1) * 8); RSV(c->ib_cnt, (n + 1) * 4); RSV(c->ib_start, (n + 2) * 8); RSV(c->scalars, 1024);
+    nd_u64 *d_nd = c->scalars.as<nd_u64>() + 8;
+    size_t tmp = 0;
+    CK(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, skey, c->ib_ukey.as<nd_u64>(), c->ib_cnt.as<uint32_t>(), d_nd, (long long)n, c->st));
+    RSV(c->cubtmp, tmp);
+    KLAUNCH("index_runs", CK(cub::DeviceRunLengthEncode::Encode(c->cubtmp.p, tmp, skey, c->ib_ukey.as<nd_u64>(), c->ib_cnt.as<uint32_t>(), d_nd, (long long)n, c->st)));
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    CK(cudaMemcpyAsync(h, d_nd, 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    c->ib_n_distinct = h[0];
+    CK(cudaMemsetAsync(c->ib_cnt.as<uint32_t>() + c->ib_n_distinct, 0, 4, c->st));
+    return scan_u32_to_u64(c, c->ib_cnt.as<uint32_t>(), c->ib_start.as<nd_u64>(), c->ib_n_distinct);
+}
+
+struct MaxI64 { __host__ __device__ nd_i64 operator()(nd_i64 a, nd_i64 b) const { return a > b ? a : b; } };
+
+// place the distinct keys (ib_ukey/cnt/start) into slice `sl` of the table; accumulates the run-length histogram in d_hist
+int idx_place(ndg_ctx *c, uint32_t sl, const nd_u64 *svals, uint32_t *d_hist, int HB)
+{
+    const uint64_t nd = c->ib_n_distinct;
+    nd_ht_slot *slice = c->idx_tab.as<nd_ht_slot>() + (uint64_t)sl * c->slice_slots;
+    CK(cudaMemsetAsync(slice, 0xff, c->slice_slots * sizeof(nd_ht_slot), c->st));
+    if (nd == 0) return 0;
+    RSV(c->ib_d, nd * 8);
+    KLAUNCH("index_table", (k_index_ideal<<<nblk(nd, 256), 256, 0, c->st>>>(c->ib_ukey.as<nd_u64>(), nd, c->key_mul, c->n_slices, c->slice_cap, c->ib_d.as<nd_i64>())));
+    size_t tmp = 0;
+    CK(cub::DeviceScan::InclusiveScan(nullptr, tmp, c->ib_d.as<nd_i64>(), c->ib_d.as<nd_i64>(), MaxI64(), (long long)nd, c->st));
+    RSV(c->cubtmp, tmp);
+    KLAUNCH("index_table", CK(cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmp, c->ib_d.as<nd_i64>(), c->ib_d.as<nd_i64>(), MaxI64(), (long long)nd, c->st)));
+    int *d_over = c->scalars.as<int>() + 2;
+    CK(cudaMemsetAsync(d_over, 0, 4, c->st));
+    KLAUNCH("index_table", (k_index_place<<<nblk(nd, 256), 256, 0, c->st>>>(c->ib_ukey.as<nd_u64>(), c->ib_cnt.as<uint32_t>(), c->ib_start.as<nd_u64>(), c->ib_d.as<nd_i64>(), nd, svals,
+                            slice, c->slice_slots, d_hist, HB, d_over)));
+    CK(cudaGetLastError());
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    CK(cudaMemcpyAsync(h, d_over, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if ((int)h[0]) return fail(c, NDG_ERR_OVERFLOW, "index table: a key was displaced beyond the %llu-slot pad of its slice (non-uniform minimizer keys?)", (unsigned long long)ND_HT_PAD);
+    return 0;
+}
+
+uint64_t idx_slice_cap(uint64_t max_distinct) { uint64_t cap = (uint64_t)(max_distinct / 0.70) + 64; return (cap + 7) & ~7ull; }
+
+int idx_upload_meta(ndg_ctx *c)
+{
+    RSV(c->t_key, (size_t)c->n_targets * 8 + 8); RSV(c->t_len, (size_t)c->n_targets * 4 + 4); RSV(c->t_id, (size_t)c->n_targets * 4 + 4);
+    CK(cudaMemcpyAsync(c->t_id.p, c->h_tid.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->t_key.p, c->h_tkey.data(), (size_t)c->n_targets * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->t_len.p, c->h_tlen.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// last stage: statistics of the whole part are known (hist, n_distinct): cutoff, metadata, ready
+int idx_finish(ndg_ctx *c, const std::vector<uint32_t> &hist, uint64_t n_distinct, uint64_t n_minimizers, ndg_index_stat_t *stat)
+{
+    if (int rc = idx_upload_meta(c)) return rc;
+    // mid_occ: ref minimap2/index.c:164-185 + options.c:66-76 (computed on the first part of a run only)
+    c->idx_hist = hist; c->idx_distinct = n_distinct;
+    if (c->opt_fresh || c->mid_occ_run <= 0) { if (int rc = derive_mid_occ(c, &c->mid_occ_run)) return rc; }
+    c->opt_fresh = false;
+    c->n_pos = n_minimizers; c->index_ready = true;
+    c->tmz.release(); c->n_tmz = 0;
+    idx_stage_release(c);
+    if (stat) {
+        stat->n_seq = c->n_targets; stat->n_minimizers = n_minimizers; stat->n_distinct = n_distinct; stat->n_singletons = hist.size() > 1 ? hist[1] : 0;
+        stat->sum_len = c->t_sum_len; stat->mid_occ = c->mid_occ();
+    }
     return NDG_OK;
 }
+
+nd_idx_view idx_view(const ndg_ctx *c)
+{
+    nd_idx_view I; I.tab = c->idx_tab.as<nd_ht_slot>(); I.pos = c->idx_pos.as<nd_u64>(); I.pos_base = c->idx_pos_base.as<nd_u64>();
+    I.slice_cap = c->slice_cap; I.slice_slots = c->slice_slots; I.key_mul = c->key_mul; I.n_slices = c->n_slices; I.key_bits = c->key_bits;
+    return I;
+}
+
+const int IDX_HB = 65536;
+
+} // namespace
+
+extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
+{
+    if (!c) return NDG_ERR_ARG;
+    if (c->idx_borrowed) return fail(c, NDG_ERR_STATE, "this context borrows another context's index: call ndg_index_begin() before building its own");
+    cudaSetDevice(c->device);
+    const uint64_t n = c->n_tmz;
+    if (n == 0) return fail(c, NDG_ERR_STATE, "index has no minimizers");
+    if (int rc = idx_key_geometry(c)) return rc;
+    RSV(c->scalars, 1024);
+    // one slice: split (x, y) -> (key, position), sort straight into the final position list
+    RSV(c->ib_lkey, n * 8); RSV(c->ib_lval, n * 8); RSV(c->ib_skey, n * 8); RSV(c->idx_pos, n * 8 + 8);
+    KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, c->ib_lkey.as<nd_u64>(), c->ib_lval.as<nd_u64>(),
+                            c->t_has_tag ? c->t_tag.as<uint32_t>() : nullptr, c->tag_shift, c->key_bits)));
+    c->tmz.release(); c->n_tmz = 0;
+    if (int rc = idx_sort(c, c->ib_lkey.as<nd_u64>(), c->ib_lval.as<nd_u64>(), n, c->ib_skey.as<nd_u64>(), c->idx_pos.as<nd_u64>())) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    c->ib_lkey.release(); c->ib_lval.release();
+    if (int rc = idx_runs(c, c->ib_skey.as<nd_u64>(), n)) return rc;
+    c->ib_skey.release();
+    c->n_slices = 1; c->slice_cap = idx_slice_cap(c->ib_n_distinct); c->slice_slots = c->slice_cap + ND_HT_PAD;
+    RSV(c->idx_tab, c->slice_slots * sizeof(nd_ht_slot)); RSV(c->idx_pos_base, 64);
+    CK(cudaMemsetAsync(c->idx_pos_base.p, 0, 64, c->st));
+    DevBuf hist;
+    if (hist.reserve(IDX_HB * 4)) return fail(c, NDG_ERR_NOMEM, "index histogram");
+    cudaMemsetAsync(hist.p, 0, IDX_HB * 4, c->st);
+    int rc = idx_place(c, 0, c->idx_pos.as<nd_u64>(), hist.as<uint32_t>(), IDX_HB);
+    std::vector<uint32_t> hh(IDX_HB);
+    if (!rc) { cudaMemcpyAsync(hh.data(), hist.p, IDX_HB * 4, cudaMemcpyDeviceToHost, c->st); if (cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(c, NDG_ERR_CUDA, "index table"); }
+    hist.release();
+    if (rc) return rc;
+    return idx_finish(c, hh, c->ib_n_distinct, n, stat);
+}
+
+// ---- N-GPU build (no counterpart in the reference, whose index is built by one process) ----------------------------------
+// rank r: ndg_index_add(own targets) + ndg_index_add_meta(the others), then
+//   split(N)            local minimizers sorted by key and cut into the N key ranges              -> counts[N]
+//   bucket(j)           device pointers of the pairs destined for rank j                           (all-to-all by the caller: NCCL or peer copies)
+//   recv_reserve(total) device buffers the caller fills with everything destined for this rank
+//   sort()              sort + run lengths of the received pairs                                   -> n_distinct of this slice
+//   place(r, cap)       all N agree on slice_cap (max n_distinct / load); this rank's slice is built inside the full-size table
+//   table_slice(j)      device pointer / bytes of slice j                                          (all-gather by the caller)
+//   pos_reserve(n[N])   full position list allocated, own segment in place                         -> device pointer of segment j (all-gather by the caller)
+//   finish(hist, nd)    global run-length histogram and distinct count (summed by the caller)      -> index ready
+// host helper (tests, planning): the slice / rank a minimizer key belongs to in an N-way sharded build of an untagged index
+extern "C" int32_t ndg_index_key_slice(uint64_t key, int32_t k, int32_t n_slices)
+{
+    if (k < 1 || k > 28 || n_slices < 1) return -1;
+    return (int32_t)nd_idx_slice(nd_idx_mix(key, 2 * k), ~0ull / (1ull << 2 * k), (uint32_t)n_slices);
+}
+
+extern "C" int ndg_index_shard_split(ndg_ctx_t *c, int32_t n_slices, uint64_t *counts)
+{
+    if (!c || n_slices < 1 || !counts) return NDG_ERR_ARG;
+    if (c->idx_borrowed) return fail(c, NDG_ERR_STATE, "borrowed index");
+    if (c->t_has_tag) return fail(c, NDG_ERR_ARG, "a tagged index is built on one GPU");
+    cudaSetDevice(c->device);
+    if (int rc = idx_key_geometry(c)) return rc;
+    RSV(c->scalars, 1024);
+    const uint64_t n = c->n_tmz;
+    c->n_slices = (uint32_t)n_slices; c->ib_n_local = n;
+    RSV(c->ib_lkey, (n + 1) * 8); RSV(c->ib_lval, (n + 1) * 8); RSV(c->ib_skey, (n + 1) * 8); RSV(c->ib_sval, (n + 1) * 8);
+    RSV(c->idx_pos_base, (size_t)(n_slices + 2) * 8);
+    std::vector<uint64_t> bounds((size_t)n_slices + 1, 0);
+    if (n) {
+        KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, c->ib_skey.as<nd_u64>(), c->ib_sval.as<nd_u64>(), nullptr, 0, c->key_bits)));
+        if (int rc = idx_sort(c, c->ib_skey.as<nd_u64>(), c->ib_sval.as<nd_u64>(), n, c->ib_lkey.as<nd_u64>(), c->ib_lval.as<nd_u64>())) return rc;
+        KLAUNCH("index_split", (k_index_slice_bounds<<<nblk(n + 1, 256), 256, 0, c->st>>>(c->ib_lkey.as<nd_u64>(), n, c->key_mul, c->n_slices, c->idx_pos_base.as<nd_u64>())));
+        CK(cudaMemcpyAsync(bounds.data(), c->idx_pos_base.p, (size_t)(n_slices + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
+    c->tmz.release(); c->n_tmz = 0;
+    c->ib_bounds = bounds;
+    for (int j = 0; j < n_slices; ++j) counts[j] = bounds[(size_t)j + 1] - bounds[(size_t)j];
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_bucket(ndg_ctx_t *c, int32_t j, const void **keys, const void **vals, uint64_t *n)
+{
+    if (!c || !keys || !vals || !n || j < 0 || (size_t)j + 1 >= c->ib_bounds.size() + 0) return NDG_ERR_ARG;
+    *keys = c->ib_lkey.as<nd_u64>() + c->ib_bounds[(size_t)j]; *vals = c->ib_lval.as<nd_u64>() + c->ib_bounds[(size_t)j];
+    *n = c->ib_bounds[(size_t)j + 1] - c->ib_bounds[(size_t)j];
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_recv_reserve(ndg_ctx_t *c, uint64_t total, void **keys, void **vals)
+{
+    if (!c || !keys || !vals) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    RSV(c->ib_rkey, (total + 1) * 8); RSV(c->ib_rval, (total + 1) * 8);
+    c->ib_n_recv = total; *keys = c->ib_rkey.p; *vals = c->ib_rval.p;
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_sort(ndg_ctx_t *c, uint64_t *n_distinct)
+{
+    if (!c || !n_distinct) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const uint64_t n = c->ib_n_recv;
+    c->ib_lkey.release(); c->ib_lval.release();      // the local buckets have been sent
+    RSV(c->ib_skey, (n + 1) * 8); RSV(c->ib_sval, (n + 1) * 8);
+    c->ib_n_sorted = n; c->ib_n_distinct = 0;
+    if (n) {
+        // pairs arrive as N sorted runs in rank order = target order, and the sort is stable: positions inside a key stay ascending
+        if (int rc = idx_sort(c, c->ib_rkey.as<nd_u64>(), c->ib_rval.as<nd_u64>(), n, c->ib_skey.as<nd_u64>(), c->ib_sval.as<nd_u64>())) return rc;
+        CK(cudaStreamSynchronize(c->st));
+        c->ib_rkey.release(); c->ib_rval.release();
+        if (int rc = idx_runs(c, c->ib_skey.as<nd_u64>(), n)) return rc;
+    }
+    c->ib_skey.release();
+    *n_distinct = c->ib_n_distinct;
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_place(ndg_ctx_t *c, int32_t my_slice, uint64_t max_distinct_per_slice, uint32_t *hist65536)
+{
+    if (!c || !hist65536 || my_slice < 0 || (uint32_t)my_slice >= c->n_slices) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    c->slice_cap = idx_slice_cap(max_distinct_per_slice); c->slice_slots = c->slice_cap + ND_HT_PAD;
+    RSV(c->idx_tab, (size_t)c->n_slices * c->slice_slots * sizeof(nd_ht_slot));
+    DevBuf hist;
+    if (hist.reserve(IDX_HB * 4)) return fail(c, NDG_ERR_NOMEM, "index histogram");
+    cudaMemsetAsync(hist.p, 0, IDX_HB * 4, c->st);
+    int rc = idx_place(c, (uint32_t)my_slice, c->ib_sval.as<nd_u64>(), hist.as<uint32_t>(), IDX_HB);
+    if (!rc) { cudaMemcpyAsync(hist65536, hist.p, IDX_HB * 4, cudaMemcpyDeviceToHost, c->st); if (cudaStreamSynchronize(c->st) != cudaSuccess) rc = fail(c, NDG_ERR_CUDA, "index table"); }
+    hist.release();
+    return rc;
+}
+
+extern "C" int ndg_index_shard_table_slice(ndg_ctx_t *c, int32_t j, void **dev, uint64_t *bytes)
+{
+    if (!c || !dev || !bytes || j < 0 || (uint32_t)j >= c->n_slices) return NDG_ERR_ARG;
+    *dev = c->idx_tab.as<nd_ht_slot>() + (uint64_t)j * c->slice_slots; *bytes = c->slice_slots * sizeof(nd_ht_slot);
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_pos_reserve(ndg_ctx_t *c, int32_t my_slice, const uint64_t *n_pos_per_slice, void **segments)
+{
+    if (!c || !n_pos_per_slice || !segments || my_slice < 0 || (uint32_t)my_slice >= c->n_slices) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    std::vector<uint64_t> base((size_t)c->n_slices + 1, 0);
+    for (uint32_t j = 0; j < c->n_slices; ++j) base[j + 1] = base[j] + n_pos_per_slice[j];
+    if (n_pos_per_slice[my_slice] != c->ib_n_sorted) return fail(c, NDG_ERR_ARG, "position count of the own slice does not match what was sorted");
+    RSV(c->idx_pos, (base[c->n_slices] + 1) * 8); RSV(c->idx_pos_base, (size_t)(c->n_slices + 2) * 8);
+    CK(cudaMemcpyAsync(c->idx_pos_base.p, base.data(), (size_t)(c->n_slices + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    if (c->ib_n_sorted) CK(cudaMemcpyAsync(c->idx_pos.as<nd_u64>() + base[(size_t)my_slice], c->ib_sval.p, c->ib_n_sorted * 8, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->ib_sval.release();
+    for (uint32_t j = 0; j < c->n_slices; ++j) segments[j] = c->idx_pos.as<nd_u64>() + base[j];
+    c->n_pos = base[c->n_slices];
+    return NDG_OK;
+}
+
+extern "C" int ndg_index_shard_finish(ndg_ctx_t *c, const uint32_t *hist65536, uint64_t n_distinct, ndg_index_stat_t *stat)
+{
+    if (!c || !hist65536) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> hh(hist65536, hist65536 + IDX_HB);
+    return idx_finish(c, hh, n_distinct, c->n_pos, stat);
+}
+
 extern "C" int ndg_index_share(ndg_ctx_t *c, ndg_ctx_t *src)
 {
     if (!c || !src || c == src) return NDG_ERR_ARG;
@@ -486,105 +796,17 @@ extern "C" int ndg_index_share(ndg_ctx_t *c, ndg_ctx_t *src)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(src->st);
     drop_index_loan(c);
-    DevBuf *own[] = { &c->idx_pos, &c->idx_tab, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
-    DevBuf *from[] = { &src->idx_pos, &src->idx_tab, &src->t_key, &src->t_len, &src->t_id, &src->t_tag };
-    for (int i = 0; i < 6; ++i) { own[i]->release(); own[i]->p = from[i]->p; own[i]->cap = from[i]->cap; }
-    c->log2cap = src->log2cap; c->n_pos = src->n_pos; c->mid_occ = src->mid_occ; c->tag_shift = src->tag_shift;
+    DevBuf *own[] = { &c->idx_pos, &c->idx_tab, &c->idx_pos_base, &c->t_key, &c->t_len, &c->t_id, &c->t_tag };
+    DevBuf *from[] = { &src->idx_pos, &src->idx_tab, &src->idx_pos_base, &src->t_key, &src->t_len, &src->t_id, &src->t_tag };
+    for (int i = 0; i < 7; ++i) { own[i]->release(); own[i]->p = from[i]->p; own[i]->cap = from[i]->cap; }
+    c->n_slices = src->n_slices; c->slice_cap = src->slice_cap; c->slice_slots = src->slice_slots; c->key_mul = src->key_mul; c->key_bits = src->key_bits;
+    c->n_pos = src->n_pos; c->tag_shift = src->tag_shift;
+    c->idx_hist = src->idx_hist; c->idx_distinct = src->idx_distinct;
+    c->mid_occ_run = src->mid_occ();                  // the run's cutoff travels with the index; ndg_set_opt() on the borrower re-derives it
+    c->ht = src->ht;                                  // regime B / step 2 on the borrower read the owner's host copy of the target bases
     c->n_targets = src->n_targets; c->t_sum_len = src->t_sum_len; c->t_has_id = src->t_has_id; c->t_has_tag = src->t_has_tag;
     c->h_tkey = src->h_tkey; c->h_tlen = src->h_tlen; c->h_tid = src->h_tid; c->h_ttag = src->h_ttag;
     c->idx_borrowed = true; c->index_ready = true;
-    return NDG_OK;
-}
-
-extern "C" int ndg_index_clear_minimizers(ndg_ctx_t *c) { if (!c) return NDG_ERR_ARG; c->n_tmz = 0; return NDG_OK; }
-
-extern "C" int ndg_index_import(ndg_ctx_t *c, const void *dev, uint64_t n)
-{
-    if (!c || (!dev && n)) return NDG_ERR_ARG;
-    cudaSetDevice(c->device);
-    if (c->tmz.grow_keep((c->n_tmz + n + 1) * 16, c->n_tmz * 16, c->st)) return fail(c, NDG_ERR_NOMEM, "minimizer buffer");
-    CK(cudaMemcpyAsync(c->tmz.as<nd_u128>() + c->n_tmz, dev, n * 16, cudaMemcpyDeviceToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    c->n_tmz += n;
-    return NDG_OK;
-}
-
-extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
-{
-    if (!c) return NDG_ERR_ARG;
-    cudaSetDevice(c->device);
-    const uint64_t n = c->n_tmz;
-    const int HB = 65536;
-    if (n == 0) return fail(c, NDG_ERR_STATE, "index has no minimizers");
-    DevBuf key_in, val_in, key_out;
-    if (key_in.reserve(n * 8) || val_in.reserve(n * 8) || key_out.reserve(n * 8)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "index sort buffers"); }
-    RSV(c->idx_pos, n * 8);
-    int end_bit = 2 * c->opt.k; if (end_bit > 64) end_bit = 64;
-    const uint32_t *d_ttag = nullptr;
-    if (c->t_has_tag) {                                  // tagged index: group tag above the 2k hash bits
-        uint32_t mx = 0; for (uint32_t t : c->h_ttag) mx = std::max(mx, t);
-        int tb = 1; while (tb < 32 && (mx >> tb)) ++tb;
-        if (2 * c->opt.k + tb > 64) return fail(c, NDG_ERR_ARG, "group tags up to %u do not fit above %d hash bits", mx, 2 * c->opt.k);
-        c->tag_shift = 2 * c->opt.k; end_bit = c->tag_shift + tb;
-        RSV(c->t_tag, (size_t)c->n_targets * 4 + 4);
-        CK(cudaMemcpyAsync(c->t_tag.p, c->h_ttag.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
-        d_ttag = c->t_tag.as<uint32_t>();
-    }
-    KLAUNCH("index_split", (k_split_xy<<<nblk(n, 256), 256, 0, c->st>>>(c->tmz.as<nd_u128>(), n, key_in.as<nd_u64>(), val_in.as<nd_u64>(), d_ttag, c->tag_shift)));
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, key_in.as<nd_u64>(), key_out.as<nd_u64>(), val_in.as<nd_u64>(), c->idx_pos.as<nd_u64>(), (long long)n, 0, end_bit, c->st);
-    if (c->cubtmp.reserve(tmp)) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_NOMEM, "cub temp"); }
-    {
-        ProfScope ps(c, "index_sort");
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, key_in.as<nd_u64>(), key_out.as<nd_u64>(), val_in.as<nd_u64>(), c->idx_pos.as<nd_u64>(), (long long)n, 0, end_bit, c->st);
-        if (e != cudaSuccess) { key_in.release(); val_in.release(); key_out.release(); return fail(c, NDG_ERR_CUDA, "radix sort: %s", cudaGetErrorString(e)); }
-    }
-    RSV(c->scalars, 1024);
-    nd_u64 *d_nd = c->scalars.as<nd_u64>() + 8;
-    cudaMemsetAsync(d_nd, 0, 8, c->st);
-    KLAUNCH("index_heads", (k_count_heads<<<nblk(n, 256), 256, 0, c->st>>>(key_out.as<nd_u64>(), n, d_nd)));
-    uint64_t *h = c->h_scalars.as<uint64_t>();
-    cudaMemcpyAsync(h, d_nd, 8, cudaMemcpyDeviceToHost, c->st);
-    cudaError_t e0 = cudaStreamSynchronize(c->st);
-    key_in.release(); val_in.release();
-    if (e0 != cudaSuccess) { key_out.release(); return fail(c, NDG_ERR_CUDA, "index: %s", cudaGetErrorString(e0)); }
-    uint64_t n_distinct = h[0];
-    int lg = 4; while ((1ULL << lg) < 2 * n_distinct) ++lg;
-    c->log2cap = lg;
-    DevBuf hist;
-    if (c->idx_tab.reserve((size_t)16 << lg) || hist.reserve(HB * 4)) { key_out.release(); hist.release(); return fail(c, NDG_ERR_NOMEM, "index table"); }
-    cudaMemsetAsync(c->idx_tab.p, 0xff, (size_t)16 << lg, c->st);
-    cudaMemsetAsync(hist.p, 0, HB * 4, c->st);
-    KLAUNCH("index_table", (k_index_table<<<nblk(n, 256), 256, 0, c->st>>>(key_out.as<nd_u64>(), n, c->idx_tab.as<nd_ht_slot>(), lg, hist.as<uint32_t>(), HB)));
-    std::vector<uint32_t> hh(HB);
-    cudaMemcpyAsync(hh.data(), hist.p, HB * 4, cudaMemcpyDeviceToHost, c->st);
-    e0 = cudaStreamSynchronize(c->st);
-    key_out.release(); hist.release();
-    if (e0 != cudaSuccess) return fail(c, NDG_ERR_CUDA, "index table: %s", cudaGetErrorString(e0));
-    // targets' metadata
-    RSV(c->t_key, (size_t)c->n_targets * 8 + 8); RSV(c->t_len, (size_t)c->n_targets * 4 + 4); RSV(c->t_id, (size_t)c->n_targets * 4 + 4);
-    CK(cudaMemcpyAsync(c->t_id.p, c->h_tid.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(c->t_key.p, c->h_tkey.data(), (size_t)c->n_targets * 8, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(c->t_len.p, c->h_tlen.data(), (size_t)c->n_targets * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    // mid_occ: ref minimap2/index.c:164-185 + options.c:66-76 (computed on the first part only)
-    if (c->mid_occ <= 0) {
-        if (c->opt.mid_occ_frac <= 0.f) c->mid_occ = INT32_MAX;
-        else {
-            uint32_t kth = (uint32_t)((1. - c->opt.mid_occ_frac) * n_distinct);
-            uint64_t acc = 0; int vbin = -1;
-            for (int b = 0; b < HB; ++b) { acc += hh[b]; if (acc > kth) { vbin = b; break; } }
-            if (vbin < 0 || vbin == HB - 1) return fail(c, NDG_ERR_OVERFLOW, "mid_occ order statistic beyond histogram range");
-            c->mid_occ = vbin + 1;
-        }
-        if (c->mid_occ < c->opt.min_mid_occ) c->mid_occ = c->opt.min_mid_occ;
-    }
-    c->n_pos = n; c->index_ready = true;
-    c->tmz.release(); c->n_tmz = 0;
-    if (stat) {
-        stat->n_seq = c->n_targets; stat->n_minimizers = n; stat->n_distinct = n_distinct; stat->n_singletons = hh[1];
-        stat->sum_len = c->t_sum_len; stat->mid_occ = c->mid_occ;
-    }
     return NDG_OK;
 }
 
@@ -595,13 +817,16 @@ extern "C" int ndg_index_get(ndg_ctx_t *c, uint64_t minier, uint64_t *pos, int c
     cudaSetDevice(c->device);
     RSV(c->scalars, 1024);
     nd_u64 *d = c->scalars.as<nd_u64>() + 16;
-    k_index_get<<<1, 1, 0, c->st>>>(c->idx_tab.as<nd_ht_slot>(), c->log2cap, minier, d);
+    k_index_get<<<1, 1, 0, c->st>>>(idx_view(c), minier, d);
     uint64_t *h = c->h_scalars.as<uint64_t>();
-    CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     *n = (int)h[1];
     int m = std::min<int>(cap, *n);
-    if (m > 0 && pos) { CK(cudaMemcpyAsync(pos, c->idx_pos.as<nd_u64>() + h[0], (size_t)m * 8, cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st)); }
+    if (m > 0 && pos) {
+        if (h[2]) pos[0] = h[0];                       // a singleton carries its position in the slot
+        else { CK(cudaMemcpyAsync(pos, c->idx_pos.as<nd_u64>() + h[0], (size_t)m * 8, cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st)); }
+    }
     return NDG_OK;
 }
 
@@ -633,6 +858,7 @@ int map_resident(ndg_ctx *c, int qidx_base)
 {
     const ndg_opt_t &o = c->opt;
     if (!c->index_ready) return fail(c, NDG_ERR_STATE, "index not finalized");
+    if (c->mid_occ() <= 0) return fail(c, NDG_ERR_STATE, "no occurrence cutoff (mid_occ): neither given (-f >= 1) nor derived from an index part");
     ReadsDev &Q = c->q;
     const int nr = Q.n_reads;
     uint64_t *h = c->h_scalars.as<uint64_t>();
@@ -646,8 +872,8 @@ int map_resident(ndg_ctx *c, int qidx_base)
     if (M == 0) return 0;
 
     // 2. probe + count
-    nd_seed_par P; P.tab = c->idx_tab.as<nd_ht_slot>(); P.log2cap = c->log2cap; P.pos = c->idx_pos.as<nd_u64>();
-    P.t_key = c->t_key.as<nd_u64>(); P.t_len = c->t_len.as<uint32_t>(); P.mid_occ = c->mid_occ; P.no_diag = o.flag_no_diag; P.no_dual = o.flag_no_dual;
+    nd_seed_par P; P.idx = idx_view(c);
+    P.t_key = c->t_key.as<nd_u64>(); P.t_len = c->t_len.as<uint32_t>(); P.mid_occ = c->mid_occ(); P.no_diag = o.flag_no_diag; P.no_dual = o.flag_no_dual;
     P.tag_shift = c->tag_shift;
     if (c->tag_shift > 0 && !Q.has_tag) return fail(c, NDG_ERR_ARG, "the index is tagged: query reads need tags too");
     nd_reads_dev V = Q.view();
@@ -893,7 +1119,7 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
     if (!c || !Q || !out || Q->n_reads <= 0) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
     if (c->aln_on) {
-        if (c->ht_word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "regime B needs ndg_set_aln_opt() before ndg_index_add() (target bases are kept on the host)");
+        if (c->ht->word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "regime B needs ndg_set_aln_opt() before ndg_index_add() (target bases are kept on the host)");
         c->aln_hits.clear();
     }
     uint64_t tot_hits = 0, tot_mz = 0, tot_a = 0, tot_seg = 0;
@@ -1224,7 +1450,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
     CK(cudaStreamSynchronize(c->st));
     const nd_hit *hh = c->h_hits.as<nd_hit>(); const nd_u128 *ha = c->h_cha.as<nd_u128>(); const int32_t *hf = c->h_chf.as<int32_t>();
 
-    ndal::SeqStore ST; ST.words = c->ht_words.data(); ST.word_off = c->ht_word_off.data(); ST.len = c->h_tlen.data(); ST.nmask = c->ht_has_n ? c->ht_nmask.data() : nullptr;
+    ndal::SeqStore ST; ST.words = c->ht->words.data(); ST.word_off = c->ht->word_off.data(); ST.len = c->h_tlen.data(); ST.nmask = c->ht->has_n ? c->ht->nmask.data() : nullptr;
     ndal::SeqStore SQ; SQ.words = Q->words; SQ.word_off = Q->word_off; SQ.len = Q->len; SQ.nmask = Q->nmask;
     GpuDp be; be.c = c;
     be.P.m = 5; memset(be.P.mat, 0, sizeof be.P.mat); ndal::simple_mat(be.P.mat, c->aln); be.P.q = c->aln.q; be.P.e = c->aln.e; be.P.q2 = c->aln.q2; be.P.e2 = c->aln.e2;
@@ -1353,12 +1579,12 @@ int step2_remap(ndg_ctx *c, const ndg_reads_t *Q, std::vector<nds2::QueryJob> &j
     if (!c->remap) { if (int rc = ndg_init(c->device, &c->remap)) return fail(c, rc, "cannot create the re-mapping context"); }
     ndg_ctx *R = c->remap;
     const uint64_t launches0 = ndg_kernel_launches(R);
-    ndg_opt_t o2 = c->opt; o2.k = c->s2.kn; o2.w = c->s2.wn; o2.flag_no_diag = 0; o2.flag_no_dual = 0; o2.mid_occ = c->mid_occ; o2.min_mid_occ = 0;
+    ndg_opt_t o2 = c->opt; o2.k = c->s2.kn; o2.w = c->s2.wn; o2.flag_no_diag = 0; o2.flag_no_dual = 0; o2.mid_occ = c->mid_occ(); o2.min_mid_occ = 0;
     if (int rc = ndg_set_opt(R, &o2)) return fail(c, rc, "%s", ndg_last_error(R));
     ndg_set_limits(R, c->sub_batch_bases, c->max_anchors);
-    const bool any_n = Q->nmask || c->ht_has_n;
+    const bool any_n = Q->nmask || c->ht->has_n;
     ReadGather IX, MP; IX.has_n = MP.has_n = any_n;
-    const uint32_t *tn = c->ht_has_n ? c->ht_nmask.data() : nullptr;
+    const uint32_t *tn = c->ht->has_n ? c->ht->nmask.data() : nullptr;
     std::vector<uint32_t> qtag(jobs.size(), 0), qslot(jobs.size(), 0), base(reqs.size(), 0);
     uint32_t next_tag = 1;
     for (size_t x = 0; x < reqs.size(); ++x) {
@@ -1370,11 +1596,11 @@ int step2_remap(ndg_ctx *c, const ndg_reads_t *Q, std::vector<nds2::QueryJob> &j
                 IX.add(Q->words, Q->word_off[m.query], Q->len[m.query], Q->nmask, qtag[(size_t)m.query]);
             }
             base[x] = qslot[(size_t)m.query];
-            MP.add(c->ht_words.data(), c->ht_word_off[(size_t)m.mapped_rid], c->h_tlen[(size_t)m.mapped_rid], tn, qtag[(size_t)m.query], true);
+            MP.add(c->ht->words.data(), c->ht->word_off[(size_t)m.mapped_rid], c->h_tlen[(size_t)m.mapped_rid], tn, qtag[(size_t)m.query], true);
         } else {                                    // up to cn targets form the mini index, the query is mapped (ref: map.c:1085-1125)
             const uint32_t tg = next_tag++;
             base[x] = (uint32_t)IX.len.size();
-            for (int32_t rid : m.group_rids) IX.add(c->ht_words.data(), c->ht_word_off[(size_t)rid], c->h_tlen[(size_t)rid], tn, tg);
+            for (int32_t rid : m.group_rids) IX.add(c->ht->words.data(), c->ht->word_off[(size_t)rid], c->h_tlen[(size_t)rid], tn, tg);
             MP.add(Q->words, Q->word_off[m.query], Q->len[m.query], Q->nmask, tg);
             ++c->s2_groups;
         }
@@ -1419,8 +1645,10 @@ extern "C" int ndg_step2_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, const uin
     if (!c->s2_on) return fail(c, NDG_ERR_STATE, "ndg_step2_begin() was not called");
     if (c->aln_on) return fail(c, NDG_ERR_STATE, "--step 2 with base-level alignment is not built");
     if (!Q->name_id || !c->t_has_id) return fail(c, NDG_ERR_ARG, "step 2 needs name_id for targets and queries");
-    if (c->ht_word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "step 2 needs ndg_step2_begin() before ndg_index_add() (target bases are kept on the host)");
+    if (c->ht->word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "step 2 needs ndg_step2_begin() before ndg_index_add() (target bases are kept on the host)");
     omp_set_num_threads(c->n_threads);
+    // the bytes handed over by the previous call are the caller's now: drop them (the reference flushes every 100 MB, lib/ovl.c:247-250)
+    if (c->s2_emitted) { c->s2w.out.erase(c->s2w.out.begin(), c->s2w.out.begin() + (std::ptrdiff_t)c->s2_emitted); c->s2_emitted = 0; }
     ndg_map_result_t R;
     if (int rc = ndg_map_batch(c, Q, &R)) return rc;
     const int nq = Q->n_reads;
@@ -1516,7 +1744,7 @@ extern "C" int ndg_ovl_encode8(uint8_t *dst, uint32_t state[2], int rev, uint32_
     return n;
 }
 
-// ref: minimap2/map.c:804-821 (check_realign_nextdenovo), used by --dvt at map.c:1302
+// (no counterpart in the reference: stitches streams that were encoded independently; the delta/flag rules are encode_ovl's, lib/ovl.c:109-150)
 extern "C" int ndg_ovl_rebase_first(const uint8_t *ovl, uint64_t n, const uint32_t prev[2], uint8_t *dst, uint32_t *skip)
 {
     if (!ovl || !prev || !dst || !skip) return NDG_ERR_ARG;
@@ -1538,6 +1766,7 @@ extern "C" int ndg_ovl_rebase_first(const uint8_t *ovl, uint64_t n, const uint32
     return m;
 }
 
+// ref: minimap2/map.c:804-821 (check_realign_nextdenovo), used by --dvt at map.c:1302
 static inline int ndg_check_dovetail(int rev, uint32_t qs, uint32_t qe, uint32_t qlen, uint32_t ts, uint32_t te, uint32_t tlen,
                                      int32_t maxhan1, int32_t maxhan2)
 {

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 import numpy as np
 from .formats import Reads
-from .options import IdxOpt, MapOpt, MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_F_NO_END_FLT, MM_I_HPC
+from .options import IdxOpt, MapOpt, MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_F_NO_END_FLT, MM_F_ALL_CHAINS, MM_I_HPC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -72,8 +72,9 @@ KSW_RES_DTYPE = np.dtype([(n_, "<i4") for n_ in ("max", "zdropped", "max_q", "ma
 assert KSW_CALL_DTYPE.itemsize == 40 and KSW_RES_DTYPE.itemsize == 48
 
 EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
-           "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta", "ndg_index_export",
-           "ndg_index_import", "ndg_index_clear_minimizers", "ndg_copy_d2d", "ndg_index_finalize", "ndg_index_get",
+           "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta",
+           "ndg_index_key_slice", "ndg_index_shard_split", "ndg_index_shard_bucket", "ndg_index_shard_recv_reserve", "ndg_index_shard_sort", "ndg_index_shard_place",
+           "ndg_index_shard_table_slice", "ndg_index_shard_pos_reserve", "ndg_index_shard_finish", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
            "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish", "ndg_index_share"]
@@ -115,10 +116,16 @@ def load_library():
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
-    L.ndg_index_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
-    L.ndg_index_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
-    L.ndg_index_clear_minimizers.argtypes = [C.c_void_p]
-    L.ndg_copy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.ndg_index_key_slice.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    L.ndg_index_key_slice.restype = C.c_int32
+    L.ndg_index_shard_split.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.ndg_index_shard_bucket.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ndg_index_shard_recv_reserve.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.ndg_index_shard_sort.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.ndg_index_shard_place.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
+    L.ndg_index_shard_table_slice.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ndg_index_shard_pos_reserve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.ndg_index_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_IndexStat)]
     L.ndg_index_finalize.argtypes = [C.c_void_p, C.POINTER(_IndexStat)]
     L.ndg_index_get.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.ndg_map_batch.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_MapResult)]
@@ -191,6 +198,10 @@ class Engine:
             raise NdgError("libndgpu error %d: %s" % (rc, self.L.ndg_last_error(self.h).decode()))
 
     def set_options(self, io: IdxOpt, mo: MapOpt):
+        if not mo.flag & MM_F_ALL_CHAINS:
+            # the library keeps every chain; the reference would prune secondaries here (mm_set_parent / mm_select_sub with
+            # best_n and pri_ratio, ref: minimap2/map.c:250-259) and its .ovl bytes would differ
+            raise NdgError("the GPU path maps in all-chain mode only (MM_F_ALL_CHAINS): use the ava-ont / ava-pb presets, -X or -P")
         self.io, self.mo = io, mo
         if mo.flag & MM_F_CIGAR:                        # regime B (ref: minimap2/map.c:484-505)
             ao = _AlnOpt(a=mo.a, b=mo.b, q=mo.q, e=mo.e, q2=mo.q2, e2=mo.e2, sc_ambi=mo.sc_ambi, zdrop=mo.zdrop, zdrop_inv=mo.zdrop_inv,
@@ -407,41 +418,113 @@ def shard_bounds(n, world):
     return [(n * r) // world for r in range(world + 1)]
 
 
-def build_index_sharded(eng: Engine, targets: Reads, rank, world, dist, torch):
-    """Multi-GPU index build: rank r sketches targets[b[r]:b[r+1]] on its GPU, one
-    all-gather of the (x, y) minimizers over NCCL, then every rank sorts/tabulates the identical
-    full set locally.  Read ids (rid) are global, so the result equals the single-GPU index."""
+class _DevView:
+    """zero-copy torch view of library-owned device memory (CUDA array interface v2)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def _meta_struct(ids, lengths):
+    """ndg_reads_t carrying only what ndg_index_add_meta() reads (names and lengths of targets sketched on another rank)"""
+    from .formats import name_keys, x31_hash
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    s = _Reads()
+    s._keep = (np.ascontiguousarray(lengths, dtype=np.uint32), name_keys(ids), x31_hash(ids), ids)
+    s.n_reads = ids.shape[0]
+    s.len, s.name_key, s.name_hash, s.name_id = _ptr(s._keep[0]), _ptr(s._keep[1]), _ptr(s._keep[2]), _ptr(s._keep[3])
+    return s
+
+
+def shard_exchange_plan(counts_matrix, rank):
+    """counts_matrix[r][j] = pairs rank r holds for rank j.  Returns (input_split_sizes, output_split_sizes, total_received) of
+    rank `rank` for the all-to-all of the sharded index build (pure host logic; also exercised by the gloo test)."""
+    m = np.asarray(counts_matrix, dtype=np.int64)
+    return [int(x) for x in m[rank]], [int(x) for x in m[:, rank]], int(m[:, rank].sum())
+
+
+def build_index_sharded(eng: Engine, mine: Reads, rank, world, dist, torch, meta=None, timings=None):
+    """N-GPU index build (ndg_index_shard_*): rank r sketches its own targets, the minimizers are exchanged by key
+    range (one all-to-all), every rank sorts 1/N of them and builds its slice of the ordered table, and the finished slices and
+    position segments are gathered.  Target order = rank order; read ids (rid) are global, so mapping results equal those of a
+    single-GPU index over the concatenated target set.  meta[r] = (ids, lengths) of rank r's targets (None entries are gathered)."""
     L, h = eng.L, eng.h
-    b = shard_bounds(targets.n, world)
-    eng._ck(L.ndg_index_begin(h))
-    if b[rank] > 0:
-        s0 = _reads_struct(targets.slice(0, b[rank]))
-        eng._ck(L.ndg_index_add_meta(h, C.byref(s0)))
-    mine = _reads_struct(targets.slice(b[rank], b[rank + 1]))
-    eng._ck(L.ndg_index_add(h, C.byref(mine)))
-    if b[rank + 1] < targets.n:
-        s1 = _reads_struct(targets.slice(b[rank + 1], targets.n))
-        eng._ck(L.ndg_index_add_meta(h, C.byref(s1)))
-    ptr, n = C.c_void_p(), C.c_uint64()
-    eng._ck(L.ndg_index_export(h, C.byref(ptr), C.byref(n)))
+    import time as _t
+    t0 = _t.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device())
-    cnt = torch.tensor([n.value], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    cnts = [int(c.item()) for c in cnts]
-    mx = max(cnts)
-    send = torch.zeros(mx * 2, dtype=torch.int64, device=dev)
-    if n.value:
-        eng._ck(L.ndg_copy_d2d(h, send.data_ptr(), ptr, n.value * 16))
-    recv = torch.empty(world * mx * 2, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(recv, send)
-    torch.cuda.synchronize()
-    eng._ck(L.ndg_index_clear_minimizers(h))
+    if meta is None:                                    # names/lengths of everybody's targets
+        meta = [None] * world
+        cnt = torch.tensor([mine.n], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        for r in range(world):
+            n_r = int(cnts[r].item())
+            buf = torch.empty(2 * n_r, dtype=torch.int64, device=dev)
+            if r == rank:
+                buf[:n_r] = torch.from_numpy(mine.ids.astype(np.int64)).to(dev); buf[n_r:] = torch.from_numpy(mine.length.astype(np.int64)).to(dev)
+            dist.broadcast(buf, src=r)
+            b = buf.cpu().numpy()
+            meta[r] = (b[:n_r].astype(np.uint32), b[n_r:].astype(np.uint32))
+    eng._ck(L.ndg_index_begin(h))
+    keep = []
     for r in range(world):
-        if cnts[r]:
-            eng._ck(L.ndg_index_import(h, recv.data_ptr() + r * mx * 16, cnts[r]))
-    del recv, send
-    return eng.finalize_index(targets)
+        if r == rank:
+            s = _reads_struct(mine); keep.append(s)
+            eng._ck(L.ndg_index_add(h, C.byref(s)))
+        else:
+            s = _meta_struct(*meta[r]); keep.append(s)
+            if s.n_reads:
+                eng._ck(L.ndg_index_add_meta(h, C.byref(s)))
+    t1 = _t.perf_counter()
+    counts = np.zeros(world, dtype=np.uint64)
+    eng._ck(L.ndg_index_shard_split(h, world, _ptr(counts)))
+    cm = torch.zeros(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cm, torch.from_numpy(counts.astype(np.int64)).to(dev))
+    cm = cm.cpu().numpy().reshape(world, world)
+    in_split, out_split, total = shard_exchange_plan(cm, rank)
+    kp, vp, n0 = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    eng._ck(L.ndg_index_shard_bucket(h, 0, C.byref(kp), C.byref(vp), C.byref(n0)))     # bucket 0 starts the sorted local arrays
+    rk, rv = C.c_void_p(), C.c_void_p()
+    eng._ck(L.ndg_index_shard_recv_reserve(h, total, C.byref(rk), C.byref(rv)))
+    n_local = int(sum(in_split))
+    empty = torch.empty(0, dtype=torch.int64, device=dev)
+    for src_p, dst_p in ((kp, rk), (vp, rv)):
+        inp = torch.as_tensor(_DevView(src_p.value, n_local), device=dev) if n_local else empty
+        out = torch.as_tensor(_DevView(dst_p.value, total), device=dev) if total else empty
+        dist.all_to_all_single(out, inp, output_split_sizes=out_split, input_split_sizes=in_split)
+    torch.cuda.synchronize()
+    t2 = _t.perf_counter()
+    nd = C.c_uint64()
+    eng._ck(L.ndg_index_shard_sort(h, C.byref(nd)))
+    st = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(st, torch.tensor([nd.value, total], dtype=torch.int64, device=dev))
+    st = st.cpu().numpy().reshape(world, 2)
+    hist = np.zeros(65536, dtype=np.uint32)
+    eng._ck(L.ndg_index_shard_place(h, rank, int(st[:, 0].max()), _ptr(hist)))
+    t3 = _t.perf_counter()
+    sp, sb = C.c_void_p(), C.c_uint64()
+    eng._ck(L.ndg_index_shard_table_slice(h, 0, C.byref(sp), C.byref(sb)))
+    words = sb.value // 8
+    full = torch.as_tensor(_DevView(sp.value, words * world), device=dev)
+    dist.all_gather_into_tensor(full, full[rank * words:(rank + 1) * words])             # in place: slice r already sits at its offset
+    npos = np.ascontiguousarray(st[:, 1].astype(np.uint64))
+    segs = (C.c_void_p * world)()
+    eng._ck(L.ndg_index_shard_pos_reserve(h, rank, _ptr(npos), segs))
+    for r in range(world):
+        if int(npos[r]):
+            dist.broadcast(torch.as_tensor(_DevView(segs[r], int(npos[r])), device=dev), src=r)
+    hs = torch.from_numpy(hist.astype(np.int64)).to(dev)
+    dist.all_reduce(hs)
+    torch.cuda.synchronize()
+    hist = np.ascontiguousarray(hs.cpu().numpy().astype(np.uint32))
+    stt = _IndexStat()
+    eng._ck(L.ndg_index_shard_finish(h, _ptr(hist), int(st[:, 0].sum()), C.byref(stt)))
+    t4 = _t.perf_counter()
+    eng.targets = None
+    eng.stat = dict(n_seq=stt.n_seq, n_minimizers=stt.n_minimizers, n_distinct=stt.n_distinct, n_singletons=stt.n_singletons, sum_len=stt.sum_len, mid_occ=stt.mid_occ)
+    if timings is not None:
+        timings.update(sketch_s=t1 - t0, exchange_s=t2 - t1, sort_place_s=t3 - t2, gather_s=t4 - t3)
+    return eng.stat
 
 
 def index_parts(targets: Reads, io: IdxOpt):

@@ -71,6 +71,29 @@ class MapOpt:                       # subset of mm_mapopt_t, minimap2/minimap.h:
     extra: dict = field(default_factory=dict)
 
 
+# Option grammar of the reference (ref: minimap2/main.c:31-100 long_options, :162 opt_str).  name -> (arity, canonical short form)
+SHORT_SPEC = "2aSDw:k:K:t:r:f:Vv:g:G:I:d:XT:s:x:Hcp:M:n:z:A:B:O:E:m:N:Qu:R:hF:LC:yYPo:"
+LONG_OPTS = {n: (a, c) for n, a, c in [
+    ("bucket-bits", 1, None), ("mb-size", 1, "-K"), ("seed", 1, None), ("no-kalloc", 0, None), ("print-qname", 0, None), ("no-self", 0, "-D"),
+    ("print-seeds", 0, None), ("max-chain-skip", 1, None), ("min-dp-len", 1, None), ("print-aln-seq", 0, None), ("splice", 0, None),
+    ("cost-non-gt-ag", 1, "-C"), ("no-long-join", 0, None), ("sr", 0, None), ("frag", 1, None), ("secondary", 1, None), ("cs", 2, None),
+    ("end-bonus", 1, None), ("no-pairing", 0, None), ("splice-flank", 1, None), ("idx-no-seq", 0, None), ("end-seed-pen", 1, None),
+    ("for-only", 0, None), ("rev-only", 0, None), ("heap-sort", 1, None), ("all-chain", 0, "-P"), ("dual", 1, None), ("max-clip-ratio", 1, None),
+    ("min-occ-floor", 1, None), ("MD", 0, None), ("lj-min-ratio", 1, None), ("score-N", 1, None), ("eqx", 0, None), ("paf-no-hit", 0, None),
+    ("split-prefix", 1, None), ("no-end-flt", 0, None), ("hard-mask-level", 0, None), ("cap-sw-mem", 1, None), ("max-qlen", 1, None),
+    ("max-chain-iter", 1, None), ("junc-bed", 1, None), ("junc-bonus", 1, None), ("sam-hit-only", 0, None), ("help", 0, "-h"),
+    ("max-intron-len", 1, "-G"), ("version", 0, "-V"), ("min-count", 1, "-n"), ("min-chain-score", 1, "-m"), ("mask-level", 1, "-M"),
+    ("min-dp-score", 1, "-s"), ("sam", 0, "-a"),
+    ("step", 1, None), ("minlen", 1, None), ("minide", 1, None), ("maxhan1", 1, None), ("maxhan2", 1, None), ("outraw", 0, None),
+    ("minmatch", 1, None), ("mode", 1, None), ("kn", 1, None), ("wn", 1, None), ("cn", 1, None), ("outctn", 0, None), ("df", 1, None), ("dvt", 0, None),
+    ("device", 1, None), ("gpus", 1, None)]}
+# options that change results and are not implemented: refused by name, never approximated
+NOT_BUILT = {"-a", "-S", "--cs", "--MD", "--eqx", "-Y", "-L", "-Q", "-y", "-R", "--splice", "--sr", "--frag", "--no-pairing", "--splice-flank", "-u", "-C",
+             "-G", "-F", "--heap-sort", "--for-only", "--rev-only", "--end-seed-pen", "--lj-min-ratio", "--split-prefix", "--junc-bed", "--junc-bonus",
+             "--sam-hit-only", "--paf-no-hit", "--secondary", "-T", "-d", "--bucket-bits", "--idx-no-seq", "--cap-sw-mem", "--max-qlen", "--print-seeds",
+             "--print-aln-seq", "--print-qname", "--df", "--outraw", "--hard-mask-level"}
+
+
 def parse_num(s: str) -> int:
     """ref: minimap2/main.c:102-111 (mm_parse_num)"""
     s = s.strip()
@@ -110,26 +133,50 @@ def parse_args(argv):
     """Two-pass parse of the minimap2-nd options the NextDenovo pipeline passes for --step 1
     (ref: nextDenovo:445-464, lib/config_parser.py:191-217).  Returns (io, mo, out, positional)."""
     io, mo = IdxOpt(), MapOpt()
-    takes = {"-x", "--step", "-k", "-w", "-t", "-I", "-K", "-o", "-r", "-g", "-n", "-m", "-f", "--minlen",
-             "--maxhan1", "--maxhan2", "--seed", "--max-chain-skip", "--max-chain-iter", "--min-occ-floor", "-v",
-             "-A", "-B", "-O", "-E", "-z", "-s", "--min-dp-score", "--end-bonus", "--max-clip-ratio",
-             "--minide", "--minmatch", "--mode", "--kn", "--wn", "--cn"}
     toks, pos, i = [], [], 0
     while i < len(argv):
         a = argv[i]
-        if a.startswith("--") and "=" in a:
-            k, v = a.split("=", 1)
-            toks.append((k, v))
-        elif a in takes:
-            if i + 1 >= len(argv):
-                raise ValueError("[ERROR] missing option argument")
-            toks.append((a, argv[i + 1]))
-            i += 1
-        elif a.startswith("-") and len(a) > 1:
-            toks.append((a, None))
-        else:
+        if a == "-" or not a.startswith("-"):
             pos.append(a)
+        elif a == "--":
+            pos += argv[i + 1:]
+            break
+        elif a.startswith("--"):
+            name, eq, val = a[2:].partition("=")
+            if name not in LONG_OPTS:
+                raise ValueError('[ERROR] unknown option in "%s"' % a)
+            has_arg, canon = LONG_OPTS[name]
+            if not eq:
+                val = None
+                if has_arg == 1:
+                    if i + 1 >= len(argv):
+                        raise ValueError("[ERROR] missing option argument")
+                    val = argv[i + 1]
+                    i += 1
+            toks.append((canon or "--" + name, val))
+        else:
+            j = 1
+            while j < len(a):
+                c = a[j]
+                at = SHORT_SPEC.find(c)
+                if at < 0 or c == ":":
+                    raise ValueError('[ERROR] unknown option in "%s"' % a)
+                if SHORT_SPEC[at + 1:at + 2] == ":":
+                    if j + 1 < len(a):
+                        val = a[j + 1:]
+                    else:
+                        if i + 1 >= len(argv):
+                            raise ValueError("[ERROR] missing option argument")
+                        val = argv[i + 1]
+                        i += 1
+                    toks.append(("-" + c, val))
+                    break
+                toks.append(("-" + c, None))
+                j += 1
         i += 1
+    for k, _ in toks:
+        if k in NOT_BUILT:
+            raise ValueError("[ERROR] option '%s' is not built in this GPU build" % k)
     for k, v in toks:                                   # pass 1 (main.c:177-205)
         if k == "-x":
             if set_opt(v, io, mo) < 0:
@@ -162,7 +209,9 @@ def parse_args(argv):
         elif k == "-c": mo.flag |= MM_F_CIGAR
         elif k == "-A": mo.a = int(v)
         elif k == "-B": mo.b = int(v)
-        elif k in ("-s", "--min-dp-score"): mo.min_dp_max = int(v)
+        elif k == "-s": mo.min_dp_max = int(v)
+        elif k == "--min-dp-len": mo.min_ksw_len = int(v)
+        elif k == "--score-N": mo.sc_ambi = int(v)
         elif k == "--end-bonus": mo.end_bonus = int(v)
         elif k == "--max-clip-ratio": mo.max_clip_ratio = float(v)
         elif k == "--no-end-flt": mo.flag |= MM_F_NO_END_FLT

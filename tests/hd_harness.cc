@@ -64,8 +64,53 @@ static int selftest_n()
     return bad != 0;
 }
 
+// ordered index table: the placement rule of k_index_place (slot_i = i + running max of (ideal_i - i)) and the forward scan of
+// nd_idx_lookup, replayed on the host with the same nd_idx_slice / nd_idx_ideal: every key is found, absent keys are not, slices
+// partition the key range monotonically, nothing leaves the pad.
+static int selftest_idx()
+{
+    unsigned long long st = 0x9E3779B97F4A7C15ULL;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    long bad = 0;
+    const int cfgs[][3] = { {30, 1, 200000}, {34, 1, 300000}, {34, 4, 300000}, {38, 8, 100000}, {56, 2, 150000}, {22, 3, 50000}, {34, 1, 3}, {34, 5, 7} };
+    for (auto &cf : cfgs) {
+        const int bits = cf[0]; const uint32_t ns = (uint32_t)cf[1]; const size_t n = (size_t)cf[2];
+        const nd_u64 range = 1ULL << bits, key_mul = ~0ULL / range;
+        std::vector<nd_u64> keys(n);
+        for (auto &k : keys) { k = rnd() % range; if (cf[0] != 56) { nd_u64 m = rnd() % range; k = k < m ? k : m; m = rnd() % range; k = k < m ? k : m; } k = nd_idx_mix(k, bits); }   // skewed like minimizers (minimum of three), then mixed
+        std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        std::vector<std::vector<nd_u64>> per(ns);
+        uint32_t prev = 0;
+        for (nd_u64 k : keys) { uint32_t sl = nd_idx_slice(k, key_mul, ns); if (sl < prev || sl >= ns) ++bad; prev = sl; per[sl].push_back(k); }
+        size_t mx = 0; for (auto &v : per) mx = std::max(mx, v.size());
+        const nd_u64 cap = ((nd_u64)(mx / 0.70) + 64 + 7) & ~7ULL, pad = 4096, slots = cap + pad;
+        std::vector<nd_u64> tab((size_t)ns * slots, ND_U64_MAX);
+        for (uint32_t sl = 0; sl < ns; ++sl) {
+            nd_i64 run = -(1LL << 62);
+            for (size_t i = 0; i < per[sl].size(); ++i) {
+                nd_i64 d = (nd_i64)nd_idx_ideal(per[sl][i], key_mul, ns, cap) - (nd_i64)i;
+                if (i && nd_idx_ideal(per[sl][i], key_mul, ns, cap) < nd_idx_ideal(per[sl][i - 1], key_mul, ns, cap)) ++bad;   // monotone inside a slice
+                run = d > run ? d : run;
+                nd_u64 slot = (nd_u64)((nd_i64)i + run);
+                if (slot >= slots - 1) { ++bad; continue; }
+                tab[(size_t)sl * slots + slot] = per[sl][i];
+            }
+        }
+        auto find = [&](nd_u64 k) -> bool {
+            const uint32_t sl = nd_idx_slice(k, key_mul, ns);
+            size_t s = (size_t)sl * slots + nd_idx_ideal(k, key_mul, ns, cap);
+            for (;; ++s) { if (tab[s] >= k) return tab[s] == k; }
+        };
+        for (nd_u64 k : keys) if (!find(k)) ++bad;
+        for (int q = 0; q < 200000; ++q) { nd_u64 k = rnd() % range; bool in = std::binary_search(keys.begin(), keys.end(), k); if (find(k) != in) ++bad; }
+    }
+    printf("idx bad=%ld\n", bad);
+    return bad != 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc == 2 && !strcmp(argv[1], "selftest_idx")) return selftest_idx();
     if (argc == 2 && !strcmp(argv[1], "selftest_n")) return selftest_n();
     if (argc < 3) { fprintf(stderr, "usage: hd_harness reads.2bit preset [max_reads] [chunk]\n"); return 2; }
     ndo_reads *R = ndo_read_2bit(argv[1]);

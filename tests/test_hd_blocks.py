@@ -28,3 +28,9 @@ def test_ambiguous_bases_chunked_sketch(harness):
     """1500 random sequences with N runs x 6 (w,k,hpc) settings: chunked state machine with the 1-bit mask == oracle"""
     out = subprocess.run([harness, "selftest_n"], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr
+
+
+def test_ordered_index_table(harness):
+    """placement rule of k_index_place + forward scan of nd_idx_lookup replayed on the host: hits, misses, slices, pad"""
+    out = subprocess.run([harness, "selftest_idx"], capture_output=True, text=True)
+    assert out.returncode == 0 and "idx bad=0" in out.stdout, out.stdout + out.stderr

@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- overlaps/s (+ aligned Gbp/s) of the read-overlap hot path on synthetic 20 kb ONT reads.
 
-Workload = BASELINE.json configs[1]: 100k synthetic 20 kb ONT reads (15 % error: 5 % sub, 4 % ins,
-6 % del), `-x ava-ont -k 17 -w 10`, self-overlap, .ovl step-1 records.  The index over all reads is
-built once (reported separately); a *step* maps one query batch of `--batch-reads` reads against it.
+Workload = BASELINE.json configs[1]: 100k synthetic 20 kb ONT reads (15 % error: 5 % sub, 4 % ins, 6 % del, 40x depth),
+`--step 1 -x ava-ont -k 17 -w 10`, self-overlap, .ovl records.  The index over all reads is built once (reported separately);
+a *step* maps one query batch of `--batch-reads` reads (3000 reads = 60 Mbp, the reference's `-K 60M` mini-batch) against it.
+Step i maps reads [i*B, (i+1)*B) of the set, in file order -- both arms time the SAME batches.
 
-  value : whole-job overlaps/s with the step's query batch already resident in HBM (kernels only,
-          CUDA events on the launching stream, max over ranks)
-  e2e   : the same through ndg_map_batch() with HOST buffers: H2D of the packed reads, all kernels,
-          D2H of the hits and the host-side .ovl encoding inside the timed region
-  roofline : dominant kernel of the step (largest accumulated device time), algorithmic bytes per
-          DESIGN.md / SURVEY.md 8(d) divided by its event-timed duration, against MEASURED_PEAKS.json
-  cpu_baseline : the unmodified reference (oracle/_ref/minimap2-nd, SSE path) on the box's host
-          cores, on a bounded sample of the same workload (same read model and depth, smaller genome)
+  value : whole-job overlaps/s with the step's query batch already resident in HBM (all kernels of the step, one CUDA-event pair
+          per step on the launching stream, max over ranks)
+  e2e   : the same through ndg_map_batch_ovl() with HOST (pinned) buffers: H2D of the packed reads, all kernels incl. the output
+          stage, D2H of the .ovl bytes inside the timed region
+  roofline : dominant kernel of the step (largest accumulated device time): algorithmic bytes per DESIGN.md / SURVEY.md 8(d)
+          divided by its event-timed duration, against MEASURED_PEAKS.json; traffic = ncu dram bytes from profiles/ (same workload)
+  cpu_baseline : the unmodified reference (oracle/_ref/minimap2-nd) on the box's host cores mapping the first batches of the same
+          set against the same 100k-read index (mapping phase, from its own stderr timestamps)
 
-`--impl reference` times that reference binary as the measured arm.
-N > 1: one process per GPU (torchrun), NCCL all-gather of the target sketches at start-up, then
-independent per-GPU query batches (no data-path collective): weak scaling.
+`--impl reference` times that reference binary as the measured arm: one process, index over the same reads, the same W+K batches
+as queries with `-K 60M` so that its mini-batches are the steps; per-step times are the differences of its
+`[M::worker_pipeline] mapped` timestamps (its 3-stage pipeline included).
+N > 1 (torchrun, one process per GPU): WEAK scaling -- the read set and the genome grow with N (N x 100k reads, depth fixed), each
+rank sketches its own 100k reads, the index is built sharded (all-to-all by minimizer range, 1/N of the sort per rank, slices
+all-gathered: engine.build_index_sharded) and replicated, then every rank maps batches of its OWN reads against the full index
+with no data-path collective.  Read names are interleaved over ranks (rank r owns ids r, r+N, ...) so that the name-order rule of
+MM_F_NO_DUAL gives every rank statistically identical work.
 """
 import argparse
 import json
@@ -48,7 +54,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=100000, help="reads in the index (configs[1]: 100k)")
     ap.add_argument("--batch-reads", type=int, default=3000, help="query reads per step")
     ap.add_argument("--sub-batch-mbp", type=int, default=64, help="device sub-batch limit in Mbp (a step must fit one sub-batch)")
-    ap.add_argument("--cpu-sample-reads", type=int, default=20000)
+    ap.add_argument("--cpu-batches", type=int, default=4, help="batches the cpu_baseline leg maps (same index, same batches as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="1,1")
     ap.add_argument("--no-ksw", action="store_true", help="skip the regime-B (ksw_extd2) kernel measurement")
@@ -103,39 +109,52 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_reads(n, genome_bp, first=0):
+def make_reads(n, genome_bp, first=0, rank=0, world=1):
+    """reads first..first+n of the seeded set; with world > 1 the j-th read of rank r is NAMED j*world + r (names interleave over
+    ranks; file order = rank blocks), world = 1 gives names first.."""
     from nextdenovo_b200 import synth
+    from nextdenovo_b200.formats import name_keys, x31_hash
     g = synth.genome(genome_bp, SEED)
-    return synth.reads(g, n, READ_LEN, seed=SEED, first=first, **ERR)
+    r = synth.reads(g, n, READ_LEN, seed=SEED, first=first, **ERR)
+    if world > 1:
+        r.ids = (np.arange(n, dtype=np.uint64) * world + rank).astype(np.uint32)
+        r.name_key, r.name_hash = name_keys(r.ids), x31_hash(r.ids)
+    return r
 
 
-def run_reference(reads, threads):
-    """Run the unmodified reference binary on `reads` (self-overlap, config-1 options).  Returns
-    (records, sum_qspan, mapping_seconds, total_seconds)."""
+def run_reference(reads, n_batches, B, threads, keep=None):
+    """The unmodified reference binary: index over `reads`, queries = the first n_batches*B reads of the same set with `-K` such
+    that its mini-batches are exactly the GPU arm's steps.  Returns per-batch (records, sum_qspan) arrays, the timestamps of its
+    `mapped` lines (one per batch, printed by the ordered output stage), the timestamp of the index line, and the process time."""
     import nextdenovo_b200 as nd
     exe = os.path.join(ROOT, "oracle", "_ref", "minimap2-nd")
     if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/minimap2-nd missing (build() makes it when /root/reference is present)")
-    with tempfile.TemporaryDirectory() as td:
-        p = os.path.join(td, "s.2bit")
-        nd.write_2bit(p, reads)
-        out = os.path.join(td, "s.ovl")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    with tempfile.TemporaryDirectory(dir=base) as td:
+        tp, qp, out = os.path.join(td, "t.2bit"), os.path.join(td, "q.2bit"), os.path.join(td, "o.ovl")
+        nd.write_2bit(tp, reads)
+        nd.write_2bit(qp, reads.slice(0, min(reads.n, n_batches * B)))
         t0 = time.time()
-        r = subprocess.run([exe, "--step", "1", "-t", str(threads), "-I", "100G", "-x", "ava-ont", "-k", "17", "-w", "10", p, p, "-o", out],
+        r = subprocess.run([exe, "--step", "1", "-t", str(threads), "-I", "100G", "-K", str(B * READ_LEN), "-x", "ava-ont", "-k", "17", "-w", "10", tp, qp, "-o", out],
                            stderr=subprocess.PIPE, text=True, check=True)
         total = time.time() - t0
-        t_idx = t_map = None
+        t_idx, t_map = None, []
         for line in r.stderr.splitlines():
             m = re.match(r"\[M::mm_idx_stat::([0-9.]+)\*", line)
-            if m:
+            if m and t_idx is None:
                 t_idx = float(m.group(1))
-            m = re.match(r"\[M::worker_pipeline::([0-9.]+)\*", line)
+            m = re.match(r"\[M::worker_pipeline::([0-9.]+)\*[0-9.]+\] mapped (\d+) sequences", line)
             if m:
-                t_map = float(m.group(1))
-        d = nd.decode_ovl8(open(out, "rb").read())
-        recs = d.shape[0]
-        sq = int((d[:, 3].astype(np.int64) - d[:, 2].astype(np.int64)).sum())
-    return recs, sq, (t_map - t_idx) if (t_idx is not None and t_map is not None) else total, total
+                t_map.append(float(m.group(1)))
+        raw = open(out, "rb").read()
+        if keep is not None:
+            keep.append(raw)
+        d = nd.decode_ovl8(raw)
+    bi = (d[:, 0].astype(np.int64) // B)
+    rec = np.bincount(bi, minlength=n_batches)[:n_batches]
+    sq = np.bincount(bi, weights=(d[:, 3].astype(np.int64) - d[:, 2].astype(np.int64)), minlength=n_batches)[:n_batches]
+    return rec, sq, t_map, t_idx, total
 
 
 def usable_cpus():
@@ -229,11 +248,6 @@ def step2_bench(eng, engine_mod, with_reference=True):
     return out
 
 
-def cpu_sample(n):
-    genome_bp = max(int(n * READ_LEN / DEPTH), 200000)
-    return make_reads(n, genome_bp), "%d reads x %d bp at %dx depth (genome %d bp), self-overlap, mapping phase only" % (n, READ_LEN, DEPTH, genome_bp)
-
-
 def ksw_cells(qlen, tlen, w):
     """in-band DP cells of one ksw_extd2 call (ref band rule: minimap2/ksw2_extd2_sse.c:128-133)"""
     r = np.arange(qlen + tlen - 1)
@@ -304,30 +318,59 @@ def ksw_bench(eng, n_calls=20000, L=413, seed=SEED):
     return out
 
 
+def workload_desc(a, world=1):
+    return "configs[1]: %d synthetic %d bp ONT reads (sub/ins/del %.0f/%.0f/%.0f %%, %dx depth), -x ava-ont -k 17 -w 10, self-overlap step 1" \
+        % (a.reads * world, READ_LEN, 100 * ERR["sub"], 100 * ERR["ins"], 100 * ERR["dele"], DEPTH)
+
+
 def main_reference(a, rank, world):
+    """Reference arm: same reads, same index, same batches as the GPU arm at N=1 (rank 0 only; other ranks exit)."""
     if rank != 0:
         return
     threads = usable_cpus()
-    reads, desc = cpu_sample(a.cpu_sample_reads)
-    rec = sq = 0
-    tsum = 0.0
-    for i in range(a.warmup + a.steps):
-        r, s, tm, _ = run_reference(reads, threads)
-        if i >= a.warmup:
-            rec += r; sq += s; tsum += tm
-    v = rec / tsum
+    B = a.batch_reads
+    nb = a.warmup + a.steps
+    if nb * B > a.reads:
+        raise SystemExit("warmup+steps batches exceed the read set")
+    reads = make_reads(a.reads, int(a.reads * READ_LEN / DEPTH))
+    rec, sq, t_map, t_idx, total = run_reference(reads, nb, B, threads)
+    if len(t_map) != nb:
+        raise SystemExit("reference printed %d batch lines, expected %d" % (len(t_map), nb))
+    t_prev = t_map[a.warmup - 1] if a.warmup > 0 else t_idx
+    tsum = t_map[nb - 1] - t_prev
+    nrec, nsq = int(rec[a.warmup:nb].sum()), int(sq[a.warmup:nb].sum())
+    v = nrec / tsum
+    sample = "%d batches x %d reads of the same set against the same %d-read index, -t %d, mapping phase (differences of the binary's own " \
+             "`mapped` timestamps, 3-stage pipeline included); process %.1f s incl. index %.1f s" % (a.steps, B, a.reads, threads, total, t_idx)
     line = {"metric": "overlaps/sec", "value": v, "unit": "overlaps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * tsum / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "impl": "reference",
-            "aligned_gbp_per_s": sq / tsum / 1e9,
-            "config": {"workload": "configs[1] sample: " + desc, "options": "--step 1 -x ava-ont -k 17 -w 10"},
-            "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": desc},
+            "aligned_gbp_per_s": nsq / tsum / 1e9, "reads_per_s": a.steps * B / tsum, "query_gbp_per_s": a.steps * B * READ_LEN / tsum / 1e9,
+            "config": {"workload": workload_desc(a), "batch_reads_per_step": B, "options": "--step 1 -x ava-ont -k 17 -w 10 -K %d" % (B * READ_LEN)},
+            "work": {"records": nrec, "sum_qspan": nsq},
+            "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+def ncu_traffic(a, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest profiles/r*_traffic.json whose workload matches
+    (written from an `ncu --set full` capture of this same command; see profiles/)."""
+    import glob
+    best = {}
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+        try:
+            t = json.load(open(p))
+            if t.get("reads") == a.reads and t.get("batch_reads") == B:
+                best = {k: (float(v), os.path.basename(p)) for k, v in t.get("kernels", {}).items()}
+        except Exception:  # noqa: BLE001
+            pass
+    return best
+
+
 def main_ours(a, rank, world, local_rank):
+    import hashlib
     import torch
     import nextdenovo_b200 as nd
     from nextdenovo_b200 import engine
@@ -340,11 +383,16 @@ def main_ours(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     hbm_peak, peak_kind = peaks()
+    B = a.batch_reads
+    nb = a.warmup + a.steps
+    if nb * B > a.reads:
+        raise SystemExit("warmup+steps = %d batches of %d reads exceed the %d-read set" % (nb, B, a.reads))
 
-    # ---- workload ---------------------------------------------------------------------------
-    genome_bp = int(a.reads * READ_LEN / DEPTH)
+    # ---- workload: N x 100k reads over a genome that grows with N (depth fixed); rank r owns reads [r*100k, (r+1)*100k) of the
+    # seeded set, named r, r+N, r+2N, ... (see the module docstring)
+    genome_bp = int(a.reads * world * READ_LEN / DEPTH)
     t0 = time.time()
-    reads = make_reads(a.reads, genome_bp)
+    reads = make_reads(a.reads, genome_bp, first=rank * a.reads, rank=rank, world=world)
     t_gen = time.time() - t0
     io, mo = nd.IdxOpt(), nd.MapOpt()
     nd.set_opt("ava-ont", io, mo)
@@ -355,26 +403,22 @@ def main_ours(a, rank, world, local_rank):
     sv, cv = [int(x) for x in a.variant.split(",")]
     eng.set_variant(sv, cv)
 
-    # ---- index: each rank sketches 1/world of the targets, NCCL all-gather, identical table everywhere
+    # ---- index
     torch.cuda.synchronize(dev)
+    idx_t = {}
+    if dist is not None:
+        dist.barrier()
     t0 = time.time()
     if world == 1:
         stat = eng.build_index(reads)
     else:
-        stat = engine.build_index_sharded(eng, reads, rank, world, dist, torch)
+        meta = [((np.arange(a.reads, dtype=np.uint64) * world + r).astype(np.uint32), np.full(a.reads, READ_LEN, dtype=np.uint32)) for r in range(world)]
+        stat = engine.build_index_sharded(eng, reads, rank, world, dist, torch, meta=meta, timings=idx_t)
     torch.cuda.synchronize(dev)
     t_index = time.time() - t0
 
-    # ---- query shards (no data-path collective).  Weak scaling needs every rank to do statistically identical
-    # work; with MM_F_NO_DUAL the number of records a read yields depends on where its *name* sorts (strcmp on
-    # decimal strings), so contiguous id ranges are not comparable.  Each rank therefore maps its own copy of the
-    # same K batches (rank r starts r batches further into the list, so ranks never work on the same batch at the
-    # same time).
-    nb = a.warmup + a.steps
-    B = a.batch_reads
     eng.set_limits(a.sub_batch_mbp << 20, 0)
-    base_batches = [reads.slice((i * B) % max(reads.n - B, 1), (i * B) % max(reads.n - B, 1) + B) for i in range(nb)]
-    batches = base_batches[:a.warmup] + [base_batches[a.warmup + (i + rank) % a.steps] for i in range(a.steps)]
+    batches = [reads.slice(i * B, (i + 1) * B) for i in range(nb)]
 
     def barrier():
         if dist is not None:
@@ -392,18 +436,15 @@ def main_ours(a, rank, world, local_rank):
     t_dev_ms = 0.0
     rec = sq = n_mz = n_a = n_hits = 0
     state = np.zeros(2, dtype=np.uint32)
+    h_res = hashlib.md5()
     for i in range(a.warmup, nb):
         eng.map_upload(batches[i])                      # untimed: inputs resident before the timed region
         torch.cuda.synchronize(dev)
         e0 = time.perf_counter()
-        r = eng.map_resident()                          # all kernels of the step; internally event-timed per kernel
+        r = eng.map_resident()                          # all kernels of the step; one CUDA-event pair around them on the launching stream
         torch.cuda.synchronize(dev)
         t_res += time.perf_counter() - e0
         n_mz += r["n_minimizers"]; n_a += r["n_anchors"]; n_hits += r["n_hits"]; t_dev_ms += r["device_ms"]
-        hits, _ = eng.map_download()
-        out = bytearray()
-        rr, ss = eng.emit_step1(hits, batches[i], state, out)
-        rec += rr; sq += ss
     barrier()
     clocks = clk.stop()
     launches = eng.kernel_launches() - launches0
@@ -412,62 +453,87 @@ def main_ours(a, rank, world, local_rank):
 
     # ---- end-to-end timing (host buffers in page-locked memory, as the contract allows)
     pinned = [engine.PinnedReads(b) for b in batches]
-    br = dict(upload=0.0, kernels=0.0, download=0.0, emit=0.0)
-    for i in range(a.warmup, nb):                       # untimed diagnostic pass: where the e2e time goes
-        b = pinned[i].reads
-        t1 = time.perf_counter(); eng.map_upload(b); t2 = time.perf_counter(); eng.map_resident(); t3 = time.perf_counter()
-        hits, _ = eng.map_download(); t4 = time.perf_counter()
-        out = bytearray(); eng.emit_step1(hits, b, state, out); t5 = time.perf_counter()
-        br["upload"] += t2 - t1; br["kernels"] += t3 - t2; br["download"] += t4 - t3; br["emit"] += t5 - t4
     for i in range(a.warmup):                           # warm-up of the end-to-end path itself
         eng.map_batch_ovl(pinned[i].reads, state)
+    state[:] = 0
     barrier()
     t_e2e = 0.0
-    rec_e = 0
+    rec_e = sq_e = 0
     h2d = d2h = 0
     e2e_steps = []
+    h_e2e = hashlib.md5()
     for i in range(a.warmup, nb):
         b = pinned[i].reads
         t1 = time.perf_counter()
         data, st_e = eng.map_batch_ovl(b, state)          # H2D, all kernels incl. the output stage, D2H of the .ovl bytes
-        t_e2e += time.perf_counter() - t1
-        e2e_steps.append(round(1e3 * (time.perf_counter() - t1), 3))
-        rec_e += st_e["records"]
+        dt = time.perf_counter() - t1
+        t_e2e += dt
+        e2e_steps.append(round(1e3 * dt, 3))
+        rec_e += st_e["records"]; sq_e += st_e["sum_qspan"]
         h2d += b.words.nbytes + b.word_off.nbytes + b.length.nbytes + b.name_key.nbytes + b.name_hash.nbytes + b.ids.nbytes
         d2h += len(data)
+        h_e2e.update(data)
     barrier()
+    rec, sq = rec_e, sq_e                               # the records of the timed batches (the resident pass maps the same batches)
+
+    # ---- the whole read set of this rank, end to end, in file order (untimed region; reported beside the headline)
+    state[:] = 0
+    h_all = hashlib.md5()
+    all_rec = all_sq = 0
+    first_bytes = []
+    t1 = time.perf_counter()
+    for i in range(0, reads.n, B):
+        data, st_e = eng.map_batch_ovl(reads.slice(i, min(i + B, reads.n)), state)
+        all_rec += st_e["records"]; all_sq += st_e["sum_qspan"]
+        h_all.update(data)
+        if i // B < a.cpu_batches:
+            first_bytes.append(data)
+    t_all = time.perf_counter() - t1
 
     # ---- reduce over ranks: total units / max time
     t_res_dev = t_dev_ms / 1e3                      # one CUDA-event pair around each step on the launching stream (gaps included)
     if dist is not None:
-        tt = torch.tensor([t_res_dev, t_e2e, t_res], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([t_res_dev, t_e2e, t_res, t_index, t_all], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cc = torch.tensor([rec, sq, rec_e, launches], dtype=torch.float64, device="cuda")
+        cc = torch.tensor([rec, sq, launches, all_rec, n_mz, n_a, n_hits], dtype=torch.float64, device="cuda")
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        t_res_dev, t_e2e, t_res = [float(x) for x in tt.tolist()]
-        rec, sq, rec_e, launches = [int(x) for x in cc.tolist()]
+        t_res_dev, t_e2e, t_res, t_index, t_all = [float(x) for x in tt.tolist()]
+        rec, sq, launches, all_rec, n_mz, n_a, n_hits = [int(x) for x in cc.tolist()]
 
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:
-        # dominant kernel + roofline (algorithmic bytes: DESIGN.md "Kernels and rooflines")
-        top = max(prof.items(), key=lambda kv: kv[1][0])
-        bytes_per = {"chain_fill_warp": 32 * n_a, "chain_fill_seq": 32 * n_a, "sort_level": 32 * n_a, "sort_seq": 32 * n_a,
-                     "sort_perm": 32 * n_a, "chain_backtrack": 16 * n_a + 56 * n_hits, "sketch": READ_LEN / 4 * B * a.steps + 16 * n_mz,
-                     "probe_count": 32 * n_mz + 8 * n_a, "fill_anchors": 16 * n_mz + 8 * n_a + 16 * n_a}
-        alg = float(bytes_per.get(top[0], 32 * n_a))
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the ncu --set full capture
-        # profiles/r01d_chain_fill_warp_ncu_full_raw.csv (65.36 MB + 21.61 MB); only quoted for that kernel and that workload
-        ncu_traffic = {"chain_fill_warp": 86.97e6} if (a.reads == 100000 and B == 3000) else {}
+        # dominant kernel + roofline.  Algorithmic bytes per kernel family, for the K timed steps of all ranks:
+        L_bytes = READ_LEN / 4 * B * a.steps * world
+        n_ovl = rec
+        bytes_per = {"sketch_fast": L_bytes + 16 * n_mz, "sketch": L_bytes + 16 * n_mz, "sketch_compact": 32 * n_mz,
+                     "probe_count": 32 * n_mz + 8 * n_a, "fill_anchors": 16 * n_mz + 8 * n_a + 16 * n_a,
+                     "sort_level": 32 * n_a, "sort_seq": 32 * n_a, "sort_init": 16 * n_a,
+                     "chain_fill_warp": 32 * n_a, "chain_fill_seq": 32 * n_a, "chain_backtrack": 16 * n_a + 56 * n_hits,
+                     "hit_order": 2 * 56 * n_hits, "emit": 56 * n_hits + 13 * n_ovl}
+        step_bytes = L_bytes + 32 * n_mz + 88 * n_a + 13 * n_ovl          # B_A of SURVEY 8(d), whole step
+        top = max(((k, v) for k, v in prof.items() if k in bytes_per), key=lambda kv: kv[1][0])
+        alg = float(bytes_per[top[0]]) / world          # per rank: prof[] holds this rank's kernel times
+        tr = ncu_traffic(a, B)
         achieved = alg / (top[1][0] / 1e3) / 1e9 if top[1][0] > 0 else 0.0
+        per_kernel = {k: {"ms_per_step": round(v[0] / a.steps, 4), "launches_per_step": v[1] / a.steps,
+                          "alg_GBps": round(bytes_per[k] / world / (v[0] / 1e3) / 1e9, 1) if k in bytes_per and v[0] > 0 else None,
+                          "frac": round(bytes_per[k] / world / (v[0] / 1e3) / 1e9 / hbm_peak, 4) if k in bytes_per and v[0] > 0 else None,
+                          "ncu_dram_bytes_per_launch": tr.get(k, (None,))[0]}
+                      for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[0] > 0}
         cpu = None
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:
             try:
-                sample, desc = cpu_sample(a.cpu_sample_reads)
                 threads = usable_cpus()
-                r_, s_, tm, tot = run_reference(sample, threads)
-                cpu = {"value": r_ / tm, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": desc,
-                       "aligned_gbp_per_s": s_ / tm / 1e9, "mapping_s": tm, "process_s": tot}
+                keep = []
+                r_rec, r_sq, t_map, t_idx, tot = run_reference(reads, a.cpu_batches, B, threads, keep=keep)
+                tm = t_map[-1] - t_idx
+                mine_bytes = b"".join(first_bytes)
+                cpu = {"value": float(r_rec.sum()) / tm, "unit": "overlaps/s", "cores": threads, "kind": "reference",
+                       "sample": "first %d batches x %d reads of the same set against the same %d-read index, mapping phase from the binary's own timestamps"
+                                 % (a.cpu_batches, B, a.reads),
+                       "aligned_gbp_per_s": float(r_sq.sum()) / tm / 1e9, "mapping_s": tm, "process_s": tot, "index_s": t_idx,
+                       "ovl_bytes_identical_to_gpu": keep[0] == mine_bytes, "ovl_bytes": len(keep[0])}
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": "overlaps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % ex}
         ksw = None
@@ -493,24 +559,30 @@ def main_ours(a, rank, world, local_rank):
             "metric": "overlaps/sec", "value": rec / t_res_dev, "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * t_res_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "aligned_gbp_per_s": sq / t_res_dev / 1e9,
-            "config": {"workload": "configs[1]: %d synthetic %d bp ONT reads (sub/ins/del %.0f/%.0f/%.0f %%, %dx depth), -x ava-ont -k 17 -w 10, self-overlap step 1"
-                                   % (a.reads, READ_LEN, 100 * ERR["sub"], 100 * ERR["ins"], 100 * ERR["dele"], DEPTH),
-                       "batch_reads_per_step": B, "parallelism": "query-sharded x%d, index replicated (all-gather of sketches)" % world,
-                       "l2": "per-step working set (index %.1f GB + anchors) exceeds L2; each step maps a different batch" % (stat["n_minimizers"] * 8 / 1e9),
+            "aligned_gbp_per_s": sq / t_res_dev / 1e9, "reads_per_s": a.steps * B * world / t_res_dev, "query_gbp_per_s": a.steps * B * world * READ_LEN / t_res_dev / 1e9,
+            "config": {"workload": workload_desc(a, world), "batch_reads_per_step": B,
+                       "parallelism": "query-sharded x%d (each rank maps its own reads), index replicated, built sharded (all-to-all by minimizer range + all-gather of slices)" % world,
+                       "l2": "per-step working set (index table %.1f GB + anchors) exceeds L2; every step maps a different batch" % (stat["n_distinct"] / 0.7 * 16 / 1e9),
                        "kernel_variant": a.variant},
-            "e2e": {"value": rec_e / t_e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
-                    "ms_per_step": 1e3 * t_e2e / a.steps, "step_ms": e2e_steps, "breakdown_ms_per_step": {k: round(1e3 * v / a.steps, 3) for k, v in br.items()}},
+            "e2e": {"value": rec / t_e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
+                    "ms_per_step": 1e3 * t_e2e / a.steps, "step_ms": e2e_steps, "ovl_md5_timed_batches_rank0": h_e2e.hexdigest()},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic.get(top[0]), "algorithmic_bytes_per_launch": alg / a.steps, "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps,
-                         "note": "integer DP / hashing kernels: issue- and latency-bound, not HBM-bound (ncu: profiles/r01_summary.md)"},
+                         "traffic": tr.get(top[0], (None,))[0], "traffic_source": tr.get(top[0], (None, None))[1],
+                         "algorithmic_bytes_per_launch": alg / top[1][1] if top[1][1] else None, "launches_per_step": top[1][1] / a.steps,
+                         "peak_kind": peak_kind, "kernel_ms_per_step": top[1][0] / a.steps,
+                         "whole_step": {"algorithmic_bytes_per_step": step_bytes / world / a.steps, "achieved": step_bytes / world / t_res_dev / 1e9,
+                                        "frac": step_bytes / world / t_res_dev / 1e9 / hbm_peak},
+                         "note": "integer DP / hashing kernels: issue- and latency-bound, not HBM-bound (ncu: profiles/)"},
             "cpu_baseline": cpu,
             "kernel_sum_ms_per_step": dev_ms / a.steps,
             "work": {"records": rec, "sum_qspan": sq, "minimizers": n_mz, "anchors": n_a, "hits": n_hits, "host_wall_resident_s": t_res},
-            "kernels_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
-            "index": {"build_s": t_index, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"]},
+            "kernels": per_kernel,
+            "whole_set": {"reads": a.reads * world, "records": all_rec, "seconds_e2e_max_rank": t_all, "overlaps_per_s": all_rec / t_all,
+                          "reads_per_s": a.reads * world / t_all, "ovl_md5_rank0": h_all.hexdigest()},
+            "index": {"build_s": t_index, "stages_s_rank0": idx_t, "n_minimizers": stat["n_minimizers"], "n_distinct": stat["n_distinct"], "mid_occ": stat["mid_occ"],
+                      "table_GB": stat["n_distinct"] / 0.7 * 16 / 1e9, "positions_GB": stat["n_minimizers"] * 8 / 1e9},
             "gen_s": t_gen,
             "ksw2_extd2": ksw,
             "regime_b": rb,

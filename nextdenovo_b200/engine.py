@@ -178,6 +178,7 @@ class Engine:
         if rc != 0:
             raise NdgError("ndg_init(device=%d) failed with %d: no usable sm_100 GPU (no CPU fallback exists)" % (device, rc))
         self.h = h
+        self.device = device
         self.io, self.mo = IdxOpt(), MapOpt()
         self.targets = None
         self.stat = None
@@ -525,6 +526,84 @@ def build_index_sharded(eng: Engine, mine: Reads, rank, world, dist, torch, meta
     if timings is not None:
         timings.update(sketch_s=t1 - t0, exchange_s=t2 - t1, sort_place_s=t3 - t2, gather_s=t4 - t3)
     return eng.stat
+
+
+def build_index_sharded_local(engs, parts, torch):
+    """The same N-way build with the N contexts living in ONE process (any mix of devices): the collectives become device-to-device
+    copies between the contexts' buffers.  This is what `bin/minimap2-nd --gpus N` does in C++ (peer copies); here it lets the whole
+    ndg_index_shard_* sequence be exercised on a single GPU (two contexts on device 0).  parts[r] = the reads of "rank" r."""
+    world = len(engs)
+    L = engs[0].L
+
+    def view(ptr, n, e):
+        return torch.as_tensor(_DevView(ptr, n), device=torch.device("cuda", e.device))
+
+    keep = []
+    for r, e in enumerate(engs):
+        e._ck(L.ndg_index_begin(e.h))
+        for j in range(world):
+            if j == r:
+                s = _reads_struct(parts[j]); keep.append(s)
+                e._ck(L.ndg_index_add(e.h, C.byref(s)))
+            else:
+                s = _meta_struct(parts[j].ids, parts[j].length); keep.append(s)
+                e._ck(L.ndg_index_add_meta(e.h, C.byref(s)))
+    cm = np.zeros((world, world), dtype=np.uint64)
+    for r, e in enumerate(engs):
+        row = np.zeros(world, dtype=np.uint64)
+        e._ck(L.ndg_index_shard_split(e.h, world, _ptr(row)))
+        cm[r] = row
+    for j, e in enumerate(engs):                         # "all-to-all": rank j receives bucket j of every rank, in rank order
+        _, out_split, total = shard_exchange_plan(cm, j)
+        rk, rv = C.c_void_p(), C.c_void_p()
+        e._ck(L.ndg_index_shard_recv_reserve(e.h, total, C.byref(rk), C.byref(rv)))
+        at = 0
+        for r, src in enumerate(engs):
+            kp, vp, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+            src._ck(L.ndg_index_shard_bucket(src.h, j, C.byref(kp), C.byref(vp), C.byref(n)))
+            if n.value:
+                view(rk.value + 8 * at, n.value, e).copy_(view(kp.value, n.value, src))
+                view(rv.value + 8 * at, n.value, e).copy_(view(vp.value, n.value, src))
+            at += n.value
+        assert at == total
+    torch.cuda.synchronize()
+    nds = []
+    for e in engs:
+        nd_ = C.c_uint64()
+        e._ck(L.ndg_index_shard_sort(e.h, C.byref(nd_)))
+        nds.append(nd_.value)
+    hist = np.zeros(65536, dtype=np.uint64)
+    for r, e in enumerate(engs):
+        hr = np.zeros(65536, dtype=np.uint32)
+        e._ck(L.ndg_index_shard_place(e.h, r, max(nds), _ptr(hr)))
+        hist += hr
+    npos = np.ascontiguousarray(cm.sum(axis=0).astype(np.uint64))
+    slices, segs = [], []
+    for r, e in enumerate(engs):
+        sp, sb = C.c_void_p(), C.c_uint64()
+        e._ck(L.ndg_index_shard_table_slice(e.h, 0, C.byref(sp), C.byref(sb)))
+        slices.append((sp.value, sb.value))
+        sg = (C.c_void_p * world)()
+        e._ck(L.ndg_index_shard_pos_reserve(e.h, r, _ptr(npos), sg))
+        segs.append([sg[j] for j in range(world)])
+    for r, e in enumerate(engs):                         # "all-gather": everybody fetches slice j / segment j from rank j
+        for j, src in enumerate(engs):
+            if j == r:
+                continue
+            w = slices[j][1] // 8
+            view(slices[r][0] + j * slices[r][1], w, e).copy_(view(slices[j][0] + j * slices[j][1], w, src))
+            if int(npos[j]):
+                view(segs[r][j], int(npos[j]), e).copy_(view(segs[j][j], int(npos[j]), src))
+    torch.cuda.synchronize()
+    h32 = np.ascontiguousarray(hist.astype(np.uint32))
+    stats = []
+    for e in engs:
+        stt = _IndexStat()
+        e._ck(L.ndg_index_shard_finish(e.h, _ptr(h32), int(sum(nds)), C.byref(stt)))
+        e.targets = None
+        e.stat = dict(n_seq=stt.n_seq, n_minimizers=stt.n_minimizers, n_distinct=stt.n_distinct, n_singletons=stt.n_singletons, sum_len=stt.sum_len, mid_occ=stt.mid_occ)
+        stats.append(e.stat)
+    return stats
 
 
 def index_parts(targets: Reads, io: IdxOpt):

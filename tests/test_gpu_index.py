@@ -1,0 +1,155 @@
+"""Index and multi-GPU parity (run on the B200 box: pytest -m gpu), through the C ABI.
+  * ndg_index_get == the reference's mm_idx_get semantics (count + ascending positions), checked against a dictionary built from the
+    oracle's sketch of every target;
+  * the N-way sharded build (ndg_index_shard_*), exercised in one process with two contexts on one GPU: mapping against the index
+    built in two halves gives the golden bytes on BOTH contexts, and the index statistics equal the single-context build;
+  * the same over NCCL with one process per GPU (torch.distributed) when the box has >= 2 GPUs;
+  * advisor findings: a borrower of a shared index that calls set_options() keeps mapping correctly (mid_occ is re-derived);
+  * the host emit path (ndg_map_batch + ndg_ovl_emit_step1) gives the same bytes as the device output stage."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _opts(preset="ava-ont", k=None, w=None):
+    import nextdenovo_b200 as nd
+    io, mo = nd.IdxOpt(), nd.MapOpt()
+    nd.set_opt(preset, io, mo)
+    if k: io.k = k
+    if w: io.w = w
+    mo.step, mo.minlen = 1, 500
+    return io, mo
+
+
+def _seq(reads, r):
+    from nextdenovo_b200.formats import unpack_bases
+    w0, w1 = int(reads.word_off[r]), int(reads.word_off[r + 1])
+    return bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[unpack_bases(reads.words[w0:w1], int(reads.length[r]))])
+
+
+def test_index_get_matches_sketch_dictionary(engine_mod, reads_sub):
+    """ref: minimap2/index.c:81-98 (mm_idx_get): n and the position list (ascending, index.c:230) of a minimizer"""
+    from oracle import oracle
+    io, mo = _opts()
+    e = engine_mod.Engine(0)
+    try:
+        e.set_options(io, mo)
+        sub = reads_sub.slice(0, 40)
+        e.build_index(sub)
+        d = {}
+        for r in range(sub.n):
+            for x, y in oracle.sketch(_seq(sub, r), io.w, io.k, rid=r):
+                d.setdefault(int(x) >> 8, []).append(int(y))
+        keys = sorted(d)
+        rng = np.random.default_rng(7)
+        pick = [keys[i] for i in rng.integers(0, len(keys), 300)] + [k for k in keys if len(d[k]) > 3][:50]
+        for k in pick:
+            pos, n = e.index_get(k)
+            assert n == len(d[k]) and pos.tolist() == sorted(d[k]), "minimizer %x" % k
+        for k in rng.integers(0, 1 << 30, 200):
+            if int(k) not in d:
+                assert e.index_get(int(k))[1] == 0
+        assert e.stat["n_distinct"] == len(keys) and e.stat["n_minimizers"] == sum(len(v) for v in d.values())
+    finally:
+        e.close()
+
+
+def test_host_emit_path_equals_device_emit(engine_mod, reads_sub, golden_dir):
+    io, mo = _opts()
+    e = engine_mod.Engine(0)
+    try:
+        ovl, st = engine_mod.run_step1(e, reads_sub, reads_sub, io, mo, device_emit=False)
+        assert ovl == open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+    finally:
+        e.close()
+
+
+def test_borrower_set_options_after_share_keeps_mid_occ(engine_mod, reads_sub, golden_dir):
+    """advisor r1: ndg_set_opt() after ndg_index_share() used to zero mid_occ and drop every seed silently"""
+    io, mo = _opts()
+    a, b = engine_mod.Engine(0), engine_mod.Engine(0)
+    try:
+        a.set_options(io, mo); b.set_options(io, mo)
+        a.build_index(reads_sub)
+        b.share_index_of(a)
+        b.set_options(io, mo)                               # after the share
+        st = np.zeros(2, dtype=np.uint32)
+        assert b.map_batch_ovl(reads_sub, st)[0] == open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+        with pytest.raises(engine_mod.NdgError):             # a borrower must not build over the owner's buffers
+            b._ck(b.L.ndg_index_finalize(b.h, None))
+    finally:
+        b.close(); a.close()
+
+
+def test_mapping_without_cutoff_is_an_error(engine_mod, reads_sub):
+    e = engine_mod.Engine(0)
+    try:
+        with pytest.raises(engine_mod.NdgError):
+            e.map_batch(reads_sub)                           # no index: NDG_ERR_STATE, never an empty result
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("preset,gold,cut", [("ava-ont", "S1_sub120_ava-ont.ovl", 60), ("ava-pb", "S3_sub120_ava-pb.ovl", 35)])
+def test_sharded_build_two_contexts_one_gpu(engine_mod, reads_sub, golden_dir, preset, gold, cut):
+    """ndg_index_shard_split/bucket/recv_reserve/sort/place/table_slice/pos_reserve/finish with N = 2: each context sketches one part
+    of the targets and builds one key range of the table; both end with the full index (same statistics as a one-context build) and
+    map to the golden bytes."""
+    import torch
+    io, mo = _opts(preset)
+    a, b, c = engine_mod.Engine(0), engine_mod.Engine(0), engine_mod.Engine(0)
+    try:
+        for e in (a, b, c):
+            e.set_options(io, mo)
+        want_stat = c.build_index(reads_sub)
+        stats = engine_mod.build_index_sharded_local([a, b], [reads_sub.slice(0, cut), reads_sub.slice(cut, reads_sub.n)], torch)
+        for s in stats:
+            for k in ("n_seq", "n_minimizers", "n_distinct", "n_singletons", "mid_occ"):
+                assert s[k] == want_stat[k], k
+        want = open(os.path.join(golden_dir, gold), "rb").read()
+        for e in (a, b):
+            st = np.zeros(2, dtype=np.uint32)
+            assert e.map_batch_ovl(reads_sub, st)[0] == want
+    finally:
+        for e in (a, b, c):
+            e.close()
+
+
+def test_sharded_build_nccl_two_gpus(built, golden_dir, tmp_path):
+    """one process per GPU, torch.distributed over NCCL (engine.build_index_sharded): every rank maps all queries against the index it
+    assembled and must produce the single-GPU golden bytes; bench.py --gpus N uses exactly this path"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, hashlib
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import nextdenovo_b200 as nd
+from nextdenovo_b200 import engine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+reads = nd.read_2bit(os.path.join(%r, "reads_test.seed.2bit"))
+io, mo = nd.IdxOpt(), nd.MapOpt(); nd.set_opt("ava-ont", io, mo); mo.step, mo.minlen = 1, 500
+e = engine.Engine(rank); e.set_options(io, mo)
+b = engine.shard_bounds(reads.n, world)
+st = engine.build_index_sharded(e, reads.slice(b[rank], b[rank + 1]), rank, world, dist, torch)
+state = np.zeros(2, dtype=np.uint32)
+ovl = e.map_batch_ovl(reads, state)[0]
+print("RESULT", rank, hashlib.md5(ovl).hexdigest(), st["n_distinct"], st["mid_occ"], flush=True)
+e.close(); dist.destroy_process_group()
+''' % (ROOT, golden_dir))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29600 + os.getpid() % 300), str(script)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = [l.split() for l in r.stdout.splitlines() if l.startswith("RESULT")]
+    assert len(res) == 2
+    for x in res:
+        assert x[2] == "9fce14e8841db2e46012c58ad8f0059c" and x[3] == "6273819" and x[4] == "74", x     # G1 of SURVEY 8(c)

@@ -173,6 +173,21 @@ def test_step1_cigar_sub120(eng, engine_mod, reads_sub, golden_dir, preset, gold
     assert s["n_chains"] > 7000 and s["n_calls"] > 300000 and s["n_launches"] >= s["n_rounds"]
 
 
+def test_g4_full_cigar_cli(built, golden_dir, tmp_path):
+    """The north star's parity target: `--step 1 -c -x ava-ont` on all 997 reads of test_data/reads_test.fa.gz must give the reference's
+    133,100 records byte for byte (ref: minimap2/align.c:565-913 + ksw2_extd2_sse.c on 5.6 M DP calls)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "reads_test.seed.2bit")
+    out = str(tmp_path / "g4.ovl")
+    r = subprocess.run([exe, "--step", "1", "-c", "-x", "ava-ont", src, src, "-o", out], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = open(out, "rb").read()
+    want = open(os.path.join(golden_dir, "G4_ava-ont_c.ovl"), "rb").read()
+    assert hashlib.md5(want).hexdigest() == "4c7e852512ee6fb463b37a0ce20926b7"
+    assert got == want, _diff_msg(got, want)
+
+
 def test_cli_cigar_matches_reference_bytes(built, golden_dir, tmp_path):
     """bin/minimap2-nd --step 1 -c: same bytes as the reference binary (golden S6)"""
     import subprocess

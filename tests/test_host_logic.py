@@ -133,3 +133,38 @@ def test_decode_ovl10_matches_ovl_cvt(golden_dir):
         txt = subprocess.run([cvt, "-m", "1", f], capture_output=True, text=True).stdout
         b = np.array([[int(x) for x in line.split("\t")] for line in txt.strip().split("\n")], dtype=np.uint32)
         assert (a == b).all()
+
+
+def test_option_grammar_is_the_references():
+    """unknown options are an error (ref: minimap2/main.c:186-188), options that are not built are refused by name, attached and
+    bundled short forms parse as with ketopt"""
+    from nextdenovo_b200 import options
+    import pytest as _pt
+    with _pt.raises(ValueError, match="unknown option"):
+        options.parse_args("--step 1 -x ava-ont --bogus a b -o x".split())
+    with _pt.raises(ValueError, match="unknown option"):
+        options.parse_args("--step 1 -x ava-ont -J a b -o x".split())
+    for bad in ("-a", "--cs", "--splice", "--sr"):
+        with _pt.raises(ValueError, match="not built"):
+            options.parse_args(("--step 1 -x ava-ont %s a b -o x" % bad).split())
+    io, mo, out, pos = options.parse_args("--step=1 -cxava-ont -k17 -w 10 --min-count 4 --mb-size 60M a b -ox.ovl".split())
+    assert (io.k, io.w, mo.min_cnt, mo.mini_batch_size, out, pos) == (17, 10, 4, 60000000, "x.ovl", ["a", "b"])
+    assert mo.flag & options.MM_F_CIGAR and mo.flag & options.MM_F_ALL_CHAINS
+    io, mo, out, pos = options.parse_args("--step 1 -k 15 a b -o x".split())       # no preset: not all-chain
+    assert not mo.flag & options.MM_F_ALL_CHAINS
+
+
+def test_cli_rejects_what_it_does_not_implement(tmp_path):
+    """bin/minimap2-nd fails with status 1 before touching a GPU: unknown option, missing all-chain mode, PAF/SAM output"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bin", "minimap2-nd")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    for args, msg in ((["--step", "1", "-x", "ava-ont", "--bogus", "a", "b", "-o", "x"], "unknown option"),
+                      (["--step", "1", "-k", "15", "a", "b", "-o", str(tmp_path / "x")], "all-chain"),
+                      (["--step", "1", "-x", "ava-ont", "-a", "a", "b", "-o", "x"], "not built"),
+                      (["--step", "1", "-x", "ava-ont", "a", "b", "-o"], "missing option argument")):
+        r = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)

@@ -14,6 +14,7 @@
 #include "nd_kernels.cuh"
 #include "nd_warp.cuh"
 #include "nd_ksw.cuh"
+#include "nd_kswrx.cuh"
 #include "nd_align.hpp"
 #include "nd_step2.hpp"
 #include <omp.h>
@@ -1154,6 +1155,62 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
     return NDG_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// register-resident ksw_extd2 (nd_kswrx.cuh): which ring a call needs, padded sequence layout, launch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+const int RX_NCFG = 5;
+const int RX_CAP[RX_NCFG] = { 512, 1024, 2048, 3072, 4096 };       // 128 * K * NW: (4,1) (4,2) (4,4) (6,4) (8,4)
+const int RX_NW[RX_NCFG] = { 1, 2, 4, 4, 4 };
+#define NDX_FLAG_AMBI 0x10000
+
+// ring class of a call, or -1 when the register-resident kernel does not take it (generic scoring, band wider than every ring)
+inline int rx_class(int qlen, int tlen, int w, int flag)
+{
+    if (flag & NDK_GENERIC_SC) return -1;
+    if (qlen <= 0 || tlen <= 0) return 0;
+    const int T = (tlen + 15) / 16 * 16;
+    if (w < 0) w = std::max(qlen, tlen);
+    for (int i = 0; i < RX_NCFG; ++i) if (T <= RX_CAP[i] || (long long)w + 66 <= RX_CAP[i]) return i;
+    return -1;
+}
+
+// bytes a call occupies in the padded layout (>= 32 zero bytes before the query, >= 48 after query and target, 4-byte aligned starts)
+inline uint64_t rx_seq_bytes(int qlen, int tlen) { return 32 + (((uint64_t)qlen + 3) & ~3ull) + 48 + (((uint64_t)tlen + 3) & ~3ull) + 48; }
+inline void rx_seq_offsets(uint64_t base, int qlen, uint64_t *q_off, uint64_t *t_off) { *q_off = base + 32; *t_off = base + 32 + (((uint64_t)qlen + 3) & ~3ull) + 48; }
+
+template <int K, int NW, bool EX>
+cudaError_t rx_launch_t(int blocks_per_sm_hint, int n_sm, cudaStream_t st, const ndk_call *calls, int n, const uint8_t *seqs, const ndk_par &P, ndk_res *res, uint8_t *pmat,
+                        uint32_t *cig, unsigned long long *rowtabs, size_t tab_entries, uint32_t *work, unsigned long long *cur, unsigned long long arena_bytes, int *blocks_out)
+{
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ksw_rx<K, NW, EX>, NW * 32, 0);
+    if (occ < 1) occ = 1;
+    if (blocks_per_sm_hint > 0 && occ > blocks_per_sm_hint) occ = blocks_per_sm_hint;
+    int blocks = std::min(n, n_sm * occ);
+    if (blocks_out) { *blocks_out = n_sm * occ; return cudaSuccess; }            // query only: how many row tables a launch may need
+    k_ksw_rx<K, NW, EX><<<blocks, NW * 32, 0, st>>>(calls, n, seqs, P, res, pmat, cig, rowtabs, tab_entries, work, cur, arena_bytes);
+    return cudaGetLastError();
+}
+
+cudaError_t rx_launch(int cfg, bool exact, int hint, int n_sm, cudaStream_t st, const ndk_call *calls, int n, const uint8_t *seqs, const ndk_par &P, ndk_res *res, uint8_t *pmat,
+                      uint32_t *cig, unsigned long long *rowtabs, size_t tab_entries, uint32_t *work, unsigned long long *cur, unsigned long long arena_bytes, int *blocks_out = nullptr)
+{
+#define RXL(K, NW) (exact ? rx_launch_t<K, NW, true>(hint, n_sm, st, calls, n, seqs, P, res, pmat, cig, rowtabs, tab_entries, work, cur, arena_bytes, blocks_out) \
+                          : rx_launch_t<K, NW, false>(hint, n_sm, st, calls, n, seqs, P, res, pmat, cig, rowtabs, tab_entries, work, cur, arena_bytes, blocks_out))
+    switch (cfg) {
+    case 0: return RXL(4, 1);
+    case 1: return RXL(4, 2);
+    case 2: return RXL(4, 4);
+    case 3: return RXL(6, 4);
+    default: return RXL(8, 4);
+    }
+#undef RXL
+}
+
+} // namespace
 
 // ------------------------------------------------------------------------------------------------
 // regime B: base-level alignment.  Host logic in nd_align.hpp; every DP call runs in k_ksw_extd2_px.

@@ -94,7 +94,7 @@ struct ndg_ctx {
     ndg_opt_t opt;
     std::string err;
     uint64_t sub_batch_bases = 64ull << 20, max_anchors = 0;
-    int sort_variant = 1, chain_variant = 1, ksw_variant = 1;
+    int sort_variant = 1, chain_variant = 1, ksw_variant = 3;   // ksw: 0 scalar, 1 packed memory-resident, 2 block-per-call, 3 register-resident (nd_kswrx.cuh)
     int chunk_bases = 512;
     int n_sm = 148;
     void *hk_scope = nullptr;
@@ -1224,12 +1224,14 @@ struct DpLaunch {
     DevBuf calls, seqs, res, cig, scratch, ncig, coff, cout, tmp, cur;
     cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr, e0 = nullptr, e1 = nullptr;
     std::vector<ndk_call> hc; std::vector<uint32_t> ids;
+    struct Grp { int cfg; bool exact; size_t begin, count; };      // register-resident kernel: calls [begin, begin+count) share a ring size / maximum mode
+    std::vector<Grp> rx; DevBuf rxtab; size_t n_legacy = 0;
     size_t n = 0, nb = 0; uint64_t seqb = 0, cig_cap = 0, fixed = 0, ext_need = 0;
     int Tmax = 16, rmax = 1, qmax = 1;
     bool busy = false;
     void release() {
         h_seq.release(); h_res.release(); h_cig.release(); h_off.release();
-        DevBuf *d[] = { &calls, &seqs, &res, &cig, &scratch, &ncig, &coff, &cout, &tmp, &cur };
+        DevBuf *d[] = { &calls, &seqs, &res, &cig, &scratch, &ncig, &coff, &cout, &tmp, &cur, &rxtab };
         for (auto x : d) x->release();
         if (st) { cudaStreamDestroy(st); cudaStreamDestroy(st2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(e0); cudaEventDestroy(e1); st = nullptr; }
     }
@@ -1238,6 +1240,7 @@ struct DpLaunch {
 struct GpuDp : ndal::Backend {
     ndg_ctx *c; ndk_par P; int rc = 0;
     DpLaunch L[2];
+    bool any_ambi = false;                          // some read holds an ambiguous base: the register-resident kernel takes its exact-equality score path
     double ext_frac = 1.0 / 16;                     // share of an extension's worst-case matrix that gets written (adapted from the arena cursor)
     double t_prepare = 0, t_wait = 0, t_hand = 0, t_plan = 0;   // host phases of the back end (NDG_ALN_DEBUG)
     ~GpuDp() { for (auto &l : L) l.release(); }
@@ -1250,32 +1253,62 @@ struct GpuDp : ndal::Backend {
         return ((rows + 63) / 64 * 64) * (uint64_t)ncol * 16;                 // whole 64-row chunks
     }
 
-    // host side of a launch: order the calls (wide ones first: they go to the block-per-call kernel), write the sequence bytes
+    // host side of a launch: order the calls by the kernel that takes them (block-per-call and warp-per-call memory-resident kernels
+    // first, then one group per ring size / maximum mode of the register-resident kernel), write the sequence bytes
     int prepare(DpLaunch &B, const std::vector<ndal::DpReq> &reqs, const ndal::SeqStore &T, const std::vector<uint32_t> &ids_in)
     {
         static const int coop_min = getenv("NDG_COOP_MIN") ? atoi(getenv("NDG_COOP_MIN")) : 1024;
+        const bool use_rx = c->ksw_variant == 3;
         const size_t n = ids_in.size();
-        B.ids.clear(); B.ids.reserve(n); B.nb = 0;
-        for (int pass = 0; pass < 2; ++pass)
-            for (size_t i = 0; i < n; ++i) {
-                const ndal::DpReq &k = reqs[ids_in[i]];
+        // class of a call: 0 block-per-call, 1 warp-per-call, 2 + 2*cfg + exact register-resident
+        std::vector<uint8_t> cls(n);
+        size_t cnt[2 + 2 * RX_NCFG] = { 0 };
+        for (size_t i = 0; i < n; ++i) {
+            const ndal::DpReq &k = reqs[ids_in[i]];
+            const int rc = use_rx ? rx_class(k.qlen, k.tlen, k.w, k.flag) : -1;
+            if (rc >= 0) cls[i] = (uint8_t)(2 + 2 * rc + ((k.flag & NDK_APPROX_MAX) ? 0 : 1));
+            else {
                 const int wd = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
-                const bool big = std::min(std::min(k.qlen, k.tlen), wd + 1) >= coop_min;
-                if (big == (pass == 0)) B.ids.push_back(ids_in[i]);
-                if (pass == 0 && big) ++B.nb;
+                cls[i] = std::min(std::min(k.qlen, k.tlen), wd + 1) >= coop_min ? 0 : 1;
             }
+            ++cnt[cls[i]];
+        }
+        size_t start[2 + 2 * RX_NCFG + 1]; start[0] = 0;
+        for (int g = 0; g < 2 + 2 * RX_NCFG; ++g) start[g + 1] = start[g] + cnt[g];
+        B.ids.assign(n, 0);
+        { size_t fill[2 + 2 * RX_NCFG]; for (int g = 0; g < 2 + 2 * RX_NCFG; ++g) fill[g] = start[g];
+          for (size_t i = 0; i < n; ++i) B.ids[fill[cls[i]]++] = ids_in[i]; }
+        B.nb = cnt[0]; B.n_legacy = cnt[0] + cnt[1];
+        B.rx.clear();
+        for (int g = 2; g < 2 + 2 * RX_NCFG; ++g) if (cnt[g]) B.rx.push_back(DpLaunch::Grp{ (g - 2) / 2, ((g - 2) & 1) != 0, start[g], cnt[g] });
         B.n = n; B.hc.resize(n);
         uint64_t seqb = 0, cig = 0; B.Tmax = 16; B.rmax = 1; B.qmax = 1;
         for (size_t i = 0; i < n; ++i) {
             const ndal::DpReq &k = reqs[B.ids[i]]; ndk_call &d = B.hc[i];
-            d.qlen = k.qlen; d.tlen = k.tlen; d.q_off = seqb; d.t_off = seqb + (uint64_t)k.qlen; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag;
+            d.qlen = k.qlen; d.tlen = k.tlen; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag;
+            if (i < B.n_legacy) { d.q_off = seqb; d.t_off = seqb + (uint64_t)k.qlen; seqb += (uint64_t)k.qlen + k.tlen; }
+            else {
+                seqb = (seqb + 3) & ~3ull;
+                unsigned long long qo, to; { uint64_t a, b2; rx_seq_offsets(seqb, k.qlen, &a, &b2); qo = a; to = b2; }
+                d.q_off = qo; d.t_off = to; seqb += rx_seq_bytes(k.qlen, k.tlen);
+                if (any_ambi) d.flag |= NDX_FLAG_AMBI;
+            }
             d.p_off = 0; d.cigar_off = cig;
-            seqb += (uint64_t)k.qlen + k.tlen; cig += (uint64_t)k.qlen + k.tlen + 2;
-            B.Tmax = std::max(B.Tmax, (k.tlen + 15) / 16 * 16); B.rmax = std::max(B.rmax, k.qlen + k.tlen); B.qmax = std::max(B.qmax, k.qlen);
+            cig += (uint64_t)k.qlen + k.tlen + 2;
+            if (i < B.n_legacy) { B.Tmax = std::max(B.Tmax, (k.tlen + 15) / 16 * 16); B.qmax = std::max(B.qmax, k.qlen); }
+            B.rmax = std::max(B.rmax, k.qlen + k.tlen);
         }
         B.seqb = seqb; B.cig_cap = cig;
         if (B.h_seq.reserve(seqb + 64)) return fail(c, NDG_ERR_NOMEM, "pinned sequence staging");
         uint8_t *hs = B.h_seq.as<uint8_t>();
+        if (n > B.n_legacy) {                           // zero padding of the register-resident layout
+            const uint64_t z0 = B.hc[B.n_legacy].q_off - 32;
+#pragma omp parallel for schedule(static)
+            for (long long blk = 0; blk < (long long)((seqb + 64 - z0 + (1 << 20) - 1) >> 20); ++blk) {
+                const uint64_t b0 = z0 + ((uint64_t)blk << 20), b1 = std::min<uint64_t>(b0 + (1 << 20), seqb + 64);
+                memset(hs + b0, 0, (size_t)(b1 - b0));
+            }
+        }
 #pragma omp parallel for schedule(dynamic, 256)
         for (long long i = 0; i < (long long)n; ++i) ndal::materialize(reqs[B.ids[(size_t)i]], T, hs + B.hc[(size_t)i].q_off, hs + B.hc[(size_t)i].t_off);
         return 0;
@@ -1290,19 +1323,19 @@ struct GpuDp : ndal::Backend {
             CK(cudaEventCreateWithFlags(&B.ev_a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&B.ev_b, cudaEventDisableTiming));
             CK(cudaEventCreate(&B.e0)); CK(cudaEventCreate(&B.e1));
         }
-        RSV(B.calls, n * sizeof(ndk_call)); RSV(B.seqs, B.seqb + 64); RSV(B.res, n * sizeof(ndk_res));
+        RSV(B.calls, n * sizeof(ndk_call)); RSV(B.seqs, B.seqb + 128); RSV(B.res, n * sizeof(ndk_res));
         RSV(B.cig, (B.cig_cap + 4) * 4); RSV(B.cur, 256);
         RSV(B.ncig, (n + 1) * 4); RSV(B.coff, (n + 1) * 8);
         if (B.h_off.reserve((n + 2) * 8) || B.h_res.reserve(n * sizeof(ndk_res))) return fail(c, NDG_ERR_NOMEM, "pinned result staging");
         CK(cudaMemcpyAsync(B.calls.p, B.hc.data(), n * sizeof(ndk_call), cudaMemcpyHostToDevice, B.st));
-        CK(cudaMemcpyAsync(B.seqs.p, B.h_seq.p, B.seqb, cudaMemcpyHostToDevice, B.st));
+        CK(cudaMemcpyAsync(B.seqs.p, B.h_seq.p, B.seqb + (B.n > B.n_legacy ? 64 : 0), cudaMemcpyHostToDevice, B.st));
         return 0;
     }
 
     // enqueue the kernels of a launch; the arena must be free (previous launch's kernels finished)
     int submit_kernels(DpLaunch &B, uint8_t *arena, uint64_t arena_bytes)
     {
-        const size_t n = B.n, nb = B.nb, ns = n - nb;
+        const size_t n = B.n, nb = B.nb, ns = B.n_legacy - nb;
         const size_t state_bytes = ((size_t)17 * B.Tmax + ((size_t)(B.qmax + 15) / 16 + 1) * 16 + 96 + 255) / 256 * 256;
         const size_t h_bytes = ((size_t)4 * B.Tmax + 255) / 256 * 256, off_bytes = ((size_t)8 * B.rmax + 255) / 256 * 256;
         const size_t tab_bytes = ((size_t)8 * ((size_t)(B.rmax >> 6) + 2) + 255) / 256 * 256;
@@ -1315,7 +1348,7 @@ struct GpuDp : ndal::Backend {
         DevBuf &scr = c->ksw_scratch;
         unsigned long long *d_cur = B.cur.as<unsigned long long>();           // [0] arena cursor, [1] two work counters
         uint32_t *d_work = reinterpret_cast<uint32_t *>(d_cur + 1);
-        CK(cudaMemsetAsync(d_cur, 0, 16, B.st));
+        CK(cudaMemsetAsync(d_cur, 0, 256, B.st));
         CK(cudaEventRecord(B.e0, B.st));
         if (nb) {                                   // second stream: both kernels share the SMs and the arena
             CK(cudaEventRecord(B.ev_a, B.st));
@@ -1331,6 +1364,24 @@ struct GpuDp : ndal::Backend {
                               arena, B.cig.as<uint32_t>(), scr.as<uint8_t>() + (size_t)cblocks * slot_bytes, slot_bytes, state_bytes, h_bytes, d_work, d_cur, arena_bytes, off_bytes);
             CK(cudaGetLastError());
             ++c->launches;
+        }
+        if (!B.rx.empty()) {                        // register-resident kernel: one launch per ring size / maximum mode, all sharing the arena
+            const size_t tab_entries = (size_t)(B.rmax >> 6) + 2;
+            std::vector<int> nblk_of(B.rx.size()); size_t tot_blocks = 0;
+            for (size_t g = 0; g < B.rx.size(); ++g) {
+                int cap = 0;
+                rx_launch(B.rx[g].cfg, B.rx[g].exact, 0, c->n_sm, B.st, nullptr, 0, nullptr, P, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &cap);
+                nblk_of[g] = (int)std::min<size_t>((size_t)cap, B.rx[g].count); tot_blocks += (size_t)nblk_of[g];
+            }
+            RSV(B.rxtab, tot_blocks * tab_entries * 8 + 64);
+            size_t tb = 0;
+            for (size_t g = 0; g < B.rx.size(); ++g) {
+                const DpLaunch::Grp &G = B.rx[g];
+                CK(rx_launch(G.cfg, G.exact, 0, c->n_sm, B.st, B.calls.as<ndk_call>() + G.begin, (int)G.count, B.seqs.as<uint8_t>(), P, B.res.as<ndk_res>() + G.begin, arena,
+                             B.cig.as<uint32_t>(), B.rxtab.as<unsigned long long>() + tb * tab_entries, tab_entries, d_work + 2 + g, d_cur, arena_bytes));
+                tb += (size_t)nblk_of[g];
+                ++c->launches;
+            }
         }
         if (nb) CK(cudaStreamWaitEvent(B.st, B.ev_b, 0));
         CK(cudaEventRecord(B.e1, B.st));
@@ -1509,7 +1560,7 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
 
     ndal::SeqStore ST; ST.words = c->ht->words.data(); ST.word_off = c->ht->word_off.data(); ST.len = c->h_tlen.data(); ST.nmask = c->ht->has_n ? c->ht->nmask.data() : nullptr;
     ndal::SeqStore SQ; SQ.words = Q->words; SQ.word_off = Q->word_off; SQ.len = Q->len; SQ.nmask = Q->nmask;
-    GpuDp be; be.c = c;
+    GpuDp be; be.c = c; be.any_ambi = ST.nmask != nullptr || SQ.nmask != nullptr;
     be.P.m = 5; memset(be.P.mat, 0, sizeof be.P.mat); ndal::simple_mat(be.P.mat, c->aln); be.P.q = c->aln.q; be.P.e = c->aln.e; be.P.q2 = c->aln.q2; be.P.e2 = c->aln.e2;
 
     // reads are aligned in groups that bound the host memory held by one round of DP results
@@ -1867,12 +1918,101 @@ extern "C" int64_t ndg_ovl_emit_step1(const ndg_hit_t *hits, int64_t n_hits,
 // ------------------------------------------------------------------------------------------------
 static_assert(sizeof(ndg_ksw_result_t) == sizeof(ndk_res), "ksw result layout");
 
+// variant 3: every call the register-resident kernel takes goes to it (grouped by ring size and maximum mode), the rest to the
+// memory-resident kernels.  Sequences are re-materialised in the padded layout nd_kswrx.cuh expects.
+static int ksw_batch_rx(ndg_ctx *c, const ndg_ksw_call_t *calls, int32_t n, const uint8_t *seqs, uint64_t seq_bytes, const ndk_par &P,
+                        ndg_ksw_result_t *res, uint32_t *cigar, const uint64_t *cigar_off)
+{
+    struct Grp { int cfg; bool exact; std::vector<int> ids; };
+    std::vector<Grp> groups;
+    std::vector<int> legacy;
+    for (int i = 0; i < n; ++i) {
+        const ndg_ksw_call_t &k = calls[i];
+        const int cls = rx_class(k.qlen, k.tlen, k.w, k.flag);
+        if (cls < 0) { legacy.push_back(i); continue; }
+        const bool ex = !(k.flag & NDK_APPROX_MAX);
+        size_t g = 0;
+        for (; g < groups.size(); ++g) if (groups[g].cfg == cls && groups[g].exact == ex) break;
+        if (g == groups.size()) groups.push_back(Grp{ cls, ex, {} });
+        groups[g].ids.push_back(i);
+    }
+    // padded sequences + call table in group order
+    std::vector<ndk_call> hc; hc.reserve((size_t)n);
+    std::vector<int> order; order.reserve((size_t)n);
+    uint64_t sb = 0, p_total = 0;
+    for (auto &g : groups) for (int i : g.ids) { order.push_back(i); sb += rx_seq_bytes(calls[i].qlen, calls[i].tlen); }
+    std::vector<uint8_t> hs(sb + 64, 0);
+    uint64_t at = 0;
+    for (int i : order) {
+        const ndg_ksw_call_t &k = calls[i];
+        ndk_call d; memset(&d, 0, sizeof d);
+        uint64_t qo, to; rx_seq_offsets(at, k.qlen, &qo, &to);
+        if (k.qlen > 0) memcpy(hs.data() + qo, seqs + k.q_off, (size_t)k.qlen);
+        if (k.tlen > 0) memcpy(hs.data() + to, seqs + k.t_off, (size_t)k.tlen);
+        bool ambi = false;
+        for (int j = 0; j < k.qlen && !ambi; ++j) ambi = seqs[k.q_off + j] == (uint8_t)(P.m - 1);
+        for (int j = 0; j < k.tlen && !ambi; ++j) ambi = seqs[k.t_off + j] == (uint8_t)(P.m - 1);
+        d.qlen = k.qlen; d.tlen = k.tlen; d.q_off = qo; d.t_off = to; d.w = k.w; d.zdrop = k.zdrop; d.end_bonus = k.end_bonus; d.flag = k.flag | (ambi ? NDX_FLAG_AMBI : 0);
+        d.cigar_off = cigar_off[i]; d.p_off = p_total;
+        if (k.qlen > 0 && k.tlen > 0 && !(k.flag & NDK_SCORE_ONLY)) {
+            int w = k.w < 0 ? std::max(k.qlen, k.tlen) : k.w;
+            int ncol = std::min(k.qlen, k.tlen); ncol = (std::min(ncol, w + 1) + 15) / 16 + 1;
+            p_total += ((uint64_t)(k.qlen + k.tlen - 1) * ncol + 1) * 16;
+        }
+        at += rx_seq_bytes(k.qlen, k.tlen);
+        hc.push_back(d);
+    }
+    const size_t nr = order.size();
+    const uint64_t cig_total = cigar_off[n];
+    if (nr) {
+        RSV(c->ksw_calls, nr * sizeof(ndk_call)); RSV(c->ksw_seqs, sb + 64); RSV(c->ksw_res, nr * sizeof(ndk_res));
+        RSV(c->ksw_p, p_total + 64); RSV(c->ksw_cig, (cig_total + 4) * 4); RSV(c->scalars, 1024);
+        CK(cudaMemcpyAsync(c->ksw_calls.p, hc.data(), nr * sizeof(ndk_call), cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync(c->ksw_seqs.p, hs.data(), sb + 64, cudaMemcpyHostToDevice, c->st));
+        uint32_t *d_work = c->scalars.as<uint32_t>() + 128;
+        CK(cudaMemsetAsync(d_work, 0, 64, c->st));
+        size_t off = 0; int gi = 0;
+        for (auto &g : groups) {
+            KLAUNCH("ksw_extd2", CK(rx_launch(g.cfg, g.exact, 0, c->n_sm, c->st, c->ksw_calls.as<ndk_call>() + off, (int)g.ids.size(), c->ksw_seqs.as<uint8_t>(), P,
+                                              c->ksw_res.as<ndk_res>() + off, c->ksw_p.as<uint8_t>(), c->ksw_cig.as<uint32_t>(), nullptr, 0, d_work + gi, nullptr, 0)));
+            off += g.ids.size(); ++gi;
+            if (gi >= 16) return fail(c, NDG_ERR_ARG, "too many kernel groups");
+        }
+        std::vector<ndk_res> hr(nr);
+        CK(cudaMemcpyAsync(hr.data(), c->ksw_res.p, nr * sizeof(ndk_res), cudaMemcpyDeviceToHost, c->st));
+        if (cigar && cig_total) CK(cudaMemcpyAsync(cigar, c->ksw_cig.p, cig_total * 4, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        for (size_t x = 0; x < nr; ++x) memcpy(&res[order[x]], &hr[x], sizeof(ndk_res));
+    }
+    if (!legacy.empty()) {                               // generic scoring / bands wider than every ring: the memory-resident kernels
+        std::vector<ndg_ksw_call_t> lc; std::vector<uint64_t> lo(1, 0);
+        for (int i : legacy) { lc.push_back(calls[i]); lo.push_back(lo.back() + (uint64_t)calls[i].qlen + calls[i].tlen + 2); }
+        std::vector<ndg_ksw_result_t> lr(lc.size()); std::vector<uint32_t> lcg(lo.back() + 4);
+        const int keep = c->ksw_variant; c->ksw_variant = 1;
+        int8_t mat[25]; memcpy(mat, P.mat, 25);
+        int rc = ndg_ksw_extd2_batch(c, lc.data(), (int32_t)lc.size(), seqs, seq_bytes, P.m, mat, P.q, P.e, P.q2, P.e2, lr.data(), lcg.data(), lo.data());
+        c->ksw_variant = keep;
+        if (rc) return rc;
+        for (size_t x = 0; x < legacy.size(); ++x) {
+            res[legacy[x]] = lr[x];
+            if (cigar) memcpy(cigar + cigar_off[legacy[x]], lcg.data() + lo[x], (size_t)lr[x].n_cigar * 4);
+        }
+    }
+    return NDG_OK;
+}
+
 extern "C" int ndg_ksw_extd2_batch(ndg_ctx_t *c, const ndg_ksw_call_t *calls, int32_t n, const uint8_t *seqs, uint64_t seq_bytes,
                                    int32_t m, const int8_t *mat, int32_t q, int32_t e, int32_t q2, int32_t e2,
                                    ndg_ksw_result_t *res, uint32_t *cigar, const uint64_t *cigar_off)
 {
     if (!c || !calls || n <= 0 || !seqs || !mat || !res || !cigar_off || m < 2 || m > 5) return NDG_ERR_ARG;
     cudaSetDevice(c->device);
+    if (c->ksw_variant == 3) {
+        ndk_par P; P.m = m; memset(P.mat, 0, sizeof P.mat); memcpy(P.mat, mat, (size_t)m * m); P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
+        for (int i = 0; i < n; ++i) if (calls[i].qlen < 0 || calls[i].tlen < 0 || calls[i].q_off + (uint64_t)calls[i].qlen > seq_bytes || calls[i].t_off + (uint64_t)calls[i].tlen > seq_bytes)
+            return fail(c, NDG_ERR_ARG, "ksw call %d out of range", i);
+        return ksw_batch_rx(c, calls, n, seqs, seq_bytes, P, res, cigar, cigar_off);
+    }
     std::vector<ndk_call> hc((size_t)n);
     uint64_t p_total = 0; int Tmax = 16, rmax = 1, qmax = 1;
     for (int i = 0; i < n; ++i) {

@@ -201,9 +201,10 @@ def test_cli_cigar_matches_reference_bytes(built, golden_dir, tmp_path):
     assert "DP calls" in r.stderr
 
 
-@pytest.mark.parametrize("ksw_variant", [1, 2])
+@pytest.mark.parametrize("ksw_variant", [1, 2, 3])
 def test_ksw_extd2_wide_bands_bit_exact(eng, ksw_variant):
-    """long calls with wide bands through the warp-per-call (1) and the block-per-call (2) kernels == the reference function"""
+    """long calls with wide bands through the warp-per-call (1), the block-per-call (2) and the register-resident (3: rings of 3072/4096 columns,
+    sliding bands, fallback for bands wider than every ring) kernels == the reference function"""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from ksw_cases import simple_mat, oracle_lib, oracle_call, ref_lib, ref_call, wide_cases
@@ -217,7 +218,7 @@ def test_ksw_extd2_wide_bands_bit_exact(eng, ksw_variant):
         chunks += [qs, ts]; off += len(qs) + len(ts)
     eng.set_ksw_variant(ksw_variant)
     res, cigs = eng.ksw_extd2_batch(calls, np.concatenate(chunks), mat, 4, 2, 24, 1)
-    eng.set_ksw_variant(1)
+    eng.set_ksw_variant(3)
     L, R = oracle_lib(), ref_lib()
     names = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end")
     bad = []
@@ -229,7 +230,7 @@ def test_ksw_extd2_wide_bands_bit_exact(eng, ksw_variant):
     assert not bad, "%d/%d calls differ; first: %s" % (len(bad), len(cases), bad[:3])
 
 
-@pytest.mark.parametrize("ksw_variant", [1, 0, 2])
+@pytest.mark.parametrize("ksw_variant", [1, 0, 2, 3])
 def test_ksw_extd2_batch_bit_exact(eng, ksw_variant):
     """ndg_ksw_extd2_batch == ksw_extd2_sse (via the oracle restatement, and the compiled reference when present):
     score, max, end points, z-drop flag, reach_end and CIGAR, for every call of a mixed batch."""
@@ -247,7 +248,7 @@ def test_ksw_extd2_batch_bit_exact(eng, ksw_variant):
     seqs = np.concatenate(chunks)
     eng.set_ksw_variant(ksw_variant)
     res, cigs = eng.ksw_extd2_batch(calls, seqs, mat, 4, 2, 24, 1)
-    eng.set_ksw_variant(1)
+    eng.set_ksw_variant(3)
     L, R = oracle_lib(), ref_lib()
     names = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end")
     bad = []

@@ -2,8 +2,9 @@
 // ref: minimap2/ksw2_extd2_sse.c:1-394, ksw2.h:119-176.  Same observable behaviour as nd_ksw.cuh (16-cell band rounding with stale
 // state, score blocks spilling into the target copy, SIMD tie order of the exact maximum), different execution model:
 //
-//   * a target column is OWNED by a lane: column t lives at ring position t mod CAP (CAP = 128*K*NW columns), warp = pos / (128K),
-//     slot = (pos / 128) mod K, lane = (pos / 4) mod 32, four consecutive columns per lane and slot.  The state of a column
+//   * a target column is OWNED by a lane: column t lives at ring position t mod CAP (CAP = 128*K*NW columns); 128 consecutive
+//     positions form a slot, slot s belongs to warp s mod NW (register set s / NW), lane = (pos / 4) mod 32, four consecutive
+//     columns per lane and slot.  (Interleaving the slots over the warps spreads a narrow band evenly.)  The state of a column
 //     (u v x y x2 y2, its score s, its target base, the 32-bit H of the exact-maximum mode) never leaves that lane's registers: no
 //     per-cell memory traffic at all except the one backtrack byte.  A band wider than the target fits as it is; a band narrower
 //     than the target slides over the ring (a lane recycles its four columns once they are 16 cells left of the band).
@@ -15,7 +16,8 @@
 //     because the tags are ordered accordingly), and the "gap continues" flags come out of the same VIMNMX that clamps at zero
 //     (a one-bit tag survives iff the candidate won);
 //   * NW warps share one alignment; they meet once per anti-diagonal (one barrier), exchanging through shared memory the x/v/x2
-//     of their last column, their part of the exact maximum and the few H / u / v values the scalar bookkeeping needs.
+//     of every slot's last column (the left neighbour of the next slot), their part of the exact maximum and the few H / u / v
+//     values the scalar bookkeeping needs.  Small K keeps the kernel under 128 registers (4+ warps per scheduler).
 // Not handled here (routed to the memory-resident kernels of nd_ksw.cuh): KSW_EZ_GENERIC_SC, bands wider than the ring.
 #pragma once
 #include "nd_ksw.cuh"
@@ -25,7 +27,7 @@
 #define NDX_HNEG (-0x40000000)
 
 struct ndx_smem {
-    unsigned bx[8], bv[8], bx2[8];            // per warp: (c1,c3) registers of x, v, x2 in lane 31 of its last slot (the left neighbour of the next warp)
+    unsigned bx[32], bv[32], bx2[32];         // per slot: (c1,c3) registers of x, v, x2 in its lane 31 (the left neighbour of the next slot's first column)
     int wmax[8]; unsigned wrank[8];           // exact mode: per-warp maximum of 16*H over [st0,en0] and the smallest SIMD rank attaining it
     int h_en0, h_en0m1, h_st0, h_last;        // exact mode: 16*H of columns en0, en0-1, st0, tlen-1 after this diagonal
     int d0, d1, pad0, pad1;                   // approximate mode: new v of column last_H0_t, new u of column last_H0_t + 1
@@ -123,11 +125,12 @@ __device__ int ndx_backtrack(bool is_rev, bool right, const uint8_t *p, const un
 // Sequence layout expected here (the host re-materialises calls for this kernel): query and target start 4-byte aligned, at least 32
 // zero bytes precede the query and at least 48 zero bytes follow both the query and the target.
 template <int K, int NW, bool EXACT>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32))
 k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk_res *res, uint8_t *pmat, uint32_t *cigars,
          unsigned long long *rowtabs, size_t tab_entries, uint32_t *work, unsigned long long *arena_cur, unsigned long long arena_bytes)
 {
-    constexpr int CAP = 128 * K * NW;
+    constexpr int SLOTS = K * NW, CAP = 128 * SLOTS;
+    static_assert(SLOTS <= 32, "ring too large for the exchange record");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gtid = threadIdx.x;
     __shared__ ndx_smem xch[2];
     __shared__ unsigned long long s_o;
@@ -196,13 +199,13 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
             slow_n = slow_n || (flag & 0x10000) != 0;           // host-set: the call contains an ambiguous base
             const unsigned M1 = ndx_rep(m - 1);
 
-            // ---- state -------------------------------------------------------------------------------------------------------------
+            // ---- state: register set k of this warp is slot k * NW + wid -------------------------------------------------------------
             unsigned U[K][2], V[K][2], X[K][2], Y[K][2], X2[K][2], Y2[K][2], S[K][2], TG[K];
             int t0[K];
             int Hh[EXACT ? K : 1][4];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                t0[k] = (wid * K + k) * 128 + 4 * lane;
+                t0[k] = (k * NW + wid) * 128 + 4 * lane;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     U[k][h] = V[k][h] = ndx_rep(I1); X[k][h] = ndx_rep(I1 + tA); Y[k][h] = ndx_rep(I1 + tB);
@@ -213,7 +216,8 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
             }
             if (gtid < 2) {
                 ndx_smem &x = xch[gtid];
-                for (int i = 0; i < 8; ++i) { x.bx[i] = ndx_rep(I1 + tA); x.bv[i] = ndx_rep(I1); x.bx2[i] = ndx_rep(I2 + tA2); x.wmax[i] = NDX_HNEG; x.wrank[i] = 0xffffffffu; }
+                for (int i = 0; i < 32; ++i) { x.bx[i] = ndx_rep(I1 + tA); x.bv[i] = ndx_rep(I1); x.bx2[i] = ndx_rep(I2 + tA2); }
+                for (int i = 0; i < 8; ++i) { x.wmax[i] = NDX_HNEG; x.wrank[i] = 0xffffffffu; }
                 x.h_en0 = x.h_en0m1 = x.h_st0 = x.h_last = NDX_HNEG; x.d0 = x.d1 = 0;
             }
             sync();
@@ -245,30 +249,37 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                 if (st > 0) { patch = !(st - 1 >= last_st && st - 1 <= last_en); bX = I1 + tA; bV = I1; bX2 = I2 + tA2; }
                 else { patch = true; bX = I1 + tA; bV = 16 * vb + NDX_B; bX2 = I2 + tA2; }
 
-                // the left neighbour of this warp's first column: lane 31 of the previous warp's last slot, previous diagonal
-                unsigned wrapX, wrapV, wrapX2;
-                if (NW == 1) { wrapX = X[K - 1][1]; wrapV = V[K - 1][1]; wrapX2 = X2[K - 1][1]; }
-                else { const int pw = (wid + NW - 1) % NW; wrapX = xo.bx[pw]; wrapV = xo.bv[pw]; wrapX2 = xo.bx2[pw]; }
+                if (ring) {                                                          // columns that fell 16 cells behind the band for good: recycle
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (t0[k] + 3 < st - 16 && t0[k] + CAP < T) {
+                            t0[k] += CAP;
+                            U[k][0] = U[k][1] = V[k][0] = V[k][1] = ndx_rep(I1); X[k][0] = X[k][1] = ndx_rep(I1 + tA); Y[k][0] = Y[k][1] = ndx_rep(I1 + tB);
+                            X2[k][0] = X2[k][1] = ndx_rep(I2 + tA2); Y2[k][0] = Y2[k][1] = ndx_rep(I2 + tB2); S[k][0] = S[k][1] = S_0;
+                            TG[k] = *reinterpret_cast<const uint32_t *>(target + t0[k]);
+                            if (EXACT) { Hh[k][0] = Hh[k][1] = Hh[k][2] = Hh[k][3] = NDX_HNEG; }
+                        }
+                }
+                // first row: y, y2, u of column r (:153-156) -- one lane of one warp, applied inside the slot loop below
+                int fr_k = -1, fr_j = 0;
+                if (en >= r) {
+                    const int pos = r % CAP, sl = pos >> 7;
+                    if (sl % NW == wid && ((pos >> 2) & 31) == lane) { fr_k = sl / NW; fr_j = pos & 3; }
+                }
 
-                int lmax = NDX_HNEG; unsigned lrank = 0xffffffffu;                   // exact mode: this lane's best 16*H and its rank
+                int lmax = NDX_HNEG;                                                 // exact mode: this lane's best 16*H over [st0, en0]
                 const int en1 = st0 + (en0 - st0) / 4 * 4;
                 const int qidx_base = r - 3;
+                const unsigned band_w = (unsigned)(en - st), live_w = (unsigned)(live_hi + 3 - st0);
 
 #pragma unroll
-                for (int k = K - 1; k >= 0; --k) {
-                    if (ring && t0[k] + 3 < st - 16 && t0[k] + CAP < T) {            // these four columns are behind the band for good: recycle
-                        t0[k] += CAP;
-                        U[k][0] = U[k][1] = V[k][0] = V[k][1] = ndx_rep(I1); X[k][0] = X[k][1] = ndx_rep(I1 + tA); Y[k][0] = Y[k][1] = ndx_rep(I1 + tB);
-                        X2[k][0] = X2[k][1] = ndx_rep(I2 + tA2); Y2[k][0] = Y2[k][1] = ndx_rep(I2 + tB2); S[k][0] = S[k][1] = S_0;
-                        TG[k] = *reinterpret_cast<const uint32_t *>(target + t0[k]);
-                        if (EXACT) { Hh[k][0] = Hh[k][1] = Hh[k][2] = Hh[k][3] = NDX_HNEG; }
-                    }
+                for (int k = 0; k < K; ++k) {
                     const int tt = t0[k];
-                    const bool act = tt >= st && tt <= en;                           // st, en are multiples of 16 (-1): all four columns or none
-                    const bool live = tt + 3 >= st0 && tt < live_hi;                 // some column gets a fresh score
-                    // approximate mode: the lanes holding columns last_H0_t / last_H0_t + 1 hand their v / u to the bookkeeping (:361-371)
-                    const bool pub0 = !EXACT && (unsigned)(last_H0_t - tt) < 4u, pub1 = !EXACT && (unsigned)(last_H0_t + 1 - tt) < 4u;
-                    if (!__any_sync(NDK_FULL, act || live || pub0 || pub1)) continue;
+                    if (fr_k == k) { ndx_setcol(Y[k][0], Y[k][1], fr_j, I1 + tB); ndx_setcol(Y2[k][0], Y2[k][1], fr_j, I2 + tB2); ndx_setcol(U[k][0], U[k][1], fr_j, 16 * vb + NDX_B); }
+                    const bool act = (unsigned)(tt - st) <= band_w;                  // st, en are multiples of 16 (-1): all four columns or none
+                    const bool live = (unsigned)(tt + 3 - st0) < live_w;             // some column gets a fresh score: tt+3 >= st0 && tt < live_hi
+                    if (!__any_sync(NDK_FULL, act || live)) continue;
+                    const int sl = k * NW + wid;                                     // this register set's slot
 
                     // ---- scores of this diagonal (:157-176), stale elsewhere ----------------------------------------------------------------
                     if (live) {
@@ -283,7 +294,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         if (slow_n) {
                             const unsigned e0 = __vminu2(TP0 ^ M1, 0x00010001u) & __vminu2(QP0 ^ M1, 0x00010001u);   // 0 where an operand is the ambiguity code
                             const unsigned e1 = __vminu2(TP1 ^ M1, 0x00010001u) & __vminu2(QP1 ^ M1, 0x00010001u);
-                            const unsigned k0 = (e0 ^ 0x00010001u) * 0xffffu, k1 = (e1 ^ 0x00010001u) * 0xffffu;                // 0xffff where ambiguous
+                            const unsigned k0 = (e0 ^ 0x00010001u) * 0xffffu, k1 = (e1 ^ 0x00010001u) * 0xffffu;      // 0xffff where ambiguous
                             s0 = (s0 & ~k0) | (S_N & k0); s1 = (s1 & ~k1) | (S_N & k1);
                         }
                         if (tt >= st0 && tt + 3 < live_hi) { S[k][0] = s0; S[k][1] = s1; }
@@ -295,83 +306,87 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         }
                     }
 
-                    // ---- left neighbours of (c0,c2): previous lane's (c1,c3), across slots and warps --------------------------------------------
-                    const unsigned pX = k > 0 ? X[k > 0 ? k - 1 : 0][1] : wrapX, pV = k > 0 ? V[k > 0 ? k - 1 : 0][1] : wrapV, pX2 = k > 0 ? X2[k > 0 ? k - 1 : 0][1] : wrapX2;
-                    const int src = (lane + 31) & 31;
-                    unsigned gX = __shfl_sync(NDK_FULL, lane == 31 ? pX : X[k][1], src);
-                    unsigned gV = __shfl_sync(NDK_FULL, lane == 31 ? pV : V[k][1], src);
-                    unsigned gX2 = __shfl_sync(NDK_FULL, lane == 31 ? pX2 : X2[k][1], src);
+                    // ---- left neighbours of (c0,c2): previous lane's (c1,c3); lane 0 takes what the previous slot's lane 31 published -------------------
+                    const int ps = sl == 0 ? SLOTS - 1 : sl - 1;
+                    unsigned gX = __shfl_up_sync(NDK_FULL, X[k][1], 1), gV = __shfl_up_sync(NDK_FULL, V[k][1], 1), gX2 = __shfl_up_sync(NDK_FULL, X2[k][1], 1);
+                    if (lane == 0) { gX = xo.bx[ps]; gV = xo.bv[ps]; gX2 = xo.bx2[ps]; }
                     if (act) {
-                    unsigned nX = __byte_perm(gX, X[k][1], 0x5432), nV = __byte_perm(gV, V[k][1], 0x5432), nX2 = __byte_perm(gX2, X2[k][1], 0x5432);
-                    if (tt == st && patch) {
-                        nX = (nX & 0xffff0000u) | (unsigned)bX; nV = (nV & 0xffff0000u) | (unsigned)bV; nX2 = (nX2 & 0xffff0000u) | (unsigned)bX2;
-                    }
-                    if (en >= r && (unsigned)(r - tt) < 4u) {                        // first row: y, y2, u of column r (:153-156)
-                        const int j = r - tt;
-                        ndx_setcol(Y[k][0], Y[k][1], j, I1 + tB); ndx_setcol(Y2[k][0], Y2[k][1], j, I2 + tB2); ndx_setcol(U[k][0], U[k][1], j, 16 * vb + NDX_B);
-                    }
-                    // ---- the recurrence: (c1,c3) reads the old (c0,c2) as its neighbours ---------------------------------------------------
-                    const unsigned oX = X[k][0], oV = V[k][0], oX2 = X2[k][0];
-                    unsigned D0, D1;
-                    ndx_pair(C, nX, nV, nX2, S[k][0], U[k][0], V[k][0], X[k][0], Y[k][0], X2[k][0], Y2[k][0], D0);
-                    ndx_pair(C, oX, oV, oX2, S[k][1], U[k][1], V[k][1], X[k][1], Y[k][1], X2[k][1], Y2[k][1], D1);
-                    if (with_cigar) *reinterpret_cast<uint32_t *>(prow + tt) = __byte_perm(D0, D1, 0x6240);   // bytes c0 c1 c2 c3
-
-                    // ---- bookkeeping operands ----------------------------------------------------------------------------------------------------
-                    if (EXACT) {
-                        if (r > 0) {
-                            if (tt >= st0 && tt + 3 < en0) {                         // four interior columns: H[t] += v[t] (:328-343)
-                                Hh[k][0] += ndx_lo(V[k][0]) - NDX_B; Hh[k][1] += ndx_lo(V[k][1]) - NDX_B; Hh[k][2] += ndx_hi(V[k][0]) - NDX_B; Hh[k][3] += ndx_hi(V[k][1]) - NDX_B;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int t = tt + j, h = Hh[k][j];
-                                    if (h >= lmax) {
-                                        const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2) : 1u + (4u << 20) + (unsigned)(t - en1);
-                                        if (h > lmax || rank < lrank) { lmax = h; lrank = rank; }
-                                    }
-                                }
-                            } else if (tt + 3 >= st0 && tt <= en0) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int t = tt + j;
-                                    if (t < st0 || t > en0) continue;
-                                    int h; unsigned rank;
-                                    if (t < en0) {
-                                        h = Hh[k][j] + ndx_col(V[k][0], V[k][1], j) - NDX_B;
-                                        rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2) : 1u + (4u << 20) + (unsigned)(t - en1);
-                                    } else {                                          // t == en0: H[en0] = H[en0-1] + u[en0] (old H of the left neighbour), :323
-                                        const int hl = en0 == en0_prev ? hp1 : hp0;  // column en0 - 1 after the previous diagonal
-                                        h = en0 > 0 ? hl + ndx_col(U[k][0], U[k][1], j) - NDX_B : Hh[k][j] + ndx_col(V[k][0], V[k][1], j) - NDX_B;
-                                        rank = 0;
-                                    }
-                                    Hh[k][j] = h;
-                                    if (h > lmax || (h == lmax && rank < lrank)) { lmax = h; lrank = rank; }
-                                }
-                            }
-                        } else if (tt == 0) {                                        // r == 0: H[0] = v[0] - qe (:345)
-                            Hh[k][0] = ndx_lo(V[k][0]) - NDX_B - 16 * qe0;
-                            lmax = Hh[k][0]; lrank = 0;
+                        unsigned nX = __byte_perm(gX, X[k][1], 0x5432), nV = __byte_perm(gV, V[k][1], 0x5432), nX2 = __byte_perm(gX2, X2[k][1], 0x5432);
+                        if (tt == st && patch) {
+                            nX = (nX & 0xffff0000u) | (unsigned)bX; nV = (nV & 0xffff0000u) | (unsigned)bV; nX2 = (nX2 & 0xffff0000u) | (unsigned)bX2;
                         }
-#define NDX_H4(j) ((j) == 0 ? Hh[k][0] : (j) == 1 ? Hh[k][1] : (j) == 2 ? Hh[k][2] : Hh[k][3])
-                        if ((unsigned)(en0 - tt) < 4u) { const int j = en0 - tt; xn.h_en0 = NDX_H4(j); }
-                        if (en0 > 0 && (unsigned)(en0 - 1 - tt) < 4u) { const int j = en0 - 1 - tt; xn.h_en0m1 = NDX_H4(j); }
-                        if ((unsigned)(st0 - tt) < 4u) { const int j = st0 - tt; xn.h_st0 = NDX_H4(j); }
-                        if ((unsigned)(tlen - 1 - tt) < 4u) { const int j = tlen - 1 - tt; xn.h_last = NDX_H4(j); }
-#undef NDX_H4
+                        // ---- the recurrence: (c1,c3) reads the old (c0,c2) as its neighbours ---------------------------------------------------
+                        const unsigned oX = X[k][0], oV = V[k][0], oX2 = X2[k][0];
+                        unsigned D0, D1;
+                        ndx_pair(C, nX, nV, nX2, S[k][0], U[k][0], V[k][0], X[k][0], Y[k][0], X2[k][0], Y2[k][0], D0);
+                        ndx_pair(C, oX, oV, oX2, S[k][1], U[k][1], V[k][1], X[k][1], Y[k][1], X2[k][1], Y2[k][1], D1);
+                        if (with_cigar) *reinterpret_cast<uint32_t *>(prow + tt) = __byte_perm(D0, D1, 0x6240);   // bytes c0 c1 c2 c3
+                        if (lane == 31) { xn.bx[sl] = X[k][1]; xn.bv[sl] = V[k][1]; xn.bx2[sl] = X2[k][1]; }
+
+                        // ---- exact maximum: H[t] += v[t] over [st0, en0), H[en0] from its left neighbour (:316-346); ranks are resolved after the loop
+                        if (EXACT) {
+                            if (r > 0) {
+                                if (tt >= st0 && tt + 3 < en0) {
+                                    Hh[k][0] += ndx_lo(V[k][0]) - NDX_B; Hh[k][1] += ndx_lo(V[k][1]) - NDX_B; Hh[k][2] += ndx_hi(V[k][0]) - NDX_B; Hh[k][3] += ndx_hi(V[k][1]) - NDX_B;
+                                    lmax = max(lmax, max(max(Hh[k][0], Hh[k][1]), max(Hh[k][2], Hh[k][3])));
+                                } else if (tt + 3 >= st0 && tt <= en0) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const int t = tt + j;
+                                        if (t < st0 || t > en0) continue;
+                                        int h;
+                                        if (t < en0) h = Hh[k][j] + ndx_col(V[k][0], V[k][1], j) - NDX_B;
+                                        else {                                        // t == en0: H[en0] = H[en0-1] + u[en0] (old H of the left neighbour), :323
+                                            const int hl = en0 == en0_prev ? hp1 : hp0;  // column en0 - 1 after the previous diagonal
+                                            h = en0 > 0 ? hl + ndx_col(U[k][0], U[k][1], j) - NDX_B : Hh[k][j] + ndx_col(V[k][0], V[k][1], j) - NDX_B;
+                                        }
+                                        Hh[k][j] = h;
+                                        lmax = max(lmax, h);
+                                    }
+                                }
+                            } else if (tt == 0) {                                    // r == 0: H[0] = v[0] - qe (:345)
+                                Hh[k][0] = ndx_lo(V[k][0]) - NDX_B - 16 * qe0;
+                                lmax = Hh[k][0];
+                            }
+                        }
                     }
-                    }   // act
-                    // the array values the reference would read, whether or not the cell was computed on this diagonal
-                    if (pub0) xn.d0 = (ndx_col(V[k][0], V[k][1], last_H0_t - tt) - NDX_B) >> 4;
-                    if (pub1) xn.d1 = (ndx_col(U[k][0], U[k][1], last_H0_t + 1 - tt) - NDX_B) >> 4;
                 }
 
-                // ---- publish, meet -----------------------------------------------------------------------------------------------------------
-                if (NW > 1 && lane == 31) { xn.bx[wid] = X[K - 1][1]; xn.bv[wid] = V[K - 1][1]; xn.bx2[wid] = X2[K - 1][1]; }
+                // ---- hand the bookkeeping its operands (one lane each) -----------------------------------------------------------------------------
+#define NDX_OWNER(col, body) { const int pos_ = (col) % CAP, sl_ = pos_ >> 7; if (sl_ % NW == wid && ((pos_ >> 2) & 31) == lane) { const int j_ = pos_ & 3, kk_ = sl_ / NW; (void)j_; (void)kk_; body } }
+#define NDX_SEL(A, out) { _Pragma("unroll") for (int k = 0; k < K; ++k) if (k == kk_) out = ndx_col(A[k][0], A[k][1], j_); }
+#define NDX_SELH(out) { _Pragma("unroll") for (int k = 0; k < K; ++k) if (k == kk_) out = j_ == 0 ? Hh[k][0] : j_ == 1 ? Hh[k][1] : j_ == 2 ? Hh[k][2] : Hh[k][3]; }
                 if (EXACT) {
                     const int wm = __reduce_max_sync(NDK_FULL, lmax);
-                    const unsigned wr = __reduce_min_sync(NDK_FULL, lmax == wm ? lrank : 0xffffffffu);
+                    // smallest SIMD-search rank among this warp's columns of [st0, en0] that attain the maximum (:320-343: en0 first, then the
+                    // 4-lane blocks lane-major, then the scalar tail)
+                    unsigned lrank = 0xffffffffu;
+                    if (lmax == wm && wm != NDX_HNEG) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int t = t0[k] + j;
+                                if (t >= st0 && t <= en0 && Hh[k][j] == wm) {
+                                    const unsigned rank = r == 0 || t == en0 ? 0u : t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 20) + (unsigned)((t - st0) >> 2) : 1u + (4u << 20) + (unsigned)(t - en1);
+                                    lrank = rank < lrank ? rank : lrank;
+                                }
+                            }
+                    }
+                    const unsigned wr = __reduce_min_sync(NDK_FULL, lrank);
                     if (lane == 0) { xn.wmax[wid] = wm; xn.wrank[wid] = wr; }
+                    NDX_OWNER(en0, { int v = 0; NDX_SELH(v) xn.h_en0 = v; })
+                    if (en0 - 1 >= st0) NDX_OWNER(en0 - 1, { int v = 0; NDX_SELH(v) xn.h_en0m1 = v; })
+                    if (r - st0 == qlen - 1) NDX_OWNER(st0, { int v = 0; NDX_SELH(v) xn.h_st0 = v; })
+                    if (r == n_diag - 1 && en0 == tlen - 1) NDX_OWNER(tlen - 1, { int v = 0; NDX_SELH(v) xn.h_last = v; })
+                } else {
+                    // the array values the reference reads (:361-371): new v of column last_H0_t, new u of column last_H0_t + 1
+                    NDX_OWNER(last_H0_t, { int v = 0; NDX_SEL(V, v) xn.d0 = (v - NDX_B) >> 4; })
+                    NDX_OWNER(last_H0_t + 1, { int v = 0; NDX_SEL(U, v) xn.d1 = (v - NDX_B) >> 4; })
                 }
+#undef NDX_OWNER
+#undef NDX_SEL
+#undef NDX_SELH
                 sync();
 
                 // ---- scores that spilled past the target copy (:103,:175): target bytes of columns 0..15 are overwritten ---------------------------------
@@ -402,7 +417,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         const int hl = en0 == en0_prev ? hp1 : hp0;
                         hp0 = xn.h_en0; hp1 = en0 - 1 >= st0 ? xn.h_en0m1 : hl; en0_prev = en0;
                     }
-                    if (en0 == tlen - 1) { const int h = xn.h_en0 >> 4; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
+                    if (en0 == tlen - 1) { const int h = hp0 >> 4; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
                     if (r - st0 == qlen - 1) { const int h = xn.h_st0 >> 4; if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; } }
                     if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
                     if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = xn.h_last >> 4;

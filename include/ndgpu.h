@@ -155,6 +155,9 @@ int ndg_index_finalize(ndg_ctx_t *ctx, ndg_index_stat_t *stat);
  *   table_slice(j, &p, &b)    where slice j lives (equal sizes)                        -> all-gather in place
  *   pos_reserve(r, n[N], seg) n[j] = pairs sorted on rank j; position list allocated; seg[j] = device pointer of segment j -> broadcast each
  *   finish(hist_sum, nd_sum)  global histogram / distinct count (mid_occ, ref: minimap2/index.c:164-185 needs the whole part) */
+/* device-to-device copy between buffers owned by two contexts (same GPU or peers), synchronous: the building block of the collectives
+ * when all N contexts live in one process (bin/minimap2-nd --gpus N) */
+int ndg_copy_between(ndg_ctx_t *dst_ctx, void *dst, ndg_ctx_t *src_ctx, const void *src, uint64_t bytes);
 /* host helper: the slice (= rank) the minimizer key (hash, < 4^k) belongs to in an n_slices-way build */
 int32_t ndg_index_key_slice(uint64_t key, int32_t k, int32_t n_slices);
 int ndg_index_shard_split(ndg_ctx_t *ctx, int32_t n_slices, uint64_t *counts);

@@ -14,6 +14,10 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
 #include <zlib.h>
 #include "ndgpu.h"
 
@@ -139,7 +143,7 @@ int main(int argc, char **argv)
     ndg_opt_t o; memset(&o, 0, sizeof o);
     o.k = 15; o.w = 10; o.min_cnt = 3; o.min_chain_score = 40; o.bw = 500; o.max_gap = 5000; o.max_chain_skip = 25; o.max_chain_iter = 5000;
     o.seed = 11; o.mid_occ_frac = 2e-4f;
-    int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0, n_threads = 0;
+    int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0, n_threads = 0, n_gpus = 1;
     uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
     const char *out = nullptr; std::vector<const char *> pos;
     bool cigar = false;
@@ -242,6 +246,7 @@ int main(int argc, char **argv)
         else if (k == "--seed") o.seed = atoi(v); else if (k == "--max-chain-skip") o.max_chain_skip = atoi(v);
         else if (k == "--max-chain-iter") o.max_chain_iter = atoi(v); else if (k == "--min-occ-floor") o.min_mid_occ = atoi(v);
         else if (k == "-v") verbose = atoi(v); else if (k == "--device") device = atoi(v); else if (k == "-t") n_threads = atoi(v);
+        else if (k == "--gpus") n_gpus = atoi(v);
         else if (k == "--dual") { if (kv.second == "yes" || kv.second == "y") o.flag_no_dual = 0; else if (kv.second == "no" || kv.second == "n") o.flag_no_dual = 1; }
         else if (k == "-f") { double x = strtod(v, nullptr); if (x < 1.0) { o.mid_occ_frac = (float)x; o.mid_occ = 0; } else o.mid_occ = (int)(x + .499); }
         else if (k == "-o") { if (kv.second != "-") out = v; }
@@ -276,16 +281,29 @@ int main(int argc, char **argv)
 
     Reads T;
     if (!read_any(pos[0], T)) { fprintf(stderr, "[ERROR] failed to open file '%s'\n", pos[0]); return 1; }
-    ndg_ctx_t *g = nullptr;
-    if (ndg_init(device, &g) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device); return 1; }
-    ndg_set_opt(g, &o);
-    if (cigar && ndg_set_aln_opt(g, &ao)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+    // ---- contexts: G GPUs (--gpus, devices device..device+G-1) x C contexts per GPU.  The contexts of a GPU share one copy of the
+    // index (ndg_index_share) and map different query batches concurrently, each on its own stream: upload, kernels and download of
+    // neighbouring batches overlap (what the reference's 3-stage kt_pipeline does with threads, ref: minimap2/map.c:1389-1390).
+    // Step 2 keeps one context: its output stage is order-dependent (filter_ovl, ref: lib/ovl.c:449-563).
+    if (n_gpus < 1) n_gpus = 1;
+    if (step == 2) n_gpus = 1;
+    const int G = n_gpus, CPG = (step == 2 || cigar) ? 1 : 2;
+    std::vector<ndg_ctx_t *> ctx((size_t)G * CPG, nullptr);
+    for (int g = 0; g < G; ++g)
+        for (int x = 0; x < CPG; ++x) {
+            ndg_ctx_t *&h = ctx[(size_t)g * CPG + x];
+            if (ndg_init(device + g, &h) != NDG_OK) { fprintf(stderr, "[ERROR] no usable B200 (sm_100) device %d; there is no CPU fallback\n", device + g); return 1; }
+            ndg_set_opt(h, &o);
+            if (cigar && ndg_set_aln_opt(h, &ao)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(h)); return 1; }
+        }
+    ndg_ctx_t *g = ctx[0];
     if (step == 2) { s2.minlen = minlen; s2.maxhan1 = maxhan1; s2.maxhan2 = maxhan2; if (ndg_step2_begin(g, &s2)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; } }
     n_threads = ndg_set_threads(g, n_threads);                  // -t: host threads (only the -c stage has host-side work worth threading)
+    if (cigar && G > 1) for (int x = 0; x < G; ++x) ndg_set_threads(ctx[(size_t)x * CPG], n_threads / G > 0 ? n_threads / G : 1);
+#define DIE(h) do { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(h)); exit(1); } while (0)
 
     uint32_t state[2] = { 0, 0 };
     uint64_t n_rec = 0, sum_qspan = 0;
-    std::vector<uint8_t> obuf;
     const uint64_t mini = mini_batch < batch_size ? mini_batch : batch_size;
     int t_at = 0, n_parts = 0;
     while (t_at < T.n()) {                                     // one index part per iteration (main.c:477)
@@ -295,9 +313,58 @@ int main(int argc, char **argv)
             while (t_at < T.n()) { size += T.len[t_at++]; if (size >= mini) break; }
             total += size;
         }
-        ndg_reads_t tv = view(T, t0i, t_at);
         ndg_index_stat_t st;
-        if (ndg_index_begin(g) || ndg_index_add(g, &tv) || ndg_index_finalize(g, &st)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
+        if (G == 1) {
+            ndg_reads_t tv = view(T, t0i, t_at);
+            if (ndg_index_begin(g) || ndg_index_add(g, &tv) || ndg_index_finalize(g, &st)) DIE(g);
+        } else {
+            // N-GPU build of the part (ndg_index_shard_*): GPU r sketches the r-th share of the targets and builds the r-th key range of
+            // the table; the collectives are peer copies between the primaries' buffers
+            std::vector<ndg_ctx_t *> P((size_t)G);
+            std::vector<int> cut((size_t)G + 1);
+            for (int r = 0; r <= G; ++r) cut[(size_t)r] = t0i + (int)((int64_t)(t_at - t0i) * r / G);
+            for (int r = 0; r < G; ++r) P[(size_t)r] = ctx[(size_t)r * CPG];
+            std::vector<std::vector<uint64_t>> cm((size_t)G, std::vector<uint64_t>((size_t)G));
+            for (int r = 0; r < G; ++r) {
+                ndg_ctx_t *h = P[(size_t)r];
+                if (ndg_index_begin(h)) DIE(h);
+                for (int j = 0; j < G; ++j) {
+                    if (cut[(size_t)j] == cut[(size_t)j + 1]) continue;
+                    ndg_reads_t tv = view(T, cut[(size_t)j], cut[(size_t)j + 1]);
+                    if (j == r ? ndg_index_add(h, &tv) : ndg_index_add_meta(h, &tv)) DIE(h);
+                }
+                if (ndg_index_shard_split(h, G, cm[(size_t)r].data())) DIE(h);
+            }
+            std::vector<uint64_t> npos((size_t)G, 0), nd((size_t)G, 0);
+            for (int j = 0; j < G; ++j) {                       // all-to-all: GPU j receives bucket j of every GPU, in GPU (= target) order
+                uint64_t tot = 0; for (int r = 0; r < G; ++r) tot += cm[(size_t)r][(size_t)j];
+                npos[(size_t)j] = tot;
+                void *rk, *rv;
+                if (ndg_index_shard_recv_reserve(P[(size_t)j], tot, &rk, &rv)) DIE(P[(size_t)j]);
+                uint64_t at = 0;
+                for (int r = 0; r < G; ++r) {
+                    const void *kp, *vp; uint64_t nn;
+                    if (ndg_index_shard_bucket(P[(size_t)r], j, &kp, &vp, &nn)) DIE(P[(size_t)r]);
+                    if (ndg_copy_between(P[(size_t)j], (uint64_t *)rk + at, P[(size_t)r], kp, nn * 8) || ndg_copy_between(P[(size_t)j], (uint64_t *)rv + at, P[(size_t)r], vp, nn * 8)) DIE(P[(size_t)j]);
+                    at += nn;
+                }
+            }
+            uint64_t nd_max = 0, nd_sum = 0;
+            for (int r = 0; r < G; ++r) { if (ndg_index_shard_sort(P[(size_t)r], &nd[(size_t)r])) DIE(P[(size_t)r]); nd_max = nd_max > nd[(size_t)r] ? nd_max : nd[(size_t)r]; nd_sum += nd[(size_t)r]; }
+            std::vector<uint32_t> hist(65536, 0), hr(65536);
+            for (int r = 0; r < G; ++r) { if (ndg_index_shard_place(P[(size_t)r], r, nd_max, hr.data())) DIE(P[(size_t)r]); for (int b = 0; b < 65536; ++b) hist[(size_t)b] += hr[(size_t)b]; }
+            std::vector<std::vector<void *>> seg((size_t)G, std::vector<void *>((size_t)G));
+            for (int r = 0; r < G; ++r) if (ndg_index_shard_pos_reserve(P[(size_t)r], r, npos.data(), seg[(size_t)r].data())) DIE(P[(size_t)r]);
+            for (int r = 0; r < G; ++r)                         // all-gather of the finished table slices and position segments
+                for (int j = 0; j < G; ++j) {
+                    if (j == r) continue;
+                    void *dp, *sp; uint64_t nb, nb2;
+                    if (ndg_index_shard_table_slice(P[(size_t)r], j, &dp, &nb) || ndg_index_shard_table_slice(P[(size_t)j], j, &sp, &nb2)) DIE(P[(size_t)r]);
+                    if (ndg_copy_between(P[(size_t)r], dp, P[(size_t)j], sp, nb) || ndg_copy_between(P[(size_t)r], seg[(size_t)r][(size_t)j], P[(size_t)j], seg[(size_t)j][(size_t)j], npos[(size_t)j] * 8)) DIE(P[(size_t)r]);
+                }
+            for (int r = 0; r < G; ++r) if (ndg_index_shard_finish(P[(size_t)r], hist.data(), nd_sum, &st)) DIE(P[(size_t)r]);
+        }
+        for (int x = 0; x < G; ++x) for (int y = 1; y < CPG; ++y) if (ndg_index_share(ctx[(size_t)x * CPG + y], ctx[(size_t)x * CPG])) DIE(ctx[(size_t)x * CPG + y]);
         ++n_parts;
         if (verbose >= 3) {
             fprintf(stderr, "[M::main::%.3f] loaded/built the index for %llu target sequence(s)\n", now() - t0, (unsigned long long)st.n_seq);
@@ -308,20 +375,58 @@ int main(int argc, char **argv)
         for (size_t qf = 1; qf < pos.size(); ++qf) {
             Reads Qown; const Reads *Q = &T;
             if (strcmp(pos[qf], pos[0]) != 0) { if (!read_any(pos[qf], Qown)) { fprintf(stderr, "ERROR: failed to open file '%s'\n", pos[qf]); return 1; } Q = &Qown; }
-            int q_at = 0;
-            while (q_at < Q->n()) {                             // bseq.c:86-123: a batch ends once >= chunk_size bases were read
-                int q0 = q_at; int64_t size = 0;
-                while (q_at < Q->n()) { size += Q->len[q_at++]; if (size >= q_batch) break; }
-                ndg_reads_t qv = view(*Q, q0, q_at);
-                ndg_map_result_t R;
-                ndg_emit_opt_t eo = { minlen, dvt, maxhan1, maxhan2 };
-                const uint8_t *bytes = nullptr; uint64_t nb = 0;
-                // mapping + output stage (filter, delta/varint records) on the GPU; only the .ovl bytes come back
-                if (step == 2 ? ndg_step2_map_batch(g, &qv, &bytes, &nb, &n_rec, &sum_qspan, &R)
-                              : ndg_map_batch_ovl(g, &qv, &eo, state, &bytes, &nb, &n_rec, &sum_qspan, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
-                if (nb && fwrite(bytes, 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
-                if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, q_at - q0);
+            std::vector<std::pair<int, int>> qb;               // bseq.c:86-123: a batch ends once >= chunk_size bases were read
+            for (int q_at = 0; q_at < Q->n();) { int q0 = q_at; int64_t size = 0; while (q_at < Q->n()) { size += Q->len[q_at++]; if (size >= q_batch) break; } qb.push_back({ q0, q_at }); }
+            const ndg_emit_opt_t eo = { minlen, dvt, maxhan1, maxhan2 };
+            if (ctx.size() == 1) {                              // one context: batches in order, the encoder state carried along
+                for (auto &b : qb) {
+                    ndg_reads_t qv = view(*Q, b.first, b.second);
+                    ndg_map_result_t R;
+                    const uint8_t *bytes = nullptr; uint64_t nb = 0;
+                    if (step == 2 ? ndg_step2_map_batch(g, &qv, &bytes, &nb, &n_rec, &sum_qspan, &R)
+                                  : ndg_map_batch_ovl(g, &qv, &eo, state, &bytes, &nb, &n_rec, &sum_qspan, &R)) DIE(g);
+                    if (nb && fwrite(bytes, 1, (size_t)nb, fo) != (size_t)nb) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+                    if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, b.second - b.first);
+                }
+                continue;
             }
+            // several contexts: workers pull batches; every batch is encoded from state (0,0); the writer puts them out in input order and
+            // re-bases the first record of each batch onto the names the stream really ended with (ndg_ovl_rebase_first)
+            struct Done { std::vector<uint8_t> bytes; uint32_t st[2]; uint64_t rec = 0, sq = 0; bool ready = false; };
+            std::vector<Done> done(qb.size());
+            std::atomic<size_t> next(0); std::mutex mu; std::condition_variable cv; std::atomic<int> failed(0);
+            auto work = [&](ndg_ctx_t *h) {
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= qb.size() || failed.load()) break;
+                    ndg_reads_t qv = view(*Q, qb[i].first, qb[i].second);
+                    ndg_map_result_t R; const uint8_t *bytes = nullptr; uint64_t nb = 0;
+                    Done &d = done[i]; d.st[0] = d.st[1] = 0;
+                    if (ndg_map_batch_ovl(h, &qv, &eo, d.st, &bytes, &nb, &d.rec, &d.sq, &R)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(h)); failed.store(1); }
+                    else d.bytes.assign(bytes, bytes + nb);
+                    { std::lock_guard<std::mutex> lk(mu); d.ready = true; }
+                    cv.notify_all();
+                }
+            };
+            std::vector<std::thread> th;
+            for (auto h : ctx) th.emplace_back(work, h);
+            for (size_t i = 0; i < qb.size(); ++i) {
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[i].ready; }); }
+                if (failed.load()) break;
+                Done &d = done[i];
+                if (!d.bytes.empty()) {
+                    uint8_t first[48]; uint32_t skip = 0;
+                    const int fl = ndg_ovl_rebase_first(d.bytes.data(), d.bytes.size(), state, first, &skip);
+                    if (fl < 0) { fprintf(stderr, "[ERROR] malformed batch stream\n"); failed.store(1); break; }
+                    if (fwrite(first, 1, (size_t)fl, fo) != (size_t)fl || fwrite(d.bytes.data() + skip, 1, d.bytes.size() - skip, fo) != d.bytes.size() - skip) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+                    state[0] = d.st[0]; state[1] = d.st[1];
+                }
+                n_rec += d.rec; sum_qspan += d.sq;
+                std::vector<uint8_t>().swap(d.bytes);
+                if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, qb[i].second - qb[i].first);
+            }
+            for (auto &t : th) t.join();
+            if (failed.load()) return 1;
         }
     }
     if (fbl) {                                                  // main.c:522-526 (out_bl)
@@ -340,6 +445,6 @@ int main(int argc, char **argv)
         for (int i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
         fprintf(stderr, "\n[M::main] Real time: %.3f sec; records: %llu; index parts: %d\n", now() - t0, (unsigned long long)n_rec, n_parts);
     }
-    ndg_destroy(g);
+    for (auto h : ctx) ndg_destroy(h);
     return 0;
 }

@@ -672,6 +672,18 @@ extern "C" int ndg_index_finalize(ndg_ctx_t *c, ndg_index_stat_t *stat)
 //   table_slice(j)      device pointer / bytes of slice j                                          (all-gather by the caller)
 //   pos_reserve(n[N])   full position list allocated, own segment in place                         -> device pointer of segment j (all-gather by the caller)
 //   finish(hist, nd)    global run-length histogram and distinct count (summed by the caller)      -> index ready
+// device-to-device copy between buffers of two contexts (same or different GPUs; peer access or staged by the driver), synchronous.
+// The collectives of a one-process N-GPU build (bin/minimap2-nd --gpus N) are made of these.
+extern "C" int ndg_copy_between(ndg_ctx_t *dst_ctx, void *dst, ndg_ctx_t *src_ctx, const void *src, uint64_t bytes)
+{
+    if (!dst_ctx || !src_ctx || (bytes && (!dst || !src))) return NDG_ERR_ARG;
+    ndg_ctx *c = dst_ctx;
+    cudaSetDevice(c->device);
+    if (bytes) CK(cudaMemcpyPeerAsync(dst, dst_ctx->device, src, src_ctx->device, bytes, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return NDG_OK;
+}
+
 // host helper (tests, planning): the slice / rank a minimizer key belongs to in an N-way sharded build of an untagged index
 extern "C" int32_t ndg_index_key_slice(uint64_t key, int32_t k, int32_t n_slices)
 {

@@ -73,7 +73,7 @@ assert KSW_CALL_DTYPE.itemsize == 40 and KSW_RES_DTYPE.itemsize == 48
 
 EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
            "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta",
-           "ndg_index_key_slice", "ndg_index_shard_split", "ndg_index_shard_bucket", "ndg_index_shard_recv_reserve", "ndg_index_shard_sort", "ndg_index_shard_place",
+           "ndg_index_key_slice", "ndg_copy_between", "ndg_index_shard_split", "ndg_index_shard_bucket", "ndg_index_shard_recv_reserve", "ndg_index_shard_sort", "ndg_index_shard_place",
            "ndg_index_shard_table_slice", "ndg_index_shard_pos_reserve", "ndg_index_shard_finish", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
@@ -116,6 +116,7 @@ def load_library():
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.ndg_copy_between.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.ndg_index_key_slice.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
     L.ndg_index_key_slice.restype = C.c_int32
     L.ndg_index_shard_split.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]

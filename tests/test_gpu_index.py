@@ -153,3 +153,34 @@ e.close(); dist.destroy_process_group()
     assert len(res) == 2
     for x in res:
         assert x[2] == "9fce14e8841db2e46012c58ad8f0059c" and x[3] == "6273819" and x[4] == "74", x     # G1 of SURVEY 8(c)
+
+
+def test_cli_two_gpus_same_bytes(built, golden_dir, tmp_path):
+    """bin/minimap2-nd --gpus 2: index part built sharded over both GPUs (peer copies), query batches pulled by 2 x 2 contexts, output
+    merged in input order with re-based batch heads: the bytes of the single-GPU run / the reference (G1, and a 3-part --dual run)"""
+    import hashlib
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "reads_test.seed.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([exe, "--step", "1", "--gpus", "2", "-K", "5M", "-x", "ava-ont", src, src, "-o", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == "9fce14e8841db2e46012c58ad8f0059c"
+    one = str(tmp_path / "one.ovl")
+    args = ["--step", "1", "--dual=yes", "-I", "12M", "-K", "3M", "-x", "ava-ont", "-k", "17", "-w", "10", src, src]
+    assert subprocess.run([exe] + args + ["-o", one], capture_output=True).returncode == 0
+    assert subprocess.run([exe, "--gpus", "2"] + args + ["-o", out], capture_output=True).returncode == 0
+    assert open(one, "rb").read() == open(out, "rb").read() and os.path.getsize(one) > 100000
+
+
+def test_cli_context_pool_small_batches(built, golden_dir, tmp_path):
+    """one GPU, two contexts sharing the index, many small query batches (-K 1M): the stitched stream equals the golden bytes"""
+    exe = os.path.join(ROOT, "bin", "minimap2-nd")
+    src = os.path.join(golden_dir, "sub120.2bit")
+    out = str(tmp_path / "o.ovl")
+    r = subprocess.run([exe, "--step", "1", "-K", "1M", "-x", "ava-ont", src, src, "-o", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+    assert r.stderr.count("mapped") >= 3

@@ -99,7 +99,8 @@ const char *ndg_version(void);
 int  ndg_set_opt(ndg_ctx_t *ctx, const ndg_opt_t *opt);
 /* tuning: bases per device sub-batch, anchors per sub-batch (0 = default) */
 int  ndg_set_limits(ndg_ctx_t *ctx, uint64_t sub_batch_bases, uint64_t max_anchors);
-/* variant 0 = one thread per read/segment (baseline kernels), 1 = warp-cooperative kernels */
+/* sort: 0 = one thread per read (baseline), 1 = block sort for reads without equal keys + exact warp-level replay of the reference's
+ * unstable sort for the others, 2 = exact replay for every read.  chain: 0 = one thread per segment (baseline), 1 = warp per segment */
 int  ndg_set_variant(ndg_ctx_t *ctx, int sort_variant, int chain_variant);
 /* ksw_extd2 kernel generation: 0 = one cell per lane, 1 = two cells per lane in s16x2 (DPX) registers */
 int  ndg_set_ksw_variant(ndg_ctx_t *ctx, int variant);

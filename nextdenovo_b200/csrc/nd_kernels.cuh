@@ -171,6 +171,109 @@ k_sketch_fast(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int w, i
     if (tid == 0) cnt[g] = base;
 }
 
+// Second generation of the fast path, for the window lengths the pipeline uses (W = 5: ava-ont / ava-pb, W = 10: the -w 10 runs).
+// Same closed form, half the instructions:
+//   * a thread owns FOUR consecutive positions: the first k-mer is cut out of the packed words, the next three are rolled exactly as
+//     the reference rolls them (fw = fw << 2 | c, rv = rv >> 2 | (3 - c) << 2(k-1), ref: minimap2/sketch.c:100-101);
+//   * the window test reads the 4 + 2(W-1) hashes around its positions once into registers and counts, without branches, the runs of
+//     neighbours that are >= each of them (a position is pushed iff left run + right run >= W-1; invalid positions -- before the first
+//     k-mer, beyond the read -- hold 0, which is smaller than every hash and so ends a run);
+//   * survivors are compacted in position order with one block-wide prefix sum instead of a ballot per 128 positions.
+template <int W>
+__global__ void __launch_bounds__(NDS_T)
+k_sketch_fast4(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int k, uint32_t rid0, int use_rid,
+               nd_u128 *staging, int S, uint32_t *cnt, uint32_t *slow)
+{
+    constexpr int PAD = 16;                               // >= W-1 zero entries on both sides of the hashed range
+    __shared__ nd_u64 sx[NDS_C + 2 * NDS_MAXW + 2 * PAD];
+    __shared__ uint8_t sz[NDS_C + 2 * NDS_MAXW + 2 * PAD];
+    __shared__ uint32_t swords[(NDS_C + 2 * NDS_MAXW) / 16 + 8];
+    __shared__ int s_r;
+    __shared__ uint32_t s_wsum[NDS_T / 32];
+    const nd_u64 g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_r = nd_find_owner(chunk_off, R.n_reads, g);
+    __syncthreads();
+    const int r = s_r, len = (int)R.len[r];
+    const int cs = (int)(g - chunk_off[r]) * NDS_C, ce = cs + NDS_C < len ? cs + NDS_C : len;
+    if (len < k + W - 1) { if (tid == 0) { slow[r] = 1; cnt[g] = 0; } return; }
+    const int lo = cs - (W - 1) > 0 ? cs - (W - 1) : 0, hi = ce + (W - 1) < len ? ce + (W - 1) : len;
+    const uint32_t *words = R.words + R.word_off[r];
+    const int w0 = (lo >> 4) - 2 > 0 ? (lo >> 4) - 2 : 0, w1 = (hi - 1) >> 4;
+    for (int i = tid; i <= w1 - w0; i += NDS_T) swords[i] = words[w0 + i];
+    for (int i = tid; i < PAD; i += NDS_T) { sx[i] = 0; sx[PAD + (hi - lo) + i] = 0; }
+    __syncthreads();
+    const nd_u64 mask = (1ULL << 2 * k) - 1;
+    const int rc_shift = 2 * (k - 1);
+    int any_sym = 0;
+    for (int base = 4 * tid; base < hi - lo; base += 4 * NDS_T) {           // one round for the chunk, a short second one for the halo
+        int p = lo + base;
+        nd_u64 fw = nd_bases32(swords - w0, p) & mask;
+        nd_u64 rv = (~nd_rev2(fw)) >> (64 - 2 * k);
+        if (p < k - 1) rv &= ~((1ULL << 2 * (k - 1 - p)) - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j, ++p) {
+            if (base + j >= hi - lo) break;
+            if (j) {
+                const nd_u64 c = (swords - w0)[p >> 4] >> (30 - 2 * (p & 15)) & 3;
+                fw = (fw << 2 | c) & mask;
+                rv = (rv >> 2) | (3ULL ^ c) << rc_shift;
+            }
+            const int z = fw < rv ? 0 : 1;
+            any_sym |= fw == rv;
+            sx[PAD + base + j] = p >= k - 1 ? (nd_hash64_masked(z ? rv : fw, mask) << 8 | (nd_u64)k) : 0;
+            sz[PAD + base + j] = (uint8_t)z;
+        }
+    }
+    if (__syncthreads_or(any_sym)) { if (tid == 0) { slow[r] = 1; cnt[g] = 0; } return; }
+    // ---- window test for positions t0 .. t0+3 from a register window of hashes ----------------------------------------------------
+    const int t0 = cs + 4 * tid;
+    nd_u64 xw[4 + 2 * (W - 1)];
+    {
+        const nd_u64 *src = sx + PAD + (t0 - lo) - (W - 1);                  // index PAD + (t - lo) holds position t
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * (W - 1); ++i) xw[i] = src[i];             // always inside sx[]; entries beyond the hashed range only feed positions >= ce
+    }
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j;
+        const nd_u64 xt = xw[W - 1 + j];
+        int a = 0, b = 0; bool okl = true, okr = true;
+#pragma unroll
+        for (int d = 1; d < W; ++d) {
+            okl = okl && xw[W - 1 + j - d] >= xt; a += okl;
+            okr = okr && xw[W - 1 + j + d] >= xt; b += okr;
+        }
+        bool f = t < ce && t >= k - 1 && a + b >= W - 1;
+        if (cs == 0 && t < k + W - 2 && t < ce && t >= k - 1) {             // first-window irregularity (sketch.c:114-121); needs the
+            const int fix = nd_first_window_fix(sx + PAD, lo, t, W, k);     // invalid entries to read as "no candidate", not as 0
+            if (fix >= 0) f = fix == 1;
+        }
+        flags |= (unsigned)f << j;
+    }
+    // ---- compaction in position order ---------------------------------------------------------------------------------------------------
+    const uint32_t mine = __popc(flags);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    uint32_t before = incl - mine, total = 0;
+#pragma unroll
+    for (int q = 0; q < NDS_T / 32; ++q) { const uint32_t c = s_wsum[q]; before += q < wid ? c : 0; total += c; }
+    const nd_u64 ridbits = (nd_u64)(use_rid ? rid0 + (uint32_t)r : 0u) << 32;
+    nd_u128 *dst = staging + g * (nd_u64)S + before;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (flags >> j & 1) {
+            const int t = t0 + j;
+            nd_u128 o; o.x = xw[W - 1 + j]; o.y = ridbits | (nd_u64)(uint32_t)t << 1 | (nd_u64)sz[PAD + t - lo];
+            *dst++ = o;
+        }
+    if (tid == 0) cnt[g] = total;
+}
+
 // one warp per chunk: staging -> packed minimizer array
 __global__ void k_sketch_compact(const nd_u128 *staging, int S, const uint32_t *cnt, const nd_u64 *pos,
                                  nd_u64 n_chunks, nd_u128 *mz)

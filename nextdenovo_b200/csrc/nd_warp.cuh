@@ -24,7 +24,7 @@
 // The most recent NDW_RING anchors (x, q, f, p, v, t) live in shared memory; older ones are read
 // from global memory.
 // ------------------------------------------------------------------------------------------------
-#define NDW_RING 256
+#define NDW_RING 64
 #define NDW_CHAIN_WARPS 4
 #define NDW_GAP_TAB 2048
 
@@ -208,12 +208,64 @@ struct ndw_sort_bufs {
     uint32_t *src_of, *tmp;    // permutation, rank lists
 };
 
-__global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs, uint32_t *n_jobs)
+// Fast path (SURVEY H1 option ii): the tie order of the reference's unstable sort is observable only among anchors with EQUAL x
+// (same target position hit from several query positions).  A read whose anchors all have distinct x has exactly one sorted order,
+// so any correct sort will do: one block sorts the read's (x, index) pairs in shared memory (bitonic network), checks neighbours
+// for equal x, and only a read that does have duplicates is handed to the exact replay below, untouched.
+#define NDW_FAST_MAX 4096
+#define NDW_FAST_T 256
+template <int CAPF>
+__global__ void __launch_bounds__(NDW_FAST_T)
+k_sort_fast(nd_u128 *a, const nd_u64 *a_off, int n_reads, int lo_excl, nd_rs_job *jobs, uint32_t *n_jobs)
+{
+    extern __shared__ unsigned char ndw_fast_smem[];
+    nd_u64 *sx = reinterpret_cast<nd_u64 *>(ndw_fast_smem);          // CAPF keys
+    nd_u64 *sy = sx + CAPF;                                           // CAPF payloads (y)
+    uint16_t *si = reinterpret_cast<uint16_t *>(sy + CAPF);           // CAPF indices
+    __shared__ int s_dup;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const nd_u64 b = a_off[r], n64 = a_off[r + 1] - b;
+    if (n64 <= (nd_u64)lo_excl || n64 > (nd_u64)CAPF) return;
+    const int n = (int)n64;
+    int m = 1; while (m < n) m <<= 1;                                 // pad to a power of two with the maximum key
+    if (tid == 0) s_dup = 0;
+    for (int i = tid; i < m; i += NDW_FAST_T) {
+        if (i < n) { const uint4 v = *reinterpret_cast<const uint4 *>(a + b + i); sx[i] = (nd_u64)v.y << 32 | v.x; sy[i] = (nd_u64)v.w << 32 | v.z; }
+        else sx[i] = ND_U64_MAX;
+        si[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (m >> 1); t += NDW_FAST_T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;       // the pair (i, i + j) of this stage
+                const bool up = (i & k) == 0;
+                const nd_u64 xi = sx[i], xp = sx[p];
+                if ((xi > xp) == up) { sx[i] = xp; sx[p] = xi; const uint16_t ti = si[i]; si[i] = si[p]; si[p] = ti; }
+            }
+            __syncthreads();
+        }
+    int dup = 0;
+    for (int i = tid; i + 1 < n; i += NDW_FAST_T) dup |= sx[i] == sx[i + 1];
+    if (dup) s_dup = 1;
+    __syncthreads();
+    if (s_dup) {                                                      // equal keys: the exact emulation decides their order
+        if (tid == 0) { const uint32_t q = atomicAdd(n_jobs, 1u); jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0; }
+        return;
+    }
+    for (int i = tid; i < n; i += NDW_FAST_T) {
+        const nd_u64 x = sx[i], y = sy[si[i]];
+        *reinterpret_cast<uint4 *>(a + b + i) = make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)y, (uint32_t)(y >> 32));
+    }
+}
+
+__global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs, uint32_t *n_jobs, int fast_max)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     nd_u64 b = a_off[r], n = a_off[r + 1] - b;
     if (n > ND_RS_SMALL) {
+        if (n <= (nd_u64)fast_max) return;                            // k_sort_fast takes it (and queues it here if it has equal keys)
         uint32_t q = atomicAdd(n_jobs, 1u);
         jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0;
     } else if (n > 1) nd_ins_sort_128x(a + b, a + b + n);
@@ -391,14 +443,22 @@ struct ndw_launch_hooks { void (*begin)(void *ctx, const char *name); void (*end
 
 // jobs: device buffer for 2 * (NA/65 + n_reads + 1) jobs; counters: 24 u32 on the device
 static inline void ndw_sort_launch(cudaStream_t st, ndw_sort_bufs W, const nd_u64 *a_off, int n_reads, nd_u64 n_a,
-                                   nd_rs_job *jobs, uint32_t *counters, int n_sm, ndw_launch_hooks hk)
+                                   nd_rs_job *jobs, uint32_t *counters, int n_sm, ndw_launch_hooks hk, bool fast_path = true)
 {
     const nd_u64 half = n_a / (ND_RS_SMALL + 1) + (nd_u64)n_reads + 1;
     nd_rs_job *buf[2] = { jobs, jobs + half };
     cudaMemsetAsync(counters, 0, 24 * sizeof(uint32_t), st);
     hk.begin(hk.ctx, "sort_init");
-    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(W.A, a_off, n_reads, buf[0], counters);
+    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(W.A, a_off, n_reads, buf[0], counters, fast_path ? NDW_FAST_MAX : 0);
     hk.end(hk.ctx);
+    if (fast_path) {                                   // distinct-key reads: block sort in shared memory, three size classes
+        cudaFuncSetAttribute(k_sort_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 18);   // per device: cheap, idempotent
+        hk.begin(hk.ctx, "sort_fast");
+        k_sort_fast<1024><<<n_reads, NDW_FAST_T, 1024 * 18, st>>>(W.A, a_off, n_reads, ND_RS_SMALL, buf[0], counters);
+        k_sort_fast<2048><<<n_reads, NDW_FAST_T, 2048 * 18, st>>>(W.A, a_off, n_reads, 1024, buf[0], counters);
+        k_sort_fast<4096><<<n_reads, NDW_FAST_T, 4096 * 18, st>>>(W.A, a_off, n_reads, 2048, buf[0], counters);
+        hk.end(hk.ctx);
+    }
     for (int lvl = 0; lvl < 8; ++lvl) {
         hk.begin(hk.ctx, "sort_level");
         k_rs_level<<<n_sm * 8, NDW_SORT_WARPS * 32, 0, st>>>(W, buf[lvl & 1], counters + lvl, buf[(lvl + 1) & 1], counters + lvl + 1, counters + 12 + lvl);

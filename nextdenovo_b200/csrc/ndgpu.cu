@@ -277,7 +277,14 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     const bool fast = !o.hpc && !D.has_nmask && o.w <= NDS_MAXW && C == NDS_C;
     RSV(c->slow, (size_t)D.n_reads * 4 + 4);
     CK(cudaMemsetAsync(c->slow.p, fast ? 0 : 1, (size_t)D.n_reads * 4, c->st));
-    if (fast)
+    static const bool old_fast = getenv("NDG_SKETCH_OLD") != nullptr;
+    if (fast && !old_fast && o.w == 5)
+        KLAUNCH("sketch_fast", (k_sketch_fast4<5><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.k, rid0, use_rid,
+                                c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
+    else if (fast && !old_fast && o.w == 10)
+        KLAUNCH("sketch_fast", (k_sketch_fast4<10><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.k, rid0, use_rid,
+                                c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
+    else if (fast)
         KLAUNCH("sketch_fast", (k_sketch_fast<<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.w, o.k, rid0, use_rid,
                                 c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
     if (o.w < 16)
@@ -922,7 +929,7 @@ int map_resident(ndg_ctx *c, int qidx_base)
         RSV(c->a2, (NA + 1) * 16);
         ndw_sort_bufs W = { c->a.as<nd_u128>(), c->a2.as<nd_u128>(), c->v.as<uint8_t>(), c->f.as<uint32_t>(), c->p.as<uint32_t>() };
         ndw_launch_hooks hk = { hk_begin, hk_end, c };
-        ndw_sort_launch(c->st, W, c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 64, c->n_sm, hk);
+        ndw_sort_launch(c->st, W, c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 64, c->n_sm, hk, c->sort_variant != 2);
     }
     CK(cudaGetLastError());
 

@@ -73,7 +73,7 @@ assert KSW_CALL_DTYPE.itemsize == 40 and KSW_RES_DTYPE.itemsize == 48
 
 EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_opt", "ndg_set_limits",
            "ndg_set_variant", "ndg_index_begin", "ndg_index_add", "ndg_index_add_meta",
-           "ndg_index_key_slice", "ndg_copy_between", "ndg_index_shard_split", "ndg_index_shard_bucket", "ndg_index_shard_recv_reserve", "ndg_index_shard_sort", "ndg_index_shard_place",
+           "ndg_index_key_slice", "ndg_copy_between", "ndg_ovl_rebase_first", "ndg_index_shard_split", "ndg_index_shard_bucket", "ndg_index_shard_recv_reserve", "ndg_index_shard_sort", "ndg_index_shard_place",
            "ndg_index_shard_table_slice", "ndg_index_shard_pos_reserve", "ndg_index_shard_finish", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
@@ -116,6 +116,7 @@ def load_library():
     L.ndg_index_begin.argtypes = [C.c_void_p]
     L.ndg_index_add.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_index_add_meta.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+    L.ndg_ovl_rebase_first.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndg_copy_between.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.ndg_index_key_slice.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
     L.ndg_index_key_slice.restype = C.c_int32
@@ -413,6 +414,60 @@ class PinnedReads:
         for p in self._ptrs:
             self.L.ndg_host_free(p)
         self._ptrs = []
+
+
+def stitch_ovl(chunks, states, state):
+    """Concatenate .ovl batches that were each encoded from state (0, 0): the first record of every batch is re-based onto the names the
+    stream really ended with (ndg_ovl_rebase_first).  chunks[i] = bytes of batch i, states[i] = its final (qname, tname); `state`
+    (uint32[2]) is the running state of the stream, updated in place.  Returns the stitched bytes."""
+    L = load_library()
+    out = bytearray()
+    first = np.zeros(48, dtype=np.uint8)
+    skip = C.c_uint32(0)
+    for data, st in zip(chunks, states):
+        if not data:
+            continue
+        buf = np.frombuffer(data, dtype=np.uint8)
+        n = L.ndg_ovl_rebase_first(_ptr(buf), len(data), _ptr(state), _ptr(first), C.byref(skip))
+        if n < 0:
+            raise NdgError("malformed .ovl batch")
+        out += first[:n].tobytes()
+        out += data[skip.value:]
+        state[0], state[1] = st[0], st[1]
+    return bytes(out)
+
+
+def map_batches_pool(engs, batches):
+    """Map query batches with a pool of contexts (one host thread each; they share an index through ndg_index_share or hold replicas on
+    several GPUs), each batch encoded from state (0, 0).  Upload, kernels and download of neighbouring batches overlap on the contexts'
+    streams.  Returns (chunks, states, stats) in batch order; stitch with stitch_ovl()."""
+    import threading
+    n = len(batches)
+    chunks, states, stats = [None] * n, [None] * n, [None] * n
+    nxt = [0]
+    lock = threading.Lock()
+    err = []
+
+    def work(e):
+        while True:
+            with lock:
+                i = nxt[0]; nxt[0] += 1
+            if i >= n or err:
+                return
+            try:
+                st = np.zeros(2, dtype=np.uint32)
+                data, s = e.map_batch_ovl(batches[i], st)
+                chunks[i], states[i], stats[i] = data, (int(st[0]), int(st[1])), s
+            except Exception as ex:  # noqa: BLE001
+                err.append(ex)
+    ts = [threading.Thread(target=work, args=(e,)) for e in engs]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if err:
+        raise err[0]
+    return chunks, states, stats
 
 
 def shard_bounds(n, world):

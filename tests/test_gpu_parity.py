@@ -59,7 +59,7 @@ def test_sketch_matches_oracle(eng, reads_sub, preset, hpc):
         assert got.shape == want.shape and (got == want).all(), "read %d" % r
 
 
-@pytest.mark.parametrize("variant", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("variant", [(0, 0), (1, 1), (2, 1)])
 @pytest.mark.parametrize("preset,gold", [("ava-ont", "S1_sub120_ava-ont.ovl"), ("ava-pb", "S3_sub120_ava-pb.ovl")])
 def test_step1_sub120(eng, engine_mod, reads_sub, golden_dir, preset, gold, variant):
     io, mo = _opts(preset)
@@ -110,10 +110,12 @@ def test_step1_full_golden(eng, engine_mod, reads_full, golden_dir, preset, k, w
     assert ovl == want, _diff_msg(ovl, want)
 
 
-def test_step1_full_baseline_kernels(eng, engine_mod, reads_full, golden_dir):
-    """the one-thread-per-read/segment kernel generation gives the same bytes"""
+@pytest.mark.parametrize("variant", [(0, 0), (2, 1)])
+def test_step1_full_baseline_kernels(eng, engine_mod, reads_full, golden_dir, variant):
+    """the one-thread-per-read/segment kernel generation, and the exact sort replay for every read (no block-sort fast path), give the
+    same bytes"""
     io, mo = _opts("ava-ont", 17, 10)
-    eng.set_variant(0, 0)
+    eng.set_variant(*variant)
     ovl, st = engine_mod.run_step1(eng, reads_full, reads_full, io, mo)
     eng.set_variant(1, 1)
     want = open(os.path.join(golden_dir, "G2_ava-ont_k17w10.ovl"), "rb").read()

@@ -197,7 +197,13 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
             // target copy happens to equal it
             bool slow_n = ((unsigned)sc_mch & 255u) == (unsigned)(m - 1) || ((unsigned)sc_mis & 255u) == (unsigned)(m - 1) || ((unsigned)sc_N & 255u) == (unsigned)(m - 1);
             slow_n = slow_n || (flag & 0x10000) != 0;           // host-set: the call contains an ambiguous base
-            const unsigned M1 = ndx_rep(m - 1);
+            unsigned M1 = ndx_rep(m - 1);
+            unsigned S_MCHr = S_MCH, S_Dr = S_D;
+            // keep the loop constants in registers: left to itself the compiler re-derives them from the scalar options on every use
+#define NDX_PIN(x) asm volatile("" : "+r"(x))
+            NDX_PIN(C.MCHMAX); NDX_PIN(C.KXA); NDX_PIN(C.KYB); NDX_PIN(C.KX2A); NDX_PIN(C.KY2B); NDX_PIN(C.CX); NDX_PIN(C.CY); NDX_PIN(C.CX2); NDX_PIN(C.CY2);
+            NDX_PIN(C.TA); NDX_PIN(C.TB); NDX_PIN(C.TA2); NDX_PIN(C.TB2); NDX_PIN(S_MCHr); NDX_PIN(S_Dr);
+#undef NDX_PIN
 
             // ---- state: register set k of this warp is slot k * NW + wid -------------------------------------------------------------
             unsigned U[K][2], V[K][2], X[K][2], Y[K][2], X2[K][2], Y2[K][2], S[K][2], TG[K];
@@ -249,7 +255,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                 if (st > 0) { patch = !(st - 1 >= last_st && st - 1 <= last_en); bX = I1 + tA; bV = I1; bX2 = I2 + tA2; }
                 else { patch = true; bX = I1 + tA; bV = 16 * vb + NDX_B; bX2 = I2 + tA2; }
 
-                if (ring) {                                                          // columns that fell 16 cells behind the band for good: recycle
+                if (ring && st != last_st) {                                         // columns that fell 16 cells behind the band for good: recycle (st moves every 32nd diagonal)
 #pragma unroll
                     for (int k = 0; k < K; ++k)
                         if (t0[k] + 3 < st - 16 && t0[k] + CAP < T) {
@@ -267,7 +273,14 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                     if (sl % NW == wid && ((pos >> 2) & 31) == lane) { fr_k = sl / NW; fr_j = pos & 3; }
                 }
 
-                int lmax = NDX_HNEG;                                                 // exact mode: this lane's best 16*H over [st0, en0]
+                // approximate mode: the lanes holding columns last_H0_t / last_H0_t + 1 hand their v / u to the bookkeeping (:361-371)
+                bool ok0 = false, ok1 = false; int k0 = 0, j0 = 0, k1 = 0, j1 = 0;
+                if (!EXACT) {
+                    const int p0 = last_H0_t % CAP, p1 = (last_H0_t + 1) % CAP;
+                    ok0 = (p0 >> 7) % NW == wid && ((p0 >> 2) & 31) == lane; k0 = (p0 >> 7) / NW; j0 = p0 & 3;
+                    ok1 = (p1 >> 7) % NW == wid && ((p1 >> 2) & 31) == lane; k1 = (p1 >> 7) / NW; j1 = p1 & 3;
+                }
+                int lmax = NDX_HNEG, lk = 0; bool ltie = false;                      // exact mode: this lane's best 16*H over [st0, en0], its register set, seen twice?
                 const int en1 = st0 + (en0 - st0) / 4 * 4;
                 const int qidx_base = r - 3;
                 const unsigned band_w = (unsigned)(en - st), live_w = (unsigned)(live_hi + 3 - st0);
@@ -278,7 +291,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                     if (fr_k == k) { ndx_setcol(Y[k][0], Y[k][1], fr_j, I1 + tB); ndx_setcol(Y2[k][0], Y2[k][1], fr_j, I2 + tB2); ndx_setcol(U[k][0], U[k][1], fr_j, 16 * vb + NDX_B); }
                     const bool act = (unsigned)(tt - st) <= band_w;                  // st, en are multiples of 16 (-1): all four columns or none
                     const bool live = (unsigned)(tt + 3 - st0) < live_w;             // some column gets a fresh score: tt+3 >= st0 && tt < live_hi
-                    if (!__any_sync(NDK_FULL, act || live)) continue;
+                    if (__any_sync(NDK_FULL, act || live)) {
                     const int sl = k * NW + wid;                                     // this register set's slot
 
                     // ---- scores of this diagonal (:157-176), stale elsewhere ----------------------------------------------------------------
@@ -289,8 +302,8 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         const uint32_t w4 = __funnelshift_r(w0, w1, 8 * (qi & 3));    // bytes b0..b3 = query[qi..qi+3]
                         const unsigned QP0 = __byte_perm(w4, 0u, 0x4143), QP1 = __byte_perm(w4, 0u, 0x4042);   // (c0,c2) = (b3,b1), (c1,c3) = (b2,b0)
                         const unsigned TP0 = __byte_perm(TG[k], 0u, 0x4240), TP1 = __byte_perm(TG[k], 0u, 0x4341);
-                        unsigned s0 = S_MCH - __vminu2(TP0 ^ QP0, 0x00010001u) * S_D;
-                        unsigned s1 = S_MCH - __vminu2(TP1 ^ QP1, 0x00010001u) * S_D;
+                        unsigned s0 = S_MCHr - __vminu2(TP0 ^ QP0, 0x00010001u) * S_Dr;
+                        unsigned s1 = S_MCHr - __vminu2(TP1 ^ QP1, 0x00010001u) * S_Dr;
                         if (slow_n) {
                             const unsigned e0 = __vminu2(TP0 ^ M1, 0x00010001u) & __vminu2(QP0 ^ M1, 0x00010001u);   // 0 where an operand is the ambiguity code
                             const unsigned e1 = __vminu2(TP1 ^ M1, 0x00010001u) & __vminu2(QP1 ^ M1, 0x00010001u);
@@ -323,12 +336,14 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         if (with_cigar) *reinterpret_cast<uint32_t *>(prow + tt) = __byte_perm(D0, D1, 0x6240);   // bytes c0 c1 c2 c3
                         if (lane == 31) { xn.bx[sl] = X[k][1]; xn.bv[sl] = V[k][1]; xn.bx2[sl] = X2[k][1]; }
 
-                        // ---- exact maximum: H[t] += v[t] over [st0, en0), H[en0] from its left neighbour (:316-346); ranks are resolved after the loop
+                        // ---- exact maximum: H[t] += v[t] over [st0, en0), H[en0] from its left neighbour (:316-346).  A lane keeps its best
+                        // 16*H and where it saw it; the SIMD-search rank of the winner is worked out after the loop
                         if (EXACT) {
                             if (r > 0) {
-                                if (tt >= st0 && tt + 3 < en0) {
+                                if (tt > st0 && tt + 3 < en0 - 1) {                  // four interior columns (st0, en0 - 1 and en0 take the other branch)
                                     Hh[k][0] += ndx_lo(V[k][0]) - NDX_B; Hh[k][1] += ndx_lo(V[k][1]) - NDX_B; Hh[k][2] += ndx_hi(V[k][0]) - NDX_B; Hh[k][3] += ndx_hi(V[k][1]) - NDX_B;
-                                    lmax = max(lmax, max(max(Hh[k][0], Hh[k][1]), max(Hh[k][2], Hh[k][3])));
+                                    const int m4 = max(max(Hh[k][0], Hh[k][1]), max(Hh[k][2], Hh[k][3]));
+                                    if (m4 >= lmax) { ltie = ltie || m4 == lmax; if (m4 > lmax) ltie = false; lmax = m4; lk = k; }
                                 } else if (tt + 3 >= st0 && tt <= en0) {
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
@@ -339,31 +354,41 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                                         else {                                        // t == en0: H[en0] = H[en0-1] + u[en0] (old H of the left neighbour), :323
                                             const int hl = en0 == en0_prev ? hp1 : hp0;  // column en0 - 1 after the previous diagonal
                                             h = en0 > 0 ? hl + ndx_col(U[k][0], U[k][1], j) - NDX_B : Hh[k][j] + ndx_col(V[k][0], V[k][1], j) - NDX_B;
+                                            xn.h_en0 = h;
                                         }
                                         Hh[k][j] = h;
-                                        lmax = max(lmax, h);
+                                        if (t == en0 - 1) xn.h_en0m1 = h;
+                                        if (t == st0) xn.h_st0 = h;
+                                        if (h >= lmax) { ltie = ltie || h == lmax; if (h > lmax) ltie = false; lmax = h; lk = k; }
                                     }
                                 }
                             } else if (tt == 0) {                                    // r == 0: H[0] = v[0] - qe (:345)
                                 Hh[k][0] = ndx_lo(V[k][0]) - NDX_B - 16 * qe0;
-                                lmax = Hh[k][0];
+                                lmax = Hh[k][0]; lk = k; xn.h_en0 = lmax; xn.h_st0 = lmax;
                             }
                         }
+                    }
+                    }   // slot touched on this diagonal
+                    // the array values the reference would read, whether or not the column was computed on this diagonal
+                    if (!EXACT) {
+                        if (ok0 && k0 == k) xn.d0 = (ndx_col(V[k][0], V[k][1], j0) - NDX_B) >> 4;
+                        if (ok1 && k1 == k) xn.d1 = (ndx_col(U[k][0], U[k][1], j1) - NDX_B) >> 4;
                     }
                 }
 
                 // ---- hand the bookkeeping its operands (one lane each) -----------------------------------------------------------------------------
-#define NDX_OWNER(col, body) { const int pos_ = (col) % CAP, sl_ = pos_ >> 7; if (sl_ % NW == wid && ((pos_ >> 2) & 31) == lane) { const int j_ = pos_ & 3, kk_ = sl_ / NW; (void)j_; (void)kk_; body } }
-#define NDX_SEL(A, out) { _Pragma("unroll") for (int k = 0; k < K; ++k) if (k == kk_) out = ndx_col(A[k][0], A[k][1], j_); }
-#define NDX_SELH(out) { _Pragma("unroll") for (int k = 0; k < K; ++k) if (k == kk_) out = j_ == 0 ? Hh[k][0] : j_ == 1 ? Hh[k][1] : j_ == 2 ? Hh[k][2] : Hh[k][3]; }
                 if (EXACT) {
                     const int wm = __reduce_max_sync(NDK_FULL, lmax);
                     // smallest SIMD-search rank among this warp's columns of [st0, en0] that attain the maximum (:320-343: en0 first, then the
-                    // 4-lane blocks lane-major, then the scalar tail)
+                    // 4-lane blocks lane-major, then the scalar tail).  Usually one lane holds the maximum once: only its register set lk is scanned.
                     unsigned lrank = 0xffffffffu;
-                    if (lmax == wm && wm != NDX_HNEG) {
+                    const bool mine = lmax == wm && wm != NDX_HNEG;
+                    const unsigned cand = __ballot_sync(NDK_FULL, mine);
+                    if (mine) {
+                        const bool full = ltie || (cand & (cand - 1)) != 0;         // a tie inside this lane or between lanes: scan every register set
 #pragma unroll
-                        for (int k = 0; k < K; ++k)
+                        for (int k = 0; k < K; ++k) {
+                            if (!full && k != lk) continue;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int t = t0[k] + j;
@@ -372,21 +397,11 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                                     lrank = rank < lrank ? rank : lrank;
                                 }
                             }
+                        }
                     }
                     const unsigned wr = __reduce_min_sync(NDK_FULL, lrank);
                     if (lane == 0) { xn.wmax[wid] = wm; xn.wrank[wid] = wr; }
-                    NDX_OWNER(en0, { int v = 0; NDX_SELH(v) xn.h_en0 = v; })
-                    if (en0 - 1 >= st0) NDX_OWNER(en0 - 1, { int v = 0; NDX_SELH(v) xn.h_en0m1 = v; })
-                    if (r - st0 == qlen - 1) NDX_OWNER(st0, { int v = 0; NDX_SELH(v) xn.h_st0 = v; })
-                    if (r == n_diag - 1 && en0 == tlen - 1) NDX_OWNER(tlen - 1, { int v = 0; NDX_SELH(v) xn.h_last = v; })
-                } else {
-                    // the array values the reference reads (:361-371): new v of column last_H0_t, new u of column last_H0_t + 1
-                    NDX_OWNER(last_H0_t, { int v = 0; NDX_SEL(V, v) xn.d0 = (v - NDX_B) >> 4; })
-                    NDX_OWNER(last_H0_t + 1, { int v = 0; NDX_SEL(U, v) xn.d1 = (v - NDX_B) >> 4; })
                 }
-#undef NDX_OWNER
-#undef NDX_SEL
-#undef NDX_SELH
                 sync();
 
                 // ---- scores that spilled past the target copy (:103,:175): target bytes of columns 0..15 are overwritten ---------------------------------
@@ -404,9 +419,13 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
 
                 // ---- scalar bookkeeping, replicated in every thread (:316-376) ----------------------------------------------------------------------
                 if (EXACT) {
-                    int best = xn.wmax[0]; unsigned brank = xn.wrank[0];
-#pragma unroll
-                    for (int o = 1; o < NW; ++o) { const int hm = xn.wmax[o]; const unsigned rk = xn.wrank[o]; if (hm > best || (hm == best && rk < brank)) { best = hm; brank = rk; } }
+                    int best; unsigned brank;
+                    if (NW == 1) { best = xn.wmax[0]; brank = xn.wrank[0]; }
+                    else {                                                           // lane w reads warp w's part; two warp reductions
+                        const int hm = lane < NW ? xn.wmax[lane & 7] : NDX_HNEG; const unsigned rk = lane < NW ? xn.wrank[lane & 7] : 0xffffffffu;
+                        best = __reduce_max_sync(NDK_FULL, hm);
+                        brank = __reduce_min_sync(NDK_FULL, hm == best ? rk : 0xffffffffu);
+                    }
                     const int max_H = best >> 4;
                     int max_t;
                     if (r == 0) max_t = 0;
@@ -420,7 +439,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                     if (en0 == tlen - 1) { const int h = hp0 >> 4; if (h > ez.mte) { ez.mte = h; ez.mte_q = r - en; } }
                     if (r - st0 == qlen - 1) { const int h = xn.h_st0 >> 4; if (h > ez.mqe) { ez.mqe = h; ez.mqe_t = st0; } }
                     if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
-                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = xn.h_last >> 4;
+                    if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = hp0 >> 4;     // H[tlen-1] = H[en0]
                 } else {
                     if (r > 0) {
                         if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {

@@ -1181,7 +1181,7 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
 namespace {
 
 const int RX_NCFG = 5;
-const int RX_CAP[RX_NCFG] = { 512, 1024, 2048, 3072, 4096 };       // 128 * K * NW: (2,2) (2,4) (2,8) (3,8) (4,8)
+const int RX_CAP[RX_NCFG] = { 512, 1024, 2048, 3072, 4096 };       // 128 * K * NW: (4,1) (4,2) (4,4) (3,8) (4,8)
 #define NDX_FLAG_AMBI 0x10000
 
 // ring class of a call, or -1 when the register-resident kernel does not take it (generic scoring, band wider than every ring)
@@ -1219,9 +1219,9 @@ cudaError_t rx_launch(int cfg, bool exact, int hint, int n_sm, cudaStream_t st, 
 #define RXL(K, NW) (exact ? rx_launch_t<K, NW, true>(hint, n_sm, st, calls, n, seqs, P, res, pmat, cig, rowtabs, tab_entries, work, cur, arena_bytes, blocks_out) \
                           : rx_launch_t<K, NW, false>(hint, n_sm, st, calls, n, seqs, P, res, pmat, cig, rowtabs, tab_entries, work, cur, arena_bytes, blocks_out))
     switch (cfg) {
-    case 0: return RXL(2, 2);
-    case 1: return RXL(2, 4);
-    case 2: return RXL(2, 8);
+    case 0: return RXL(4, 1);
+    case 1: return RXL(4, 2);
+    case 2: return RXL(4, 4);
     case 3: return RXL(3, 8);
     default: return RXL(4, 8);
     }

@@ -470,3 +470,4 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
         sync();
     }
 }
+

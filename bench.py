@@ -4,7 +4,9 @@
 Workload = BASELINE.json configs[1]: 100k synthetic 20 kb ONT reads (15 % error: 5 % sub, 4 % ins, 6 % del, 40x depth),
 `--step 1 -x ava-ont -k 17 -w 10`, self-overlap, .ovl records.  The index over all reads is built once (reported separately);
 a *step* maps one query batch of `--batch-reads` reads (3000 reads = 60 Mbp, the reference's `-K 60M` mini-batch) against it.
-Step i maps reads [i*B, (i+1)*B) of the set, in file order -- both arms time the SAME batches.
+The batches are strided samples of the set (batch i = reads i, i+S, i+2S, ... with S = n // B), so that every step carries the
+set's average work: the number of records a read yields depends on where its NAME sorts (MM_F_NO_DUAL keeps a pair only on the
+read whose decimal name is smaller in strcmp order), and contiguous name ranges are not comparable.  Both arms time the SAME batches.
 
   value : whole-job overlaps/s with the step's query batch already resident in HBM (all kernels of the step, one CUDA-event pair
           per step on the launching stream, max over ranks)
@@ -122,8 +124,27 @@ def make_reads(n, genome_bp, first=0, rank=0, world=1):
     return r
 
 
-def run_reference(reads, n_batches, B, threads, keep=None):
-    """The unmodified reference binary: index over `reads`, queries = the first n_batches*B reads of the same set with `-K` such
+def step_batches(reads, B, n):
+    """the first n strided batches of B reads (see the module docstring)"""
+    from nextdenovo_b200.formats import take_reads
+    S = reads.n // B
+    if n > S:
+        raise SystemExit("warmup+steps = %d batches of %d reads exceed the %d-read set (%d batches)" % (n, B, reads.n, S))
+    return [take_reads(reads, np.arange(B, dtype=np.int64) * S + i) for i in range(n)]
+
+
+def concat_reads(parts):
+    from nextdenovo_b200.formats import Reads
+    off = [np.zeros(1, dtype=np.uint64)]
+    base = 0
+    for p in parts:
+        off.append(p.word_off[1:].astype(np.uint64) + np.uint64(base)); base += int(p.word_off[-1])
+    return Reads(np.concatenate([p.words for p in parts]), np.concatenate(off), np.concatenate([p.length for p in parts]), np.concatenate([p.ids for p in parts]),
+                 np.concatenate([p.name_key for p in parts]), np.concatenate([p.name_hash for p in parts]))
+
+
+def run_reference(reads, queries, n_batches, B, threads, keep=None):
+    """The unmodified reference binary: index over `reads`, queries = `queries` (the GPU arm's batches, concatenated) with `-K` such
     that its mini-batches are exactly the GPU arm's steps.  Returns per-batch (records, sum_qspan) arrays, the timestamps of its
     `mapped` lines (one per batch, printed by the ordered output stage), the timestamp of the index line, and the process time."""
     import nextdenovo_b200 as nd
@@ -134,7 +155,7 @@ def run_reference(reads, n_batches, B, threads, keep=None):
     with tempfile.TemporaryDirectory(dir=base) as td:
         tp, qp, out = os.path.join(td, "t.2bit"), os.path.join(td, "q.2bit"), os.path.join(td, "o.ovl")
         nd.write_2bit(tp, reads)
-        nd.write_2bit(qp, reads.slice(0, min(reads.n, n_batches * B)))
+        nd.write_2bit(qp, queries)
         t0 = time.time()
         r = subprocess.run([exe, "--step", "1", "-t", str(threads), "-I", "100G", "-K", str(B * READ_LEN), "-x", "ava-ont", "-k", "17", "-w", "10", tp, qp, "-o", out],
                            stderr=subprocess.PIPE, text=True, check=True)
@@ -151,7 +172,9 @@ def run_reference(reads, n_batches, B, threads, keep=None):
         if keep is not None:
             keep.append(raw)
         d = nd.decode_ovl8(raw)
-    bi = (d[:, 0].astype(np.int64) // B)
+    bidx = np.full(int(reads.ids.max()) + 1, n_batches, dtype=np.int64)     # query name -> batch
+    bidx[queries.ids.astype(np.int64)] = np.arange(queries.n, dtype=np.int64) // B
+    bi = bidx[d[:, 0].astype(np.int64)]
     rec = np.bincount(bi, minlength=n_batches)[:n_batches]
     sq = np.bincount(bi, weights=(d[:, 3].astype(np.int64) - d[:, 2].astype(np.int64)), minlength=n_batches)[:n_batches]
     return rec, sq, t_map, t_idx, total
@@ -330,10 +353,8 @@ def main_reference(a, rank, world):
     threads = usable_cpus()
     B = a.batch_reads
     nb = a.warmup + a.steps
-    if nb * B > a.reads:
-        raise SystemExit("warmup+steps batches exceed the read set")
     reads = make_reads(a.reads, int(a.reads * READ_LEN / DEPTH))
-    rec, sq, t_map, t_idx, total = run_reference(reads, nb, B, threads)
+    rec, sq, t_map, t_idx, total = run_reference(reads, concat_reads(step_batches(reads, B, nb)), nb, B, threads)
     if len(t_map) != nb:
         raise SystemExit("reference printed %d batch lines, expected %d" % (len(t_map), nb))
     t_prev = t_map[a.warmup - 1] if a.warmup > 0 else t_idx
@@ -385,8 +406,6 @@ def main_ours(a, rank, world, local_rank):
     hbm_peak, peak_kind = peaks()
     B = a.batch_reads
     nb = a.warmup + a.steps
-    if nb * B > a.reads:
-        raise SystemExit("warmup+steps = %d batches of %d reads exceed the %d-read set" % (nb, B, a.reads))
 
     # ---- workload: N x 100k reads over a genome that grows with N (depth fixed); rank r owns reads [r*100k, (r+1)*100k) of the
     # seeded set, named r, r+N, r+2N, ... (see the module docstring)
@@ -418,7 +437,7 @@ def main_ours(a, rank, world, local_rank):
     t_index = time.time() - t0
 
     eng.set_limits(a.sub_batch_mbp << 20, 0)
-    batches = [reads.slice(i * B, (i + 1) * B) for i in range(nb)]
+    batches = step_batches(reads, B, nb)
 
     def barrier():
         if dist is not None:
@@ -505,9 +524,11 @@ def main_ours(a, rank, world, local_rank):
         data, st_e = eng.map_batch_ovl(reads.slice(i, min(i + B, reads.n)), state)
         all_rec += st_e["records"]; all_sq += st_e["sum_qspan"]
         h_all.update(data)
-        if i // B < a.cpu_batches:
-            first_bytes.append(data)
     t_all = time.perf_counter() - t1
+    if rank == 0 and not a.no_cpu_baseline and world == 1:               # the bytes the cpu_baseline leg is checked against
+        state[:] = 0
+        for i in range(a.cpu_batches):
+            first_bytes.append(eng.map_batch_ovl(batches[i], state)[0])
 
     # ---- reduce over ranks: total units / max time
     t_res_dev = t_dev_ms / 1e3                      # one CUDA-event pair around each step on the launching stream (gaps included)
@@ -545,7 +566,7 @@ def main_ours(a, rank, world, local_rank):
             try:
                 threads = usable_cpus()
                 keep = []
-                r_rec, r_sq, t_map, t_idx, tot = run_reference(reads, a.cpu_batches, B, threads, keep=keep)
+                r_rec, r_sq, t_map, t_idx, tot = run_reference(reads, concat_reads(batches[:a.cpu_batches]), a.cpu_batches, B, threads, keep=keep)
                 tm = t_map[-1] - t_idx
                 mine_bytes = b"".join(first_bytes)
                 cpu = {"value": float(r_rec.sum()) / tm, "unit": "overlaps/s", "cores": threads, "kind": "reference",

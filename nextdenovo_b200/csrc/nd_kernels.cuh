@@ -180,7 +180,7 @@ k_sketch_fast(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int w, i
 //     k-mer, beyond the read -- hold 0, which is smaller than every hash and so ends a run);
 //   * survivors are compacted in position order with one block-wide prefix sum instead of a ballot per 128 positions.
 template <int W>
-__global__ void __launch_bounds__(NDS_T)
+__global__ void __launch_bounds__(NDS_T, 8)
 k_sketch_fast4(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int k, uint32_t rid0, int use_rid,
                nd_u128 *staging, int S, uint32_t *cnt, uint32_t *slow)
 {

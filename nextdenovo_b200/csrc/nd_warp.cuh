@@ -470,7 +470,7 @@ static inline void ndw_chain_fill_launch(cudaStream_t st, nd_seg_view S, nd_read
                                          int max_span, int uniform_span, nd_chain_bufs B, uint32_t *work_counter, int n_sm)
 {
     cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
-    unsigned blocks = (unsigned)(n_sm * 8);
+    unsigned blocks = (unsigned)(n_sm * 16);           // 64 warps per SM: the kernel is latency-bound (serial dependence over a segment's anchors)
     unsigned need = (S.n_seg + NDW_CHAIN_WARPS - 1) / NDW_CHAIN_WARPS;
     if (need < blocks) blocks = need ? need : 1;
     k_chain_fill_warp<<<blocks, NDW_CHAIN_WARPS * 32, 0, st>>>(S, Q, avg_qspan, par, max_span, uniform_span, B, work_counter);

@@ -34,6 +34,20 @@ class Reads:
                      None if self.nmask is None else self.nmask[w0 // 2:w1 // 2 + 1])
 
 
+def take_reads(r: "Reads", idx):
+    """a new batch made of reads idx[0], idx[1], ... of r (copies the 2-bit words; an ambiguity mask is not carried)"""
+    idx = np.asarray(idx, dtype=np.int64)
+    w0 = r.word_off[idx].astype(np.int64)
+    nw = (r.word_off[idx + 1].astype(np.int64) - w0)
+    off = np.zeros(idx.shape[0] + 1, dtype=np.uint64)
+    np.cumsum(nw, out=off[1:])
+    if idx.shape[0] and (nw == nw[0]).all():                       # fixed-length reads: one fancy-indexed gather
+        words = r.words[(w0[:, None] + np.arange(int(nw[0]), dtype=np.int64)[None, :]).reshape(-1)]
+    else:
+        words = np.concatenate([r.words[a:a + n] for a, n in zip(w0.tolist(), nw.tolist())]) if idx.shape[0] else np.zeros(0, dtype=np.uint32)
+    return Reads(np.ascontiguousarray(words, dtype=np.uint32), off, r.length[idx].copy(), r.ids[idx].copy(), r.name_key[idx].copy(), r.name_hash[idx].copy())
+
+
 def _ndigits(ids):
     ids = ids.astype(np.uint64)
     nd = np.ones(ids.shape, dtype=np.int64)

@@ -193,6 +193,19 @@ int ndg_map_upload(ndg_ctx_t *ctx, const ndg_reads_t *queries);      /* H2D only
 int ndg_map_resident(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* kernels only; hits stay on device */
 int ndg_map_download(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* D2H of the hits */
 
+/* ---- PAF extras: what mm_write_paf3 prints beyond the coordinates (ref: minimap2/format.c:282-318) and what mm_set_mapq / mm_est_err
+ * need (ref: minimap2/hit.c:446-491, minimap2/esterr.c:30-64, minimap2/map.c:91-124 rep_len).  Off by default: nothing of this
+ * reaches .ovl.  After ndg_set_paf(ctx, 1) every ndg_map_batch() also fills, parallel to its hit list:
+ *   per hit  : regime A: the raw counts of mm_est_err (n_match, n_span = en - st + 1 or -1 when the chain start is not found);
+ *              regime B: dp_score, dp_max, n_ambi of mm_extra_t, the CIGAR (BAM encoding, into the pool), the chain scores;
+ *              flags bit0 inv, bit1 id == parent (only split-off and inversion hits in all-chain mode), bits 2-3 split, bit4 has a CIGAR
+ *   per query: rep_len, the number of minimizers that passed the occurrence filter and the sum of their spans (avg_k = sum/n).
+ * The float arithmetic (logf) is the writer's, on the host, as in the reference. */
+typedef struct { int32_t n_match, n_span, dp_score, dp_max, n_ambi, score0, chain_score; uint32_t flags, n_cigar; uint64_t cigar_off; } ndg_hit_extra_t;
+typedef struct { int32_t rep_len, n_mini; uint64_t sum_span; } ndg_query_extra_t;
+int ndg_set_paf(ndg_ctx_t *ctx, int on);
+int ndg_map_extras(ndg_ctx_t *ctx, const ndg_hit_extra_t **hit_extra, const ndg_query_extra_t **query_extra, const uint32_t **cigar_pool);
+
 /* ---- `--step 2` (cns_align): first-pass mapping, per-query re-mapping of the dovetail candidates against throw-away mini
  * indexes, 10-field records after the contained/dovetail bookkeeping, `.bl` side file.
  * Replaces the step-2 branch of worker_for() and of the writer (ref: minimap2/map.c:988-1128,1305-1328, lib/ovl.c:205-253,339-361,

@@ -5,7 +5,7 @@
 // (ref: nextDenovo:445-464): two-pass option handling (minimap2/main.c:177-363), index parts
 // (minimap2/index.c:284-288,353-358), query batches (minimap2/bseq.c:86-123), ordered .ovl output
 // (minimap2/map.c:1245-1352).  Input: .2bit (what seq_dump writes, lib/bseq.c:93-139) or FASTA/FASTQ[.gz] with decimal names; other
-// modes of the reference binary (--step 3, PAF/SAM, chain selection without MM_F_ALL_CHAINS) are rejected by name, never approximated;
+// modes of the reference binary (--step 3, SAM, chain selection without MM_F_ALL_CHAINS) are rejected by name, never approximated;
 // unknown options are an error as in the reference.
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +20,7 @@
 #include <atomic>
 #include <zlib.h>
 #include "ndgpu.h"
+#include "nd_paf.hpp"
 
 struct Reads {
     std::vector<uint32_t> words, len, id, hash, nmask;   // nmask: 1 bit per base at nmask[word_off/2 + (i>>5)] (FASTA/Q input only)
@@ -146,7 +147,7 @@ int main(int argc, char **argv)
     int step = 0, minlen = 500, maxhan1 = 5000, maxhan2 = 500, dvt = 0, verbose = 3, device = 0, n_threads = 0, n_gpus = 1;
     uint64_t batch_size = 4000000000ULL, mini_batch = 50000000ULL; int64_t q_batch = 500000000;
     const char *out = nullptr; std::vector<const char *> pos;
-    bool cigar = false;
+    bool cigar = false, outraw = false;                         // outraw: text (PAF) instead of .ovl records (ref: minimap2/main.c:191,216,274, map.c:1293)
     ndg_step2_opt_t s2 = { 2000, 5000, 500, 100, 2, 20, 17, 10, 0, 0.05f };   // minimap2/main.c:194-198, options.c:50-62
     ndg_aln_opt_t ao = { 2, 4, 4, 2, 24, 1, 1, 400, 200, -1, 80, 200, 0, 1.0f };   // minimap2/options.c:37-44
     const double t0 = now();
@@ -204,7 +205,7 @@ int main(int argc, char **argv)
         static const char *not_built[] = { "-a", "-S", "--cs", "--MD", "--eqx", "-Y", "-L", "-Q", "-y", "-R", "--splice", "--sr", "--frag", "--no-pairing", "--splice-flank",
             "-u", "-C", "-G", "-F", "--heap-sort", "--for-only", "--rev-only", "--end-seed-pen", "--lj-min-ratio", "--split-prefix", "--junc-bed", "--junc-bonus",
             "--sam-hit-only", "--paf-no-hit", "--secondary", "-T", "-d", "--bucket-bits", "--idx-no-seq", "--cap-sw-mem", "--max-qlen", "--print-seeds", "--print-aln-seq",
-            "--print-qname", "--df", "--outraw", "--hard-mask-level", 0 };
+            "--print-qname", "--df", "--hard-mask-level", 0 };
         for (auto &kv : tok) for (const char **x = not_built; *x; ++x) if (kv.first == *x) {
             fprintf(stderr, "[ERROR] option '%s' is not built in this GPU build (it implements `--step 1 [-c]` and `--step 2` with .ovl output)\n", kv.first.c_str()); return 1; }
     }
@@ -215,6 +216,7 @@ int main(int argc, char **argv)
             else { fprintf(stderr, "[ERROR] unknown preset '%s'\n", kv.second.c_str()); return 1; }
         } else if (kv.first == "--step") {
             step = atoi(kv.second.c_str());
+            outraw = true;                                      // main.c:191; `-o FILE` switches back to records (main.c:274)
             if (step == 1) minlen = 500;
             else if (step == 2) { minlen = 2000; maxhan1 = 5000; maxhan2 = 500; s2.minide = 0.05f; s2.minmatch = 100; s2.kn = 17; s2.wn = 10; s2.cn = 20; }
             else if (step == 3) minlen = 2000;
@@ -249,7 +251,8 @@ int main(int argc, char **argv)
         else if (k == "--gpus") n_gpus = atoi(v);
         else if (k == "--dual") { if (kv.second == "yes" || kv.second == "y") o.flag_no_dual = 0; else if (kv.second == "no" || kv.second == "n") o.flag_no_dual = 1; }
         else if (k == "-f") { double x = strtod(v, nullptr); if (x < 1.0) { o.mid_occ_frac = (float)x; o.mid_occ = 0; } else o.mid_occ = (int)(x + .499); }
-        else if (k == "-o") { if (kv.second != "-") out = v; }
+        else if (k == "-o") { if (kv.second != "-") { out = v; if (step) outraw = false; } }
+        else if (k == "--outraw") outraw = true;
         else if (k == "-V" || k == "--version") { puts("2.17-r941-ndgpu"); return 0; }
     }
     if (pos.size() < 2) {
@@ -260,8 +263,10 @@ int main(int argc, char **argv)
         fprintf(stderr, "[ERROR] this GPU build maps in all-chain mode only (MM_F_ALL_CHAINS): use -x ava-ont|ava-pb, -X or -P\n");
         return 1;
     }
-    if ((step != 1 && step != 2) || !out || (step == 2 && cigar)) {
-        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` and `--step 2 ... -o FILE` (.ovl output) only\n");
+    const bool paf = outraw || !step;                           // map.c:1293: `outraw || !step` prints PAF lines
+    if (paf && step != 0 && step != 1) { fprintf(stderr, "[ERROR] PAF output is built for plain mapping and `--step 1 [-c]` only\n"); return 1; }
+    if (!paf && ((step != 1 && step != 2) || !out || (step == 2 && cigar))) {
+        fprintf(stderr, "[ERROR] this GPU build implements `--step 1 [-c] ... -o FILE` and `--step 2 ... -o FILE` (.ovl output), and PAF text without `-o`/with --outraw\n");
         return 1;
     }
     if (step == 2 && s2.mode != 0 && s2.mode != 2) { fprintf(stderr, "[ERROR] --mode %d is not built (0 and 2 are)\n", s2.mode); return 1; }
@@ -271,7 +276,7 @@ int main(int argc, char **argv)
         if ((ao.q + ao.e) + (ao.q2 + ao.e2) > 127) { fprintf(stderr, "[ERROR]\033[1;31m scoring system violating ({-O}+{-E})+({-O2}+{-E2}) <= 127\033[0m\n"); return 1; }
         if (ao.zdrop < ao.zdrop_inv) { fprintf(stderr, "[ERROR]\033[1;31m Z-drop should not be less than inversion-Z-drop\033[0m\n"); return 1; }
     }
-    FILE *fo = fopen(out, "wb");                                // main.c:259-262 (freopen)
+    FILE *fo = out ? fopen(out, "wb") : stdout;                 // main.c:259-262 (freopen)
     if (!fo) { fprintf(stderr, "[ERROR]\033[1;31m failed to write the output to file '%s'\033[0m\n", out); return 1; }
     FILE *fbl = nullptr;
     if (step == 2) {                                            // main.c:263-272: FILE.bl next to the records
@@ -286,8 +291,8 @@ int main(int argc, char **argv)
     // neighbouring batches overlap (what the reference's 3-stage kt_pipeline does with threads, ref: minimap2/map.c:1389-1390).
     // Step 2 keeps one context: its output stage is order-dependent (filter_ovl, ref: lib/ovl.c:449-563).
     if (n_gpus < 1) n_gpus = 1;
-    if (step == 2) n_gpus = 1;
-    const int G = n_gpus, CPG = (step == 2 || cigar) ? 1 : 2;
+    if (step == 2 || paf) n_gpus = 1;
+    const int G = n_gpus, CPG = (step == 2 || cigar || paf) ? 1 : 2;
     std::vector<ndg_ctx_t *> ctx((size_t)G * CPG, nullptr);
     for (int g = 0; g < G; ++g)
         for (int x = 0; x < CPG; ++x) {
@@ -297,6 +302,7 @@ int main(int argc, char **argv)
             if (cigar && ndg_set_aln_opt(h, &ao)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(h)); return 1; }
         }
     ndg_ctx_t *g = ctx[0];
+    if (paf && ndg_set_paf(g, 1)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
     if (step == 2) { s2.minlen = minlen; s2.maxhan1 = maxhan1; s2.maxhan2 = maxhan2; if (ndg_step2_begin(g, &s2)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; } }
     n_threads = ndg_set_threads(g, n_threads);                  // -t: host threads (only the -c stage has host-side work worth threading)
     if (cigar && G > 1) for (int x = 0; x < G; ++x) ndg_set_threads(ctx[(size_t)x * CPG], n_threads / G > 0 ? n_threads / G : 1);
@@ -378,6 +384,32 @@ int main(int argc, char **argv)
             std::vector<std::pair<int, int>> qb;               // bseq.c:86-123: a batch ends once >= chunk_size bases were read
             for (int q_at = 0; q_at < Q->n();) { int q0 = q_at; int64_t size = 0; while (q_at < Q->n()) { size += Q->len[q_at++]; if (size >= q_batch) break; } qb.push_back({ q0, q_at }); }
             const ndg_emit_opt_t eo = { minlen, dvt, maxhan1, maxhan2 };
+            if (paf) {                                          // text output: one line per hit, in query order (map.c:1289-1296)
+                const ndpaf::Par pp = { o.min_chain_score, ao.a, 0, cigar ? 1 : 0 };
+                std::string text; std::vector<int> mapq;
+                for (auto &b : qb) {
+                    ndg_reads_t qv = view(*Q, b.first, b.second);
+                    ndg_map_result_t R;
+                    const ndg_hit_extra_t *he = nullptr; const ndg_query_extra_t *qe = nullptr; const uint32_t *cg = nullptr;
+                    if (ndg_map_batch(g, &qv, &R) || ndg_map_extras(g, &he, &qe, &cg)) DIE(g);
+                    text.clear();
+                    for (int64_t i = 0; i < R.n_hits;) {
+                        int64_t j = i; while (j < R.n_hits && R.hits[j].qidx == R.hits[i].qidx) ++j;
+                        const int qi = R.hits[i].qidx, qa = b.first + qi;
+                        ndpaf::set_mapq(pp, R.hits + i, he + i, (int)(j - i), qe[qi].rep_len, mapq);
+                        for (int64_t k = i; k < j; ++k) {
+                            const ndg_hit_t &h = R.hits[k];
+                            ndpaf::write_hit(text, pp, Q->id[(size_t)qa], (int)Q->len[(size_t)qa], T.id[(size_t)(t0i + h.rid)], (int)T.len[(size_t)(t0i + h.rid)], h, he[k], qe[qi], mapq[(size_t)(k - i)], cg);
+                            text.push_back('\n');
+                            ++n_rec; sum_qspan += (uint64_t)(h.qe - h.qs);
+                        }
+                        i = j;
+                    }
+                    if (!text.empty() && fwrite(text.data(), 1, text.size(), fo) != text.size()) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+                    if (verbose >= 3) fprintf(stderr, "[M::worker_pipeline::%.3f] mapped %d sequences\n", now() - t0, b.second - b.first);
+                }
+                continue;
+            }
             if (ctx.size() == 1) {                              // one context: batches in order, the encoder state carried along
                 for (auto &b : qb) {
                     ndg_reads_t qv = view(*Q, b.first, b.second);
@@ -434,7 +466,7 @@ int main(int argc, char **argv)
         if (ndg_step2_finish(g, &bl, &nbl)) { fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1; }
         if ((nbl && fwrite(bl, 1, (size_t)nbl, fbl) != (size_t)nbl) || fclose(fbl) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
     }
-    if (fclose(fo) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
+    if ((fo == stdout ? fflush(fo) : fclose(fo)) != 0) { fprintf(stderr, "[ERROR] failed to write the results\n"); exit(EXIT_FAILURE); }
     if (verbose >= 3 && cigar) {
         ndg_aln_stat_t as; ndg_aln_stats(g, &as);
         fprintf(stderr, "[M::align] chains %llu; DP calls %llu in %llu rounds / %llu launches (%llu retried); %.3g cells; DP kernels %.3f s (backend wall %.3f s); alignment stage %.3f s on %d host threads\n", (unsigned long long)as.n_chains,

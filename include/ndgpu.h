@@ -220,6 +220,20 @@ int ndg_step2_map_batch(ndg_ctx_t *ctx, const ndg_reads_t *queries, const uint8_
                         ndg_map_result_t *work);
 int ndg_step2_finish(ndg_ctx_t *ctx, const char **bl_text, uint64_t *bl_bytes);
 
+/* ---- `ovl_sort`: the step that consumes the .ovl files of the overlap path (ref: util/ovl_sort.c:1-1143, nextDenovo:344-354):
+ * decode every 8-field stream, drop self hits and spans < 500, emit each record from both reads' point of view when the read is a
+ * seed (seed_name/seed_len, what `-i` lists), sort by (qname, match descending, query span ascending; ties in input order),
+ * then per query read: the read's own record first, the depth-capped admission of its overlaps on a 64-base histogram, the
+ * chimera / low-coverage / contained verdict (labels `c` and `k` of the .bl file), and the surviving records as one 8-field
+ * stream.  Everything between the input bytes and the output bytes runs on the GPU.  Equal to the reference binary whenever that
+ * holds its input in memory (one read thread, no spill files: the case of a pipeline block; with spill files the reference
+ * filters every chunk separately and once more while merging).  opt: -k (40), -l (300; 0 = no .bl), -H.
+ * ovl / bl_text: owned by the context, valid until the next call. */
+typedef struct { int32_t max_bin_cov, max_flank_len, is_hq; } ndg_ovlsort_opt_t;
+int ndg_ovl_sort(ndg_ctx_t *ctx, const uint8_t *const *streams, const uint64_t *stream_bytes, int32_t n_streams,
+                 const uint32_t *seed_name, const uint32_t *seed_len, uint64_t n_seeds, const ndg_ovlsort_opt_t *opt,
+                 const uint8_t **ovl, uint64_t *n_bytes, const char **bl_text, uint64_t *bl_bytes, uint64_t *n_rec_in, uint64_t *n_rec_out);
+
 /* ---- sketch only, for tests: replaces mm_sketch (ref: minimap2/sketch.c:358-361) ----------- */
 /* returns minimizers of all reads, concatenated; off has n_reads+1 entries */
 int ndg_sketch(ndg_ctx_t *ctx, const ndg_reads_t *reads, uint32_t rid0, uint64_t *xy, uint64_t cap, uint64_t *off);

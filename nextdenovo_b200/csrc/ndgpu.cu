@@ -15,6 +15,7 @@
 #include "nd_warp.cuh"
 #include "nd_ksw.cuh"
 #include "nd_kswrx.cuh"
+#include "nd_ovlsort_gpu.cuh"
 #include "nd_align.hpp"
 #include "nd_step2.hpp"
 #include <omp.h>
@@ -142,6 +143,8 @@ struct ndg_ctx {
     bool paf_on = false;
     DevBuf pf_flag, pf_rank, pf_mp, pf_q, pf_he; HostBuf h_pf;
     std::vector<ndg_hit_extra_t> paf_he; std::vector<ndg_query_extra_t> paf_qe; std::vector<uint32_t> paf_cig;
+    // ndg_ovl_sort results
+    HostBuf os_out; std::string os_bl;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -394,7 +397,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
     for (auto b : bufs) b->release();
     c->q.release();
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
-    c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release(); c->h_pf.release();
+    c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release(); c->h_pf.release(); c->os_out.release();
     if (c->remap) { ndg_destroy(c->remap); c->remap = nullptr; }
     cudaStreamDestroy(c->st);
     delete c;
@@ -1709,6 +1712,173 @@ int align_resident(ndg_ctx *c, const ndg_reads_t *Q, int r0, int r1)
 }
 
 } // namespace
+
+// ------------------------------------------------------------------------------------------------
+// ovl_sort on the GPU (nd_ovlsort_gpu.cuh, nd_ovlsort.cuh).  ref: util/ovl_sort.c
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevScope {                                  // transient device buffers of one ndg_ovl_sort call
+    std::vector<DevBuf *> all;
+    DevBuf *get() { DevBuf *b = new DevBuf(); all.push_back(b); return b; }
+    ~DevScope() { for (auto b : all) { b->release(); delete b; } }
+};
+}
+
+extern "C" int ndg_ovl_sort(ndg_ctx_t *c, const uint8_t *const *streams, const uint64_t *stream_bytes, int32_t n_streams,
+                            const uint32_t *seed_name, const uint32_t *seed_len, uint64_t n_seeds, const ndg_ovlsort_opt_t *opt,
+                            const uint8_t **ovl, uint64_t *n_bytes, const char **bl_text, uint64_t *bl_bytes, uint64_t *n_rec_in, uint64_t *n_rec_out)
+{
+    if (!c || !streams || !stream_bytes || n_streams < 0 || !seed_name || !seed_len || !opt || !ovl || !n_bytes) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    RSV(c->scalars, 1024);
+    uint64_t *h = c->h_scalars.as<uint64_t>();
+    DevScope S;
+    // seeds: sorted by name for the device lookups; the shortest seed feeds the clipping rule (ref: util/ovl_sort.c:106-133,538)
+    ndos_par P; P.max_bin_cov = opt->max_bin_cov; P.max_flank_len = opt->max_flank_len; P.is_hq = opt->is_hq; P.with_bl = opt->max_flank_len != 0; P.min_seed_len = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> sd(n_seeds);
+    for (uint64_t i = 0; i < n_seeds; ++i) sd[i] = { seed_name[i], seed_len[i] };
+    std::stable_sort(sd.begin(), sd.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+    { size_t k = 0; for (size_t i = 0; i < sd.size(); ++i) if (i == 0 || sd[i].first != sd[i - 1].first) sd[k++] = sd[i]; sd.resize(k); }   // the first entry of a name wins (kh_put absent test)
+    {   // min_seed_len follows the file order of the first occurrences (:126); the minimum over distinct names is the same number
+        for (auto &x : sd) if ((int)x.second < P.min_seed_len || !P.min_seed_len) P.min_seed_len = (int)x.second;
+    }
+    const uint64_t NS = sd.size();
+    std::vector<uint32_t> hn(NS), hl(NS);
+    for (uint64_t i = 0; i < NS; ++i) { hn[i] = sd[i].first; hl[i] = sd[i].second; }
+    DevBuf &d_sn = *S.get(), &d_sl = *S.get();
+    RSV(d_sn, (NS + 1) * 4); RSV(d_sl, (NS + 1) * 4);
+    if (NS) { CK(cudaMemcpyAsync(d_sn.p, hn.data(), NS * 4, cudaMemcpyHostToDevice, c->st)); CK(cudaMemcpyAsync(d_sl.p, hl.data(), NS * 4, cudaMemcpyHostToDevice, c->st)); }
+
+    // ---- 1. decode + reader filter, stream by stream; the qualifying records are appended in stream order ----------------------------------
+    DevBuf &R = *S.get();
+    uint64_t NR = 0, n_in = 0;
+    DevBuf &d_b = *S.get(), &flag = *S.get(), &vidx = *S.get(), &vals = *S.get(), &dq = *S.get(), &dt = *S.get(), &qn = *S.get(), &tn = *S.get(), &ok = *S.get(),
+           &f1 = *S.get(), &f5 = *S.get(), &nf1 = *S.get(), &nf5 = *S.get(), &keep = *S.get(), &pos = *S.get();
+    for (int s = 0; s < n_streams; ++s) {
+        const uint64_t nb = stream_bytes[s];
+        if (!nb) continue;
+        RSV(d_b, nb + 16); RSV(flag, (nb + 1) * 4); RSV(vidx, (nb + 1) * 8);
+        CK(cudaMemcpyAsync(d_b.p, streams[s], nb, cudaMemcpyHostToDevice, c->st));
+        KLAUNCH("ovl_sort", (k_os_term<<<nblk(nb + 1, 256), 256, 0, c->st>>>(d_b.as<uint8_t>(), nb, flag.as<uint32_t>())));
+        if (int rc = scan_u32_to_u64(c, flag.as<uint32_t>(), vidx.as<nd_u64>(), nb)) return rc;
+        CK(cudaMemcpyAsync(h, vidx.as<nd_u64>() + nb, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        const uint64_t nrec = h[0] / 8;
+        if (!nrec) continue;
+        n_in += nrec;
+        RSV(vals, (h[0] + 8) * 4); RSV(dq, (nrec + 1) * 4); RSV(dt, (nrec + 1) * 4); RSV(qn, (nrec + 1) * 4); RSV(tn, (nrec + 1) * 4);
+        RSV(ok, nrec + 16); RSV(f1, (nrec + 1) * 4); RSV(f5, (nrec + 1) * 4); RSV(nf1, (nrec + 1) * 8); RSV(nf5, (nrec + 1) * 8); RSV(keep, (2 * nrec + 2) * 4); RSV(pos, (2 * nrec + 2) * 8);
+        KLAUNCH("ovl_sort", (k_os_values<<<nblk(nb, 256), 256, 0, c->st>>>(d_b.as<uint8_t>(), nb, vidx.as<nd_u64>(), vals.as<uint32_t>())));
+        KLAUNCH("ovl_sort", (k_os_deltas<<<nblk(nrec, 256), 256, 0, c->st>>>(vals.as<uint32_t>(), nrec, dq.as<uint32_t>(), dt.as<uint32_t>())));
+        {
+            size_t tmp = 0;
+            CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, dq.as<uint32_t>(), qn.as<uint32_t>(), (long long)nrec, c->st));
+            RSV(c->cubtmp, tmp);
+            KLAUNCH("ovl_sort", CK(cub::DeviceScan::InclusiveSum(c->cubtmp.p, tmp, dq.as<uint32_t>(), qn.as<uint32_t>(), (long long)nrec, c->st)));
+            KLAUNCH("ovl_sort", CK(cub::DeviceScan::InclusiveSum(c->cubtmp.p, tmp, dt.as<uint32_t>(), tn.as<uint32_t>(), (long long)nrec, c->st)));
+        }
+        KLAUNCH("ovl_sort", (k_os_cand<<<nblk(nrec + 1, 256), 256, 0, c->st>>>(vals.as<uint32_t>(), qn.as<uint32_t>(), tn.as<uint32_t>(), nrec, d_sn.as<uint32_t>(), d_sl.as<uint32_t>(), NS,
+                             ok.as<uint8_t>(), f1.as<uint32_t>(), f5.as<uint32_t>())));
+        if (int rc = scan_u32_to_u64(c, f1.as<uint32_t>(), nf1.as<nd_u64>(), nrec)) return rc;
+        if (int rc = scan_u32_to_u64(c, f5.as<uint32_t>(), nf5.as<nd_u64>(), nrec)) return rc;
+        KLAUNCH("ovl_sort", (k_os_keep<<<nblk(nrec + 1, 256), 256, 0, c->st>>>(ok.as<uint8_t>(), nf1.as<nd_u64>(), nf5.as<nd_u64>(), nrec, keep.as<uint32_t>())));
+        CK(cudaMemsetAsync(keep.as<uint32_t>() + 2 * nrec, 0, 8, c->st));
+        if (int rc = scan_u32_to_u64(c, keep.as<uint32_t>(), pos.as<nd_u64>(), 2 * nrec)) return rc;
+        CK(cudaMemcpyAsync(h, pos.as<nd_u64>() + 2 * nrec, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        const uint64_t add = h[0];
+        if (R.grow_keep((NR + add + 1) * sizeof(ndos_rec), NR * sizeof(ndos_rec), c->st)) return fail(c, NDG_ERR_NOMEM, "ovl_sort records");
+        KLAUNCH("ovl_sort", (k_os_scatter<<<nblk(nrec, 256), 256, 0, c->st>>>(vals.as<uint32_t>(), qn.as<uint32_t>(), tn.as<uint32_t>(), nrec, keep.as<uint32_t>(), pos.as<nd_u64>(), NR, R.as<ndos_rec>())));
+        CK(cudaGetLastError());
+        NR += add;
+    }
+    if (n_rec_in) *n_rec_in = n_in;
+    c->os_bl.clear();
+    *ovl = nullptr; *n_bytes = 0;
+    if (bl_text) *bl_text = c->os_bl.c_str();
+    if (bl_bytes) *bl_bytes = 0;
+    if (n_rec_out) *n_rec_out = 0;
+    if (NR == 0) { CK(cudaStreamSynchronize(c->st)); return NDG_OK; }
+    if (NR >= (1ULL << 32) - 16) return fail(c, NDG_ERR_OVERFLOW, "ovl_sort: %llu records in one call", (unsigned long long)NR);
+
+    // ---- 2. order: (qname, match descending, span ascending), ties in input order (two stable radix passes on an index) --------------------
+    DevBuf &k32 = *S.get(), &k32b = *S.get(), &ix = *S.get(), &ixb = *S.get(), &k64 = *S.get(), &k64b = *S.get();
+    RSV(k32, NR * 4); RSV(k32b, NR * 4); RSV(ix, NR * 4); RSV(ixb, NR * 4); RSV(k64, NR * 8); RSV(k64b, NR * 8);
+    KLAUNCH("ovl_sort", (k_os_key_span<<<nblk(NR, 256), 256, 0, c->st>>>(R.as<ndos_rec>(), NR, k32.as<uint32_t>(), ix.as<uint32_t>())));
+    {
+        size_t t1 = 0, t2 = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, t1, k32.as<uint32_t>(), k32b.as<uint32_t>(), ix.as<uint32_t>(), ixb.as<uint32_t>(), (long long)NR, 0, 32, c->st));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, t2, k64.as<nd_u64>(), k64b.as<nd_u64>(), ixb.as<uint32_t>(), ix.as<uint32_t>(), (long long)NR, 0, 64, c->st));
+        RSV(c->cubtmp, std::max(t1, t2));
+        KLAUNCH("ovl_sort", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, t1, k32.as<uint32_t>(), k32b.as<uint32_t>(), ix.as<uint32_t>(), ixb.as<uint32_t>(), (long long)NR, 0, 32, c->st)));
+        KLAUNCH("ovl_sort", (k_os_key_main<<<nblk(NR, 256), 256, 0, c->st>>>(R.as<ndos_rec>(), ixb.as<uint32_t>(), NR, k64.as<nd_u64>())));
+        KLAUNCH("ovl_sort", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, t2, k64.as<nd_u64>(), k64b.as<nd_u64>(), ixb.as<uint32_t>(), ix.as<uint32_t>(), (long long)NR, 0, 64, c->st)));
+    }
+    // ---- 3. reads: boundaries, the read's own record in front, per-read scratch ---------------------------------------------------------
+    DevBuf &start = *S.get(), &nstart = *S.get();
+    RSV(start, (NR + 1) * 4); RSV(nstart, (NR + 1) * 8);
+    KLAUNCH("ovl_sort", (k_os_starts<<<nblk(NR + 1, 256), 256, 0, c->st>>>(R.as<ndos_rec>(), ix.as<uint32_t>(), NR, start.as<uint32_t>())));
+    if (int rc = scan_u32_to_u64(c, start.as<uint32_t>(), nstart.as<nd_u64>(), NR)) return rc;
+    CK(cudaMemcpyAsync(h, nstart.as<nd_u64>() + NR, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NQ = h[0], NT = NR + NQ;
+    DevBuf &L = *S.get(), &q_off = *S.get(), &q_len = *S.get(), &binl = *S.get(), &bin_off = *S.get(), &acc = *S.get(), &dead = *S.get(), &label = *S.get(), &qname = *S.get();
+    RSV(L, (NT + 1) * sizeof(ndos_rec)); RSV(q_off, (NQ + 1) * 8); RSV(q_len, (NQ + 1) * 4); RSV(binl, (NQ + 1) * 4); RSV(bin_off, (NQ + 1) * 8);
+    RSV(acc, (NT + 1) * 4); RSV(dead, NT + 16); RSV(label, NQ + 16); RSV(qname, (NQ + 1) * 4);
+    KLAUNCH("ovl_sort", (k_os_layout<<<nblk(NR, 256), 256, 0, c->st>>>(R.as<ndos_rec>(), ix.as<uint32_t>(), start.as<uint32_t>(), nstart.as<nd_u64>(), NR, d_sn.as<uint32_t>(), d_sl.as<uint32_t>(), NS,
+                         L.as<ndos_rec>(), q_off.as<nd_u64>(), q_len.as<uint32_t>())));
+    KLAUNCH("ovl_sort", (k_os_binlen<<<nblk(NQ + 1, 256), 256, 0, c->st>>>(q_len.as<uint32_t>(), NQ, binl.as<uint32_t>())));
+    if (int rc = scan_u32_to_u64(c, binl.as<uint32_t>(), bin_off.as<nd_u64>(), NQ)) return rc;
+    CK(cudaMemcpyAsync(h, bin_off.as<nd_u64>() + NQ, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    DevBuf &bins = *S.get();
+    RSV(bins, (h[0] + 16) * 2);
+    // ---- 4. the per-read filter ----------------------------------------------------------------------------------------------------------
+    KLAUNCH("ovl_sort_reads", (k_os_reads<<<nblk(NQ, 64), 64, 0, c->st>>>(P, L.as<ndos_rec>(), q_off.as<nd_u64>(), q_len.as<uint32_t>(), NQ, NT, bin_off.as<nd_u64>(), bins.as<uint16_t>(),
+                               acc.as<uint32_t>(), dead.as<uint8_t>(), label.as<char>())));
+    CK(cudaGetLastError());
+    // ---- 5. survivors -> 8-field stream ----------------------------------------------------------------------------------------------------
+    DevBuf &live = *S.get(), &kidx = *S.get(), &len = *S.get(), &off = *S.get(), &outb = *S.get();
+    RSV(live, NT + 16); RSV(kidx, (NT + 1) * 4);
+    KLAUNCH("ovl_sort", (k_os_live<<<nblk(NT, 256), 256, 0, c->st>>>(L.as<ndos_rec>(), dead.as<uint8_t>(), NT, live.as<uint8_t>())));
+    uint32_t *d_nk = c->scalars.as<uint32_t>() + 200;
+    {
+        size_t tmp = 0;
+        cub::CountingInputIterator<uint32_t> it(0);
+        CK(cub::DeviceSelect::Flagged(nullptr, tmp, it, live.as<uint8_t>(), kidx.as<uint32_t>(), d_nk, (long long)NT, c->st));
+        RSV(c->cubtmp, tmp);
+        KLAUNCH("ovl_sort", CK(cub::DeviceSelect::Flagged(c->cubtmp.p, tmp, it, live.as<uint8_t>(), kidx.as<uint32_t>(), d_nk, (long long)NT, c->st)));
+    }
+    CK(cudaMemcpyAsync(h, d_nk, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t NK = (uint32_t)h[0];
+    uint64_t out_bytes = 0;
+    if (NK) {
+        RSV(len, (NK + 1) * 4); RSV(off, (NK + 1) * 8);
+        KLAUNCH("ovl_sort", (k_os_len<<<nblk(NK + 1, 256), 256, 0, c->st>>>(L.as<ndos_rec>(), kidx.as<uint32_t>(), NK, len.as<uint32_t>())));
+        if (int rc = scan_u32_to_u64(c, len.as<uint32_t>(), off.as<nd_u64>(), NK)) return rc;
+        CK(cudaMemcpyAsync(h, off.as<nd_u64>() + NK, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        out_bytes = h[0];
+        RSV(outb, out_bytes + 64);
+        KLAUNCH("ovl_sort", (k_os_write<<<nblk(NK, 256), 256, 0, c->st>>>(L.as<ndos_rec>(), kidx.as<uint32_t>(), NK, off.as<nd_u64>(), outb.as<uint8_t>())));
+        CK(cudaGetLastError());
+        if (c->os_out.reserve(out_bytes + 64)) return fail(c, NDG_ERR_NOMEM, "pinned ovl_sort output");
+        CK(cudaMemcpyAsync(c->os_out.p, outb.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+    }
+    // labels -> .bl text (ref: util/ovl_sort.c:384-387: "<qname> c" contained, "<qname> k" chimeric)
+    KLAUNCH("ovl_sort", (k_os_qnames<<<nblk(NQ, 256), 256, 0, c->st>>>(L.as<ndos_rec>(), q_off.as<nd_u64>(), NQ, qname.as<uint32_t>())));
+    std::vector<char> hlab(NQ); std::vector<uint32_t> hqn(NQ);
+    CK(cudaMemcpyAsync(hlab.data(), label.p, NQ, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hqn.data(), qname.p, NQ * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (P.with_bl) { char line[32]; for (uint64_t q = 0; q < NQ; ++q) if (hlab[q]) { snprintf(line, sizeof line, "%u %c\n", hqn[q], hlab[q]); c->os_bl += line; } }
+    *ovl = c->os_out.as<uint8_t>(); *n_bytes = out_bytes;
+    if (bl_text) *bl_text = c->os_bl.c_str();
+    if (bl_bytes) *bl_bytes = c->os_bl.size();
+    if (n_rec_out) *n_rec_out = NK;
+    return NDG_OK;
+}
 
 extern "C" int ndg_set_paf(ndg_ctx_t *c, int on)
 {

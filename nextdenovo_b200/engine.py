@@ -77,7 +77,8 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_index_shard_table_slice", "ndg_index_shard_pos_reserve", "ndg_index_shard_finish", "ndg_index_finalize", "ndg_index_get",
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
-           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish", "ndg_index_share"]
+           "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish", "ndg_index_share",
+           "ndg_set_paf", "ndg_map_extras", "ndg_ovl_sort"]
 
 _lib = None
 
@@ -110,6 +111,8 @@ def load_library():
     L.ndg_aln_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.ndg_index_share.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndg_set_paf.argtypes = [C.c_void_p, C.c_int]
+    L.ndg_ovl_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p] + [C.c_void_p] * 6
     L.ndg_step2_begin.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_step2_map_batch.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.ndg_step2_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -361,6 +364,22 @@ class Engine:
         self._ck(self.L.ndg_ksw_extd2_batch(self.h, _ptr(calls), n, _ptr(seqs), seqs.shape[0], m, _ptr(mat), q, e, q2, e2,
                                             _ptr(res), _ptr(cig), _ptr(coff)))
         return res, [cig[int(coff[i]):int(coff[i]) + int(res["n_cigar"][i])] for i in range(n)]
+
+    def ovl_sort(self, streams, seed_names, seed_lens, max_bin_cov=40, max_flank_len=300, is_hq=False):
+        """`ovl_sort` on the GPU (ref: util/ovl_sort.c; ndg_ovl_sort): streams = the bytes of the input 8-field .ovl files in fofn order,
+        seeds = the (name, length) list of the `-i` index.  Returns (sorted .ovl bytes, .bl text, records read, records written)."""
+        n = len(streams)
+        bufs = [np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, dtype=np.uint8) for b in streams]
+        ptrs = (C.c_void_p * max(n, 1))(*[x.ctypes.data for x in bufs])
+        sizes = np.array([len(b) for b in streams], dtype=np.uint64) if n else np.zeros(1, dtype=np.uint64)
+        sn = np.ascontiguousarray(seed_names, dtype=np.uint32); sl = np.ascontiguousarray(seed_lens, dtype=np.uint32)
+        opt = (C.c_int32 * 3)(int(max_bin_cov), int(max_flank_len), 1 if is_hq else 0)
+        ovl, nb, bl, nbl, n_in, n_out = C.c_void_p(), C.c_uint64(), C.c_char_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.ndg_ovl_sort(self.h, ptrs, _ptr(sizes), n, _ptr(sn), _ptr(sl), C.c_uint64(sn.shape[0]), opt,
+                                     C.byref(ovl), C.byref(nb), C.byref(bl), C.byref(nbl), C.byref(n_in), C.byref(n_out)))
+        data = C.string_at(ovl.value, nb.value) if nb.value else b""
+        text = C.string_at(bl, nbl.value) if nbl.value else b""
+        return data, text, int(n_in.value), int(n_out.value)
 
     def prof(self):
         names = (C.c_char_p * 64)()

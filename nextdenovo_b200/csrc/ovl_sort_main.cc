@@ -74,9 +74,11 @@ int main(int argc, char **argv)
     std::vector<const uint8_t *> ptr; std::vector<uint64_t> sz;
     for (auto &b : files) { ptr.push_back(b.data()); sz.push_back(b.size()); }
     const uint8_t *ovl = nullptr; uint64_t nb = 0, nbl = 0, n_in = 0, n_out = 0; const char *bl = nullptr;
+    const auto t1 = std::chrono::steady_clock::now();
     if (ndg_ovl_sort(g, ptr.data(), sz.data(), (int32_t)ptr.size(), sn.data(), sl.data(), sn.size(), &o, &ovl, &nb, &bl, &nbl, &n_in, &n_out)) {
         fprintf(stderr, "[ERROR] %s\n", ndg_last_error(g)); return 1;
     }
+    const double t_call = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     FILE *fo = fopen(out, "wb");
     if (!fo || (nb && fwrite(ovl, 1, (size_t)nb, fo) != (size_t)nb) || fclose(fo) != 0) { fprintf(stderr, "[WARNING] Failed create overlap file %s!\n", out); return 1; }
     if (o.max_flank_len) {
@@ -84,8 +86,8 @@ int main(int argc, char **argv)
         FILE *fb = fopen(bn.c_str(), "w");
         if (!fb || (nbl && fwrite(bl, 1, (size_t)nbl, fb) != (size_t)nbl) || fclose(fb) != 0) { fprintf(stderr, "[WARNING] Failed create rid file %s!\n", bn.c_str()); return 1; }
     }
-    fprintf(stderr, "[ovl_sort-ndgpu] %zu files, %llu records in, %llu out, %.3f s\n", files.size(), (unsigned long long)n_in, (unsigned long long)n_out,
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    fprintf(stderr, "[ovl_sort-ndgpu] %zu files, %llu records in, %llu out; ndg_ovl_sort %.3f s (upload, all kernels, download), process %.3f s\n", files.size(), (unsigned long long)n_in,
+            (unsigned long long)n_out, t_call, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     ndg_destroy(g);
     return 0;
 }

@@ -496,7 +496,11 @@ def main_ours(a, rank, world, local_rank):
     for i in range(a.warmup, nb):
         b = pinned[i].reads
         t1 = time.perf_counter()
-        data, st_e = eng.map_batch_ovl(b, state)          # H2D, all kernels incl. the output stage, D2H of the .ovl bytes
+        if i == a.warmup:
+            eng.map_prefetch(b)                           # the first batch's copy starts inside the timed region as well
+        if i + 1 < nb:
+            eng.map_prefetch(pinned[i + 1].reads)         # the next batch's H2D copy overlaps this batch's kernels (ndg_map_prefetch)
+        data, st_e = eng.map_batch_ovl(b, state)          # (H2D of this batch: prefetched,) all kernels incl. the output stage, D2H of the .ovl bytes
         dt = time.perf_counter() - t1
         t_e2e += dt
         e2e_steps.append(round(1e3 * dt, 3))
@@ -619,7 +623,7 @@ def main_ours(a, rank, world, local_rank):
                        "kernel_variant": a.variant},
             "e2e": {"value": rec / t_e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                     "ms_per_step": 1e3 * t_e2e / a.steps, "step_ms": e2e_steps, "ovl_md5_rank0": h_e2e.hexdigest(),
-                    "how": "the K timed batches from pinned host buffers through ndg_map_batch_ovl (H2D, all kernels incl. the output stage, D2H of the .ovl bytes), one call per step",
+                    "how": "the K timed batches from pinned host buffers through ndg_map_prefetch + ndg_map_batch_ovl (every batch's H2D copy, all kernels incl. the output stage and the D2H of the .ovl bytes lie inside the timed region; the copy of batch i+1 runs on a copy stream under the kernels of batch i), one call per step",
                     "two_context_pool": {"value": rec / t_pool, "ms_per_step": 1e3 * t_pool / a.steps, "same_bytes": pool_md5 == h_e2e.hexdigest(),
                                          "how": "the same batches on two contexts sharing the index (two host threads, two streams), stitched with ndg_ovl_rebase_first: what bin/minimap2-nd runs"}},
             "gpu_launches": launches,

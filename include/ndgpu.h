@@ -188,6 +188,11 @@ int ndg_map_batch(ndg_ctx_t *ctx, const ndg_reads_t *queries, ndg_map_result_t *
 typedef struct { int32_t minlen, dvt, maxhan1, maxhan2; } ndg_emit_opt_t;
 int ndg_map_batch_ovl(ndg_ctx_t *ctx, const ndg_reads_t *queries, const ndg_emit_opt_t *eo, uint32_t state[2],
                       const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work);
+/* Start the host-to-device copy of the NEXT query batch on a copy stream and return at once (what the reference's pipeline step 0
+ * does for the next batch while step 1 maps the current one, ref: minimap2/map.c:1389-1390).  The following ndg_map_batch_ovl() on
+ * the same buffers finds the batch resident.  A batch larger than one device sub-batch is left to the mapping call.  The host
+ * buffers must stay untouched until that call returns. */
+int ndg_map_prefetch(ndg_ctx_t *ctx, const ndg_reads_t *queries);
 /* the same in three steps, for measurement with inputs resident in HBM */
 int ndg_map_upload(ndg_ctx_t *ctx, const ndg_reads_t *queries);      /* H2D only (single sub-batch) */
 int ndg_map_resident(ndg_ctx_t *ctx, ndg_map_result_t *out);          /* kernels only; hits stay on device */

@@ -179,22 +179,27 @@ k_sketch_fast(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int w, i
 //     neighbours that are >= each of them (a position is pushed iff left run + right run >= W-1; invalid positions -- before the first
 //     k-mer, beyond the read -- hold 0, which is smaller than every hash and so ends a run);
 //   * survivors are compacted in position order with one block-wide prefix sum instead of a ballot per 128 positions.
+// which read a chunk belongs to, once per chunk (a 12-step binary search by one thread at the head of every sketch block kept the
+// other 127 waiting at its first barrier)
+__global__ void k_chunk_owner(const nd_u64 *chunk_off, int n_reads, nd_u64 n_chunks, uint32_t *owner)
+{
+    nd_u64 g = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_chunks) owner[g] = (uint32_t)nd_find_owner(chunk_off, n_reads, g);
+}
+
 template <int W>
 __global__ void __launch_bounds__(NDS_T, 8)
-k_sketch_fast4(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int k, uint32_t rid0, int use_rid,
+k_sketch_fast4(nd_reads_dev R, const nd_u64 *chunk_off, const uint32_t *owner, nd_u64 n_chunks, int k, uint32_t rid0, int use_rid,
                nd_u128 *staging, int S, uint32_t *cnt, uint32_t *slow)
 {
     constexpr int PAD = 16;                               // >= W-1 zero entries on both sides of the hashed range
     __shared__ nd_u64 sx[NDS_C + 2 * NDS_MAXW + 2 * PAD];
     __shared__ uint8_t sz[NDS_C + 2 * NDS_MAXW + 2 * PAD];
     __shared__ uint32_t swords[(NDS_C + 2 * NDS_MAXW) / 16 + 8];
-    __shared__ int s_r;
     __shared__ uint32_t s_wsum[NDS_T / 32];
     const nd_u64 g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_r = nd_find_owner(chunk_off, R.n_reads, g);
-    __syncthreads();
-    const int r = s_r, len = (int)R.len[r];
+    const int r = (int)owner[g], len = (int)R.len[r];
     const int cs = (int)(g - chunk_off[r]) * NDS_C, ce = cs + NDS_C < len ? cs + NDS_C : len;
     if (len < k + W - 1) { if (tid == 0) { slow[r] = 1; cnt[g] = 0; } return; }
     const int lo = cs - (W - 1) > 0 ? cs - (W - 1) : 0, hi = ce + (W - 1) < len ? ce + (W - 1) : len;
@@ -206,14 +211,21 @@ k_sketch_fast4(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int k, 
     const nd_u64 mask = (1ULL << 2 * k) - 1;
     const int rc_shift = 2 * (k - 1);
     int any_sym = 0;
-    for (int base = 4 * tid; base < hi - lo; base += 4 * NDS_T) {           // one round for the chunk, a short second one for the halo
+    // the chunk plus its halo is hi - lo <= 512 + 2(W-1) positions: every thread hashes one run of four, the first few threads a run of
+    // five (a second round for the halo alone kept 123 of 128 threads waiting at the barrier for as long as the first round took)
+    {
+        const int extra = hi - lo > 4 * NDS_T ? hi - lo - 4 * NDS_T : 0;      // <= 2(W-1) < NDS_T
+        const int base = 4 * tid + (tid < extra ? tid : extra), run = 4 + (tid < extra ? 1 : 0);
         int p = lo + base;
-        nd_u64 fw = nd_bases32(swords - w0, p) & mask;
-        nd_u64 rv = (~nd_rev2(fw)) >> (64 - 2 * k);
-        if (p < k - 1) rv &= ~((1ULL << 2 * (k - 1 - p)) - 1);
+        nd_u64 fw = 0, rv = 0;
+        if (base < hi - lo) {
+            fw = nd_bases32(swords - w0, p) & mask;
+            rv = (~nd_rev2(fw)) >> (64 - 2 * k);
+            if (p < k - 1) rv &= ~((1ULL << 2 * (k - 1 - p)) - 1);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j, ++p) {
-            if (base + j >= hi - lo) break;
+        for (int j = 0; j < 5; ++j, ++p) {
+            if (j >= run || base + j >= hi - lo) break;
             if (j) {
                 const nd_u64 c = (swords - w0)[p >> 4] >> (30 - 2 * (p & 15)) & 3;
                 fw = (fw << 2 | c) & mask;
@@ -588,6 +600,13 @@ __global__ void k_hit_keys(const nd_hit *hits, nd_u64 n, nd_u64 *zkey, uint32_t 
 {
     nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { zkey[i] = hits[i].zkey; idx[i] = (uint32_t)i; }
+}
+// one composite key when it fits 64 bits: query index above the complement of zkey (zkey < 2^shift because a chain score never
+// exceeds the query length): ascending order = by query, then zkey descending
+__global__ void k_hit_keys1(const nd_hit *hits, nd_u64 n, int shift, nd_u64 *key, uint32_t *idx)
+{
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { key[i] = (nd_u64)(uint32_t)hits[i].qidx << shift | (((1ULL << shift) - 1) - hits[i].zkey); idx[i] = (uint32_t)i; }
 }
 __global__ void k_hit_qidx(const nd_hit *hits, const uint32_t *idx, nd_u64 n, uint32_t *qidx)
 {

@@ -76,7 +76,7 @@ struct ProfPending { int id; cudaEvent_t a, b; };
 
 struct ReadsDev {            // a batch of reads resident on the device
     DevBuf words, word_off, len, nmask, name_key, name_hash, name_id, chunk_off, tag; bool has_tag = false;
-    int n_reads = 0; uint64_t n_words = 0, n_chunks = 0, n_bases = 0; bool has_nmask = false;
+    int n_reads = 0; uint64_t n_words = 0, n_chunks = 0, n_bases = 0; bool has_nmask = false; uint32_t max_len = 0;
     nd_reads_dev view() const {
         nd_reads_dev v;
         v.words = words.as<uint32_t>(); v.word_off = word_off.as<nd_u64>(); v.len = len.as<uint32_t>();
@@ -119,7 +119,7 @@ struct ndg_ctx {
     int mid_occ() const { return mid_occ_user > 0 ? mid_occ_user : mid_occ_run; }
     // mapping workspace
     ReadsDev q;
-    DevBuf staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
+    DevBuf chunk_owner, staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
            ksw_calls, ksw_seqs, ksw_res, ksw_p, ksw_cig, ksw_scratch,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
@@ -127,6 +127,10 @@ struct ndg_ctx {
     int overflow_flag = 0;
     // upload staging
     HostBuf up;
+    // a query batch uploaded ahead of its mapping call (ndg_map_prefetch): second read buffer, copy stream, staging of its own
+    ReadsDev q_next; HostBuf up_next; cudaStream_t st_copy = nullptr; cudaEvent_t ev_next = nullptr;
+    const void *pf_words = nullptr; const void *pf_len = nullptr; int pf_n = 0; bool pf_valid = false;
+    ndg_reads_t pf_req; bool pf_req_valid = false;      // a prefetch asked for while the previous one had not been taken yet: started by the mapping call that takes it
     // regime B (base-level alignment)
     bool aln_on = false; ndal::Opt aln; ndg_aln_stat_t aln_stat = {};
     std::shared_ptr<HostTargets> ht = std::make_shared<HostTargets>();   // host copy of the target bases (shared with borrowers of the index)
@@ -220,20 +224,24 @@ int scan_u32_to_u64(ndg_ctx *c, const uint32_t *in, nd_u64 *out, uint64_t n)
 }
 
 // copy a host read batch (or a slice of it) to the device; computes chunk offsets
-int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
+int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1, cudaStream_t st_ = nullptr, HostBuf *stage_ = nullptr, bool wait = true)
 {
+    cudaStream_t st = st_ ? st_ : c->st;
+    HostBuf &up = stage_ ? *stage_ : c->up;
     int n = r1 - r0;
     if (n <= 0) return fail(c, NDG_ERR_ARG, "empty read batch");
     uint64_t w0 = R->word_off[r0], w1 = R->word_off[r1], nw = w1 - w0;
     size_t hdr = (size_t)(n + 1) * 8 * 2 + (size_t)n * (4 + 8 + 4 + 4);
-    if (c->up.reserve(hdr)) return fail(c, NDG_ERR_NOMEM, "pinned staging");
-    uint64_t *h_woff = c->up.as<uint64_t>(), *h_coff = h_woff + (n + 1), *h_key = h_coff + (n + 1);
+    if (up.reserve(hdr)) return fail(c, NDG_ERR_NOMEM, "pinned staging");
+    uint64_t *h_woff = up.as<uint64_t>(), *h_coff = h_woff + (n + 1), *h_key = h_coff + (n + 1);
     uint32_t *h_len = reinterpret_cast<uint32_t *>(h_key + n), *h_hash = h_len + n, *h_id = h_hash + n;
     uint64_t chunks = 0, bases = 0;
+    D.max_len = 0;
     for (int i = 0; i < n; ++i) {
         h_woff[i] = R->word_off[r0 + i] - w0;
         h_coff[i] = chunks;
         uint32_t L = R->len[r0 + i];
+        if (L > D.max_len) D.max_len = L;
         chunks += (L + c->chunk_bases - 1) / c->chunk_bases;
         bases += L;
         h_len[i] = L;
@@ -245,21 +253,21 @@ int upload_reads(ndg_ctx *c, ReadsDev &D, const ndg_reads_t *R, int r0, int r1)
     D.n_reads = n; D.n_words = nw; D.n_chunks = chunks; D.n_bases = bases; D.has_nmask = R->nmask != nullptr;
     RSV(D.words, (nw + 4) * 4); RSV(D.word_off, (size_t)(n + 1) * 8); RSV(D.chunk_off, (size_t)(n + 1) * 8);
     RSV(D.len, (size_t)n * 4); RSV(D.name_key, (size_t)n * 8); RSV(D.name_hash, (size_t)n * 4); RSV(D.name_id, (size_t)n * 4);
-    CK(cudaMemcpyAsync(D.words.p, R->words + w0, nw * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.word_off.p, h_woff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.chunk_off.p, h_coff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.len.p, h_len, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.name_key.p, h_key, (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.name_hash.p, h_hash, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(D.name_id.p, h_id, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(D.words.p, R->words + w0, nw * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.word_off.p, h_woff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.chunk_off.p, h_coff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.len.p, h_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.name_key.p, h_key, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.name_hash.p, h_hash, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.name_id.p, h_id, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (R->nmask) {
         for (int i = 0; i <= n; ++i) if (R->word_off[r0 + i] & 1) return fail(c, NDG_ERR_ARG, "nmask requires an even word offset for every read (read %d)", r0 + i);
         RSV(D.nmask, (nw / 2 + 4) * 4);
-        CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, ((nw + 1) / 2) * 4, cudaMemcpyHostToDevice, c->st));   // exactly the mask words the slice covers
+        CK(cudaMemcpyAsync(D.nmask.p, R->nmask + w0 / 2, ((nw + 1) / 2) * 4, cudaMemcpyHostToDevice, st));   // exactly the mask words the slice covers
     }
     D.has_tag = R->tag != nullptr;
-    if (R->tag) { RSV(D.tag, (size_t)n * 4); CK(cudaMemcpyAsync(D.tag.p, R->tag + r0, (size_t)n * 4, cudaMemcpyHostToDevice, c->st)); }
-    CK(cudaStreamSynchronize(c->st));   // staging buffer is reused by the next call
+    if (R->tag) { RSV(D.tag, (size_t)n * 4); CK(cudaMemcpyAsync(D.tag.p, R->tag + r0, (size_t)n * 4, cudaMemcpyHostToDevice, st)); }
+    if (wait) CK(cudaStreamSynchronize(st));   // staging buffer is reused by the next call
     return 0;
 }
 
@@ -285,11 +293,15 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     RSV(c->slow, (size_t)D.n_reads * 4 + 4);
     CK(cudaMemsetAsync(c->slow.p, fast ? 0 : 1, (size_t)D.n_reads * 4, c->st));
     static const bool old_fast = getenv("NDG_SKETCH_OLD") != nullptr;
+    if (fast && !old_fast && (o.w == 5 || o.w == 10)) {
+        RSV(c->chunk_owner, (nc + 1) * 4);
+        KLAUNCH("misc", (k_chunk_owner<<<nblk(nc, 256), 256, 0, c->st>>>(D.chunk_off.as<nd_u64>(), D.n_reads, nc, c->chunk_owner.as<uint32_t>())));
+    }
     if (fast && !old_fast && o.w == 5)
-        KLAUNCH("sketch_fast", (k_sketch_fast4<5><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.k, rid0, use_rid,
+        KLAUNCH("sketch_fast", (k_sketch_fast4<5><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), c->chunk_owner.as<uint32_t>(), nc, o.k, rid0, use_rid,
                                 c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
     else if (fast && !old_fast && o.w == 10)
-        KLAUNCH("sketch_fast", (k_sketch_fast4<10><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.k, rid0, use_rid,
+        KLAUNCH("sketch_fast", (k_sketch_fast4<10><<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), c->chunk_owner.as<uint32_t>(), nc, o.k, rid0, use_rid,
                                 c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
     else if (fast)
         KLAUNCH("sketch_fast", (k_sketch_fast<<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.w, o.k, rid0, use_rid,
@@ -393,9 +405,10 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
                        &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag,
-                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he };
+                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he, &c->chunk_owner };
     for (auto b : bufs) b->release();
-    c->q.release();
+    c->q.release(); c->q_next.release(); c->up_next.release();
+    if (c->st_copy) { cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_next); }
     c->h_ovl.release(); c->h_scalars.release(); c->h_hits.release(); c->h_stage.release(); c->up.release();
     c->h_kseq.release(); c->h_kres.release(); c->h_kcig.release(); c->h_koff.release(); c->h_cha.release(); c->h_chf.release(); c->h_pf.release(); c->os_out.release();
     if (c->remap) { ndg_destroy(c->remap); c->remap = nullptr; }
@@ -988,16 +1001,25 @@ int map_resident(ndg_ctx *c, int qidx_base)
     // 7. order hits: by query, then by zkey descending (ref: minimap2/hit.c:69-71)
     RSV(c->zkey, NH * 8); RSV(c->zkey2, NH * 8); RSV(c->hidx, NH * 4); RSV(c->hidx2, NH * 4); RSV(c->hq, NH * 4); RSV(c->hq2, NH * 4);
     RSV(c->hits_sorted, NH * sizeof(nd_hit));
+    int qbits = 1; while ((1 << qbits) < nr + 1 && qbits < 31) ++qbits;
+    int sbits = 1; while ((1ull << sbits) <= (uint64_t)Q.max_len && sbits < 32) ++sbits;       // chain score <= query length < 2^sbits
+    if (32 + sbits + qbits <= 64) {                                                           // one sort on a composite key
+        size_t t1 = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, 32 + sbits + qbits, c->st));
+        RSV(c->cubtmp, t1);
+        KLAUNCH("hit_order", (k_hit_keys1<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), NH, 32 + sbits, c->zkey.as<nd_u64>(), c->hidx2.as<uint32_t>())));
+        KLAUNCH("hit_order", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, 32 + sbits + qbits, c->st)));
+    } else {
     KLAUNCH("hit_order", (k_hit_keys<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), NH, c->zkey.as<nd_u64>(), c->hidx.as<uint32_t>())));
     {
         size_t t1 = 0, t2 = 0;
         CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx.as<uint32_t>(), c->hidx2.as<uint32_t>(), (long long)NH, 0, 64, c->st));
-        int qbits = 1; while ((1 << qbits) < nr + 1 && qbits < 31) ++qbits;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, t2, c->hq.as<uint32_t>(), c->hq2.as<uint32_t>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, qbits, c->st));
         RSV(c->cubtmp, std::max(t1, t2));
         KLAUNCH("hit_order", CK(cub::DeviceRadixSort::SortPairsDescending(c->cubtmp.p, t1, c->zkey.as<nd_u64>(), c->zkey2.as<nd_u64>(), c->hidx.as<uint32_t>(), c->hidx2.as<uint32_t>(), (long long)NH, 0, 64, c->st)));
         KLAUNCH("hit_order", (k_hit_qidx<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), c->hidx2.as<uint32_t>(), NH, c->hq.as<uint32_t>())));
         KLAUNCH("hit_order", CK(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, t2, c->hq.as<uint32_t>(), c->hq2.as<uint32_t>(), c->hidx2.as<uint32_t>(), c->hidx.as<uint32_t>(), (long long)NH, 0, qbits, c->st)));
+    }
     }
     KLAUNCH("hit_order", (k_hit_gather<<<nblk(NH, 256), 256, 0, c->st>>>(c->hits.as<nd_hit>(), c->hidx.as<uint32_t>(), NH, qidx_base, c->hits_sorted.as<nd_hit>())));
     CK(cudaGetLastError());
@@ -1124,6 +1146,43 @@ int paf_resident(ndg_ctx *c, int r0, int r1)
 }
 }
 
+namespace {
+// the batch Q was uploaded ahead (same buffers, same size): make it the resident batch once its copy has finished
+bool take_prefetched(ndg_ctx *c, const ndg_reads_t *Q)
+{
+    if (!c->pf_valid) return false;
+    c->pf_valid = false;
+    if (c->pf_words != (const void *)Q->words || c->pf_len != (const void *)Q->len || c->pf_n != Q->n_reads) return false;
+    if (cudaStreamWaitEvent(c->st, c->ev_next, 0) != cudaSuccess) return false;
+    std::swap(c->q, c->q_next);
+    return true;
+}
+}
+
+namespace {
+int start_prefetch(ndg_ctx *c, const ndg_reads_t *Q)
+{
+    c->pf_valid = false;
+    uint64_t bases = 0; for (int i = 0; i < Q->n_reads; ++i) bases += Q->len[i];
+    if (bases > c->sub_batch_bases) return NDG_OK;                 // would be cut into sub-batches: the mapping call uploads as usual
+    if (!c->st_copy) { CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming)); }
+    else CK(cudaEventSynchronize(c->ev_next));                     // the staging block of the previous prefetch is free again
+    if (int rc = upload_reads(c, c->q_next, Q, 0, Q->n_reads, c->st_copy, &c->up_next, false)) return rc;
+    CK(cudaEventRecord(c->ev_next, c->st_copy));
+    c->pf_words = Q->words; c->pf_len = Q->len; c->pf_n = Q->n_reads; c->pf_valid = true;
+    return NDG_OK;
+}
+}
+
+extern "C" int ndg_map_prefetch(ndg_ctx_t *c, const ndg_reads_t *Q)
+{
+    if (!c || !Q || Q->n_reads <= 0) return NDG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->pf_valid) { c->pf_req = *Q; c->pf_req_valid = true; return NDG_OK; }     // second buffer still holds the batch about to be mapped
+    c->pf_req_valid = false;
+    return start_prefetch(c, Q);
+}
+
 extern "C" int ndg_map_batch_ovl(ndg_ctx_t *c, const ndg_reads_t *Q, const ndg_emit_opt_t *eo, uint32_t state[2],
                                  const uint8_t **ovl, uint64_t *n_bytes, uint64_t *n_rec, uint64_t *sum_qspan, ndg_map_result_t *work)
 {
@@ -1153,7 +1212,9 @@ extern "C" int ndg_map_batch_ovl(ndg_ctx_t *c, const ndg_reads_t *Q, const ndg_e
     while (r0 < Q->n_reads) {
         int r1 = r0; uint64_t bases = 0;
         while (r1 < Q->n_reads && (r1 == r0 || bases + Q->len[r1] <= budget)) bases += Q->len[r1++];
-        if (int rc = upload_reads(c, c->q, Q, r0, r1)) return rc;
+        if (r0 == 0 && r1 == Q->n_reads && take_prefetched(c, Q)) { /* uploaded ahead by ndg_map_prefetch() */ }
+        else if (int rc = upload_reads(c, c->q, Q, r0, r1)) return rc;
+        if (c->pf_req_valid) { c->pf_req_valid = false; if (int rc = start_prefetch(c, &c->pf_req)) return rc; }   // the next batch travels while this one is mapped
         int rc = map_resident(c, r0);
         if (rc == NDG_ERR_OVERFLOW && r1 - r0 > 1 && c->err.find("anchors") != std::string::npos) { budget = std::max<uint64_t>(bases / 2, 1); continue; }
         if (rc) return rc;

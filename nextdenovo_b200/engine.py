@@ -78,7 +78,7 @@ EXPORTS = ["ndg_init", "ndg_destroy", "ndg_last_error", "ndg_version", "ndg_set_
            "ndg_map_batch", "ndg_map_upload", "ndg_map_resident", "ndg_map_download", "ndg_sketch",
            "ndg_debug_fetch", "ndg_prof_get", "ndg_prof_reset", "ndg_kernel_launches", "ndg_ovl_encode8",
            "ndg_ovl_emit_step1", "ndg_ksw_extd2_batch", "ndg_host_alloc", "ndg_host_free", "ndg_map_batch_ovl", "ndg_set_ksw_variant", "ndg_set_aln_opt", "ndg_aln_stats", "ndg_set_threads", "ndg_step2_begin", "ndg_step2_map_batch", "ndg_step2_finish", "ndg_index_share",
-           "ndg_set_paf", "ndg_map_extras", "ndg_ovl_sort"]
+           "ndg_set_paf", "ndg_map_extras", "ndg_ovl_sort", "ndg_map_prefetch"]
 
 _lib = None
 
@@ -112,6 +112,7 @@ def load_library():
     L.ndg_set_threads.argtypes = [C.c_void_p, C.c_int]
     L.ndg_index_share.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_set_paf.argtypes = [C.c_void_p, C.c_int]
+    L.ndg_map_prefetch.argtypes = [C.c_void_p, C.POINTER(_Reads)]
     L.ndg_ovl_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p] + [C.c_void_p] * 6
     L.ndg_step2_begin.argtypes = [C.c_void_p, C.c_void_p]
     L.ndg_step2_map_batch.argtypes = [C.c_void_p] + [C.c_void_p] * 6
@@ -291,6 +292,13 @@ class Engine:
         data = C.string_at(ptr.value, nb.value) if nb.value else b""
         return data, dict(records=nrec.value, sum_qspan=sq.value, n_hits=res.n_hits, n_minimizers=res.n_minimizers,
                           n_anchors=res.n_anchors, n_segments=res.n_segments)
+
+    def map_prefetch(self, queries: Reads):
+        """start the upload of the NEXT batch; the following map_batch_ovl(queries, ...) finds it resident (ndg_map_prefetch)"""
+        s = _reads_struct(queries)
+        keep = getattr(self, "_pf_keep", [])
+        keep.append((s, queries)); self._pf_keep = keep[-3:]           # the library keeps the pointers until the batch has been mapped
+        self._ck(self.L.ndg_map_prefetch(self.h, C.byref(s)))
 
     def map_upload(self, queries: Reads):
         s = _reads_struct(queries)

@@ -9,7 +9,7 @@ keep_small() { for f in "$@"; do if [ -f "$f" ] && [ $(stat -c %s "$f") -gt 2500
 if [ "$WHAT" = all ] || [ "$WHAT" = a ]; then
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_bench.csv $B > gpurun_out/${TAG}_launches_bench.log 2>&1
   echo "launch list exit $?"
-  timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -c 28 -f -o /tmp/${TAG}_regimeA $B > gpurun_out/${TAG}_regimeA.log 2>&1
+  timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -c 48 -f -o /tmp/${TAG}_regimeA $B > gpurun_out/${TAG}_regimeA.log 2>&1
   echo "regime A full exit $?"
   ncu -i /tmp/${TAG}_regimeA.ncu-rep --page raw --csv > gpurun_out/${TAG}_regimeA_raw.csv 2>/dev/null
   for k in k_sketch_fast4 k_chain_fill_warp k_probe_count k_rs_init; do

@@ -404,32 +404,44 @@ __device__ __forceinline__ bool nd_skip_seed(const nd_seed_par &P, nd_u64 r, uin
 // one thread per query minimizer
 __global__ void __launch_bounds__(256)
 k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
-              nd_u64 *m_off, uint32_t *m_n, uint32_t *m_keep)
+              nd_u64 *m_off, uint32_t *m_n, uint32_t *m_keep, uint32_t *kept_list, uint32_t *n_kept)
 {
     nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_mz) return;
-    nd_u128 z = mz[m];
-    nd_u64 off = 0; uint32_t n = 0, keep = 0; bool inl = false;
-    nd_u64 key = z.x >> 8; int r = -1;
-    if (P.tag_shift > 0) { r = nd_find_owner(mz_off, Q.n_reads, m); key |= (nd_u64)Q.tag[r] << P.tag_shift; }
-    n = nd_idx_lookup(P.idx, key, &off, &inl);
-    if (n && n < (uint32_t)P.mid_occ) {
-        if (r < 0) r = nd_find_owner(mz_off, Q.n_reads, m);
-        nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y;
-        int self;
-        if (inl) keep = !nd_skip_seed(P, off, q_pos, qkey, qlen, &self);
-        else for (uint32_t kk = 0; kk < n; ++kk) keep += !nd_skip_seed(P, __ldg(P.idx.pos + off + kk), q_pos, qkey, qlen, &self);
-    } else n = n ? ND_MN_REP : 0;                                                // repetitive (n >= mid_occ) vs absent from the index
-    m_off[m] = off; m_n[m] = inl ? (n | 0x80000000u) : n; m_keep[m] = keep;     // top bit: m_off is the position itself
+    uint32_t keep = 0;
+    if (m < n_mz) {
+        nd_u128 z = mz[m];
+        nd_u64 off = 0; uint32_t n = 0; bool inl = false;
+        nd_u64 key = z.x >> 8; int r = -1;
+        if (P.tag_shift > 0) { r = nd_find_owner(mz_off, Q.n_reads, m); key |= (nd_u64)Q.tag[r] << P.tag_shift; }
+        n = nd_idx_lookup(P.idx, key, &off, &inl);
+        if (n && n < (uint32_t)P.mid_occ) {
+            if (r < 0) r = nd_find_owner(mz_off, Q.n_reads, m);
+            nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y;
+            int self;
+            if (inl) keep = !nd_skip_seed(P, off, q_pos, qkey, qlen, &self);
+            else for (uint32_t kk = 0; kk < n; ++kk) keep += !nd_skip_seed(P, __ldg(P.idx.pos + off + kk), q_pos, qkey, qlen, &self);
+        } else n = n ? ND_MN_REP : 0;                                            // repetitive (n >= mid_occ) vs absent from the index
+        m_off[m] = off; m_n[m] = inl ? (n | 0x80000000u) : n; m_keep[m] = keep; // top bit: m_off is the position itself
+    }
+    // the few minimizers that yield anchors (one in five here) go on a list, so that the fill kernel runs with full warps; its order
+    // is arbitrary, the anchors' places come from the prefix sums of m_keep
+    const unsigned has = __ballot_sync(0xffffffffu, keep > 0);
+    if (has) {
+        const int lane = threadIdx.x & 31, leader = __ffs(has) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(n_kept, (uint32_t)__popc(has));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep > 0) kept_list[base + __popc(has & ((1u << lane) - 1))] = (uint32_t)m;
+    }
 }
 
 __global__ void __launch_bounds__(256)
-k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
+k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, const uint32_t *kept_list, nd_u64 n_kept,
                const nd_u64 *m_off, const uint32_t *m_n, const uint32_t *m_keep, const nd_u64 *a_pos, nd_u128 *a)
 {
-    nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_mz) return;
-    if (m_keep[m] == 0) return;
+    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_kept) return;
+    const nd_u64 m = kept_list[i];
     nd_u128 z = mz[m];
     int r = nd_find_owner(mz_off, Q.n_reads, m);
     nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y, q_span = (uint32_t)(z.x & 0xff);

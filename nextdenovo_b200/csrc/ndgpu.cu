@@ -119,7 +119,7 @@ struct ndg_ctx {
     int mid_occ() const { return mid_occ_user > 0 ? mid_occ_user : mid_occ_run; }
     // mapping workspace
     ReadsDev q;
-    DevBuf chunk_owner, staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
+    DevBuf chunk_owner, kept_list, staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
            ksw_calls, ksw_seqs, ksw_res, ksw_p, ksw_cig, ksw_scratch,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
@@ -405,7 +405,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
                        &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag,
-                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he, &c->chunk_owner };
+                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he, &c->chunk_owner, &c->kept_list };
     for (auto b : bufs) b->release();
     c->q.release(); c->q_next.release(); c->up_next.release();
     if (c->st_copy) { cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_next); }
@@ -918,22 +918,26 @@ int map_resident(ndg_ctx *c, int qidx_base)
     P.tag_shift = c->tag_shift;
     if (c->tag_shift > 0 && !Q.has_tag) return fail(c, NDG_ERR_ARG, "the index is tagged: query reads need tags too");
     nd_reads_dev V = Q.view();
-    RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8);
+    if (M >= (1ULL << 32) - 64) return fail(c, NDG_ERR_OVERFLOW, "sub-batch yields %llu minimizers; lower sub_batch_bases", (unsigned long long)M);
+    RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8); RSV(c->kept_list, (M + 1) * 4);
     CK(cudaMemsetAsync(c->m_keep.as<uint32_t>() + M, 0, 4, c->st));
+    uint32_t *d_nkept = c->scalars.as<uint32_t>() + 208;
+    CK(cudaMemsetAsync(d_nkept, 0, 4, c->st));
     KLAUNCH("probe_count", (k_probe_count<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
-                            c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>())));
+                            c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->kept_list.as<uint32_t>(), d_nkept)));
     CK(cudaGetLastError());
     if (int rc = scan_u32_to_u64(c, c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), M)) return rc;
     CK(cudaMemcpyAsync(h, c->a_pos.as<nd_u64>() + M, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(h + 1, d_nkept, 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const uint64_t NA = h[0];
+    const uint64_t NA = h[0], NKEPT = (uint32_t)h[1];
     c->n_a = NA;
     if (NA == 0) return 0;
     if (NA >= (1ULL << 32) - 64) return fail(c, NDG_ERR_OVERFLOW, "sub-batch yields %llu anchors; lower sub_batch_bases", (unsigned long long)NA);
 
     // 3. fill + per-read stats
     RSV(c->a, (NA + 1) * 16); RSV(c->a_off, (size_t)(nr + 1) * 8); RSV(c->avgq, (size_t)nr * 4 + 4);
-    KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
+    KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(NKEPT, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->kept_list.as<uint32_t>(), NKEPT, c->m_off.as<nd_u64>(),
                              c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), c->a.as<nd_u128>())));
     KLAUNCH("read_stats", (k_read_stats<<<nblk((uint64_t)(nr + 1) * 32, 128), 128, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_keep.as<uint32_t>(),
                            c->a_pos.as<nd_u64>(), nr, c->a_off.as<nd_u64>(), c->avgq.as<float>())));

@@ -213,6 +213,10 @@ int main(int argc, char **argv)
         if (kv.first == "-x") {
             if (kv.second == "ava-ont") { all_chains = true; o.hpc = 0; o.k = 15; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; o.bw = 2000; }
             else if (kv.second == "ava-pb") { all_chains = true; o.hpc = 1; o.k = 19; o.w = 5; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25; }
+            else if (kv.second == "ava-hifi") {                  // options.c:98-109: long k-mers (k = w = 51, HPC), own scoring, mid_occ_frac 1e-4
+                all_chains = true; o.hpc = 1; o.k = 51; o.w = 51; o.flag_no_diag = o.flag_no_dual = 1; o.min_chain_score = 100; o.max_gap = 10000; o.max_chain_skip = 25;
+                o.mid_occ_frac = 1e-4f; ao.a = 1; ao.b = 4; ao.q = 6; ao.q2 = 26; ao.e = 2; ao.e2 = 1;
+            }
             else { fprintf(stderr, "[ERROR] unknown preset '%s'\n", kv.second.c_str()); return 1; }
         } else if (kv.first == "--step") {
             step = atoi(kv.second.c_str());

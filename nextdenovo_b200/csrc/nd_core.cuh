@@ -121,22 +121,74 @@ ND_HD bool nd_iter_start(const nd_seqview &s, int p, int hpc)
 // the look-back was too short for that (ambiguous bases, symmetric k-mers, long homopolymers) it
 // is doubled and the warm-up restarted; a warm-up that starts at position 0 is exact by
 // construction.
-template <int RW>
+// Long k-mers (k > 28; the ava-hifi preset uses k = 51): ref: minimap2/sketch.c:215-356.  The k-mer is 2k bits in four words (word 0 =
+// newest bases), the strands are compared as 256-bit integers, the hash is hash64 of the top (partial) word under its mask plus the
+// unmasked hash of every lower word that is not zero.  Two quirks of the reference are part of its output and kept:
+//   * for k a multiple of 32 the top-word mask is computed as (1 << 64) - 1, which x86 evaluates to 0;
+//   * the homopolymer run queue has 32 entries whatever k is, so for k > 31 a run is overwritten before it is popped and `span` is
+//     A + (sum of the last k mod 32 runs) with A = the sum of the first k - (k mod 32) runs after the last reset (read start or
+//     ambiguous base) -- history a chunk does not see.  A chunk that starts mid-read therefore computes A for the true reset point
+//     and for its own warm-up start (two short forward scans) and shifts `span` by the difference once its queue is primed.
+struct nd_k256 { nd_u64 u[4]; };
+ND_HD nd_u64 nd_hash64_nomask(nd_u64 key) { return nd_mix64(key); }
+ND_HD void nd_k256_push(nd_k256 &F, nd_k256 &R, int c, int k_idx, nd_u64 mask, int rc_shift)
+{
+    F.u[3] = F.u[3] << 2 | F.u[2] >> 62; F.u[2] = F.u[2] << 2 | F.u[1] >> 62; F.u[1] = F.u[1] << 2 | F.u[0] >> 62; F.u[0] = F.u[0] << 2 | (nd_u64)c;
+    R.u[0] = R.u[0] >> 2 | R.u[1] << 62; R.u[1] = R.u[1] >> 2 | R.u[2] << 62; R.u[2] = R.u[2] >> 2 | R.u[3] << 62; R.u[3] >>= 2;
+    if (k_idx == 0) { F.u[0] &= mask; R.u[0] |= (nd_u64)(3 ^ c) << rc_shift; }
+    else if (k_idx == 1) { F.u[1] &= mask; R.u[1] |= (nd_u64)(3 ^ c) << rc_shift; }
+    else if (k_idx == 2) { F.u[2] &= mask; R.u[2] |= (nd_u64)(3 ^ c) << rc_shift; }
+    else { F.u[3] &= mask; R.u[3] |= (nd_u64)(3 ^ c) << rc_shift; }
+}
+ND_HD int nd_k256_cmp(const nd_k256 &a, const nd_k256 &b)
+{
+    if (a.u[3] != b.u[3]) return a.u[3] < b.u[3] ? -1 : 1;
+    if (a.u[2] != b.u[2]) return a.u[2] < b.u[2] ? -1 : 1;
+    if (a.u[1] != b.u[1]) return a.u[1] < b.u[1] ? -1 : 1;
+    if (a.u[0] != b.u[0]) return a.u[0] < b.u[0] ? -1 : 1;
+    return 0;
+}
+ND_HD nd_u64 nd_k256_hash(const nd_k256 &K, int k_idx, nd_u64 mask)
+{
+    const nd_u64 top = k_idx == 0 ? K.u[0] : k_idx == 1 ? K.u[1] : k_idx == 2 ? K.u[2] : K.u[3];
+    nd_u64 h = nd_hash64_masked(top, mask);
+    if (k_idx > 2 && K.u[2]) h += nd_hash64_nomask(K.u[2]);
+    if (k_idx > 1 && K.u[1]) h += nd_hash64_nomask(K.u[1]);
+    if (k_idx > 0 && K.u[0]) h += nd_hash64_nomask(K.u[0]);
+    return h;
+}
+// sum of the first `cnt` homopolymer runs starting at iteration boundary p (stops early at an ambiguous base or the read end)
+ND_HD int nd_first_runs(const nd_seqview &s, int p, int cnt)
+{
+    int sum = 0;
+    while (cnt > 0 && p < s.len) {
+        const int c = nd_base(s, p);
+        if (c == 4) break;
+        int run = 1;
+        while (p + run < s.len && nd_base(s, p + run) == c) ++run;
+        sum += run; p += run; --cnt;
+    }
+    return sum;
+}
+
+template <int RW, bool LONGK>
 ND_HD_NOINLINE int nd_sketch_chunk(const nd_seqview s, int w, int k, int hpc, uint32_t rid,
                                    int cs, int ce, nd_u128 *out, int cap)
 {
-    const nd_u64 mask = (1ULL << 2 * k) - 1;
-    const int rc_shift = 2 * (k - 1);
+    const int k_idx = (k - 1) / 32, top_bits = (((k - 1) & 31) + 1) << 1;
+    const nd_u64 mask = LONGK ? (1ULL << (top_bits & 63)) - 1 : (1ULL << 2 * k) - 1;
+    const int rc_shift = LONGK ? ((k - 1) & 31) << 1 : 2 * (k - 1);
     const nd_u128 none = { ND_U64_MAX, ND_U64_MAX };
     nd_u128 ring[RW], cur;
     nd_u64 fw, rv;
-    int runq[32], rq_head, rq_n;               // HPC: lengths of the last k runs (ref: sketch.c:40-58)
+    nd_k256 F, R;
+    int runq[32], rq_head, rq_n;               // HPC: run lengths, a 32-entry ring as the reference's tiny_queue_t (ref: sketch.c:40-58)
     int slot, cur_slot, l, span;
     int lookback = 2 * k + w + 8;
     int start, i, j, n;
 
     for (;;) {
-        int units = 0, slots = 0;
+        int units = 0, slots = 0, adj = 0;
         bool primed, verified, retry = false;
         start = cs;
         if (cs > 0) {                          // back up to an iteration boundary `lookback` iterations earlier
@@ -145,7 +197,14 @@ ND_HD_NOINLINE int nd_sketch_chunk(const nd_seqview s, int w, int k, int hpc, ui
             while (start > 0 && !nd_iter_start(s, start, hpc)) --start;
         }
         primed = verified = (start == 0);
+        if (LONGK && hpc && k > 31 && start > 0) {   // span offset of the wrapped run queue (header comment)
+            int rp = start;                    // true reset point: after the last ambiguous base before `start`, or the read start
+            if (s.nmask) { while (rp > 0 && nd_base(s, rp - 1) != 4) --rp; } else rp = 0;
+            const int first = k - (k & 31);
+            adj = nd_first_runs(s, rp, first) - nd_first_runs(s, start, first);
+        }
         fw = rv = 0; cur = none; rq_head = rq_n = 0;
+        F.u[0] = F.u[1] = F.u[2] = F.u[3] = 0; R = F;
         slot = cur_slot = l = span = 0; n = 0;
         for (j = 0; j < w; ++j) ring[j] = none;
 
@@ -173,18 +232,29 @@ ND_HD_NOINLINE int nd_sketch_chunk(const nd_seqview s, int w, int k, int hpc, ui
                     span += run;
                     if (rq_n > k) { span -= runq[rq_head]; rq_head = (rq_head + 1) & 31; --rq_n; }
                 } else span = l + 1 < k ? l + 1 : k;
-                fw = (fw << 2 | (nd_u64)c) & mask;
-                rv = (rv >> 2) | (nd_u64)(3 ^ c) << rc_shift;
-                if (!primed && units < k) { ++units; continue; }   // phase 1: history only
-                if (fw == rv) continue;        // strand-symmetric k-mer: no slot
-                z = fw < rv ? 0 : 1;
+                bool sym;
+                if (!LONGK) {
+                    fw = (fw << 2 | (nd_u64)c) & mask;
+                    rv = (rv >> 2) | (nd_u64)(3 ^ c) << rc_shift;
+                    sym = fw == rv; z = fw < rv ? 0 : 1;
+                } else {
+                    nd_k256_push(F, R, c, k_idx, mask, rc_shift);
+                    const int cmp = nd_k256_cmp(F, R);
+                    sym = cmp == 0; z = cmp < 0 ? 0 : 1;
+                }
+                if (!primed && units < k) {                        // phase 1: history only
+                    if (++units == k) { span += adj; adj = 0; }    // queue primed: from here on `span` is the reference's
+                    continue;
+                }
+                if (sym) continue;             // strand-symmetric k-mer: no slot
                 ++l;
                 if (l >= k && span < 256) {
-                    cand.x = nd_hash64_masked(z ? rv : fw, mask) << 8 | (nd_u64)span;
+                    const nd_u64 h = LONGK ? nd_k256_hash(z ? R : F, k_idx, mask) : nd_hash64_masked(z ? rv : fw, mask);
+                    cand.x = h << 8 | (nd_u64)span;
                     cand.y = (nd_u64)rid << 32 | (nd_u64)(uint32_t)i << 1 | (nd_u64)z;
                 }
             } else {
-                l = 0; rq_n = rq_head = 0; span = 0;
+                l = 0; rq_n = rq_head = 0; span = 0; adj = 0;     // a real reset: the emulated queue is exact from here on
                 if (!primed && units < k) continue;
             }
             ++slots;

@@ -84,7 +84,7 @@ struct nd_reads_dev {
 };
 
 // one thread per chunk of C bases; chunk_off[r] = index of read r's first chunk
-template <int RW>
+template <int RW, bool LONGK>
 __global__ void __launch_bounds__(128)
 k_sketch_chunks(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int C, int w, int k, int hpc,
                 uint32_t rid0, int use_rid, nd_u128 *staging, int S, uint32_t *cnt, int *overflow, const uint32_t *slow)
@@ -100,7 +100,7 @@ k_sketch_chunks(nd_reads_dev R, const nd_u64 *chunk_off, nd_u64 n_chunks, int C,
     sv.words = R.words + R.word_off[r];
     sv.nmask = R.nmask ? R.nmask + (R.word_off[r] >> 1) : nullptr;
     sv.len = len;
-    int n = nd_sketch_chunk<RW>(sv, w, k, hpc, use_rid ? rid0 + (uint32_t)r : 0u, cs, ce, staging + g * (nd_u64)S, S);
+    int n = nd_sketch_chunk<RW, LONGK>(sv, w, k, hpc, use_rid ? rid0 + (uint32_t)r : 0u, cs, ce, staging + g * (nd_u64)S, S);
     if (n > S) { atomicExch(overflow, 1); n = S; }
     cnt[g] = (uint32_t)n;
 }
@@ -404,7 +404,7 @@ __device__ __forceinline__ bool nd_skip_seed(const nd_seed_par &P, nd_u64 r, uin
 // one thread per query minimizer
 __global__ void __launch_bounds__(256)
 k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
-              nd_u64 *m_off, uint32_t *m_n, uint32_t *m_keep, uint32_t *kept_list, uint32_t *n_kept)
+              nd_u64 *m_off, uint32_t *m_n, uint32_t *m_keep)
 {
     nd_u64 m = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t keep = 0;
@@ -423,25 +423,29 @@ k_probe_count(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz
         } else n = n ? ND_MN_REP : 0;                                            // repetitive (n >= mid_occ) vs absent from the index
         m_off[m] = off; m_n[m] = inl ? (n | 0x80000000u) : n; m_keep[m] = keep; // top bit: m_off is the position itself
     }
-    // the few minimizers that yield anchors (one in five here) go on a list, so that the fill kernel runs with full warps; its order
-    // is arbitrary, the anchors' places come from the prefix sums of m_keep
-    const unsigned has = __ballot_sync(0xffffffffu, keep > 0);
-    if (has) {
-        const int lane = threadIdx.x & 31, leader = __ffs(has) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(n_kept, (uint32_t)__popc(has));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep > 0) kept_list[base + __popc(has & ((1u << lane) - 1))] = (uint32_t)m;
-    }
 }
 
 __global__ void __launch_bounds__(256)
-k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, const uint32_t *kept_list, nd_u64 n_kept,
+k_fill_anchors(nd_seed_par P, nd_reads_dev Q, const nd_u128 *mz, const nd_u64 *mz_off, nd_u64 n_mz,
                const nd_u64 *m_off, const uint32_t *m_n, const uint32_t *m_keep, const nd_u64 *a_pos, nd_u128 *a)
 {
-    nd_u64 i = (nd_u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_kept) return;
-    const nd_u64 m = kept_list[i];
+    // one minimizer in five yields anchors: the block first packs the indices of those among its 256 minimizers into shared memory, so
+    // that the fill loop below runs in the first few warps with all lanes busy instead of in every warp with a handful
+    __shared__ uint16_t s_idx[256];
+    __shared__ uint32_t s_wcnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const nd_u64 m0 = (nd_u64)blockIdx.x * blockDim.x;
+    const bool has = m0 + tid < n_mz && m_keep[m0 + tid] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    if (lane == 0) s_wcnt[wid] = (uint32_t)__popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const uint32_t cq = s_wcnt[q]; before += q < wid ? cq : 0; total += cq; }
+    if (has) s_idx[before + __popc(bal & ((1u << lane) - 1))] = (uint16_t)tid;
+    __syncthreads();
+    if ((uint32_t)tid >= total) return;
+    const nd_u64 m = m0 + s_idx[tid];
     nd_u128 z = mz[m];
     int r = nd_find_owner(mz_off, Q.n_reads, m);
     nd_u64 qkey = Q.name_key[r]; uint32_t qlen = Q.len[r], q_pos = (uint32_t)z.y, q_span = (uint32_t)(z.x & 0xff);

@@ -119,7 +119,7 @@ struct ndg_ctx {
     int mid_occ() const { return mid_occ_user > 0 ? mid_occ_user : mid_occ_run; }
     // mapping workspace
     ReadsDev q;
-    DevBuf chunk_owner, kept_list, staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
+    DevBuf chunk_owner, staging, cnt, slow, pos, mz, mz_off, m_off, m_n, m_keep, a_pos, a, a2, a_off, avgq, jobs, flags, seg_start,
            ksw_calls, ksw_seqs, ksw_res, ksw_p, ksw_cig, ksw_scratch,
            f, p, v, t, e, hits, hits_sorted, zkey, zkey2, hidx, hidx2, hq, hq2, cubtmp, scalars;
     HostBuf h_scalars, h_hits, h_stage;
@@ -277,7 +277,7 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
                  nd_u64 *off_out, uint64_t *n_out)
 {
     const ndg_opt_t &o = c->opt;
-    if (o.k < 1 || o.k > 28 || o.w < 1 || o.w > 255) return fail(c, NDG_ERR_ARG, "k must be in [1,28] and w in [1,255] (long-k-mer sketch not implemented on the GPU path)");
+    if (o.k < 1 || o.k > 128 || o.w < 1 || o.w > 255) return fail(c, NDG_ERR_ARG, "k must be in [1,128] and w in [1,255]");
     int C = c->chunk_bases, S = C + o.w + 8;
     uint64_t nc = D.n_chunks;
     *n_out = 0;
@@ -289,7 +289,7 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     CK(cudaMemsetAsync(c->cnt.as<uint32_t>() + nc, 0, 4, c->st));
     nd_reads_dev V = D.view();
     // fast path (closed form) where its preconditions can hold; flagged reads fall through to the state machine
-    const bool fast = !o.hpc && !D.has_nmask && o.w <= NDS_MAXW && C == NDS_C;
+    const bool fast = !o.hpc && !D.has_nmask && o.w <= NDS_MAXW && C == NDS_C && o.k <= 28;
     RSV(c->slow, (size_t)D.n_reads * 4 + 4);
     CK(cudaMemsetAsync(c->slow.p, fast ? 0 : 1, (size_t)D.n_reads * 4, c->st));
     static const bool old_fast = getenv("NDG_SKETCH_OLD") != nullptr;
@@ -306,12 +306,11 @@ int sketch_reads(ndg_ctx *c, const ReadsDev &D, uint32_t rid0, int use_rid, DevB
     else if (fast)
         KLAUNCH("sketch_fast", (k_sketch_fast<<<(unsigned)nc, NDS_T, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, o.w, o.k, rid0, use_rid,
                                 c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), c->slow.as<uint32_t>())));
-    if (o.w < 16)
-        KLAUNCH("sketch", (k_sketch_chunks<16><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
-                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over, c->slow.as<uint32_t>())));
-    else
-        KLAUNCH("sketch", (k_sketch_chunks<256><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid,
-                           c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over, c->slow.as<uint32_t>())));
+#define ND_SKETCH_LAUNCH(RW, LK) KLAUNCH("sketch", (k_sketch_chunks<RW, LK><<<nblk(nc, 128), 128, 0, c->st>>>(V, D.chunk_off.as<nd_u64>(), nc, C, o.w, o.k, o.hpc, rid0, use_rid, \
+                                        c->staging.as<nd_u128>(), S, c->cnt.as<uint32_t>(), d_over, c->slow.as<uint32_t>())))
+    if (o.k <= 28) { if (o.w < 16) ND_SKETCH_LAUNCH(16, false); else ND_SKETCH_LAUNCH(256, false); }
+    else { if (o.w < 64) ND_SKETCH_LAUNCH(64, true); else ND_SKETCH_LAUNCH(256, true); }           // long k-mers (ava-hifi: k = w = 51)
+#undef ND_SKETCH_LAUNCH
     CK(cudaGetLastError());
     if (int rc = scan_u32_to_u64(c, c->cnt.as<uint32_t>(), c->pos.as<nd_u64>(), nc)) return rc;
     uint64_t *h = c->h_scalars.as<uint64_t>();
@@ -405,7 +404,7 @@ extern "C" void ndg_destroy(ndg_ctx_t *c)
                        &c->m_keep, &c->a_pos, &c->a, &c->a2, &c->a_off, &c->ksw_calls, &c->ksw_seqs, &c->ksw_res, &c->ksw_p, &c->ksw_cig, &c->ksw_scratch, &c->avgq, &c->jobs, &c->flags, &c->seg_start, &c->f, &c->p, &c->v, &c->t, &c->e,
                        &c->hits, &c->hits_sorted, &c->zkey, &c->zkey2, &c->hidx, &c->hidx2, &c->hq, &c->hq2, &c->cubtmp, &c->scalars,
                        &c->ksw_ncig, &c->ksw_coff, &c->ksw_cout, &c->ch_cnt, &c->ch_off, &c->ch_a, &c->ch_fend, &c->t_tag,
-                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he, &c->chunk_owner, &c->kept_list };
+                       &c->pf_flag, &c->pf_rank, &c->pf_mp, &c->pf_q, &c->pf_he, &c->chunk_owner };
     for (auto b : bufs) b->release();
     c->q.release(); c->q_next.release(); c->up_next.release();
     if (c->st_copy) { cudaStreamDestroy(c->st_copy); cudaEventDestroy(c->ev_next); }
@@ -548,7 +547,7 @@ void idx_stage_release(ndg_ctx *c)
 // key geometry of the part being built: keys are < key_range (2k hash bits, group tags above them for a tagged index)
 int idx_key_geometry(ndg_ctx *c)
 {
-    int bits = 2 * c->opt.k;
+    int bits = std::min(2 * c->opt.k, 56);             // long k-mers (k > 28) are hashed down to 64 bits and keep the low 56 (x = hash << 8 | span)
     c->tag_shift = 0;
     if (c->t_has_tag) {
         uint32_t mx = 0; for (uint32_t t : c->h_ttag) mx = std::max(mx, t);
@@ -715,8 +714,9 @@ extern "C" int ndg_copy_between(ndg_ctx_t *dst_ctx, void *dst, ndg_ctx_t *src_ct
 // host helper (tests, planning): the slice / rank a minimizer key belongs to in an N-way sharded build of an untagged index
 extern "C" int32_t ndg_index_key_slice(uint64_t key, int32_t k, int32_t n_slices)
 {
-    if (k < 1 || k > 28 || n_slices < 1) return -1;
-    return (int32_t)nd_idx_slice(nd_idx_mix(key, 2 * k), ~0ull / (1ull << 2 * k), (uint32_t)n_slices);
+    if (k < 1 || k > 128 || n_slices < 1) return -1;
+    const int bits = std::min(2 * k, 56);
+    return (int32_t)nd_idx_slice(nd_idx_mix(key, bits), ~0ull / (1ull << bits), (uint32_t)n_slices);
 }
 
 extern "C" int ndg_index_shard_split(ndg_ctx_t *c, int32_t n_slices, uint64_t *counts)
@@ -919,25 +919,22 @@ int map_resident(ndg_ctx *c, int qidx_base)
     if (c->tag_shift > 0 && !Q.has_tag) return fail(c, NDG_ERR_ARG, "the index is tagged: query reads need tags too");
     nd_reads_dev V = Q.view();
     if (M >= (1ULL << 32) - 64) return fail(c, NDG_ERR_OVERFLOW, "sub-batch yields %llu minimizers; lower sub_batch_bases", (unsigned long long)M);
-    RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8); RSV(c->kept_list, (M + 1) * 4);
+    RSV(c->m_off, M * 8); RSV(c->m_n, M * 4); RSV(c->m_keep, (M + 1) * 4); RSV(c->a_pos, (M + 1) * 8);
     CK(cudaMemsetAsync(c->m_keep.as<uint32_t>() + M, 0, 4, c->st));
-    uint32_t *d_nkept = c->scalars.as<uint32_t>() + 208;
-    CK(cudaMemsetAsync(d_nkept, 0, 4, c->st));
     KLAUNCH("probe_count", (k_probe_count<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
-                            c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->kept_list.as<uint32_t>(), d_nkept)));
+                            c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>())));
     CK(cudaGetLastError());
     if (int rc = scan_u32_to_u64(c, c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), M)) return rc;
     CK(cudaMemcpyAsync(h, c->a_pos.as<nd_u64>() + M, 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(h + 1, d_nkept, 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const uint64_t NA = h[0], NKEPT = (uint32_t)h[1];
+    const uint64_t NA = h[0];
     c->n_a = NA;
     if (NA == 0) return 0;
     if (NA >= (1ULL << 32) - 64) return fail(c, NDG_ERR_OVERFLOW, "sub-batch yields %llu anchors; lower sub_batch_bases", (unsigned long long)NA);
 
     // 3. fill + per-read stats
     RSV(c->a, (NA + 1) * 16); RSV(c->a_off, (size_t)(nr + 1) * 8); RSV(c->avgq, (size_t)nr * 4 + 4);
-    KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(NKEPT, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->kept_list.as<uint32_t>(), NKEPT, c->m_off.as<nd_u64>(),
+    KLAUNCH("fill_anchors", (k_fill_anchors<<<nblk(M, 256), 256, 0, c->st>>>(P, V, c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), M, c->m_off.as<nd_u64>(),
                              c->m_n.as<uint32_t>(), c->m_keep.as<uint32_t>(), c->a_pos.as<nd_u64>(), c->a.as<nd_u128>())));
     KLAUNCH("read_stats", (k_read_stats<<<nblk((uint64_t)(nr + 1) * 32, 128), 128, 0, c->st>>>(c->mz.as<nd_u128>(), c->mz_off.as<nd_u64>(), c->m_keep.as<uint32_t>(),
                            c->a_pos.as<nd_u64>(), nr, c->a_off.as<nd_u64>(), c->avgq.as<float>())));

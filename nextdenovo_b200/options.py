@@ -124,6 +124,13 @@ def set_opt(preset, io: IdxOpt, mo: MapOpt) -> int:
         io.k, io.w = 19, 5
         mo.flag |= MM_F_ALL_CHAINS | MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_NO_LJOIN
         mo.min_chain_score, mo.max_gap, mo.max_chain_skip = 100, 10000, 25
+    elif preset == "ava-hifi":                           # ref: minimap2/options.c:98-109 (long k-mers: sketch.c:283-356)
+        io.flag |= MM_I_HPC
+        io.k, io.w = 51, 51
+        mo.a, mo.b, mo.q, mo.q2, mo.e, mo.e2 = 1, 4, 6, 26, 2, 1
+        mo.mid_occ_frac = 1e-4
+        mo.flag |= MM_F_ALL_CHAINS | MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_NO_LJOIN
+        mo.min_chain_score, mo.max_gap, mo.max_chain_skip = 100, 10000, 25
     else:
         return -1
     return 0

@@ -76,16 +76,37 @@ static inline int base_code(char ch) /* ref: minimap2/sketch.c:9-26 (seq_nt4_tab
  *   - the first full window (l == w+k-1) emits ring entries equal to cur;
  *   - the final cur is always flushed.
  */
+/* long k-mers (k > 28, the ava-hifi preset: k = 51).  ref: minimap2/sketch.c:215-281: the k-mer is 2k bits in four 64-bit words (word 0
+ * = the newest bases), strands compared as 256-bit integers, hash = hash64 of the top (partial) word under its mask plus the unmasked
+ * hash of every lower word that is not zero. */
+typedef struct { uint64_t u[4]; } ndo_u256;
+static uint64_t ndo_hash64_nomask(uint64_t key)
+{
+    key = (~key + (key << 21));
+    key ^= key >> 24;
+    key = (key + (key << 3) + (key << 8));
+    key ^= key >> 14;
+    key = (key + (key << 2) + (key << 4));
+    key ^= key >> 28;
+    key = (key + (key << 31));
+    return key;
+}
+
 size_t ndo_sketch(const char *seq, int len, int w, int k, uint32_t rid, int hpc, ndo_u128 *out, size_t n)
 {
-    const uint64_t mask = (1ULL << 2 * k) - 1, rc_shift = 2 * (k - 1);
+    const int longk = k > 28;
+    const int k_idx = (k - 1) / 32, lshift = ((k - 1) & 31) << 1, top_bits = (((k - 1) & 31) + 1) << 1;
+    /* k a multiple of 32: the reference shifts 1ULL by 64, which x86 executes as a shift by 0: the mask is 0 and the top word is wiped (kept) */
+    const uint64_t mask = longk ? (1ULL << (top_bits & 63)) - 1 : (1ULL << 2 * k) - 1, rc_shift = longk ? (uint64_t)lshift : 2 * (k - 1);
     const ndo_u128 none = { UINT64_MAX, UINT64_MAX };
     uint64_t fw = 0, rv = 0;
+    ndo_u256 F = { { 0, 0, 0, 0 } }, R = { { 0, 0, 0, 0 } };
     ndo_u128 ring[256], cur = none;
-    int runq[32], rq_head = 0, rq_n = 0;       /* homopolymer run lengths of the last k runs */
+    int runq[32], rq_head = 0, rq_n = 0;       /* homopolymer run lengths: a 32-entry ring, as the reference's tiny_queue_t -- for k > 31 it
+                                                * wraps before an entry is popped, so `span` is NOT the sum of the last k runs there (kept) */
     int slot = 0, cur_slot = 0, l = 0, span = 0, i, j;
 
-    assert(len > 0 && w > 0 && w < 256 && k > 0 && k <= 28);
+    assert(len > 0 && w > 0 && w < 256 && k > 0 && k <= 128);
     for (j = 0; j < w; ++j) ring[j] = none;
 
     for (i = 0; i < len; ++i) {
@@ -101,13 +122,33 @@ size_t ndo_sketch(const char *seq, int len, int w, int k, uint32_t rid, int hpc,
                 span += run;
                 if (rq_n > k) { span -= runq[rq_head]; rq_head = (rq_head + 1) & 31; --rq_n; }
             } else span = l + 1 < k ? l + 1 : k;
-            fw = (fw << 2 | (uint64_t)c) & mask;
-            rv = (rv >> 2) | (uint64_t)(3 ^ c) << rc_shift;
-            if (fw == rv) continue;                         /* symmetric k-mer: no slot consumed */
-            strand = fw < rv ? 0 : 1;
+            if (!longk) {
+                fw = (fw << 2 | (uint64_t)c) & mask;
+                rv = (rv >> 2) | (uint64_t)(3 ^ c) << rc_shift;
+                if (fw == rv) continue;                     /* symmetric k-mer: no slot consumed */
+                strand = fw < rv ? 0 : 1;
+            } else {
+                int cmp = 0, q;
+                F.u[3] = F.u[3] << 2 | F.u[2] >> 62; F.u[2] = F.u[2] << 2 | F.u[1] >> 62; F.u[1] = F.u[1] << 2 | F.u[0] >> 62; F.u[0] = F.u[0] << 2 | (uint64_t)c;
+                F.u[k_idx] &= mask;
+                R.u[0] = R.u[0] >> 2 | R.u[1] << 62; R.u[1] = R.u[1] >> 2 | R.u[2] << 62; R.u[2] = R.u[2] >> 2 | R.u[3] << 62; R.u[3] >>= 2;
+                R.u[k_idx] |= (uint64_t)(3 ^ c) << rc_shift;
+                for (q = 3; q >= 0 && !cmp; --q) cmp = F.u[q] < R.u[q] ? -1 : F.u[q] > R.u[q] ? 1 : 0;
+                if (cmp == 0) continue;
+                strand = cmp < 0 ? 0 : 1;
+            }
             ++l;
             if (l >= k && span < 256) {
-                cand.x = ndo_hash64(strand ? rv : fw, mask) << 8 | (uint64_t)span;
+                uint64_t h;
+                if (!longk) h = ndo_hash64(strand ? rv : fw, mask);
+                else {
+                    const ndo_u256 *K = strand ? &R : &F;
+                    h = ndo_hash64(K->u[k_idx], mask);
+                    if (k_idx > 2 && K->u[2]) h += ndo_hash64_nomask(K->u[2]);
+                    if (k_idx > 1 && K->u[1]) h += ndo_hash64_nomask(K->u[1]);
+                    if (k_idx > 0 && K->u[0]) h += ndo_hash64_nomask(K->u[0]);
+                }
+                cand.x = h << 8 | (uint64_t)span;
                 cand.y = (uint64_t)rid << 32 | (uint32_t)i << 1 | (uint64_t)strand;
             }
         } else { l = 0; rq_n = rq_head = 0; span = 0; }

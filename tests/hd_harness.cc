@@ -29,7 +29,8 @@ static int selftest_n()
     unsigned long long st = 88172645463325252ULL;
     auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
     long bad = 0, tot = 0;
-    const int cfg[][3] = { {5, 15, 0}, {10, 17, 0}, {7, 16, 0}, {5, 19, 1}, {3, 11, 1}, {1, 9, 0} };
+    const int cfg[][3] = { {5, 15, 0}, {10, 17, 0}, {7, 16, 0}, {5, 19, 1}, {3, 11, 1}, {1, 9, 0},
+                           {51, 51, 1}, {51, 51, 0}, {7, 33, 1}, {9, 32, 1}, {20, 64, 1}, {5, 40, 0}, {13, 29, 1}, {6, 100, 1} };   // long k-mers (k > 28)
     for (int it = 0; it < 1500; ++it) {
         int len = 1 + (int)(rnd() % 1200);
         std::string s(len, 'A');
@@ -51,7 +52,7 @@ static int selftest_n()
             for (int cs = 0; cs < len; cs += cl) {
                 int ce = cs + cl < len ? cs + cl : len;
                 std::vector<nd_u128> tmp(cl + c[0] + 8);
-                int n = nd_sketch_chunk<16>(sv, c[0], c[1], c[2], 9, cs, ce, tmp.data(), (int)tmp.size());
+                int n = (c[1] > 28 ? nd_sketch_chunk<64, true>(sv, c[0], c[1], c[2], 9, cs, ce, tmp.data(), (int)tmp.size()) : nd_sketch_chunk<16, false>(sv, c[0], c[1], c[2], 9, cs, ce, tmp.data(), (int)tmp.size()));
                 got.insert(got.end(), tmp.begin(), tmp.begin() + std::min<int>(n, (int)tmp.size()));
             }
             bool ok = got.size() == n_ref;
@@ -142,7 +143,7 @@ int main(int argc, char **argv)
         for (int cs = 0; cs < len; cs += cl) {
             int ce = cs + cl < len ? cs + cl : len;
             std::vector<nd_u128> tmp(cl + o.w + 8);
-            int n = nd_sketch_chunk<16>(sv, o.w, o.k, o.hpc, 0, cs, ce, tmp.data(), (int)tmp.size());
+            int n = (o.k > 28 ? nd_sketch_chunk<64, true>(sv, o.w, o.k, o.hpc, 0, cs, ce, tmp.data(), (int)tmp.size()) : nd_sketch_chunk<16, false>(sv, o.w, o.k, o.hpc, 0, cs, ce, tmp.data(), (int)tmp.size()));
             if (n > (int)tmp.size()) { fprintf(stderr, "overflow read %d\n", r); return 1; }
             got.insert(got.end(), tmp.begin(), tmp.begin() + n);
         }

@@ -184,3 +184,33 @@ def test_cli_context_pool_small_batches(built, golden_dir, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
     assert r.stderr.count("mapped") >= 3
+
+
+def test_prefetched_batches_equal_plain_calls(engine_mod, reads_sub, golden_dir):
+    """ndg_map_prefetch: batches uploaded ahead on the copy stream (immediately, or deferred until the previous one is taken) map to the
+    same bytes as plain calls; a prefetch that does not match the next call, or exceeds a sub-batch, is simply not used"""
+    io, mo = _opts()
+    e = engine_mod.Engine(0)
+    try:
+        e.set_options(io, mo)
+        e.build_index(reads_sub)
+        parts = [engine_mod.PinnedReads(reads_sub.slice(a, b)) for a, b in ((0, 30), (30, 75), (75, 76), (76, reads_sub.n))]
+        want = open(os.path.join(golden_dir, "S1_sub120_ava-ont.ovl"), "rb").read()
+        st = np.zeros(2, dtype=np.uint32); got = b""
+        e.map_prefetch(parts[0].reads)
+        for i, p in enumerate(parts):
+            if i + 1 < len(parts):
+                e.map_prefetch(parts[i + 1].reads)               # deferred: the second buffer still holds batch i
+            got += e.map_batch_ovl(p.reads, st)[0]
+        assert got == want
+        st[:] = 0; got = b""
+        e.map_prefetch(parts[2].reads)                           # wrong batch prefetched: ignored
+        for p in parts:
+            got += e.map_batch_ovl(p.reads, st)[0]
+        assert got == want
+        e.set_limits(1 << 20, 0)                                 # 1 Mbp sub-batches: the prefetch declines, the call uploads piecewise
+        st[:] = 0
+        e.map_prefetch(parts[3].reads)
+        assert e.map_batch_ovl(parts[0].reads, st)[0] + e.map_batch_ovl(parts[1].reads, st)[0] + e.map_batch_ovl(parts[2].reads, st)[0] + e.map_batch_ovl(parts[3].reads, st)[0] == want
+    finally:
+        e.close()

@@ -66,7 +66,8 @@ def _ref_sketch(L, seq, w, k, rid, hpc):
     return out
 
 
-@pytest.mark.parametrize("w,k,hpc", [(5, 15, 0), (10, 17, 0), (5, 19, 1), (3, 16, 0), (1, 11, 0), (12, 28, 1)])
+@pytest.mark.parametrize("w,k,hpc", [(5, 15, 0), (10, 17, 0), (5, 19, 1), (3, 16, 0), (1, 11, 0), (12, 28, 1),
+                                     (51, 51, 1), (51, 51, 0), (7, 29, 1), (9, 32, 1), (5, 33, 0), (20, 64, 1), (11, 65, 0), (6, 97, 1), (4, 128, 0)])
 def test_sketch_vs_reference(ref, w, k, hpc):
     """ndo_sketch == mm_sketch on random, low-complexity, N-containing and very short sequences"""
     rng = np.random.default_rng(7 + w * 31 + k)

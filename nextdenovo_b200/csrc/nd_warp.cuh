@@ -54,13 +54,18 @@ k_chain_fill_warp(nd_seg_view S, nd_reads_dev Q, const float *avg_qspan, nd_chai
     // Most segments are a stray anchor or two and cannot reach min_cnt / min_chain_score: a warp claims 32 segments with one atomic,
     // every lane sizes one of them, and only the viable ones are chained (one queue round trip per segment used to be the largest
     // stall of this kernel).
+    const uint32_t n_batches = (S.n_seg + 31u) >> 5;
     for (;;) {
         uint32_t s0 = 0;
         if (lane == 0) s0 = atomicAdd(work, 32u);
         s0 = __shfl_sync(NDW_FULL, s0, 0);
         if (s0 >= S.n_seg) break;
         nd_u64 b_l = 0; int n_l = 0; bool ok_l = false;
-        if (s0 + (uint32_t)lane < S.n_seg) ok_l = nd_seg_bounds(S, s0 + (uint32_t)lane, par, max_span, &b_l, &n_l);
+        // lane l of batch b sizes segment l * n_batches + b: the viable segments of a read lie next to each other (the group filter
+        // of the sort puts the stray anchors behind them), and a warp that drew 32 of them in a row would chain them one after another
+        // while its neighbours idle (measured: 0.33 -> 0.57 ms with consecutive claims)
+        const uint32_t s_l = (uint32_t)lane * n_batches + (s0 >> 5);
+        if (s_l < S.n_seg) ok_l = nd_seg_bounds(S, s_l, par, max_span, &b_l, &n_l);
         unsigned viable = __ballot_sync(NDW_FULL, ok_l);
       while (viable) {
         const int src = __ffs(viable) - 1; viable &= viable - 1;
@@ -223,26 +228,114 @@ struct ndw_sort_bufs {
 // for equal x, and only a read that does have duplicates is handed to the exact replay below, untouched.
 #define NDW_FAST_MAX 4096
 #define NDW_FAST_T 256
+
+// Group filter in front of the block sort.  An anchor can only end in a chain if its (strand, target read) group -- the high 32 bits
+// of x -- holds at least min_cnt anchors whose spans could add up to min_chain_score (the same test nd_seg_bounds applies per segment;
+// a group is a superset of its segments).  Most anchors of a read against a large index are stray k-mer hits in groups of one or two
+// (their number grows with the index: +0.8 M per step for every doubling at k = 17), and the sort is the stage they cost most in.
+// Dropping them is exact when the read's remaining anchors have distinct x: their sorted order is then unique, groups never share a
+// segment (different high bits are more than max_gap apart), and the predecessor window of chain.c:50 never crosses a group.  If the
+// kept anchors do hold equal x the read goes to the exact replay with ALL its anchors, untouched.  One block per read counts the groups
+// in a shared-memory hash table; dropped anchors are replaced, behind the sorted ones, by placeholders that are each a segment of one
+// (x above every real target, more than max_gap apart), which the chain kernels skip.
+#define NDW_FILT_HS 4096
+#define NDW_FILT_MAXN 16384
+#define NDW_FILT_EMPTY 0xffffffffu
+__global__ void __launch_bounds__(NDW_FAST_T)
+k_group_filter(const nd_u128 *a, const nd_u64 *a_off, int n_reads, int min_cnt, int min_sc, int max_span, uint32_t max_gap, uint8_t *keep, uint32_t *n_kept)
+{
+    __shared__ uint32_t hk[NDW_FILT_HS], hc[NDW_FILT_HS];
+    __shared__ int s_fail;
+    __shared__ uint32_t s_distinct, s_kept;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const nd_u64 b = a_off[r], n64 = a_off[r + 1] - b;
+    if (n64 <= 1) { if (tid == 0) { n_kept[r] = (uint32_t)n64; if (n64) keep[b] = 1; } return; }
+    const bool can = n64 <= NDW_FILT_MAXN && n64 * ((nd_u64)max_gap + 1) < (1ULL << 32);
+    const uint32_t n = can ? (uint32_t)n64 : 0;
+    for (int i = tid; i < NDW_FILT_HS; i += NDW_FAST_T) { hk[i] = NDW_FILT_EMPTY; hc[i] = 0; }
+    if (tid == 0) { s_fail = can ? 0 : 1; s_distinct = 0; s_kept = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += NDW_FAST_T) {
+        const uint32_t key = (uint32_t)(a[b + i].x >> 32);
+        if (key == NDW_FILT_EMPTY) { s_fail = 1; continue; }
+        uint32_t h = (key * 2654435761u) >> 20;
+        for (int tries = 0;; ++tries) {
+            const uint32_t old = atomicCAS(&hk[h], NDW_FILT_EMPTY, key);
+            if (old == NDW_FILT_EMPTY) { if (atomicAdd(&s_distinct, 1u) >= NDW_FILT_HS * 3 / 4) s_fail = 1; }
+            if (old == NDW_FILT_EMPTY || old == key) { atomicAdd(&hc[h], 1u); break; }
+            h = (h + 1) & (NDW_FILT_HS - 1);
+            if (tries >= NDW_FILT_HS) { s_fail = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_fail) {                                                       // no filtering for this read: everything is kept
+        for (nd_u64 i = tid; i < n64; i += NDW_FAST_T) keep[b + i] = 1;
+        if (tid == 0) n_kept[r] = n64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)n64;
+        return;
+    }
+    uint32_t mine = 0;
+    for (uint32_t i = tid; i < n; i += NDW_FAST_T) {
+        const uint32_t key = (uint32_t)(a[b + i].x >> 32);
+        uint32_t h = (key * 2654435761u) >> 20;
+        while (hk[h] != key) h = (h + 1) & (NDW_FILT_HS - 1);
+        const uint32_t c = hc[h];
+        const bool k = (int)c >= min_cnt && (nd_i64)c * max_span >= (nd_i64)min_sc;
+        keep[b + i] = k ? 1 : 0;
+        mine += k;
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_kept, mine);
+    __syncthreads();
+    if (tid == 0) n_kept[r] = s_kept;
+}
+
+// Fast path (SURVEY H1 option ii): the tie order of the reference's unstable sort is observable only among anchors with EQUAL x
+// (same target position hit from several query positions).  A read whose (kept) anchors all have distinct x has exactly one sorted
+// order, so any correct sort will do: one block sorts the read's (x, index) pairs in shared memory (bitonic network), checks neighbours
+// for equal x, and only a read that does have duplicates is handed to the exact replay below, untouched.
 template <int CAPF>
 __global__ void __launch_bounds__(NDW_FAST_T)
-k_sort_fast(nd_u128 *a, const nd_u64 *a_off, int n_reads, int lo_excl, nd_rs_job *jobs, uint32_t *n_jobs)
+k_sort_fast(nd_u128 *a, const nd_u64 *a_off, int n_reads, int lo_excl, const uint8_t *keep, const uint32_t *n_kept, uint32_t max_gap, nd_rs_job *jobs, uint32_t *n_jobs)
 {
     extern __shared__ unsigned char ndw_fast_smem[];
     nd_u64 *sx = reinterpret_cast<nd_u64 *>(ndw_fast_smem);          // CAPF keys
     nd_u64 *sy = sx + CAPF;                                           // CAPF payloads (y)
     uint16_t *si = reinterpret_cast<uint16_t *>(sy + CAPF);           // CAPF indices
     __shared__ int s_dup;
-    const int r = blockIdx.x, tid = threadIdx.x;
+    __shared__ uint32_t s_w[NDW_FAST_T / 32];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const nd_u64 b = a_off[r], n64 = a_off[r + 1] - b;
-    if (n64 <= (nd_u64)lo_excl || n64 > (nd_u64)CAPF) return;
-    const int n = (int)n64;
-    int m = 1; while (m < n) m <<= 1;                                 // pad to a power of two with the maximum key
+    const long long nk64 = keep ? (long long)n_kept[r] : (long long)n64;
+    if (nk64 <= (long long)lo_excl || nk64 > (long long)CAPF) return;
+    if (n64 < 2) return;
+    const int n = (int)n64, nk = (int)nk64;
+    int m = 1; while (m < nk) m <<= 1;                                // pad to a power of two with the maximum key
     if (tid == 0) s_dup = 0;
-    for (int i = tid; i < m; i += NDW_FAST_T) {
-        if (i < n) { const uint4 v = *reinterpret_cast<const uint4 *>(a + b + i); sx[i] = (nd_u64)v.y << 32 | v.x; sy[i] = (nd_u64)v.w << 32 | v.z; }
-        else sx[i] = ND_U64_MAX;
-        si[i] = (uint16_t)i;
+    if (!keep || nk == n) {
+        for (int i = tid; i < n; i += NDW_FAST_T) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(a + b + i);
+            sx[i] = (nd_u64)v.y << 32 | v.x; sy[i] = (nd_u64)v.w << 32 | v.z; si[i] = (uint16_t)i;
+        }
+        __syncthreads();
+    } else {                                                          // load the kept anchors only (block-wide compaction, 256 at a time)
+        int base = 0;
+        for (int i0 = 0; i0 < n; i0 += NDW_FAST_T) {
+            const int i = i0 + tid;
+            const bool f = i < n && keep[b + i];
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (f) v = *reinterpret_cast<const uint4 *>(a + b + i);
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) s_w[wid] = (uint32_t)__popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < NDW_FAST_T / 32; ++q) { const int cq = (int)s_w[q]; before += q < wid ? cq : 0; total += cq; }
+            if (f) { const int pos = base + before + __popc(bal & ((1u << lane) - 1)); sx[pos] = (nd_u64)v.y << 32 | v.x; sy[pos] = (nd_u64)v.w << 32 | v.z; si[pos] = (uint16_t)pos; }
+            base += total;
+            __syncthreads();
+        }
     }
+    for (int i = nk + tid; i < m; i += NDW_FAST_T) { sx[i] = ND_U64_MAX; si[i] = (uint16_t)i; }
     __syncthreads();
     for (int k = 2; k <= m; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -255,26 +348,30 @@ k_sort_fast(nd_u128 *a, const nd_u64 *a_off, int n_reads, int lo_excl, nd_rs_job
             __syncthreads();
         }
     int dup = 0;
-    for (int i = tid; i + 1 < n; i += NDW_FAST_T) dup |= sx[i] == sx[i + 1];
+    for (int i = tid; i + 1 < nk; i += NDW_FAST_T) dup |= sx[i] == sx[i + 1];
     if (dup) s_dup = 1;
     __syncthreads();
-    if (s_dup) {                                                      // equal keys: the exact emulation decides their order
+    if (s_dup) {                                                      // equal keys: the exact emulation decides their order -- over ALL anchors of the read
         if (n <= ND_RS_SMALL) { if (tid == 0) nd_ins_sort_128x(a + b, a + b + n); return; }   // the reference insertion-sorts these (ksort.h:147)
         if (tid == 0) { const uint32_t q = atomicAdd(n_jobs, 1u); jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0; }
         return;
     }
-    for (int i = tid; i < n; i += NDW_FAST_T) {
+    for (int i = tid; i < nk; i += NDW_FAST_T) {
         const nd_u64 x = sx[i], y = sy[si[i]];
         *reinterpret_cast<uint4 *>(a + b + i) = make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)y, (uint32_t)(y >> 32));
     }
+    for (int i = nk + tid; i < n; i += NDW_FAST_T) {                  // placeholders for the dropped anchors: one-anchor segments above every real target
+        const uint32_t lowx = (uint32_t)(i - nk) * (max_gap + 1u);
+        *reinterpret_cast<uint4 *>(a + b + i) = make_uint4(lowx, 0xffffffffu, 0u, 0u);
+    }
 }
 
-__global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs, uint32_t *n_jobs, int fast_max)
+__global__ void k_rs_init(nd_u128 *a, const nd_u64 *a_off, int n_reads, nd_rs_job *jobs, uint32_t *n_jobs, int fast_max, const uint32_t *n_kept)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     nd_u64 b = a_off[r], n = a_off[r + 1] - b;
-    if (n <= (nd_u64)fast_max) return;                                // k_sort_fast takes it: block sort; equal keys are queued here or insertion-sorted
+    if (fast_max > 0 && (n_kept ? (nd_u64)n_kept[r] : n) <= (nd_u64)fast_max) return;   // k_sort_fast takes it: block sort; equal keys are queued there or insertion-sorted
     if (n > ND_RS_SMALL) {
         uint32_t q = atomicAdd(n_jobs, 1u);
         jobs[q].beg = (uint32_t)b; jobs[q].n = (uint32_t)n; jobs[q].shift = 56; jobs[q].buf = 0;
@@ -451,22 +548,32 @@ k_rs_level(ndw_sort_bufs W, const nd_rs_job *jobs_in, const uint32_t *n_in, nd_r
 // host-side sequencing ------------------------------------------------------------------------
 struct ndw_launch_hooks { void (*begin)(void *ctx, const char *name); void (*end)(void *ctx); void *ctx; };
 
-// jobs: device buffer for 2 * (NA/65 + n_reads + 1) jobs; counters: 24 u32 on the device
+// jobs: device buffer for 2 * (NA/65 + n_reads + 1) jobs; counters: 24 u32 on the device; keep / n_kept: scratch of the group filter
+// (n_a bytes, n_reads u32) or null to sort every anchor
+struct ndw_filter_par { uint8_t *keep; uint32_t *n_kept; int min_cnt, min_sc, max_span; uint32_t max_gap; };
 static inline void ndw_sort_launch(cudaStream_t st, ndw_sort_bufs W, const nd_u64 *a_off, int n_reads, nd_u64 n_a,
-                                   nd_rs_job *jobs, uint32_t *counters, int n_sm, ndw_launch_hooks hk, bool fast_path = true)
+                                   nd_rs_job *jobs, uint32_t *counters, int n_sm, ndw_launch_hooks hk, bool fast_path, ndw_filter_par F)
 {
     const nd_u64 half = n_a / (ND_RS_SMALL + 1) + (nd_u64)n_reads + 1;
     nd_rs_job *buf[2] = { jobs, jobs + half };
     cudaMemsetAsync(counters, 0, 24 * sizeof(uint32_t), st);
+    const bool filt = fast_path && F.keep && F.n_kept;
+    if (filt) {
+        hk.begin(hk.ctx, "sort_filter");
+        k_group_filter<<<n_reads, NDW_FAST_T, 0, st>>>(W.A, a_off, n_reads, F.min_cnt, F.min_sc, F.max_span, F.max_gap, F.keep, F.n_kept);
+        hk.end(hk.ctx);
+    }
     hk.begin(hk.ctx, "sort_init");
-    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(W.A, a_off, n_reads, buf[0], counters, fast_path ? NDW_FAST_MAX : 0);
+    k_rs_init<<<(n_reads + 127) / 128, 128, 0, st>>>(W.A, a_off, n_reads, buf[0], counters, fast_path ? NDW_FAST_MAX : 0, filt ? F.n_kept : nullptr);
     hk.end(hk.ctx);
-    if (fast_path) {                                   // distinct-key reads: block sort in shared memory, three size classes
+    if (fast_path) {                                   // distinct-key reads: block sort in shared memory, four size classes
         cudaFuncSetAttribute(k_sort_fast<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 18);   // per device: cheap, idempotent
+        const uint8_t *kp = filt ? F.keep : nullptr; const uint32_t *nk = filt ? F.n_kept : nullptr;
         hk.begin(hk.ctx, "sort_fast");
-        k_sort_fast<1024><<<n_reads, NDW_FAST_T, 1024 * 18, st>>>(W.A, a_off, n_reads, 1, buf[0], counters);
-        k_sort_fast<2048><<<n_reads, NDW_FAST_T, 2048 * 18, st>>>(W.A, a_off, n_reads, 1024, buf[0], counters);
-        k_sort_fast<4096><<<n_reads, NDW_FAST_T, 4096 * 18, st>>>(W.A, a_off, n_reads, 2048, buf[0], counters);
+        k_sort_fast<512><<<n_reads, NDW_FAST_T, 512 * 18, st>>>(W.A, a_off, n_reads, -1, kp, nk, F.max_gap, buf[0], counters);
+        k_sort_fast<1024><<<n_reads, NDW_FAST_T, 1024 * 18, st>>>(W.A, a_off, n_reads, 512, kp, nk, F.max_gap, buf[0], counters);
+        k_sort_fast<2048><<<n_reads, NDW_FAST_T, 2048 * 18, st>>>(W.A, a_off, n_reads, 1024, kp, nk, F.max_gap, buf[0], counters);
+        k_sort_fast<4096><<<n_reads, NDW_FAST_T, 4096 * 18, st>>>(W.A, a_off, n_reads, 2048, kp, nk, F.max_gap, buf[0], counters);
         hk.end(hk.ctx);
     }
     for (int lvl = 0; lvl < 8; ++lvl) {

@@ -951,7 +951,11 @@ int map_resident(ndg_ctx *c, int qidx_base)
         RSV(c->a2, (NA + 1) * 16);
         ndw_sort_bufs W = { c->a.as<nd_u128>(), c->a2.as<nd_u128>(), c->v.as<uint8_t>(), c->f.as<uint32_t>(), c->p.as<uint32_t>() };
         ndw_launch_hooks hk = { hk_begin, hk_end, c };
-        ndw_sort_launch(c->st, W, c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 64, c->n_sm, hk, c->sort_variant != 2);
+        // group filter scratch: c->flags (segment flags later, NA bytes) and c->t (chain scratch later, >= nr u32)
+        RSV(c->flags, NA + 16); RSV(c->t, std::max<size_t>(NA * 4, (size_t)nr * 4 + 16));
+        static const bool no_filter = getenv("NDG_NO_GROUP_FILTER") != nullptr;
+        ndw_filter_par FP = { no_filter ? nullptr : c->flags.as<uint8_t>(), no_filter ? nullptr : c->t.as<uint32_t>(), o.min_cnt, o.min_chain_score, o.hpc ? 255 : o.k, (uint32_t)o.max_gap };
+        ndw_sort_launch(c->st, W, c->a_off.as<nd_u64>(), nr, NA, c->jobs.as<nd_rs_job>(), c->scalars.as<uint32_t>() + 64, c->n_sm, hk, c->sort_variant != 2, FP);
     }
     CK(cudaGetLastError());
 

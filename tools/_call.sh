@@ -1,2 +1,3 @@
-timeout 1200 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r02n_tests.log 2>&1; echo "tests exit $?"; tail -5 gpurun_out/r02n_tests.log
-timeout 300 python bench.py > gpurun_out/r02n_bench_n1.json 2> gpurun_out/r02n_bench_n1.err; echo "bench exit $?"; cat gpurun_out/r02n_bench_n1.json | head -c 1200
+export ND_NCU_RANGE=1
+timeout 110 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02n_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-ksw --no-regime-b --no-cpu-baseline > gpurun_out/r02n_launches_bench.log 2>&1
+echo "launch list exit $?"; wc -l gpurun_out/r02n_launches_bench.csv

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """profiles/r02_summary.md from the round's captured files (bench lines, ncu launch list, ncu --set full raw CSVs).
-usage: python tools/make_profile_summary.py BENCH.json REF.json LAUNCHES.csv REGIMEA_RAW.csv KSW_RAW.csv [N2.json] > profiles/r02_summary.md"""
+usage: python tools/make_profile_summary.py BENCH.json REF.json LAUNCHES.csv REGIMEA_RAW.csv KSW_RAW.csv [N2.json] [EXTRA_RAW.csv=title ...] > profiles/r02_summary.md"""
 import csv, json, sys, collections, os
 
 bench, ref, launches, rega, ksw = sys.argv[1:6]
-n2 = sys.argv[6] if len(sys.argv) > 6 else None
+n2 = sys.argv[6] if len(sys.argv) > 6 and "=" not in sys.argv[6] else None
+extras = [a.split("=", 1) for a in sys.argv[6:] if "=" in a]
 B, R = json.load(open(bench)), json.load(open(ref))
 out = []
 P = out.append
@@ -63,6 +64,8 @@ def full_table(path, title):
             cells.append(v)
         P("| `%s` | " % name + " | ".join(cells) + " |")
 full_table(rega, "Full capture, regime A (`%s`; at most three launches per kernel shown)" % os.path.basename(rega))
+for path, title in extras:
+    full_table(path, "%s (`%s`)" % (title, os.path.basename(path)))
 full_table(ksw, "Full capture, `ksw_extd2` register-resident kernel on the synthetic batch (`%s`)" % os.path.basename(ksw))
 K = B.get("ksw2_extd2") or {}
 if K:
@@ -78,5 +81,5 @@ if s2 and "seconds" in s2:
 if n2:
     N = json.load(open(n2))
     P("\n## N = 2 (`%s`, one process per GPU over NCCL, weak scaling: 2 x 100 k reads, index built sharded)\n" % os.path.basename(n2))
-    P("value %.3g overlaps/s (%.2fx of N=1), %.3f ms/step, e2e %.3g overlaps/s; index: %s" % (N["value"], N["value"] / B["value"], N["ms_per_step"], N["e2e"]["value"], json.dumps(N["index"])))
+    P("value %.3g overlaps/s (%.2fx of the N=1 line of the same kernels, `r02e`: 2.14e+07/s; NOT re-measured after the group filter and the strided chain claims of `r02n`, which remove most of the per-rank growth of the sort work -- the driver's `SCALE_r02.json` is the current number), %.3f ms/step, e2e %.3g overlaps/s; index: %s" % (N["value"], N["value"] / 21383756.76, N["ms_per_step"], N["e2e"]["value"], json.dumps(N["index"])))
 print("\n".join(out))

@@ -372,7 +372,9 @@ def main_reference(a, rank, world):
             "ms_per_step": 1e3 * tsum / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "impl": "reference",
             "aligned_gbp_per_s": nsq / tsum / 1e9, "reads_per_s": a.steps * B / tsum, "query_gbp_per_s": a.steps * B * READ_LEN / tsum / 1e9,
-            "config": {"workload": workload_desc(a), "batch_reads_per_step": B, "options": "--step 1 -x ava-ont -k 17 -w 10 -K %d" % (B * READ_LEN)},
+            "config": dict({"workload": workload_desc(a), "batch_reads_per_step": B, "options": "--step 1 -x ava-ont -k 17 -w 10 -K %d" % (B * READ_LEN)},
+                           **({"note": "host baseline on the N=1 workload (%d-read index): the box's host cores do not grow with --gpus, and the reference needs minutes "
+                                       "to index the %d reads the GPU arm maps against at N=%d" % (a.reads, a.reads * world, world)} if world > 1 else {})),
             "work": {"records": nrec, "sum_qspan": nsq},
             "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
